@@ -1,0 +1,173 @@
+/* pcgc_b200.h -- C ABI of libpcgc_b200.so: the B200 (sm_100a) implementation of PCGCv1's per-cube
+ * compress/decompress hot path.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Every entry point names the reference interface it replaces (paths into NJUVISION/PCGCv1).
+ * The reference has no FFI of its own (it is Python on TF 1.13); the binding a maintainer adds
+ * is the ctypes stub shown in INTEGRATION.md (pcgcv1_b200/_lib.py is that stub).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative pcgc_status; pcgc_last_error(ctx) gives text.
+ *   - "dev" pointers are CUDA device pointers on the ctx's device, "host" pointers are CPU memory.
+ *   - tensors are dense, channels-last NDHWC float32 unless stated (the reference's layout).
+ *   - all device work is enqueued on the ctx stream (pcgc_set_stream); nothing synchronises unless
+ *     the function returns a host value (documented per function).
+ *   - a ctx is not thread-safe; different ctxs (one per GPU) are independent.  Host coder entry
+ *     points (pcgc_range_*) take no ctx and are re-entrant.
+ */
+#ifndef PCGC_B200_H_
+#define PCGC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCGC_B200_ABI_VERSION 1
+
+typedef struct pcgc_ctx pcgc_ctx;
+
+typedef enum {
+  PCGC_OK = 0,
+  PCGC_ERR_BAD_ARG = -1,    /* null pointer, unknown enum, shape mismatch */
+  PCGC_ERR_BAD_RANGE = -2,  /* symbol range unsupported (single-symbol alphabet, N > PCGC_MAX_SYMBOLS) or k out of range */
+  PCGC_ERR_CUDA = -3,       /* a CUDA call failed; text in pcgc_last_error */
+  PCGC_ERR_OOM = -4,
+  PCGC_ERR_NOT_READY = -5,  /* weights of a required layer were never loaded */
+  PCGC_ERR_OVERFLOW = -6,   /* output buffer too small */
+  PCGC_ERR_CORRUPT = -7     /* bitstream inconsistent with the CDFs */
+} pcgc_status;
+
+/* Nets = the reference's Keras models (checkpoint top-level keys, transform.py:107-111). */
+typedef enum {
+  PCGC_NET_VOX_ANALYSIS = 0,   /* models/model_voxception.py:71-144  AnalysisTransform  */
+  PCGC_NET_VOX_SYNTHESIS = 1,  /* models/model_voxception.py:147-214 SynthesisTransform */
+  PCGC_NET_HYPER_ENCODER = 2,  /* models/model_voxception.py:217-252 HyperEncoder       */
+  PCGC_NET_HYPER_DECODER = 3,  /* models/model_voxception.py:255-308 HyperDecoder       */
+  PCGC_NET_SIMPLE_ANALYSIS = 4,  /* models/model_simple.py:12-51  AnalysisTransform  */
+  PCGC_NET_SIMPLE_SYNTHESIS = 5, /* models/model_simple.py:54-95  SynthesisTransform */
+  PCGC_NET_COUNT = 6
+} pcgc_net;
+
+typedef enum { PCGC_DTYPE_U8 = 0, PCGC_DTYPE_F32 = 1, PCGC_DTYPE_F64 = 2 } pcgc_dtype;
+
+/* Conv engines.  AUTO = tcgen05 implicit GEMM where a layer qualifies, FP32 CUDA-core kernel elsewhere. */
+typedef enum { PCGC_ENGINE_AUTO = 0, PCGC_ENGINE_FFMA = 1, PCGC_ENGINE_UMMA = 2 } pcgc_engine;
+
+#define PCGC_MAX_SYMBOLS 64   /* largest max_v-min_v+1 the conditional CDF kernels accept */
+
+/* ---- context ------------------------------------------------------------------------------- */
+int pcgc_abi_version(void);
+int pcgc_create(pcgc_ctx** out, int device);
+void pcgc_destroy(pcgc_ctx* ctx);
+const char* pcgc_last_error(const pcgc_ctx* ctx);
+/* stream: a cudaStream_t cast to void* (NULL = legacy default stream). */
+int pcgc_set_stream(pcgc_ctx* ctx, void* stream);
+int pcgc_set_engine(pcgc_ctx* ctx, int engine);
+/* number of kernels this library has launched on ctx since creation (bench "gpu_launches"). */
+int64_t pcgc_launch_count(const pcgc_ctx* ctx);
+int pcgc_synchronize(pcgc_ctx* ctx);
+
+/* ---- weights (replaces tf.train.Checkpoint.restore, transform.py:36-38,70-72,107-112,214-218) -- */
+/* kernel: HOST float32 in the Keras layout ([k,k,k,Cin,Cout]; Conv3DTranspose [k,k,k,Cout,Cin]),
+ * kshape = its 5 dims, bias: HOST float32 [Cout] or NULL for use_bias=False layers.
+ * layer = the Keras name= of the layer ("conv_in", "vrn1_1_conv1_1", "up_1", ...). */
+int pcgc_load_conv(pcgc_ctx* ctx, int net, const char* layer, const float* kernel, const int64_t kshape[5],
+                   const float* bias);
+/* EntropyBottleneck variables (models/entropy_model.py:42-68), HOST float32:
+ * matrices = matrix_0..3 concatenated ([C,3,1],[C,3,3],[C,3,3],[C,1,3]), biases = bais_0..3
+ * ([C,3,1]x3,[C,1,1]), factors = factor_0..3 (same shapes as biases).  slot 0 = "estimator"
+ * of the checkpoint; slot 1 is free for a second bottleneck. */
+int pcgc_load_bottleneck(pcgc_ctx* ctx, int slot, int channels, const float* matrices, const float* biases,
+                         const float* factors);
+
+/* ---- transforms (dev pointers) --------------------------------------------------------------- */
+/* AnalysisTransform()(x), one call for B cubes instead of tf.map_fn(parallel_iterations=1)
+ * (transform.py:42-48,116-122).  cubes: [B,64,64,64,1] of `dtype`; y: [B,16,16,16,16] (voxception)
+ * or [B,8,8,8,32] (simple).  net = PCGC_NET_VOX_ANALYSIS | PCGC_NET_SIMPLE_ANALYSIS. */
+int pcgc_analysis(pcgc_ctx* ctx, int net, const void* cubes_dev, int dtype, int B, float* y_dev);
+/* SynthesisTransform()(y) (transform.py:79-84,181-183,251-256): logits [B,64,64,64,1]. */
+int pcgc_synthesis(pcgc_ctx* ctx, int net, const float* y_dev, int B, float* logits_dev);
+/* HyperEncoder()(y) (transform.py:125-131): y [B,16,16,16,16] -> z [B,8,8,8,8]. */
+int pcgc_hyper_encode(pcgc_ctx* ctx, const float* y_dev, int B, float* z_dev);
+/* HyperDecoder()(z_hat) followed by scales = max(scales, 1e-9) (transform.py:138-146,225-233):
+ * z_hat [B,8,8,8,8] -> loc, scale [B,16,16,16,16]; scale = max(|.|, scale_floor).
+ * Bit-reproducible across calls, batch sizes and devices of the same type. */
+int pcgc_hyper_decode(pcgc_ctx* ctx, const float* z_hat_dev, int B, float scale_floor, float* loc_dev,
+                      float* scale_dev);
+
+/* ---- factorized entropy model (models/entropy_model.py) ---------------------------------------- */
+/* EntropyBottleneck.__call__(x, training=False) (:153-181): x_hat = round-half-even(x),
+ * p = max(|sigmoid(s*u)-sigmoid(s*l)|, bound).  x: [n_vox, C] (C fastest).  Optional outputs
+ * (NULL to skip): x_hat_dev, p_dev [n_vox*C]; bits_dev (double, sum(log2 p) * -1);
+ * minmax_dev int32[2] = {floor(min x_hat), ceil(max x_hat)} (:249-250).  No host sync. */
+int pcgc_factorized_quantize_likelihood(pcgc_ctx* ctx, int slot, const float* x_dev, int64_t n_vox, int C,
+                                        float likelihood_bound, float* x_hat_dev, float* p_dev,
+                                        double* bits_dev, int32_t* minmax_dev);
+/* EntropyBottleneck._get_cdf (:183-221): int32 cdf [C, N+1] to HOST, N = max_v-min_v+1 >= 2.
+ * Synchronises the ctx stream. */
+int pcgc_factorized_cdf(pcgc_ctx* ctx, int slot, int min_v, int max_v, float likelihood_bound, int precision,
+                        int32_t* cdf_host);
+
+/* ---- conditional (Laplace) entropy model (models/conditional_entropy_model.py) ------------------ */
+/* SymmetricConditional.__call__(y, loc, scale, training=False) (:71-93) per cube.
+ * y, loc, scale: [B, E] (E elements per cube, 65536 for voxception).  Optional outputs:
+ * y_hat_dev, p_dev [B,E]; bits_dev double[B]; minmax_dev int32[2B] = {min_v, max_v} per cube
+ * (:153-154).  No host sync. */
+int pcgc_laplace_quantize_likelihood(pcgc_ctx* ctx, const float* y_dev, const float* loc_dev,
+                                     const float* scale_dev, int B, int64_t E, float likelihood_bound,
+                                     float* y_hat_dev, float* p_dev, double* bits_dev, int32_t* minmax_dev);
+/* Encoder side of SymmetricConditional._get_cdf + range_encode's table lookup (:95-124,142-161):
+ * for every element builds its quantised CDF row over min_v[b]..max_v[b] and emits only the
+ * interval of the element's own symbol: interval = lower | (upper-lower-1) << 16.
+ * y_hat: [B,E] rounded latents; minmax_dev int32[2B] (device, e.g. from the call above). */
+int pcgc_laplace_intervals(pcgc_ctx* ctx, const float* y_hat_dev, const float* loc_dev, const float* scale_dev,
+                           int B, int64_t E, const int32_t* minmax_dev, float likelihood_bound, int precision,
+                           uint32_t* intervals_dev);
+/* Decoder side (:186-195): full rows.  Cube b's rows start at row_offset[b] (in uint16 units,
+ * HOST array of B+1 prefix sums of E*N_b) and hold cdf[0..N_b-1] as uint16 (cdf[N_b] = 2^precision
+ * is implied).  minmax_host int32[2B]. */
+int pcgc_laplace_cdf(pcgc_ctx* ctx, const float* loc_dev, const float* scale_dev, int B, int64_t E,
+                     const int32_t* minmax_host, float likelihood_bound, int precision,
+                     const int64_t* row_offset_host, uint16_t* cdf_dev);
+
+/* ---- top-k occupancy classification (dataprocess/inout_points.py:147-179) ---------------------- */
+/* select_voxels: per cube k = ks[b] (caller computes int(rho * n_points)); threshold = k-th
+ * largest logit; mask = logits >= threshold (ties kept).  k == 0 reproduces the reference's
+ * values[-0] quirk (threshold = smallest logit > -2.0).  Outputs: mask_dev uint8 [B,V],
+ * thres_dev float[B] (optional), count_dev int32[B] (optional, voxels set). */
+int pcgc_topk_select(pcgc_ctx* ctx, const float* logits_dev, int B, int64_t V, const int32_t* ks_dev,
+                     uint8_t* mask_dev, float* thres_dev, int32_t* count_dev);
+/* fixed_thres bypass of select_voxels (:157-160). */
+int pcgc_threshold_select(pcgc_ctx* ctx, const float* logits_dev, int B, int64_t V, float thres,
+                          uint8_t* mask_dev, int32_t* count_dev);
+
+/* ---- host range coder (replaces coder_ops.range_encode / range_decode / pmf_to_quantized_cdf,
+ *      models/entropy_model.py:218,258,298; models/conditional_entropy_model.py:122,161,195) ------ */
+/* pmf float32 [rows,N] -> cdf int32 [rows,N+1]. */
+int pcgc_pmf_to_quantized_cdf(const float* pmf, int64_t rows, int N, int precision, int32_t* cdf);
+/* Symbols sym[i] coded with row (i % cdf_rows) of cdf [cdf_rows, N+1] (the EntropyBottleneck
+ * broadcast [1,C,N+1] against data [M,C]).  out/cap: caller buffer; *len receives the size. */
+int pcgc_range_encode(const int16_t* sym, int64_t n, const int32_t* cdf, int cdf_rows, int N, int precision,
+                      uint8_t* out, int64_t cap, int64_t* len);
+int pcgc_range_decode(const uint8_t* data, int64_t nbytes, int64_t n, const int32_t* cdf, int cdf_rows, int N,
+                      int precision, int16_t* sym);
+/* Per-element intervals from pcgc_laplace_intervals -> one string. */
+int pcgc_range_encode_intervals(const uint32_t* intervals, int64_t n, int precision, uint8_t* out, int64_t cap,
+                                int64_t* len);
+/* Per-element rows from pcgc_laplace_cdf (N uint16 per element, last implied) -> symbols. */
+int pcgc_range_decode_rows(const uint8_t* data, int64_t nbytes, int64_t n, const uint16_t* rows, int N,
+                           int precision, int16_t* sym);
+/* Many independent strings at once on a host thread pool (threads <= 0: all cores).
+ * Cube b: intervals + b*E, output written at out + b*stride, length in lens[b]. */
+int pcgc_range_encode_intervals_batch(const uint32_t* intervals, int B, int64_t E, int precision, uint8_t* out,
+                                      int64_t stride, int64_t* lens, int threads);
+int pcgc_range_decode_rows_batch(const uint8_t* const* data, const int64_t* nbytes, int B, int64_t E,
+                                 const uint16_t* rows, const int64_t* row_offset, const int32_t* minmax,
+                                 int precision, int16_t* sym, int threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCGC_B200_H_ */

@@ -1,0 +1,627 @@
+// C ABI of libpcgc_b200.so: context, weights, the per-net layer programs and the entry points
+// declared in include/pcgc_b200.h.  Layer tables restate models/model_voxception.py:21-54,83-122,
+// 153-192,224-244,263-297 and models/model_simple.py:21-42,58-86 (names = the Keras name= args).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "umma_conv.cuh"
+
+using namespace pcgc;
+
+namespace {
+
+struct LayerSpec {
+  std::string name;
+  int cin, cout, k, stride;
+  bool transposed, bias, relu;
+};
+
+enum Buf { BUF_IN = 0, BUF_X0, BUF_A, BUF_B, BUF_T1, BUF_T2, BUF_OUT0, BUF_OUT1, BUF_COUNT };
+
+struct Op {
+  int layer;
+  int in, in_n, in_cs, in_co;
+  int out, out_cs, out_co;
+  int res, res_cs, res_co;      // res < 0: none
+  int flags;
+};
+
+struct LayerW {
+  bool loaded = false;
+  int n_classes = 0;
+  ConvDesc cls[8];
+  float* bias = nullptr;
+  UmmaWeights umma;             // packed bf16 hi/lo weights when the layer qualifies for tcgen05
+};
+
+struct Net {
+  std::vector<LayerSpec> specs;
+  std::vector<LayerW> w;
+  std::vector<Op> ops;
+  int in_n = 0, in_c = 0;       // external input grid / channels
+  size_t elems[BUF_COUNT] = {0};   // floats per cube of each internal buffer
+  int find(const char* name) const {
+    for (size_t i = 0; i < specs.size(); ++i) if (specs[i].name == name) return (int)i;
+    return -1;
+  }
+};
+
+void add_vrn_specs(Net& n, const std::string& p, int c) {
+  n.specs.push_back({p + "_conv1_1", c, c / 4, 3, 1, false, true, true});
+  n.specs.push_back({p + "_conv1_2", c / 4, c / 2, 3, 1, false, true, true});
+  n.specs.push_back({p + "_conv2_1", c, c / 4, 1, 1, false, true, true});
+  n.specs.push_back({p + "_conv2_2", c / 4, c / 4, 3, 1, false, true, true});
+  n.specs.push_back({p + "_conv2_3", c / 4, c / 2, 1, 1, false, true, true});
+}
+
+struct Builder {
+  Net& n;
+  explicit Builder(Net& net) : n(net) {}
+  void need(int buf, size_t e) { if (buf != BUF_IN && buf < BUF_OUT0) n.elems[buf] = std::max(n.elems[buf], e); }
+  // returns the output grid edge
+  int conv(const char* name, int in, int in_n, int in_cs, int in_co, int out, int out_cs, int out_co,
+           int res = -1, int res_cs = 0, int res_co = 0, int extra_flags = 0) {
+    const int li = n.find(name);
+    const LayerSpec& s = n.specs[li];
+    const int out_n = s.transposed ? in_n * s.stride : in_n / s.stride;
+    Op op{li, in, in_n, in_cs, in_co, out, out_cs, out_co, res, res_cs, res_co, (s.relu ? EPI_RELU : 0) | extra_flags};
+    n.ops.push_back(op);
+    need(in, (size_t)in_n * in_n * in_n * in_cs);
+    need(out, (size_t)out_n * out_n * out_n * out_cs);
+    return out_n;
+  }
+  // _VoxceptionResNet.call (model_voxception.py:56-68): X -> Y, both C channels on an n^3 grid.
+  void vrn(const std::string& p, int c, int nn, int X, int Y) {
+    conv((p + "_conv1_1").c_str(), X, nn, c, 0, BUF_T1, c / 2, 0);
+    conv((p + "_conv2_1").c_str(), X, nn, c, 0, BUF_T1, c / 2, c / 4);
+    conv((p + "_conv1_2").c_str(), BUF_T1, nn, c / 2, 0, Y, c, 0, X, c, 0);           // relu(x + concat[..])
+    conv((p + "_conv2_2").c_str(), BUF_T1, nn, c / 2, c / 4, BUF_T2, c / 4, 0);
+    conv((p + "_conv2_3").c_str(), BUF_T2, nn, c / 4, 0, Y, c, c / 2, X, c, c / 2);
+  }
+};
+
+void build_net(Net& n, int kind) {
+  n.specs.clear(); n.ops.clear();
+  Builder b(n);
+  auto S = [&](const char* name, int cin, int cout, int k = 3, int stride = 1, bool tr = false, bool bias = true,
+               bool relu = true) { n.specs.push_back({name, cin, cout, k, stride, tr, bias, relu}); };
+  switch (kind) {
+    case PCGC_NET_VOX_ANALYSIS: {
+      S("conv_in", 1, 16);
+      for (int i = 1; i <= 3; ++i) add_vrn_specs(n, "vrn1_" + std::to_string(i), 16);
+      S("down_1", 16, 32, 3, 2, false, false, true);
+      for (int i = 1; i <= 3; ++i) add_vrn_specs(n, "vrn2_" + std::to_string(i), 32);
+      S("down_2", 32, 64, 3, 2, false, false, true);
+      for (int i = 1; i <= 3; ++i) add_vrn_specs(n, "vrn3_" + std::to_string(i), 64);
+      S("conv_out", 64, 16, 3, 1, false, true, false);
+      n.in_n = 64; n.in_c = 1;
+      b.conv("conv_in", BUF_X0, 64, 1, 0, BUF_A, 16, 0);
+      b.vrn("vrn1_1", 16, 64, BUF_A, BUF_B); b.vrn("vrn1_2", 16, 64, BUF_B, BUF_A); b.vrn("vrn1_3", 16, 64, BUF_A, BUF_B);
+      b.conv("down_1", BUF_B, 64, 16, 0, BUF_A, 32, 0);
+      b.vrn("vrn2_1", 32, 32, BUF_A, BUF_B); b.vrn("vrn2_2", 32, 32, BUF_B, BUF_A); b.vrn("vrn2_3", 32, 32, BUF_A, BUF_B);
+      b.conv("down_2", BUF_B, 32, 32, 0, BUF_A, 64, 0);
+      b.vrn("vrn3_1", 64, 16, BUF_A, BUF_B); b.vrn("vrn3_2", 64, 16, BUF_B, BUF_A); b.vrn("vrn3_3", 64, 16, BUF_A, BUF_B);
+      b.conv("conv_out", BUF_B, 16, 64, 0, BUF_OUT0, 16, 0);
+    } break;
+    case PCGC_NET_VOX_SYNTHESIS: {
+      S("deconv_in", 16, 64);
+      for (int i = 1; i <= 3; ++i) add_vrn_specs(n, "dvrn1_" + std::to_string(i), 64);
+      S("up_1", 64, 32, 3, 2, true, true, true);
+      for (int i = 1; i <= 3; ++i) add_vrn_specs(n, "dvrn2_" + std::to_string(i), 32);
+      S("up_2", 32, 16, 3, 2, true, true, true);
+      for (int i = 1; i <= 3; ++i) add_vrn_specs(n, "dvrn3_" + std::to_string(i), 16);
+      S("deconv_out", 16, 1, 3, 1, false, true, false);
+      n.in_n = 16; n.in_c = 16;
+      b.conv("deconv_in", BUF_IN, 16, 16, 0, BUF_A, 64, 0);
+      b.vrn("dvrn1_1", 64, 16, BUF_A, BUF_B); b.vrn("dvrn1_2", 64, 16, BUF_B, BUF_A); b.vrn("dvrn1_3", 64, 16, BUF_A, BUF_B);
+      b.conv("up_1", BUF_B, 16, 64, 0, BUF_A, 32, 0);
+      b.vrn("dvrn2_1", 32, 32, BUF_A, BUF_B); b.vrn("dvrn2_2", 32, 32, BUF_B, BUF_A); b.vrn("dvrn2_3", 32, 32, BUF_A, BUF_B);
+      b.conv("up_2", BUF_B, 32, 32, 0, BUF_A, 16, 0);
+      b.vrn("dvrn3_1", 16, 64, BUF_A, BUF_B); b.vrn("dvrn3_2", 16, 64, BUF_B, BUF_A); b.vrn("dvrn3_3", 16, 64, BUF_A, BUF_B);
+      b.conv("deconv_out", BUF_B, 64, 16, 0, BUF_OUT0, 1, 0);
+    } break;
+    case PCGC_NET_HYPER_ENCODER: {
+      S("conv1", 16, 16); S("conv2", 16, 16, 3, 2); S("conv3", 16, 8, 3, 1, false, true, false);
+      n.in_n = 16; n.in_c = 16;
+      b.conv("conv1", BUF_IN, 16, 16, 0, BUF_A, 16, 0);
+      b.conv("conv2", BUF_A, 16, 16, 0, BUF_B, 16, 0);
+      b.conv("conv3", BUF_B, 8, 16, 0, BUF_OUT0, 8, 0);
+    } break;
+    case PCGC_NET_HYPER_DECODER: {
+      S("deconv1", 8, 16); S("deconv2", 16, 16, 3, 2, true); S("deconv3", 16, 32);
+      S("deconv4_1", 32, 16, 3, 1, false, true, false); S("deconv4_2", 32, 16, 3, 1, false, true, false);
+      n.in_n = 8; n.in_c = 8;
+      b.conv("deconv1", BUF_IN, 8, 8, 0, BUF_A, 16, 0);
+      b.conv("deconv2", BUF_A, 8, 16, 0, BUF_B, 16, 0);
+      b.conv("deconv3", BUF_B, 16, 16, 0, BUF_A, 32, 0);
+      b.conv("deconv4_1", BUF_A, 16, 32, 0, BUF_OUT0, 16, 0);
+      b.conv("deconv4_2", BUF_A, 16, 32, 0, BUF_OUT1, 16, 0, -1, 0, 0, EPI_ABS | EPI_FLOOR);  // abs (:308) + max(.,1e-9) (transform.py:146)
+    } break;
+    case PCGC_NET_SIMPLE_ANALYSIS: {
+      S("conv_1", 1, 32, 9, 2); S("conv_2", 32, 32, 5, 2); S("conv_3", 32, 32, 5, 2, false, false, false);
+      n.in_n = 64; n.in_c = 1;
+      b.conv("conv_1", BUF_X0, 64, 1, 0, BUF_A, 32, 0);
+      b.conv("conv_2", BUF_A, 32, 32, 0, BUF_B, 32, 0);
+      b.conv("conv_3", BUF_B, 16, 32, 0, BUF_OUT0, 32, 0);
+    } break;
+    case PCGC_NET_SIMPLE_SYNTHESIS: {
+      S("deconv_1", 32, 32, 5, 2, true); S("deconv_2", 32, 32, 5, 2, true); S("deconv_3", 32, 1, 9, 2, true, true, false);
+      n.in_n = 8; n.in_c = 32;
+      b.conv("deconv_1", BUF_IN, 8, 32, 0, BUF_A, 32, 0);
+      b.conv("deconv_2", BUF_A, 16, 32, 0, BUF_B, 32, 0);
+      b.conv("deconv_3", BUF_B, 32, 32, 0, BUF_OUT0, 1, 0);
+    } break;
+  }
+  n.w.assign(n.specs.size(), LayerW());
+}
+
+}  // namespace
+
+struct pcgc_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int engine = PCGC_ENGINE_AUTO;
+  int64_t launches = 0;
+  std::string err;
+  Net nets[PCGC_NET_COUNT];
+  BottleneckDev bn[2];
+  // workspaces
+  float* bufs[BUF_COUNT] = {nullptr};
+  size_t buf_cap[BUF_COUNT] = {0};
+  double* scratch = nullptr; size_t scratch_cap = 0;
+  float* pmf_dev = nullptr;
+  int* err_flag = nullptr;          // device int
+  int32_t* mm_dev = nullptr; size_t mm_cap = 0;
+  int64_t* off_dev = nullptr; size_t off_cap = 0;
+  int sub_batch = 32;
+};
+
+namespace {
+
+int fail(pcgc_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? PCGC_ERR_OOM : PCGC_ERR_CUDA, "%s: %s", #call, \
+                  cudaGetErrorString(e_));                                                    \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int ensure(pcgc_ctx* ctx, float** p, size_t* cap, size_t elems) {
+  if (*cap >= elems) return PCGC_OK;
+  if (*p) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(*p)); *p = nullptr; *cap = 0; }
+  CK(cudaMalloc((void**)p, elems * sizeof(float)));
+  *cap = elems;
+  return PCGC_OK;
+}
+
+int ensure_scratch(pcgc_ctx* ctx, size_t n) {
+  if (ctx->scratch_cap >= n) return PCGC_OK;
+  if (ctx->scratch) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(ctx->scratch)); ctx->scratch = nullptr; }
+  CK(cudaMalloc((void**)&ctx->scratch, n * sizeof(double)));
+  ctx->scratch_cap = n;
+  return PCGC_OK;
+}
+
+// pad-before of TF SAME for an even extent: stride 1 -> (k-1)/2 ; stride 2 -> (k-2)/2
+int same_pad_before(int k, int stride) { return stride == 1 ? (k - 1) / 2 : (k - 2) / 2; }
+
+int check_err_flag(pcgc_ctx* ctx, const char* what) {
+  int h = 0;
+  CK(cudaMemcpyAsync(&h, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (h != 0) {
+    CK(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), ctx->stream));
+    return fail(ctx, h, "%s: device-side check failed (code %d)", what, h);
+  }
+  return PCGC_OK;
+}
+
+int run_net(pcgc_ctx* ctx, int kind, const float* in_ext, const void* cubes, int cubes_dtype, int B, float* out0,
+            float* out1, float floor_v) {
+  Net& n = ctx->nets[kind];
+  for (size_t i = 0; i < n.w.size(); ++i)
+    if (!n.w[i].loaded) return fail(ctx, PCGC_ERR_NOT_READY, "net %d: layer '%s' has no weights", kind, n.specs[i].name.c_str());
+  if (B <= 0) return PCGC_OK;
+  const int SB = std::min(B, ctx->sub_batch);
+  for (int bi = BUF_X0; bi < BUF_OUT0; ++bi) {
+    size_t e = n.elems[bi];
+    if (bi == BUF_X0 && cubes) e = std::max(e, (size_t)n.in_n * n.in_n * n.in_n * n.in_c);
+    if (e) { int r = ensure(ctx, &ctx->bufs[bi], &ctx->buf_cap[bi], e * SB); if (r) return r; }
+  }
+  const size_t in_elems = (size_t)n.in_n * n.in_n * n.in_n * n.in_c;
+  // output sizes per cube
+  size_t out_elems[2] = {0, 0};
+  for (const Op& op : n.ops) {
+    const LayerSpec& s = n.specs[op.layer];
+    const int out_n = s.transposed ? op.in_n * s.stride : op.in_n / s.stride;
+    if (op.out == BUF_OUT0) out_elems[0] = (size_t)out_n * out_n * out_n * op.out_cs;
+    if (op.out == BUF_OUT1) out_elems[1] = (size_t)out_n * out_n * out_n * op.out_cs;
+  }
+  for (int b0 = 0; b0 < B; b0 += SB) {
+    const int nb = std::min(SB, B - b0);
+    float* ptr[BUF_COUNT];
+    for (int i = 0; i < BUF_COUNT; ++i) ptr[i] = ctx->bufs[i];
+    ptr[BUF_OUT0] = out0 ? out0 + (size_t)b0 * out_elems[0] : nullptr;
+    ptr[BUF_OUT1] = out1 ? out1 + (size_t)b0 * out_elems[1] : nullptr;
+    if (cubes) {
+      const size_t esz = cubes_dtype == PCGC_DTYPE_U8 ? 1 : (cubes_dtype == PCGC_DTYPE_F32 ? 4 : 8);
+      CK(launch_u8_to_f32((const char*)cubes + (size_t)b0 * in_elems * esz, cubes_dtype, ctx->bufs[BUF_X0],
+                          (int64_t)nb * in_elems, ctx->stream, &ctx->launches));
+      ptr[BUF_IN] = ctx->bufs[BUF_X0];
+    } else {
+      ptr[BUF_IN] = const_cast<float*>(in_ext) + (size_t)b0 * in_elems;
+    }
+    for (const Op& op : n.ops) {
+      const LayerSpec& s = n.specs[op.layer];
+      LayerW& lw = n.w[op.layer];
+      const int out_n = s.transposed ? op.in_n * s.stride : op.in_n / s.stride;
+      ConvCall c;
+      c.in = ptr[op.in]; c.in_n = op.in_n; c.in_cs = op.in_cs; c.in_co = op.in_co;
+      c.out = ptr[op.out]; c.out_n = out_n; c.out_cs = op.out_cs; c.out_co = op.out_co;
+      c.bias = lw.bias;
+      c.res = op.res >= 0 ? ptr[op.res] : nullptr; c.res_cs = op.res_cs; c.res_co = op.res_co;
+      c.flags = op.flags; c.floor_v = floor_v;
+      c.B = nb;
+      if (!c.out) return fail(ctx, PCGC_ERR_BAD_ARG, "net %d: missing output pointer", kind);
+      bool done = false;
+      if (ctx->engine != PCGC_ENGINE_FFMA && lw.umma.ok && lw.n_classes == 1) {
+        c.d = lw.cls[0]; c.tn = out_n;
+        cudaError_t e = launch_conv_umma(c, lw.umma, ctx->stream, &ctx->launches);
+        if (e == cudaSuccess) done = true;
+        else if (e != cudaErrorNotSupported) return fail(ctx, PCGC_ERR_CUDA, "umma conv '%s': %s", s.name.c_str(), cudaGetErrorString(e));
+      }
+      if (!done) {
+        if (ctx->engine == PCGC_ENGINE_UMMA && lw.umma.ok)
+          return fail(ctx, PCGC_ERR_CUDA, "umma conv '%s' unavailable", s.name.c_str());
+        for (int k = 0; k < lw.n_classes; ++k) {
+          c.d = lw.cls[k];
+          c.tn = s.transposed ? op.in_n : out_n;
+          cudaError_t e = launch_conv_ffma(c, ctx->stream, &ctx->launches);
+          if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "conv '%s': %s", s.name.c_str(), cudaGetErrorString(e));
+        }
+      }
+    }
+  }
+  return PCGC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pcgc_create(pcgc_ctx** out, int device) {
+  if (!out) return PCGC_ERR_BAD_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return PCGC_ERR_CUDA;
+  pcgc_ctx* ctx = new pcgc_ctx();
+  ctx->device = device;
+  DeviceGuard g(device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+    // sm_100a SASS only: refuse loudly instead of failing at the first launch
+    delete ctx;
+    return PCGC_ERR_CUDA;
+  }
+  for (int k = 0; k < PCGC_NET_COUNT; ++k) build_net(ctx->nets[k], k);
+  if (cudaMalloc((void**)&ctx->err_flag, sizeof(int)) != cudaSuccess ||
+      cudaMemset(ctx->err_flag, 0, sizeof(int)) != cudaSuccess ||
+      cudaMalloc((void**)&ctx->pmf_dev, 32 * 512 * sizeof(float)) != cudaSuccess) {
+    delete ctx;
+    return PCGC_ERR_CUDA;
+  }
+  *out = ctx;
+  return PCGC_OK;
+}
+
+void pcgc_destroy(pcgc_ctx* ctx) {
+  if (!ctx) return;
+  DeviceGuard g(ctx->device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < BUF_COUNT; ++i) if (ctx->bufs[i]) cudaFree(ctx->bufs[i]);
+  for (auto& n : ctx->nets)
+    for (auto& lw : n.w) {
+      for (int k = 0; k < lw.n_classes; ++k) if (lw.cls[k].w) cudaFree((void*)lw.cls[k].w);
+      if (lw.bias) cudaFree(lw.bias);
+      free_umma_weights(lw.umma);
+    }
+  for (auto& b : ctx->bn) if (b.params) cudaFree(b.params);
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->pmf_dev) cudaFree(ctx->pmf_dev);
+  if (ctx->err_flag) cudaFree(ctx->err_flag);
+  if (ctx->mm_dev) cudaFree(ctx->mm_dev);
+  if (ctx->off_dev) cudaFree(ctx->off_dev);
+  delete ctx;
+}
+
+const char* pcgc_last_error(const pcgc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+int pcgc_set_stream(pcgc_ctx* ctx, void* stream) {
+  if (!ctx) return PCGC_ERR_BAD_ARG;
+  ctx->stream = (cudaStream_t)stream;
+  return PCGC_OK;
+}
+
+int pcgc_set_engine(pcgc_ctx* ctx, int engine) {
+  if (!ctx || engine < 0 || engine > 2) return PCGC_ERR_BAD_ARG;
+  ctx->engine = engine;
+  return PCGC_OK;
+}
+
+int64_t pcgc_launch_count(const pcgc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int pcgc_synchronize(pcgc_ctx* ctx) {
+  if (!ctx) return PCGC_ERR_BAD_ARG;
+  DeviceGuard g(ctx->device);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PCGC_OK;
+}
+
+int pcgc_load_conv(pcgc_ctx* ctx, int net, const char* layer, const float* kernel, const int64_t kshape[5],
+                   const float* bias) {
+  if (!ctx || net < 0 || net >= PCGC_NET_COUNT || !layer || !kernel || !kshape) return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_load_conv: bad argument");
+  DeviceGuard g(ctx->device);
+  Net& n = ctx->nets[net];
+  const int li = n.find(layer);
+  if (li < 0) return fail(ctx, PCGC_ERR_BAD_ARG, "net %d has no layer '%s'", net, layer);
+  const LayerSpec& s = n.specs[li];
+  const int k = s.k;
+  const int64_t want[5] = {k, k, k, s.transposed ? s.cout : s.cin, s.transposed ? s.cin : s.cout};
+  for (int i = 0; i < 5; ++i)
+    if (kshape[i] != want[i]) return fail(ctx, PCGC_ERR_BAD_ARG, "layer '%s': kernel dim %d is %lld, expected %lld", layer, i, (long long)kshape[i], (long long)want[i]);
+  if ((bias != nullptr) != s.bias) return fail(ctx, PCGC_ERR_BAD_ARG, "layer '%s': use_bias=%d in the reference", layer, (int)s.bias);
+  LayerW& lw = n.w[li];
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int c = 0; c < lw.n_classes; ++c) if (lw.cls[c].w) { cudaFree((void*)lw.cls[c].w); lw.cls[c].w = nullptr; }
+  if (lw.bias) { cudaFree(lw.bias); lw.bias = nullptr; }
+  free_umma_weights(lw.umma);
+  lw.loaded = false;
+
+  auto K = [&](int kz, int ky, int kx, int ci, int co) -> float {   // value of tap (kz,ky,kx) from ci to co
+    if (s.transposed) return kernel[((((size_t)kz * k + ky) * k + kx) * s.cout + co) * s.cin + ci];
+    return kernel[((((size_t)kz * k + ky) * k + kx) * s.cin + ci) * s.cout + co];
+  };
+  std::vector<float> packed;
+  if (!s.transposed) {
+    lw.n_classes = 1;
+    ConvDesc& d = lw.cls[0];
+    d.kz = d.ky = d.kx = k; d.stride = s.stride;
+    d.pz = d.py = d.px = same_pad_before(k, s.stride);
+    d.ostride = 1; d.oz = d.oy = d.ox = 0; d.cin = s.cin; d.cout = s.cout;
+    packed.resize((size_t)k * k * k * s.cin * s.cout);
+    for (int ky = 0; ky < k; ++ky) for (int kx = 0; kx < k; ++kx) for (int ci = 0; ci < s.cin; ++ci)
+      for (int kz = 0; kz < k; ++kz) for (int co = 0; co < s.cout; ++co)
+        packed[((((size_t)ky * k + kx) * s.cin + ci) * k + kz) * s.cout + co] = K(kz, ky, kx, ci, co);
+    float* dw = nullptr;
+    CK(cudaMalloc((void**)&dw, packed.size() * sizeof(float)));
+    CK(cudaMemcpy(dw, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+    d.w = dw;
+  } else {
+    // stride-2 Conv3DTranspose = 8 output-parity classes, each a stride-1 gather conv over the input grid
+    const int pb = same_pad_before(k, 2);
+    lw.n_classes = 8;
+    for (int cls = 0; cls < 8; ++cls) {
+      const int r[3] = {(cls >> 2) & 1, (cls >> 1) & 1, cls & 1};   // parity of (o+pb) per axis z,y,x
+      int km[3], q0[3], o0[3], P[3];
+      for (int a = 0; a < 3; ++a) {
+        km[a] = (k - r[a] + 1) / 2;
+        q0[a] = std::max(0, (pb - r[a] + 1) / 2);
+        o0[a] = 2 * q0[a] + r[a] - pb;
+        P[a] = (km[a] - 1) - q0[a];
+      }
+      ConvDesc& d = lw.cls[cls];
+      d.kz = km[0]; d.ky = km[1]; d.kx = km[2]; d.stride = 1;
+      d.pz = P[0]; d.py = P[1]; d.px = P[2];
+      d.ostride = 2; d.oz = o0[0]; d.oy = o0[1]; d.ox = o0[2]; d.cin = s.cin; d.cout = s.cout;
+      packed.assign((size_t)km[0] * km[1] * km[2] * s.cin * s.cout, 0.f);
+      for (int jy = 0; jy < km[1]; ++jy) for (int jx = 0; jx < km[2]; ++jx) for (int ci = 0; ci < s.cin; ++ci)
+        for (int jz = 0; jz < km[0]; ++jz) for (int co = 0; co < s.cout; ++co) {
+          const int kz = r[0] + 2 * (km[0] - 1 - jz), ky = r[1] + 2 * (km[1] - 1 - jy), kx = r[2] + 2 * (km[2] - 1 - jx);
+          packed[((((size_t)jy * km[2] + jx) * s.cin + ci) * km[0] + jz) * s.cout + co] = K(kz, ky, kx, ci, co);
+        }
+      float* dw = nullptr;
+      CK(cudaMalloc((void**)&dw, packed.size() * sizeof(float)));
+      CK(cudaMemcpy(dw, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+      d.w = dw;
+    }
+  }
+  if (bias) {
+    CK(cudaMalloc((void**)&lw.bias, s.cout * sizeof(float)));
+    CK(cudaMemcpy(lw.bias, bias, s.cout * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  if (!s.transposed && s.stride == 1 && s.k == 3) {
+    cudaError_t e = pack_umma_weights(kernel, s.cin, s.cout, lw.umma);
+    if (e != cudaSuccess && e != cudaErrorNotSupported) return fail(ctx, PCGC_ERR_CUDA, "pack_umma_weights('%s'): %s", layer, cudaGetErrorString(e));
+  }
+  lw.loaded = true;
+  return PCGC_OK;
+}
+
+int pcgc_load_bottleneck(pcgc_ctx* ctx, int slot, int channels, const float* matrices, const float* biases,
+                         const float* factors) {
+  if (!ctx || slot < 0 || slot > 1 || channels < 1 || channels > 512 || !matrices || !biases || !factors)
+    return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_load_bottleneck: bad argument");
+  DeviceGuard g(ctx->device);
+  const int C = channels;
+  // input: matrix_0 [C,3,1], matrix_1 [C,3,3], matrix_2 [C,3,3], matrix_3 [C,1,3]; bais/factor [C,3,1]x3,[C,1,1]
+  const float* m[4] = {matrices, matrices + 3 * C, matrices + 12 * C, matrices + 21 * C};
+  const float* bb[4] = {biases, biases + 3 * C, biases + 6 * C, biases + 9 * C};
+  const float* ff[4] = {factors, factors + 3 * C, factors + 6 * C, factors + 9 * C};
+  auto softplus = [](float x) -> float {   // tf.nn.softplus in float32 (entropy_model.py:87)
+    if (x > 20.f) return x;
+    if (x < -20.f) return expf(x);
+    return log1pf(expf(x));
+  };
+  std::vector<float> p((size_t)C * 44);
+  for (int c = 0; c < C; ++c) {
+    float* q = p.data() + (size_t)c * 44;
+    for (int j = 0; j < 3; ++j) { q[j] = softplus(m[0][c * 3 + j]); q[3 + j] = bb[0][c * 3 + j]; q[6 + j] = tanhf(ff[0][c * 3 + j]); }
+    q += 9;
+    for (int l = 1; l <= 2; ++l) {
+      for (int j = 0; j < 9; ++j) q[j] = softplus(m[l][c * 9 + j]);
+      for (int j = 0; j < 3; ++j) { q[9 + j] = bb[l][c * 3 + j]; q[12 + j] = tanhf(ff[l][c * 3 + j]); }
+      q += 15;
+    }
+    for (int j = 0; j < 3; ++j) q[j] = softplus(m[3][c * 3 + j]);
+    q[3] = bb[3][c]; q[4] = tanhf(ff[3][c]);
+  }
+  BottleneckDev& bn = ctx->bn[slot];
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (bn.params) { cudaFree(bn.params); bn.params = nullptr; }
+  CK(cudaMalloc((void**)&bn.params, p.size() * sizeof(float)));
+  CK(cudaMemcpy(bn.params, p.data(), p.size() * sizeof(float), cudaMemcpyHostToDevice));
+  bn.channels = C;
+  return PCGC_OK;
+}
+
+int pcgc_analysis(pcgc_ctx* ctx, int net, const void* cubes_dev, int dtype, int B, float* y_dev) {
+  if (!ctx || !cubes_dev || !y_dev || (net != PCGC_NET_VOX_ANALYSIS && net != PCGC_NET_SIMPLE_ANALYSIS) || dtype < 0 || dtype > 2)
+    return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_analysis: bad argument");
+  DeviceGuard g(ctx->device);
+  return run_net(ctx, net, nullptr, cubes_dev, dtype, B, y_dev, nullptr, 0.f);
+}
+
+int pcgc_synthesis(pcgc_ctx* ctx, int net, const float* y_dev, int B, float* logits_dev) {
+  if (!ctx || !y_dev || !logits_dev || (net != PCGC_NET_VOX_SYNTHESIS && net != PCGC_NET_SIMPLE_SYNTHESIS))
+    return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_synthesis: bad argument");
+  DeviceGuard g(ctx->device);
+  return run_net(ctx, net, y_dev, nullptr, 0, B, logits_dev, nullptr, 0.f);
+}
+
+int pcgc_hyper_encode(pcgc_ctx* ctx, const float* y_dev, int B, float* z_dev) {
+  if (!ctx || !y_dev || !z_dev) return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_hyper_encode: bad argument");
+  DeviceGuard g(ctx->device);
+  return run_net(ctx, PCGC_NET_HYPER_ENCODER, y_dev, nullptr, 0, B, z_dev, nullptr, 0.f);
+}
+
+int pcgc_hyper_decode(pcgc_ctx* ctx, const float* z_hat_dev, int B, float scale_floor, float* loc_dev, float* scale_dev) {
+  if (!ctx || !z_hat_dev || !loc_dev || !scale_dev) return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_hyper_decode: bad argument");
+  DeviceGuard g(ctx->device);
+  return run_net(ctx, PCGC_NET_HYPER_DECODER, z_hat_dev, nullptr, 0, B, loc_dev, scale_dev, scale_floor);
+}
+
+int pcgc_factorized_quantize_likelihood(pcgc_ctx* ctx, int slot, const float* x_dev, int64_t n_vox, int C,
+                                        float likelihood_bound, float* x_hat_dev, float* p_dev, double* bits_dev,
+                                        int32_t* minmax_dev) {
+  if (!ctx || slot < 0 || slot > 1 || !x_dev || n_vox < 0) return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_factorized_quantize_likelihood: bad argument");
+  DeviceGuard g(ctx->device);
+  if (!ctx->bn[slot].params) return fail(ctx, PCGC_ERR_NOT_READY, "bottleneck slot %d not loaded", slot);
+  if (C != ctx->bn[slot].channels || C % 4) return fail(ctx, PCGC_ERR_BAD_ARG, "channels %d != loaded %d (must be a multiple of 4)", C, ctx->bn[slot].channels);
+  if (n_vox == 0) return PCGC_OK;
+  int r = ensure_scratch(ctx, 148 * 8 + 8); if (r) return r;
+  CK(launch_factorized(ctx->bn[slot], x_dev, n_vox, C, likelihood_bound, x_hat_dev, p_dev, bits_dev, minmax_dev,
+                       ctx->scratch, ctx->stream, &ctx->launches));
+  return PCGC_OK;
+}
+
+int pcgc_factorized_cdf(pcgc_ctx* ctx, int slot, int min_v, int max_v, float likelihood_bound, int precision,
+                        int32_t* cdf_host) {
+  if (!ctx || slot < 0 || slot > 1 || !cdf_host) return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_factorized_cdf: bad argument");
+  DeviceGuard g(ctx->device);
+  const BottleneckDev& bn = ctx->bn[slot];
+  if (!bn.params) return fail(ctx, PCGC_ERR_NOT_READY, "bottleneck slot %d not loaded", slot);
+  const int N = max_v - min_v + 1;
+  if (N < 2) return fail(ctx, PCGC_ERR_BAD_RANGE, "single-symbol alphabet [%d,%d]: pmf_to_quantized_cdf needs >= 2 symbols (entropy_model.py:192-193)", min_v, max_v);
+  if ((size_t)N * bn.channels > 32 * 512) return fail(ctx, PCGC_ERR_BAD_RANGE, "symbol range too large");
+  CK(launch_factorized_pmf(bn, min_v, max_v, likelihood_bound, ctx->pmf_dev, ctx->stream, &ctx->launches));
+  std::vector<float> pmf((size_t)N * bn.channels);
+  CK(cudaMemcpyAsync(pmf.data(), ctx->pmf_dev, pmf.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  int r = pcgc_pmf_to_quantized_cdf(pmf.data(), bn.channels, N, precision, cdf_host);
+  if (r) return fail(ctx, r, "pmf_to_quantized_cdf failed");
+  return PCGC_OK;
+}
+
+int pcgc_laplace_quantize_likelihood(pcgc_ctx* ctx, const float* y_dev, const float* loc_dev, const float* scale_dev,
+                                     int B, int64_t E, float likelihood_bound, float* y_hat_dev, float* p_dev,
+                                     double* bits_dev, int32_t* minmax_dev) {
+  if (!ctx || !y_dev || !loc_dev || !scale_dev || B < 0 || E <= 0 || E % 4) return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_laplace_quantize_likelihood: bad argument");
+  DeviceGuard g(ctx->device);
+  if (B == 0) return PCGC_OK;
+  int r = ensure_scratch(ctx, (size_t)B * 16 + 8); if (r) return r;
+  CK(launch_laplace(y_dev, loc_dev, scale_dev, B, E, likelihood_bound, y_hat_dev, p_dev, bits_dev, minmax_dev,
+                    ctx->scratch, ctx->stream, &ctx->launches));
+  return PCGC_OK;
+}
+
+int pcgc_laplace_intervals(pcgc_ctx* ctx, const float* y_hat_dev, const float* loc_dev, const float* scale_dev, int B,
+                           int64_t E, const int32_t* minmax_dev, float likelihood_bound, int precision,
+                           uint32_t* intervals_dev) {
+  if (!ctx || !y_hat_dev || !loc_dev || !scale_dev || !minmax_dev || !intervals_dev || B < 0 || precision != 16)
+    return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_laplace_intervals: bad argument (precision must be 16)");
+  DeviceGuard g(ctx->device);
+  if (B == 0) return PCGC_OK;
+  CK(launch_laplace_intervals(y_hat_dev, loc_dev, scale_dev, B, E, minmax_dev, likelihood_bound, precision,
+                              intervals_dev, ctx->err_flag, ctx->stream, &ctx->launches));
+  return check_err_flag(ctx, "pcgc_laplace_intervals");
+}
+
+int pcgc_laplace_cdf(pcgc_ctx* ctx, const float* loc_dev, const float* scale_dev, int B, int64_t E,
+                     const int32_t* minmax_host, float likelihood_bound, int precision,
+                     const int64_t* row_offset_host, uint16_t* cdf_dev) {
+  if (!ctx || !loc_dev || !scale_dev || !minmax_host || !row_offset_host || !cdf_dev || B < 0 || precision != 16)
+    return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_laplace_cdf: bad argument (precision must be 16)");
+  DeviceGuard g(ctx->device);
+  if (B == 0) return PCGC_OK;
+  for (int b = 0; b < B; ++b) {
+    const int N = minmax_host[2 * b + 1] - minmax_host[2 * b] + 1;
+    if (N < 2 || N > PCGC_MAX_SYMBOLS) return fail(ctx, PCGC_ERR_BAD_RANGE, "cube %d: symbol range [%d,%d] unsupported", b, minmax_host[2 * b], minmax_host[2 * b + 1]);
+  }
+  if (ctx->mm_cap < (size_t)2 * B) {
+    if (ctx->mm_dev) { CK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->mm_dev); }
+    CK(cudaMalloc((void**)&ctx->mm_dev, sizeof(int32_t) * 2 * B)); ctx->mm_cap = 2 * B;
+  }
+  if (ctx->off_cap < (size_t)B + 1) {
+    if (ctx->off_dev) { CK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->off_dev); }
+    CK(cudaMalloc((void**)&ctx->off_dev, sizeof(int64_t) * (B + 1))); ctx->off_cap = B + 1;
+  }
+  CK(cudaMemcpyAsync(ctx->mm_dev, minmax_host, sizeof(int32_t) * 2 * B, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->off_dev, row_offset_host, sizeof(int64_t) * (B + 1), cudaMemcpyHostToDevice, ctx->stream));
+  CK(launch_laplace_cdf(loc_dev, scale_dev, B, E, ctx->mm_dev, ctx->off_dev, likelihood_bound, precision, cdf_dev,
+                        ctx->err_flag, ctx->stream, &ctx->launches));
+  // the host arrays were pageable: make sure the copies are done before the caller reuses them
+  return check_err_flag(ctx, "pcgc_laplace_cdf");
+}
+
+int pcgc_topk_select(pcgc_ctx* ctx, const float* logits_dev, int B, int64_t V, const int32_t* ks_dev, uint8_t* mask_dev,
+                     float* thres_dev, int32_t* count_dev) {
+  if (!ctx || !logits_dev || !ks_dev || !mask_dev || B < 0 || V <= 0 || V % 4) return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_topk_select: bad argument");
+  DeviceGuard g(ctx->device);
+  if (B == 0) return PCGC_OK;
+  CK(launch_topk(logits_dev, B, V, ks_dev, mask_dev, thres_dev, count_dev, ctx->err_flag, ctx->stream, &ctx->launches));
+  return check_err_flag(ctx, "pcgc_topk_select");
+}
+
+int pcgc_threshold_select(pcgc_ctx* ctx, const float* logits_dev, int B, int64_t V, float thres, uint8_t* mask_dev,
+                          int32_t* count_dev) {
+  if (!ctx || !logits_dev || !mask_dev || B < 0 || V <= 0 || V % 4) return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_threshold_select: bad argument");
+  DeviceGuard g(ctx->device);
+  if (B == 0) return PCGC_OK;
+  CK(launch_threshold(logits_dev, B, V, thres, mask_dev, count_dev, ctx->stream, &ctx->launches));
+  return PCGC_OK;
+}
+
+}  // extern "C"

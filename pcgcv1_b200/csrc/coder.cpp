@@ -1,0 +1,235 @@
+// Host range coder of libpcgc_b200.so -- the reference's sequential tail, kept on the host as
+// BASELINE.json's north_star asks.  Replaces coder_ops.range_encode / range_decode /
+// pmf_to_quantized_cdf (models/entropy_model.py:218,258-259,298-299;
+// models/conditional_entropy_model.py:122,161,195).  The upstream C++ (tensorflow-gpu==1.13.1,
+// tensorflow/contrib/coder/kernels/range_coder.cc) is not vendored; this is a fresh
+// carry-propagating 32-bit range coder with 16-bit renormalisation built to the published
+// contract: interval update a=(size*lower)>>p, b=((size*upper)>>p)-1; big-endian 16-bit words;
+// finalisation picks the multiple of 2^16 inside the interval and drops trailing zero bytes.
+// Per-cube strings are independent, so the batch entry points fan out over a thread pool.
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <thread>
+#include <vector>
+
+#include "../../include/pcgc_b200.h"
+#include "cdf_norm.h"
+
+namespace {
+
+struct Encoder {
+  uint64_t base = 0;            // bit 32 holds a carry that has not been propagated yet
+  uint32_t size_minus1 = 0xFFFFFFFFu;
+  bool have_cache = false;
+  uint32_t cache = 0;           // delayed 16-bit word
+  int64_t pending = 0;          // delayed 0xFFFF words following `cache`
+  uint8_t* out;
+  int64_t n = 0, cap;
+  bool overflow = false;
+  int precision;
+
+  Encoder(uint8_t* o, int64_t c, int p) : out(o), cap(c), precision(p) {}
+
+  inline void emit16(uint32_t w) {
+    if (n + 2 > cap) { overflow = true; return; }
+    out[n++] = (uint8_t)(w >> 8);
+    out[n++] = (uint8_t)w;
+  }
+  inline void shift() {
+    const uint32_t carry = (uint32_t)(base >> 32);
+    const uint32_t low32 = (uint32_t)base;
+    if (low32 < 0xFFFF0000u || carry) {
+      if (have_cache) emit16((cache + carry) & 0xFFFF);
+      for (; pending > 0; --pending) emit16((0xFFFF + carry) & 0xFFFF);
+      cache = (low32 >> 16) & 0xFFFF;
+      have_cache = true;
+    } else {
+      ++pending;
+    }
+    base = (uint64_t)(low32 & 0xFFFF) << 16;
+  }
+  inline void encode(uint32_t lower, uint32_t upper) {
+    const uint64_t size = (uint64_t)size_minus1 + 1;
+    const uint32_t a = (uint32_t)((size * lower) >> precision);
+    const uint32_t b = (uint32_t)(((size * upper) >> precision) - 1);
+    base += a;
+    size_minus1 = b - a;
+    if ((size_minus1 >> 16) == 0) {
+      shift();
+      size_minus1 = (size_minus1 << 16) | 0xFFFF;
+    }
+  }
+  inline int64_t finish() {
+    const uint64_t v = (base + 0xFFFF) >> 16;
+    const uint32_t carry = (uint32_t)(v >> 16), word = (uint32_t)(v & 0xFFFF);
+    if (have_cache) emit16((cache + carry) & 0xFFFF);
+    for (; pending > 0; --pending) emit16((0xFFFF + carry) & 0xFFFF);
+    emit16(word);
+    if (overflow) return -1;
+    while (n > 0 && out[n - 1] == 0) --n;
+    return n;
+  }
+};
+
+struct Decoder {
+  const uint8_t* p;
+  int64_t nbytes, pos = 0;
+  uint32_t base = 0, size_minus1 = 0xFFFFFFFFu, value;
+  int precision;
+
+  Decoder(const uint8_t* d, int64_t n, int prec) : p(d), nbytes(n), precision(prec) {
+    value = read16() << 16;
+    value |= read16();
+  }
+  inline uint32_t read16() {
+    uint32_t v = 0;
+    for (int k = 0; k < 2; ++k) { v <<= 8; if (pos < nbytes) v |= p[pos++]; }
+    return v;
+  }
+  // cdf(i) for i in [0, N]; returns the symbol.
+  template <typename CdfAt>
+  inline int decode(int N, CdfAt cdf) {
+    const uint64_t size = (uint64_t)size_minus1 + 1;
+    const uint64_t offset = (((uint64_t)(uint32_t)(value - base) + 1) << precision) - 1;
+    int lo = 1, hi = N;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (size * (uint64_t)cdf(mid) > offset) hi = mid; else lo = mid + 1;
+    }
+    const int s = lo - 1;
+    const uint32_t a = (uint32_t)((size * (uint64_t)cdf(s)) >> precision);
+    const uint32_t b = (uint32_t)(((size * (uint64_t)cdf(s + 1)) >> precision) - 1);
+    base += a;
+    size_minus1 = b - a;
+    if ((size_minus1 >> 16) == 0) {
+      base <<= 16;
+      size_minus1 = (size_minus1 << 16) | 0xFFFF;
+      value = (value << 16) | read16();
+    }
+    return s;
+  }
+};
+
+template <typename F>
+void parallel_for(int n, int threads, F f) {
+  int hw = (int)std::thread::hardware_concurrency();
+  if (hw <= 0) hw = 1;
+  if (threads <= 0 || threads > hw) threads = hw;
+  if (threads > n) threads = n;
+  if (threads <= 1) { for (int i = 0; i < n; ++i) f(i); return; }
+  std::atomic<int> next(0);
+  std::vector<std::thread> pool;
+  pool.reserve(threads);
+  for (int t = 0; t < threads; ++t)
+    pool.emplace_back([&] { for (int i; (i = next.fetch_add(1)) < n;) f(i); });
+  for (auto& th : pool) th.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+int pcgc_abi_version(void) { return PCGC_B200_ABI_VERSION; }
+
+int pcgc_pmf_to_quantized_cdf(const float* pmf, int64_t rows, int N, int precision, int32_t* cdf) {
+  if (!pmf || !cdf || rows < 0 || precision < 1 || precision > 16) return PCGC_ERR_BAD_ARG;
+  if (N < 2) return PCGC_ERR_BAD_RANGE;   // upstream: "`pmf` size should be at least 2 in the last axis"
+  std::vector<int32_t> v(N);
+  std::vector<double> g(N);
+  for (int64_t r = 0; r < rows; ++r) {
+    if (pcgc::quantize_pmf_row(pmf + r * N, N, precision, v.data(), g.data()) != 0) return PCGC_ERR_BAD_RANGE;
+    int32_t* row = cdf + r * (N + 1);
+    int32_t acc = 0;
+    row[0] = 0;
+    for (int i = 0; i < N; ++i) { acc += v[i]; row[i + 1] = acc; }
+  }
+  return PCGC_OK;
+}
+
+int pcgc_range_encode(const int16_t* sym, int64_t n, const int32_t* cdf, int cdf_rows, int N, int precision,
+                      uint8_t* out, int64_t cap, int64_t* len) {
+  if (!sym || !cdf || !out || !len || cdf_rows < 1 || N < 1) return PCGC_ERR_BAD_ARG;
+  Encoder e(out, cap, precision);
+  int r = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int s = sym[i];
+    if (s < 0 || s >= N) return PCGC_ERR_BAD_RANGE;
+    const int32_t* row = cdf + (int64_t)r * (N + 1);
+    if (!(row[s] < row[s + 1])) return PCGC_ERR_BAD_ARG;
+    e.encode((uint32_t)row[s], (uint32_t)row[s + 1]);
+    if (++r == cdf_rows) r = 0;
+  }
+  const int64_t m = e.finish();
+  if (m < 0) return PCGC_ERR_OVERFLOW;
+  *len = m;
+  return PCGC_OK;
+}
+
+int pcgc_range_decode(const uint8_t* data, int64_t nbytes, int64_t n, const int32_t* cdf, int cdf_rows, int N,
+                      int precision, int16_t* sym) {
+  if ((!data && nbytes) || !cdf || !sym || cdf_rows < 1 || N < 1) return PCGC_ERR_BAD_ARG;
+  Decoder d(data, nbytes, precision);
+  int r = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int32_t* row = cdf + (int64_t)r * (N + 1);
+    sym[i] = (int16_t)d.decode(N, [row](int k) { return (uint32_t)row[k]; });
+    if (++r == cdf_rows) r = 0;
+  }
+  return PCGC_OK;
+}
+
+int pcgc_range_encode_intervals(const uint32_t* iv, int64_t n, int precision, uint8_t* out, int64_t cap,
+                                int64_t* len) {
+  if (!iv || !out || !len) return PCGC_ERR_BAD_ARG;
+  Encoder e(out, cap, precision);
+  for (int64_t i = 0; i < n; ++i) {
+    const uint32_t lower = iv[i] & 0xFFFF;
+    const uint32_t upper = lower + (iv[i] >> 16) + 1;
+    e.encode(lower, upper);
+  }
+  const int64_t m = e.finish();
+  if (m < 0) return PCGC_ERR_OVERFLOW;
+  *len = m;
+  return PCGC_OK;
+}
+
+int pcgc_range_decode_rows(const uint8_t* data, int64_t nbytes, int64_t n, const uint16_t* rows, int N,
+                           int precision, int16_t* sym) {
+  if ((!data && nbytes) || !rows || !sym || N < 1) return PCGC_ERR_BAD_ARG;
+  Decoder d(data, nbytes, precision);
+  const uint32_t top = 1u << precision;
+  for (int64_t i = 0; i < n; ++i) {
+    const uint16_t* row = rows + i * N;
+    sym[i] = (int16_t)d.decode(N, [row, N, top](int k) { return k == N ? top : (uint32_t)row[k]; });
+  }
+  return PCGC_OK;
+}
+
+int pcgc_range_encode_intervals_batch(const uint32_t* iv, int B, int64_t E, int precision, uint8_t* out,
+                                      int64_t stride, int64_t* lens, int threads) {
+  if (!iv || !out || !lens || B < 0) return PCGC_ERR_BAD_ARG;
+  std::atomic<int> rc(PCGC_OK);
+  parallel_for(B, threads, [&](int b) {
+    int r = pcgc_range_encode_intervals(iv + (int64_t)b * E, E, precision, out + (int64_t)b * stride, stride, lens + b);
+    if (r != PCGC_OK) rc.store(r);
+  });
+  return rc.load();
+}
+
+int pcgc_range_decode_rows_batch(const uint8_t* const* data, const int64_t* nbytes, int B, int64_t E,
+                                 const uint16_t* rows, const int64_t* row_offset, const int32_t* minmax,
+                                 int precision, int16_t* sym, int threads) {
+  if (!data || !nbytes || !rows || !row_offset || !minmax || !sym || B < 0) return PCGC_ERR_BAD_ARG;
+  std::atomic<int> rc(PCGC_OK);
+  parallel_for(B, threads, [&](int b) {
+    const int N = minmax[2 * b + 1] - minmax[2 * b] + 1;
+    int r = pcgc_range_decode_rows(data[b], nbytes[b], E, rows + row_offset[b], N, precision, sym + (int64_t)b * E);
+    if (r != PCGC_OK) rc.store(r);
+  });
+  return rc.load();
+}
+
+}  // extern "C"

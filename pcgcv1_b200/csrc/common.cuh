@@ -1,0 +1,68 @@
+// Internal definitions shared by the translation units of libpcgc_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "../../include/pcgc_b200.h"
+
+namespace pcgc {
+
+// One convolution as the kernels see it: a stride-S "gather" convolution over an input grid with
+// a (KZ,KY,KX) tap box.  Forward Conv3D layers map 1:1; a stride-2 Conv3DTranspose is split into
+// 8 output-parity classes, each of which is such a convolution over the INPUT grid whose outputs
+// interleave (out index = t*ostride + ooff).  No atomics, fixed summation order => deterministic.
+struct ConvDesc {
+  int kz, ky, kx;        // tap box
+  int stride;            // input step per output step (1 or 2)
+  int pz, py, px;        // pad-before per axis: in = t*stride - p + tap
+  int ostride;           // output interleave (1; 2 for transposed-conv parity classes)
+  int oz, oy, ox;        // output offset per axis (parity class)
+  int cin, cout;
+  const float* w = nullptr;   // device, [KY][KX][Cin][KZ][Cout] fp32
+};
+
+enum EpilogueFlags : int { EPI_RELU = 1, EPI_ABS = 2, EPI_RES = 4, EPI_FLOOR = 8 };
+
+struct ConvCall {
+  ConvDesc d;
+  const float* in;  int in_n;  int in_cs;  int in_co;     // input grid edge, channel stride/offset
+  float* out;       int out_n; int out_cs; int out_co;    // full output grid edge, channel stride/offset
+  int tn;                                                 // extent of the t grid (outputs per axis per class)
+  const float* bias;                                      // [Cout] or null
+  const float* res; int res_cs; int res_co;               // residual (same grid as out) or null
+  int flags; float floor_v;
+  int B;
+};
+
+cudaError_t launch_conv_ffma(const ConvCall& c, cudaStream_t s, int64_t* launches);
+cudaError_t launch_u8_to_f32(const void* in, int dtype, float* out, int64_t n, cudaStream_t s, int64_t* launches);
+
+// entropy.cu
+struct BottleneckDev {
+  int channels = 0;
+  float* params = nullptr;   // device: per channel 58 floats, see entropy.cu
+};
+cudaError_t launch_factorized(const BottleneckDev& bn, const float* x, int64_t n_vox, int C, float bound,
+                              float* x_hat, float* p, double* bits, int32_t* minmax, double* scratch,
+                              cudaStream_t s, int64_t* launches);
+cudaError_t launch_factorized_pmf(const BottleneckDev& bn, int min_v, int max_v, float bound, float* pmf,
+                                  cudaStream_t s, int64_t* launches);
+cudaError_t launch_laplace(const float* y, const float* loc, const float* scale, int B, int64_t E, float bound,
+                           float* y_hat, float* p, double* bits, int32_t* minmax, double* scratch,
+                           cudaStream_t s, int64_t* launches);
+cudaError_t launch_laplace_intervals(const float* y_hat, const float* loc, const float* scale, int B, int64_t E,
+                                     const int32_t* minmax, float bound, int precision, uint32_t* intervals,
+                                     int* err_flag, cudaStream_t s, int64_t* launches);
+cudaError_t launch_laplace_cdf(const float* loc, const float* scale, int B, int64_t E, const int32_t* minmax_dev,
+                               const int64_t* row_offset_dev, float bound, int precision, uint16_t* cdf,
+                               int* err_flag, cudaStream_t s, int64_t* launches);
+// topk.cu
+cudaError_t launch_topk(const float* logits, int B, int64_t V, const int32_t* ks, uint8_t* mask, float* thres,
+                        int32_t* count, int* err_flag, cudaStream_t s, int64_t* launches);
+cudaError_t launch_threshold(const float* logits, int B, int64_t V, float thres, uint8_t* mask, int32_t* count,
+                             cudaStream_t s, int64_t* launches);
+
+}  // namespace pcgc

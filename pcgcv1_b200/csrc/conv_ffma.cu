@@ -1,0 +1,245 @@
+// FP32 CUDA-core convolution for every Conv3D / Conv3DTranspose shape of the reference
+// (models/model_voxception.py:21-54,83-122,153-192,224-297; models/model_simple.py:21-86).
+//
+// One kernel template covers them all: a stride-S gather convolution with a (KZ,KY,KX) tap box
+// over a channels-last grid.  A CTA owns an 8x8x8 tile of outputs; the haloed input brick of CC
+// input channels is staged channel-planar in shared memory, the matching weight slab
+// [KY][KX][CC][KZ][CoutBlock] beside it.  A thread owns one (x,y) column: 4 consecutive z outputs
+// x CT output channels in registers, sliding a (3S+KZ)-deep register window along z so every
+// staged input is read from shared memory once per (ky,kx,ci).  The reduction order
+// (ci-chunk, ky, kx, ci, kz) is fixed and independent of batch size and grid => bit-reproducible
+// (the property README.md:111-114 / eval.py:96-100 lack).  Epilogue: +bias, ReLU, residual add+ReLU
+// (the VRN block's concat/add/relu, model_voxception.py:64-67), |.| and floor (HyperDecoder scale).
+//
+// This is the exact-FP32 engine: used for layers the tcgen05 engine does not take (stride 2,
+// transposed, 1^3, Cin=1, k=5/9) and as the on-device cross-check for the tcgen05 engine.
+#include "common.cuh"
+
+namespace pcgc {
+
+struct FfmaArgs {
+  const float* in; float* out; const float* w; const float* bias; const float* res;
+  int in_n, in_cs, in_co;
+  int out_n, out_cs, out_co;
+  int res_cs, res_co;
+  int tn;                 // t-grid edge (multiple of 8)
+  int ky, kx;             // runtime tap extents (kz is a template parameter)
+  int pz, py, px;
+  int ostride, oz, oy, ox;
+  int cin, cout;
+  int cc;                 // input channels staged per chunk
+  int plane;              // padded floats per staged channel plane
+  int ey, ex, exp_;       // brick extents (y, x) and padded x pitch
+  int flags; float floor_v;
+};
+
+template <int KZ, int S, int CT>
+__global__ void __launch_bounds__(512) conv_ffma_kernel(const FfmaArgs a) {
+  constexpr int EZ = 7 * S + KZ;
+  constexpr int WIN = 3 * S + KZ;
+  extern __shared__ float smem[];
+  const int G = blockDim.y;
+  const int CB = G * CT;                         // couts handled by this CTA
+  float* s_in = smem;
+  float* s_w = smem + a.cc * a.plane;
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 7, ty = (tid >> 3) & 7, tzg = tid >> 6;
+  const int cg = threadIdx.y;
+  const int nthreads = blockDim.x * blockDim.y;
+  const int ltid = threadIdx.y * blockDim.x + tid;
+
+  const int tiles = a.tn >> 3;
+  int bid = blockIdx.x;
+  const int bx = bid % tiles; bid /= tiles;
+  const int by = bid % tiles; bid /= tiles;
+  const int bz = bid % tiles; bid /= tiles;
+  const int b = bid;
+  const int co_base = blockIdx.y * CB;
+
+  // input coordinates of the brick origin
+  const int iz0 = bz * 8 * S - a.pz, iy0 = by * 8 * S - a.py, ix0 = bx * 8 * S - a.px;
+  const float* in_b = a.in + (size_t)b * a.in_n * a.in_n * a.in_n * a.in_cs + a.in_co;
+
+  float acc[4][CT];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int c = 0; c < CT; ++c) acc[j][c] = 0.f;
+
+  const int brick_vox = EZ * a.ey * a.ex;
+  const int kyx = a.ky * a.kx;
+
+  for (int c0 = 0; c0 < a.cin; c0 += a.cc) {
+    const int ccn = min(a.cc, a.cin - c0);
+    __syncthreads();
+    // ---- stage the input brick: global NDHWC -> shared channel-planar ----
+    for (int i = ltid; i < brick_vox * a.cc; i += nthreads) {
+      const int c = i % a.cc;
+      int e = i / a.cc;
+      const int x = e % a.ex; e /= a.ex;
+      const int y = e % a.ey; const int z = e / a.ey;
+      const int gz = iz0 + z, gy = iy0 + y, gx = ix0 + x;
+      float v = 0.f;
+      if (c < ccn && (unsigned)gz < (unsigned)a.in_n && (unsigned)gy < (unsigned)a.in_n && (unsigned)gx < (unsigned)a.in_n)
+        v = __ldg(in_b + ((size_t)(gz * a.in_n + gy) * a.in_n + gx) * a.in_cs + c0 + c);
+      s_in[c * a.plane + (z * a.ey + y) * a.exp_ + x] = v;
+    }
+    // ---- stage the weight slab: global [KY][KX][Cin][KZ][Cout] -> shared [KY*KX][CC][KZ][CB] ----
+    for (int i = ltid; i < kyx * a.cc * KZ * CB; i += nthreads) {
+      const int co = i % CB;
+      int e = i / CB;
+      const int kz = e % KZ; e /= KZ;
+      const int c = e % a.cc; const int t = e / a.cc;
+      float v = 0.f;
+      if (c < ccn && co_base + co < a.cout)
+        v = __ldg(a.w + (((size_t)t * a.cin + c0 + c) * KZ + kz) * a.cout + co_base + co);
+      s_w[i] = v;
+    }
+    __syncthreads();
+
+    // ---- accumulate ----
+    for (int t = 0; t < kyx; ++t) {
+      const int ky = t / a.kx, kx = t - ky * a.kx;
+      const float* ip = s_in + ((tzg * 4 * S) * a.ey + ty * S + ky) * a.exp_ + tx * S + kx;
+      const float* wp = s_w + (size_t)t * a.cc * KZ * CB + cg * CT;
+      for (int c = 0; c < ccn; ++c) {
+        float win[WIN];
+#pragma unroll
+        for (int i = 0; i < WIN; ++i) win[i] = ip[c * a.plane + i * a.ey * a.exp_];
+        const float* wc = wp + c * KZ * CB;
+#pragma unroll
+        for (int kz = 0; kz < KZ; ++kz) {
+          float wv[CT];
+          if constexpr (CT % 4 == 0) {
+#pragma unroll
+            for (int q = 0; q < CT / 4; ++q) {
+              const float4 f = *reinterpret_cast<const float4*>(wc + kz * CB + 4 * q);
+              wv[4 * q] = f.x; wv[4 * q + 1] = f.y; wv[4 * q + 2] = f.z; wv[4 * q + 3] = f.w;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < CT; ++q) wv[q] = wc[kz * CB + q];
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < CT; ++q) acc[j][q] = fmaf(win[j * S + kz], wv[q], acc[j][q]);
+        }
+      }
+    }
+  }
+
+  // ---- epilogue ----
+  const int t_y = by * 8 + ty, t_x = bx * 8 + tx;
+  const int o_y = t_y * a.ostride + a.oy, o_x = t_x * a.ostride + a.ox;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int t_z = bz * 8 + tzg * 4 + j;
+    const int o_z = t_z * a.ostride + a.oz;
+    const size_t vox = (((size_t)b * a.out_n + o_z) * a.out_n + o_y) * a.out_n + o_x;
+    float* op = a.out + vox * a.out_cs + a.out_co;
+    const float* rp = a.res ? a.res + vox * a.res_cs + a.res_co : nullptr;
+#pragma unroll
+    for (int q = 0; q < CT; ++q) {
+      const int co = co_base + cg * CT + q;
+      if (co < a.cout) {
+        float v = acc[j][q];
+        if (a.bias) v += __ldg(a.bias + co);
+        if (a.flags & EPI_RELU) v = fmaxf(v, 0.f);
+        if (rp) v = fmaxf(v + __ldg(rp + co), 0.f);
+        if (a.flags & EPI_ABS) v = fabsf(v);
+        if (a.flags & EPI_FLOOR) v = fmaxf(v, a.floor_v);
+        op[co] = v;
+      }
+    }
+  }
+}
+
+template <int KZ, int S>
+static cudaError_t launch_kzs(const FfmaArgs& a, int B, cudaStream_t s) {
+  int ct = a.cout >= 8 ? 8 : (a.cout >= 4 ? 4 : 1);
+  int groups = (a.cout + ct - 1) / ct;
+  int G = groups < 4 ? groups : 4;
+  int gy = (groups + G - 1) / G;
+  const int CB = G * ct;
+  FfmaArgs b = a;
+  constexpr int EZ = 7 * S + KZ;
+  b.ey = 7 * S + a.ky; b.ex = 7 * S + a.kx; b.exp_ = b.ex;
+  // choose the channel chunk so that brick + weights fit a ~96 KB budget
+  int cc = a.cin < 16 ? a.cin : 16;
+  size_t smem = 0;
+  for (;; cc = (cc + 1) / 2) {
+    int plane = EZ * b.ey * b.exp_;
+    int want = cc >= 2 ? 32 / (cc > 32 ? 32 : cc) : 0;       // plane % 32 == 32/cc -> conflict-free staging
+    if (cc >= 2) { while (plane % 32 != want % 32) ++plane; }
+    b.plane = plane; b.cc = cc;
+    smem = ((size_t)cc * plane + (size_t)a.ky * a.kx * cc * KZ * CB) * sizeof(float);
+    if (smem <= 96 * 1024 || cc == 1) break;
+  }
+  if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+  const int tiles = a.tn / 8;
+  dim3 grid((unsigned)((size_t)tiles * tiles * tiles * B), gy, 1), block(128, G, 1);
+  cudaError_t e = cudaSuccess;
+#define PCGC_LAUNCH(CTV)                                                                              \
+  do {                                                                                                \
+    e = cudaFuncSetAttribute(conv_ffma_kernel<KZ, S, CTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             (int)smem);                                                              \
+    if (e == cudaSuccess) { conv_ffma_kernel<KZ, S, CTV><<<grid, block, smem, s>>>(b); e = cudaGetLastError(); } \
+  } while (0)
+  if (ct == 8) PCGC_LAUNCH(8); else if (ct == 4) PCGC_LAUNCH(4); else PCGC_LAUNCH(1);
+#undef PCGC_LAUNCH
+  return e;
+}
+
+cudaError_t launch_conv_ffma(const ConvCall& c, cudaStream_t s, int64_t* launches) {
+  FfmaArgs a;
+  a.in = c.in; a.out = c.out; a.w = c.d.w; a.bias = c.bias; a.res = c.res;
+  a.in_n = c.in_n; a.in_cs = c.in_cs; a.in_co = c.in_co;
+  a.out_n = c.out_n; a.out_cs = c.out_cs; a.out_co = c.out_co;
+  a.res_cs = c.res_cs; a.res_co = c.res_co;
+  a.tn = c.tn; a.ky = c.d.ky; a.kx = c.d.kx;
+  a.pz = c.d.pz; a.py = c.d.py; a.px = c.d.px;
+  a.ostride = c.d.ostride; a.oz = c.d.oz; a.oy = c.d.oy; a.ox = c.d.ox;
+  a.cin = c.d.cin; a.cout = c.d.cout;
+  a.flags = c.flags; a.floor_v = c.floor_v;
+  a.cc = 0; a.plane = 0; a.ey = a.ex = a.exp_ = 0;
+  if (c.tn % 8 != 0 || c.B <= 0) return cudaErrorInvalidValue;
+  if (launches) ++*launches;
+  const int key = c.d.kz * 10 + c.d.stride;
+  switch (key) {
+    case 11: return launch_kzs<1, 1>(a, c.B, s);
+    case 21: return launch_kzs<2, 1>(a, c.B, s);
+    case 31: return launch_kzs<3, 1>(a, c.B, s);
+    case 41: return launch_kzs<4, 1>(a, c.B, s);
+    case 51: return launch_kzs<5, 1>(a, c.B, s);
+    case 32: return launch_kzs<3, 2>(a, c.B, s);
+    case 52: return launch_kzs<5, 2>(a, c.B, s);
+    case 92: return launch_kzs<9, 2>(a, c.B, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// ---- input conversion: occupancy cubes of any host dtype -> float32 ---------------------------
+template <typename T>
+__global__ void to_f32_kernel(const T* __restrict__ in, float* __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = (float)in[i];
+}
+
+cudaError_t launch_u8_to_f32(const void* in, int dtype, float* out, int64_t n, cudaStream_t s, int64_t* launches) {
+  const int threads = 256;
+  int64_t blocks = (n + threads - 1) / threads;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (launches) ++*launches;
+  switch (dtype) {
+    case PCGC_DTYPE_U8: to_f32_kernel<uint8_t><<<(unsigned)blocks, threads, 0, s>>>((const uint8_t*)in, out, n); break;
+    case PCGC_DTYPE_F32: to_f32_kernel<float><<<(unsigned)blocks, threads, 0, s>>>((const float*)in, out, n); break;
+    case PCGC_DTYPE_F64: to_f32_kernel<double><<<(unsigned)blocks, threads, 0, s>>>((const double*)in, out, n); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace pcgc

@@ -1,0 +1,282 @@
+// Fused, HBM-bound entropy-model kernels (sm_100a).
+//   factorized:  models/entropy_model.py:72-181  (quantise + per-channel 1-3-3-3-1 density + bits + min/max)
+//   conditional: models/conditional_entropy_model.py:21-124 (quantise + LAPLACE likelihood + bits +
+//                per-cube min/max; per-element quantised CDF rows / symbol intervals for the coder)
+// The arithmetic follows the reference's operation order in FP32 (expf/tanhf, IEEE division; this
+// file must NOT be compiled with --use_fast_math).  Reductions are two-stage with a fixed order
+// (block partials -> one finalising block), min/max use integer atomics: results are reproducible.
+#include <float.h>
+#include <limits.h>
+
+#include "cdf_norm.h"
+#include "common.cuh"
+
+namespace pcgc {
+
+constexpr int BN_PARAMS = 44;   // per channel: see api.cu pack_bottleneck()
+
+// _logits_cumulative (entropy_model.py:72-98) for one value and one channel's parameters.
+__device__ __forceinline__ float bn_logits(float x, const float* __restrict__ p) {
+  float h[3], g[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {               // layer 0: [3,1]
+    float t = p[j] * x + p[3 + j];
+    h[j] = t + p[6 + j] * tanhf(t);
+  }
+  const float* q = p + 9;
+#pragma unroll
+  for (int l = 0; l < 2; ++l) {               // layers 1,2: [3,3]
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float t = q[3 * j] * h[0];
+      t = fmaf(q[3 * j + 1], h[1], t);
+      t = fmaf(q[3 * j + 2], h[2], t);
+      t += q[9 + j];
+      g[j] = t + q[12 + j] * tanhf(t);
+    }
+    h[0] = g[0]; h[1] = g[1]; h[2] = g[2];
+    q += 15;
+  }
+  float t = q[0] * h[0];                      // layer 3: [1,3]
+  t = fmaf(q[1], h[1], t);
+  t = fmaf(q[2], h[2], t);
+  t += q[3];
+  return t + q[4] * tanhf(t);
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float signf_(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
+
+// _likelihood (entropy_model.py:131-139) at an already quantised value.
+__device__ __forceinline__ float bn_likelihood(float xq, const float* __restrict__ p) {
+  const float lower = bn_logits(xq - 0.5f, p);
+  const float upper = bn_logits(xq + 0.5f, p);
+  const float sgn = -signf_(lower + upper);
+  return fabsf(sigmoidf_(sgn * upper) - sigmoidf_(sgn * lower));
+}
+
+// Laplace likelihood (conditional_entropy_model.py:21-56), operation for operation.
+__device__ __forceinline__ float laplace_cdf(float t, float loc, float scale) {
+  const float e = expf(-fabsf(t - loc) / scale);
+  const float c_l = 0.5f * e;
+  const float c_r = 1.0f - 0.5f * e;
+  return (t <= loc) ? c_l : ((t > loc) ? c_r : 0.f);     // NaN -> both masks false -> 0 like the reference
+}
+__device__ __forceinline__ float laplace_likelihood(float x, float loc, float scale) {
+  float upper = x + 0.5f, lower = x - 0.5f;
+  const float sgn = signf_(upper + lower - loc);        // sign(2x - loc): the reference's quirk (:47)
+  upper = -sgn * (upper - loc) + loc;
+  lower = -sgn * (lower - loc) + loc;
+  return fabsf(laplace_cdf(upper, loc, scale) - laplace_cdf(lower, loc, scale));
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void init_minmax_kernel(int32_t* mm, int n_pairs) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pairs) { mm[2 * i] = INT_MAX; mm[2 * i + 1] = INT_MIN; }
+}
+
+struct BlockStats { double bits; int mn, mx; };
+
+template <int THREADS>
+__device__ __forceinline__ BlockStats block_reduce(double bits, int mn, int mx) {
+  __shared__ double s_b[THREADS / 32];
+  __shared__ int s_mn[THREADS / 32], s_mx[THREADS / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    bits += __shfl_down_sync(0xffffffffu, bits, o);
+    mn = min(mn, __shfl_down_sync(0xffffffffu, mn, o));
+    mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s_b[w] = bits; s_mn[w] = mn; s_mx[w] = mx; }
+  __syncthreads();
+  BlockStats r{0.0, INT_MAX, INT_MIN};
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < THREADS / 32; ++i) { r.bits += s_b[i]; r.mn = min(r.mn, s_mn[i]); r.mx = max(r.mx, s_mx[i]); }
+  }
+  return r;
+}
+
+// Final, fixed-order sum of per-block partials: out[g] = sum_j partial[g*per + j].
+__global__ void finalize_bits_kernel(const double* __restrict__ partial, int per, double* __restrict__ out) {
+  const int g = blockIdx.x;
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int j = 0; j < per; ++j) s += partial[(size_t)g * per + j];
+    out[g] = s;
+  }
+}
+
+constexpr int ENT_THREADS = 256;
+constexpr int ENT_VEC = 4;
+
+// ---- factorized: one thread = 4 consecutive elements (C % 4 == 0 => 4 consecutive channels) ----
+__global__ void __launch_bounds__(ENT_THREADS)
+factorized_kernel(const float* __restrict__ x, int64_t n, int C, const float* __restrict__ params, float bound,
+                  float* __restrict__ x_hat, float* __restrict__ p_out, double* __restrict__ partial,
+                  int32_t* __restrict__ minmax) {
+  extern __shared__ float s_par[];
+  for (int i = threadIdx.x; i < C * BN_PARAMS; i += ENT_THREADS) s_par[i] = params[i];
+  __syncthreads();
+  double bits = 0.0;
+  int mn = INT_MAX, mx = INT_MIN;
+  const int64_t nvec = n / ENT_VEC;
+  for (int64_t v = (int64_t)blockIdx.x * ENT_THREADS + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * ENT_THREADS) {
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + v);
+    float xs[4] = {xv.x, xv.y, xv.z, xv.w}, q[4], pr[4];
+    const int c0 = (int)((v * ENT_VEC) % C);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      q[k] = rintf(xs[k]);                                        // tf.math.round: half to even
+      pr[k] = fmaxf(bn_likelihood(q[k], s_par + (c0 + k) * BN_PARAMS), bound);
+      bits -= (double)log2f(pr[k]);
+      const int qi = (int)q[k];
+      mn = min(mn, qi); mx = max(mx, qi);
+    }
+    if (x_hat) reinterpret_cast<float4*>(x_hat)[v] = make_float4(q[0], q[1], q[2], q[3]);
+    if (p_out) reinterpret_cast<float4*>(p_out)[v] = make_float4(pr[0], pr[1], pr[2], pr[3]);
+  }
+  const BlockStats r = block_reduce<ENT_THREADS>(bits, mn, mx);
+  if (threadIdx.x == 0) {
+    if (partial) partial[blockIdx.x] = r.bits;
+    if (minmax && r.mn <= r.mx) { atomicMin(minmax, r.mn); atomicMax(minmax + 1, r.mx); }
+  }
+}
+
+cudaError_t launch_factorized(const BottleneckDev& bn, const float* x, int64_t n_vox, int C, float bound,
+                              float* x_hat, float* p, double* bits, int32_t* minmax, double* scratch,
+                              cudaStream_t s, int64_t* launches) {
+  const int64_t n = n_vox * C;
+  if (C % 4 != 0 || C != bn.channels) return cudaErrorInvalidValue;
+  int64_t want = (n / ENT_VEC + ENT_THREADS - 1) / ENT_THREADS;
+  const int blocks = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+  if (minmax) { init_minmax_kernel<<<1, 32, 0, s>>>(minmax, 1); if (launches) ++*launches; }
+  factorized_kernel<<<blocks, ENT_THREADS, C * BN_PARAMS * sizeof(float), s>>>(x, n, C, bn.params, bound, x_hat, p,
+                                                                              bits ? scratch : nullptr, minmax);
+  if (launches) ++*launches;
+  if (bits) { finalize_bits_kernel<<<1, 32, 0, s>>>(scratch, blocks, bits); if (launches) ++*launches; }
+  return cudaGetLastError();
+}
+
+// pmf of EntropyBottleneck._get_cdf (:195-215): [C, N] likelihoods of the integers min_v..max_v.
+__global__ void factorized_pmf_kernel(const float* __restrict__ params, int C, int min_v, int N, float bound,
+                                      float* __restrict__ pmf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * N) return;
+  const int c = i / N, k = i - c * N;
+  pmf[i] = fmaxf(bn_likelihood((float)(min_v + k), params + c * BN_PARAMS), bound);
+}
+
+cudaError_t launch_factorized_pmf(const BottleneckDev& bn, int min_v, int max_v, float bound, float* pmf,
+                                  cudaStream_t s, int64_t* launches) {
+  const int N = max_v - min_v + 1;
+  const int tot = bn.channels * N;
+  factorized_pmf_kernel<<<(tot + 127) / 128, 128, 0, s>>>(bn.params, bn.channels, min_v, N, bound, pmf);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+// ---- conditional: grid (blocks_per_cube, B); per-cube min/max and bits ------------------------
+__global__ void __launch_bounds__(ENT_THREADS)
+laplace_kernel(const float* __restrict__ y, const float* __restrict__ loc, const float* __restrict__ scale,
+               int64_t E, float bound, float* __restrict__ y_hat, float* __restrict__ p_out,
+               double* __restrict__ partial, int32_t* __restrict__ minmax) {
+  const int b = blockIdx.y;
+  const size_t base = (size_t)b * E;
+  double bits = 0.0;
+  int mn = INT_MAX, mx = INT_MIN;
+  const int64_t nvec = E / ENT_VEC;
+  for (int64_t v = (int64_t)blockIdx.x * ENT_THREADS + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * ENT_THREADS) {
+    const size_t o = base / ENT_VEC + v;
+    const float4 yv = __ldg(reinterpret_cast<const float4*>(y) + o);
+    const float4 lv = __ldg(reinterpret_cast<const float4*>(loc) + o);
+    const float4 sv = __ldg(reinterpret_cast<const float4*>(scale) + o);
+    const float ys[4] = {yv.x, yv.y, yv.z, yv.w}, ls[4] = {lv.x, lv.y, lv.z, lv.w}, ss[4] = {sv.x, sv.y, sv.z, sv.w};
+    float q[4], pr[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      q[k] = rintf(ys[k]);
+      pr[k] = fmaxf(laplace_likelihood(q[k], ls[k], ss[k]), bound);
+      bits -= (double)log2f(pr[k]);
+      const int qi = (int)q[k];
+      mn = min(mn, qi); mx = max(mx, qi);
+    }
+    if (y_hat) reinterpret_cast<float4*>(y_hat)[o] = make_float4(q[0], q[1], q[2], q[3]);
+    if (p_out) reinterpret_cast<float4*>(p_out)[o] = make_float4(pr[0], pr[1], pr[2], pr[3]);
+  }
+  const BlockStats r = block_reduce<ENT_THREADS>(bits, mn, mx);
+  if (threadIdx.x == 0) {
+    if (partial) partial[(size_t)b * gridDim.x + blockIdx.x] = r.bits;
+    if (minmax && r.mn <= r.mx) { atomicMin(minmax + 2 * b, r.mn); atomicMax(minmax + 2 * b + 1, r.mx); }
+  }
+}
+
+cudaError_t launch_laplace(const float* y, const float* loc, const float* scale, int B, int64_t E, float bound,
+                           float* y_hat, float* p, double* bits, int32_t* minmax, double* scratch, cudaStream_t s,
+                           int64_t* launches) {
+  if (E % ENT_VEC != 0) return cudaErrorInvalidValue;
+  int64_t per = (E / ENT_VEC + ENT_THREADS - 1) / ENT_THREADS;
+  if (per > 16) per = 16;                          // 16 blocks x 256 threads x 4 elements x 4 iterations per cube
+  if (minmax) { init_minmax_kernel<<<(B + 127) / 128, 128, 0, s>>>(minmax, B); if (launches) ++*launches; }
+  dim3 grid((unsigned)per, (unsigned)B);
+  laplace_kernel<<<grid, ENT_THREADS, 0, s>>>(y, loc, scale, E, bound, y_hat, p, bits ? scratch : nullptr, minmax);
+  if (launches) ++*launches;
+  if (bits) { finalize_bits_kernel<<<B, 32, 0, s>>>(scratch, (int)per, bits); if (launches) ++*launches; }
+  return cudaGetLastError();
+}
+
+// ---- per-element quantised CDF rows (SymmetricConditional._get_cdf, :95-124) -------------------
+// One thread per element: pmf over min_v..max_v -> quantize_pmf_row -> cumulative sums.
+template <bool INTERVALS>
+__global__ void __launch_bounds__(128)
+laplace_cdf_kernel(const float* __restrict__ y_hat, const float* __restrict__ loc, const float* __restrict__ scale,
+                   int64_t E, const int32_t* __restrict__ minmax, const int64_t* __restrict__ row_offset, float bound,
+                   int precision, uint32_t* __restrict__ intervals, uint16_t* __restrict__ cdf, int* __restrict__ err) {
+  const int b = blockIdx.y;
+  const int min_v = minmax[2 * b], max_v = minmax[2 * b + 1];
+  const int N = max_v - min_v + 1;
+  if (N < 2 || N > PCGC_MAX_SYMBOLS) { if (threadIdx.x == 0 && blockIdx.x == 0) atomicExch(err, PCGC_ERR_BAD_RANGE); return; }
+  float pmf[PCGC_MAX_SYMBOLS];
+  int32_t v[PCGC_MAX_SYMBOLS];
+  double g[PCGC_MAX_SYMBOLS];
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+    const size_t o = (size_t)b * E + e;
+    const float l = __ldg(loc + o), s = __ldg(scale + o);
+    for (int k = 0; k < N; ++k) pmf[k] = fmaxf(laplace_likelihood((float)(min_v + k), l, s), bound);
+    if (quantize_pmf_row(pmf, N, precision, v, g) != 0) { atomicExch(err, PCGC_ERR_BAD_RANGE); continue; }
+    if (INTERVALS) {
+      const int sym = (int)__ldg(y_hat + o) - min_v;
+      if (sym < 0 || sym >= N) { atomicExch(err, PCGC_ERR_BAD_RANGE); intervals[o] = 0; continue; }
+      uint32_t lower = 0;
+      for (int k = 0; k < sym; ++k) lower += (uint32_t)v[k];
+      intervals[o] = lower | ((uint32_t)(v[sym] - 1) << 16);
+    } else {
+      uint16_t* row = cdf + row_offset[b] + (size_t)e * N;
+      uint32_t acc = 0;
+      for (int k = 0; k < N; ++k) { row[k] = (uint16_t)acc; acc += (uint32_t)v[k]; }
+    }
+  }
+}
+
+cudaError_t launch_laplace_intervals(const float* y_hat, const float* loc, const float* scale, int B, int64_t E,
+                                     const int32_t* minmax, float bound, int precision, uint32_t* intervals,
+                                     int* err_flag, cudaStream_t s, int64_t* launches) {
+  dim3 grid((unsigned)((E + 127) / 128), (unsigned)B);
+  laplace_cdf_kernel<true><<<grid, 128, 0, s>>>(y_hat, loc, scale, E, minmax, nullptr, bound, precision, intervals,
+                                               nullptr, err_flag);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_laplace_cdf(const float* loc, const float* scale, int B, int64_t E, const int32_t* minmax_dev,
+                               const int64_t* row_offset_dev, float bound, int precision, uint16_t* cdf,
+                               int* err_flag, cudaStream_t s, int64_t* launches) {
+  dim3 grid((unsigned)((E + 127) / 128), (unsigned)B);
+  laplace_cdf_kernel<false><<<grid, 128, 0, s>>>(nullptr, loc, scale, E, minmax_dev, row_offset_dev, bound, precision,
+                                                nullptr, cdf, err_flag);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+}  // namespace pcgc

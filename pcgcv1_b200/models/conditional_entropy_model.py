@@ -1,0 +1,95 @@
+"""Drop-in for ``models/conditional_entropy_model.py``: ``SymmetricConditional`` -- the per-element
+LAPLACE model conditioned on the hyper decoder's (loc, scale) (conditional_entropy_model.py:21-201;
+north_star calls it "Gaussian", the code is Laplace and that is what runs).
+
+``compress``/``decompress`` keep the reference semantics (the whole tensor is ONE string with one
+symbol range); ``compress_cubes``/``decompress_cubes`` are the batched form of the per-cube loops in
+``transform.py:157-168,238-247``: one string and one (min_v, max_v) per cube, CDF rows built on the
+GPU for all cubes in one launch and the strings coded on a host thread pool."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import runtime
+
+
+class SymmetricConditional:
+    def __init__(self, likelihood_bound=1e-9, range_coder_precision=16, codec=None):
+        self._likelihood_bound = float(likelihood_bound)
+        self._range_coder_precision = int(range_coder_precision)
+        if self._range_coder_precision != 16:
+            raise NotImplementedError("the CDF kernels emit 16-bit tables (the reference's only setting)")
+        self._codec = codec
+
+    def bind(self, codec):
+        self._codec = codec
+        return self
+
+    @property
+    def codec(self):
+        if self._codec is None:
+            self._codec = runtime.get_codec("voxception", "")
+        return self._codec
+
+    def _dev3(self, inputs, loc, scale):
+        c = self.codec
+        return (c.to_device(inputs, torch.float32), c.to_device(loc, torch.float32), c.to_device(scale, torch.float32))
+
+    def __call__(self, inputs, loc, scale, training=False):
+        """-> (round(inputs), max(likelihood, bound)) (conditional_entropy_model.py:71-93)."""
+        if training:
+            raise NotImplementedError("noise quantisation (training=True) is not on the codec hot path")
+        y, l, s = self._dev3(inputs, loc, scale)
+        y_hat, p, _, _ = self.codec.laplace(y.reshape(1, -1), l.reshape(1, -1), s.reshape(1, -1), self._likelihood_bound,
+                                            want_p=True, want_bits=False)
+        return runtime.DeviceResult(y_hat.reshape(y.shape)), runtime.DeviceResult(p.reshape(y.shape))
+
+    def estimate_bits(self, inputs, loc, scale) -> np.ndarray:
+        """per leading-index bits: sum(log2 p) * -1 (train_hyper.py:148-150)."""
+        y, l, s = self._dev3(inputs, loc, scale)
+        B = y.shape[0]
+        _, _, bits, _ = self.codec.laplace(y.reshape(B, -1), l.reshape(B, -1), s.reshape(B, -1), self._likelihood_bound,
+                                           want_p=False, want_bits=True)
+        return bits.cpu().numpy()
+
+    # ---- reference semantics: one string for the whole tensor -----------------------------------
+    def compress(self, inputs, loc, scale):
+        y, l, s = self._dev3(inputs, loc, scale)
+        strings, mins, maxs = self.compress_cubes(y.reshape(1, -1), l.reshape(1, -1), s.reshape(1, -1))
+        return runtime.HostResult(strings[0]), runtime.HostResult(np.int32(mins[0])), runtime.HostResult(np.int32(maxs[0]))
+
+    def decompress(self, strings, loc, scale, min_v, max_v, datashape):
+        strings = runtime.unwrap(strings)
+        if isinstance(strings, np.ndarray):
+            strings = strings.item() if strings.ndim == 0 else strings[0]
+        datashape = [int(v) for v in np.asarray(runtime.unwrap(datashape)).reshape(-1)]
+        c = self.codec
+        l = c.to_device(loc, torch.float32).reshape(1, -1)
+        s = c.to_device(scale, torch.float32).reshape(1, -1)
+        y = self.decompress_cubes([strings], l, s, [int(np.asarray(runtime.unwrap(min_v)))], [int(np.asarray(runtime.unwrap(max_v)))])
+        return runtime.DeviceResult(y.reshape(datashape))
+
+    # ---- batched per-cube form -------------------------------------------------------------------
+    def compress_cubes(self, ys, locs, scales, threads: int = 0):
+        """ys/locs/scales torch float32 [B, ...] on the device -> (list of B strings, min_vs[B], max_vs[B])."""
+        c = self.codec
+        B = ys.shape[0]
+        y2, l2, s2 = ys.reshape(B, -1), locs.reshape(B, -1), scales.reshape(B, -1)
+        y_hat, _, _, mm = c.laplace(y2, l2, s2, self._likelihood_bound, want_p=False, want_bits=False)
+        iv = c.laplace_intervals(y_hat, l2, s2, mm, self._likelihood_bound)
+        mm_h = mm.cpu().numpy()
+        strings = runtime.range_encode_intervals_batch(iv.cpu().numpy(), threads)
+        return strings, mm_h[:, 0].copy(), mm_h[:, 1].copy()
+
+    def decompress_cubes(self, strings, locs, scales, min_vs, max_vs, threads: int = 0):
+        """-> torch float32 [B, E] on the device."""
+        c = self.codec
+        B = locs.shape[0]
+        l2, s2 = locs.reshape(B, -1), scales.reshape(B, -1)
+        E = l2.shape[1]
+        mm = np.stack([np.asarray(min_vs, np.int32).reshape(-1), np.asarray(max_vs, np.int32).reshape(-1)], -1)
+        rows, off = c.laplace_cdf(l2, s2, mm, self._likelihood_bound)
+        sym = runtime.range_decode_rows_batch(list(strings), E, rows.cpu().numpy(), off, mm, threads)
+        vals = (sym.astype(np.int32) + mm[:, :1]).astype(np.float32)
+        return c.to_device(vals)

@@ -1,0 +1,388 @@
+"""Host-side runtime: one ``Codec`` = one pcgc_ctx on one GPU with one set of weights.
+
+PyTorch is used ONLY for device/pinned buffers and the current CUDA stream; every computation
+goes through the C ABI (``_lib``).  No CPU fallback: without CUDA + libpcgc_b200.so the
+constructor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib, netspec, weights as W
+
+_NET_IDS = {
+    ("voxception", "analysis_transform"): _lib.NET_VOX_ANALYSIS,
+    ("voxception", "synthesis_transform"): _lib.NET_VOX_SYNTHESIS,
+    ("voxception", "hyper_encoder"): _lib.NET_HYPER_ENCODER,
+    ("voxception", "hyper_decoder"): _lib.NET_HYPER_DECODER,
+    ("simple", "analysis_transform"): _lib.NET_SIMPLE_ANALYSIS,
+    ("simple", "synthesis_transform"): _lib.NET_SIMPLE_SYNTHESIS,
+}
+_DTYPES = {np.dtype(np.uint8): _lib.DTYPE_U8, np.dtype(np.bool_): _lib.DTYPE_U8,
+           np.dtype(np.float32): _lib.DTYPE_F32, np.dtype(np.float64): _lib.DTYPE_F64}
+_TORCH_DTYPES = {torch.uint8: _lib.DTYPE_U8, torch.bool: _lib.DTYPE_U8, torch.float32: _lib.DTYPE_F32,
+                 torch.float64: _lib.DTYPE_F64}
+
+
+def model_name(model) -> str:
+    """'voxception' | 'simple' from a model module (test.py:72 importlib seam), a name, or a class."""
+    name = model if isinstance(model, str) else getattr(model, "MODEL_NAME", None) or getattr(model, "__name__", "")
+    name = name.rsplit(".", 1)[-1]
+    if "simple" in name:
+        return "simple"
+    if "voxception" in name:
+        return "voxception"
+    raise ValueError("unknown model %r (expected models.model_voxception or models.model_simple)" % (model,))
+
+
+class DeviceResult:
+    """What the drop-in API returns where the reference returns a TF eager tensor: callers do
+    ``.numpy()`` on it (test.py:81,89,101-103,115).  ``.tensor`` is the torch CUDA buffer."""
+
+    def __init__(self, tensor: torch.Tensor):
+        self.tensor = tensor
+
+    def numpy(self) -> np.ndarray:
+        return self.tensor.detach().cpu().numpy()
+
+    @property
+    def shape(self):
+        return tuple(self.tensor.shape)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a.astype(dtype) if dtype is not None else a
+
+    def __len__(self):
+        return self.tensor.shape[0]
+
+    def __getitem__(self, i):
+        return DeviceResult(self.tensor[i])
+
+
+class HostResult:
+    """Host-resident result (strings, min/max scalars, shapes) with the same ``.numpy()`` face."""
+
+    def __init__(self, value):
+        self.value = value
+
+    def numpy(self):
+        return self.value
+
+    def __array__(self, dtype=None, copy=None):
+        return np.asarray(self.value, dtype=dtype)
+
+    def __len__(self):
+        return len(self.value)
+
+    def __getitem__(self, i):
+        return self.value[i]
+
+    def __int__(self):
+        return int(self.value)
+
+    def __repr__(self):
+        return "HostResult(%r)" % (self.value,)
+
+
+def unwrap(x):
+    if isinstance(x, (DeviceResult,)):
+        return x.tensor
+    if isinstance(x, HostResult):
+        return x.value
+    return x
+
+
+class Codec:
+    """One GPU context + weights.  Methods take/return torch CUDA tensors (buffers only)."""
+
+    def __init__(self, model: str = "voxception", ckpt_dir: str = "", device: Optional[int] = None,
+                 weights: Optional[Dict[str, np.ndarray]] = None, engine: int = _lib.ENGINE_AUTO):
+        if not torch.cuda.is_available():
+            raise RuntimeError("pcgcv1_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _lib.lib()
+        self.model = model
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.dev = torch.device("cuda", self.device)
+        h = C.c_void_p()
+        rc = self.lib.pcgc_create(C.byref(h), self.device)
+        if rc != 0:
+            raise _lib.PcgcError(rc, "pcgc_create failed on device %d (needs compute capability 10.x)" % self.device)
+        self.ctx = h
+        self.set_engine(engine)
+        self.weights = weights if weights is not None else W.load(ckpt_dir, model)
+        self._load_weights()
+        self.latent_c = netspec.LATENT_CHANNELS[model]
+        self.latent_n = 64 // netspec.LATENT_DOWN[model]
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def __del__(self):
+        try:
+            if getattr(self, "ctx", None):
+                self.lib.pcgc_destroy(self.ctx)
+                self.ctx = None
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        _lib.check(rc, self.ctx)
+
+    def _stream(self):
+        self._check(self.lib.pcgc_set_stream(self.ctx, C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)))
+
+    def set_engine(self, engine: int):
+        self._check(self.lib.pcgc_set_engine(self.ctx, int(engine)))
+
+    def launch_count(self) -> int:
+        return int(self.lib.pcgc_launch_count(self.ctx))
+
+    def _load_weights(self):
+        w = self.weights
+        for (m, net), layers in netspec.NETS.items():
+            if m != self.model:
+                continue
+            nid = _NET_IDS[(m, net)]
+            for l in layers:
+                k = np.ascontiguousarray(w["%s/%s/kernel" % (net, l.name)], dtype=np.float32)
+                shape = (C.c_int64 * 5)(*k.shape)
+                b = w.get("%s/%s/bias" % (net, l.name))
+                bptr = None
+                if b is not None:
+                    b = np.ascontiguousarray(b, dtype=np.float32)
+                    bptr = b.ctypes.data
+                self._check(self.lib.pcgc_load_conv(self.ctx, nid, l.name.encode(), k.ctypes.data, shape, bptr))
+        for slot, prefix in ((0, "estimator/"), (1, "estimator_y/")):
+            if prefix + "matrix_0" in w:
+                self.load_bottleneck(slot, {k[len(prefix):]: v for k, v in w.items() if k.startswith(prefix)})
+
+    def load_bottleneck(self, slot: int, p: Dict[str, np.ndarray]):
+        c = p["matrix_0"].shape[0]
+        cat = lambda name: np.ascontiguousarray(
+            np.concatenate([np.asarray(p["%s_%d" % (name, i)], np.float32).reshape(-1) for i in range(4)]))
+        m, b, f = cat("matrix"), cat("bais"), cat("factor")
+        self._check(self.lib.pcgc_load_bottleneck(self.ctx, slot, c, m.ctypes.data, b.ctypes.data, f.ctypes.data))
+        if not hasattr(self, "bn_channels"):
+            self.bn_channels = {}
+        self.bn_channels[slot] = c
+
+    def to_device(self, a, dtype=None) -> torch.Tensor:
+        """numpy / torch / Result -> contiguous torch tensor on this codec's device."""
+        a = unwrap(a)
+        if isinstance(a, torch.Tensor):
+            t = a.to(self.dev, non_blocking=True)
+        else:
+            a = np.ascontiguousarray(a)
+            if a.dtype == np.bool_:
+                a = a.view(np.uint8)
+            t = torch.from_numpy(a).to(self.dev, non_blocking=True)
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        return t.contiguous()
+
+    def bottleneck_slot(self, channels: int) -> int:
+        for slot, c in getattr(self, "bn_channels", {}).items():
+            if c == channels:
+                return slot
+        raise RuntimeError("no EntropyBottleneck with %d channels is loaded" % channels)
+
+    # -- transforms ---------------------------------------------------------------------------
+    def analysis(self, cubes: torch.Tensor) -> torch.Tensor:
+        """[B,64,64,64,1] uint8/float32/float64 -> y [B,n,n,n,C] float32."""
+        if cubes.dtype not in _TORCH_DTYPES:
+            cubes = cubes.to(torch.float32)
+        if tuple(cubes.shape[1:]) != (64, 64, 64, 1):
+            raise ValueError("cubes must be [B,64,64,64,1], got %s" % (tuple(cubes.shape),))
+        B = cubes.shape[0]
+        n, c = self.latent_n, self.latent_c
+        y = torch.empty((B, n, n, n, c), dtype=torch.float32, device=self.dev)
+        self._stream()
+        self._check(self.lib.pcgc_analysis(self.ctx, _NET_IDS[(self.model, "analysis_transform")], cubes.data_ptr(),
+                                           _TORCH_DTYPES[cubes.dtype], B, y.data_ptr()))
+        return y
+
+    def synthesis(self, y: torch.Tensor) -> torch.Tensor:
+        n, c = self.latent_n, self.latent_c
+        if tuple(y.shape[1:]) != (n, n, n, c) or y.dtype != torch.float32:
+            raise ValueError("y must be float32 [B,%d,%d,%d,%d], got %s %s" % (n, n, n, c, tuple(y.shape), y.dtype))
+        B = y.shape[0]
+        x = torch.empty((B, 64, 64, 64, 1), dtype=torch.float32, device=self.dev)
+        self._stream()
+        self._check(self.lib.pcgc_synthesis(self.ctx, _NET_IDS[(self.model, "synthesis_transform")], y.data_ptr(), B,
+                                            x.data_ptr()))
+        return x
+
+    def hyper_encode(self, y: torch.Tensor) -> torch.Tensor:
+        if tuple(y.shape[1:]) != (16, 16, 16, 16) or y.dtype != torch.float32:
+            raise ValueError("y must be float32 [B,16,16,16,16]")
+        B = y.shape[0]
+        z = torch.empty((B, 8, 8, 8, 8), dtype=torch.float32, device=self.dev)
+        self._stream()
+        self._check(self.lib.pcgc_hyper_encode(self.ctx, y.data_ptr(), B, z.data_ptr()))
+        return z
+
+    def hyper_decode(self, z_hat: torch.Tensor, scale_floor: float = 1e-9) -> Tuple[torch.Tensor, torch.Tensor]:
+        if tuple(z_hat.shape[1:]) != (8, 8, 8, 8) or z_hat.dtype != torch.float32:
+            raise ValueError("z_hat must be float32 [B,8,8,8,8]")
+        B = z_hat.shape[0]
+        loc = torch.empty((B, 16, 16, 16, 16), dtype=torch.float32, device=self.dev)
+        scale = torch.empty_like(loc)
+        self._stream()
+        self._check(self.lib.pcgc_hyper_decode(self.ctx, z_hat.data_ptr(), B, scale_floor, loc.data_ptr(), scale.data_ptr()))
+        return loc, scale
+
+    # -- entropy models -------------------------------------------------------------------------
+    def factorized(self, slot: int, x: torch.Tensor, bound: float = 1e-9, want_p: bool = True, want_bits: bool = True):
+        """-> (x_hat, p|None, bits (double[1] tensor)|None, minmax int32[2] tensor)."""
+        Cc = x.shape[-1]
+        n_vox = x.numel() // Cc
+        x_hat = torch.empty_like(x)
+        p = torch.empty_like(x) if want_p else None
+        bits = torch.zeros(1, dtype=torch.float64, device=self.dev) if want_bits else None
+        mm = torch.empty(2, dtype=torch.int32, device=self.dev)
+        self._stream()
+        self._check(self.lib.pcgc_factorized_quantize_likelihood(
+            self.ctx, slot, x.data_ptr(), n_vox, Cc, bound, x_hat.data_ptr(), p.data_ptr() if want_p else None,
+            bits.data_ptr() if want_bits else None, mm.data_ptr()))
+        return x_hat, p, bits, mm
+
+    def factorized_cdf(self, slot: int, min_v: int, max_v: int, bound: float = 1e-9, precision: int = 16) -> np.ndarray:
+        Cc = self.bn_channels[slot]
+        N = int(max_v) - int(min_v) + 1
+        cdf = np.empty((Cc, max(N, 1) + 1), np.int32)
+        self._stream()
+        self._check(self.lib.pcgc_factorized_cdf(self.ctx, slot, int(min_v), int(max_v), bound, precision, cdf.ctypes.data))
+        return cdf
+
+    def laplace(self, y: torch.Tensor, loc: torch.Tensor, scale: torch.Tensor, bound: float = 1e-9,
+                want_p: bool = True, want_bits: bool = True):
+        """per cube -> (y_hat, p|None, bits double[B]|None, minmax int32[B,2])."""
+        B = y.shape[0]
+        E = y.numel() // max(B, 1)
+        y_hat = torch.empty_like(y)
+        p = torch.empty_like(y) if want_p else None
+        bits = torch.zeros(B, dtype=torch.float64, device=self.dev) if want_bits else None
+        mm = torch.empty((B, 2), dtype=torch.int32, device=self.dev)
+        self._stream()
+        self._check(self.lib.pcgc_laplace_quantize_likelihood(
+            self.ctx, y.data_ptr(), loc.data_ptr(), scale.data_ptr(), B, E, bound, y_hat.data_ptr(),
+            p.data_ptr() if want_p else None, bits.data_ptr() if want_bits else None, mm.data_ptr()))
+        return y_hat, p, bits, mm
+
+    def laplace_intervals(self, y_hat, loc, scale, mm: torch.Tensor, bound: float = 1e-9) -> torch.Tensor:
+        B = y_hat.shape[0]
+        E = y_hat.numel() // max(B, 1)
+        iv = torch.empty((B, E), dtype=torch.int32, device=self.dev)     # uint32 payload
+        self._stream()
+        self._check(self.lib.pcgc_laplace_intervals(self.ctx, y_hat.data_ptr(), loc.data_ptr(), scale.data_ptr(), B, E,
+                                                    mm.data_ptr(), bound, 16, iv.data_ptr()))
+        return iv
+
+    def laplace_cdf(self, loc, scale, minmax_host: np.ndarray, bound: float = 1e-9):
+        """-> (rows uint16 device tensor, row_offset int64 host array [B+1])."""
+        B = loc.shape[0]
+        E = loc.numel() // max(B, 1)
+        mm = np.ascontiguousarray(minmax_host, dtype=np.int32).reshape(B, 2)
+        N = (mm[:, 1] - mm[:, 0] + 1).astype(np.int64)
+        off = np.zeros(B + 1, np.int64)
+        np.cumsum(N * E, out=off[1:])
+        rows = torch.empty(int(off[-1]), dtype=torch.int16, device=self.dev)    # uint16 payload
+        self._stream()
+        self._check(self.lib.pcgc_laplace_cdf(self.ctx, loc.data_ptr(), scale.data_ptr(), B, E, mm.ctypes.data, bound, 16,
+                                              off.ctypes.data, rows.data_ptr()))
+        return rows, off
+
+    # -- top-k ---------------------------------------------------------------------------------
+    def topk(self, logits: torch.Tensor, ks: torch.Tensor):
+        """logits float32 [B,...]; ks int32 [B] -> (mask uint8 same shape, thres float[B], count int32[B])."""
+        B = logits.shape[0]
+        V = logits.numel() // max(B, 1)
+        mask = torch.empty(logits.shape, dtype=torch.uint8, device=self.dev)
+        thres = torch.empty(B, dtype=torch.float32, device=self.dev)
+        cnt = torch.empty(B, dtype=torch.int32, device=self.dev)
+        self._stream()
+        self._check(self.lib.pcgc_topk_select(self.ctx, logits.data_ptr(), B, V, ks.data_ptr(), mask.data_ptr(),
+                                              thres.data_ptr(), cnt.data_ptr()))
+        return mask, thres, cnt
+
+    def threshold(self, logits: torch.Tensor, thres: float):
+        B = logits.shape[0]
+        V = logits.numel() // max(B, 1)
+        mask = torch.empty(logits.shape, dtype=torch.uint8, device=self.dev)
+        cnt = torch.empty(B, dtype=torch.int32, device=self.dev)
+        self._stream()
+        self._check(self.lib.pcgc_threshold_select(self.ctx, logits.data_ptr(), B, V, float(thres), mask.data_ptr(), cnt.data_ptr()))
+        return mask, cnt
+
+
+_CODECS: Dict[tuple, Codec] = {}
+
+
+def get_codec(model="voxception", ckpt_dir: str = "", device: Optional[int] = None) -> Codec:
+    """Cached codec per (model, checkpoint, device): the reference rebuilds and restores its Keras
+    models on every call (transform.py:33-38); weights here are uploaded once."""
+    name = model_name(model)
+    dev = torch.cuda.current_device() if (device is None and torch.cuda.is_available()) else device
+    key = (name, os.path.abspath(ckpt_dir) if ckpt_dir else "", dev)
+    c = _CODECS.get(key)
+    if c is None:
+        c = Codec(name, ckpt_dir, dev)
+        _CODECS[key] = c
+    return c
+
+
+# ---- host coder helpers (no ctx) ---------------------------------------------------------------
+def range_encode(sym: np.ndarray, cdf: np.ndarray, precision: int = 16) -> bytes:
+    """sym int16 [n] coded with cdf row (i % rows); cdf int32 [rows, N+1]."""
+    L = _lib.lib()
+    sym = np.ascontiguousarray(sym, dtype=np.int16).reshape(-1)
+    cdf = np.ascontiguousarray(cdf, dtype=np.int32)
+    rows, N = cdf.shape[0], cdf.shape[1] - 1
+    cap = 2 * sym.size + 64
+    out = np.empty(cap, np.uint8)
+    ln = C.c_int64()
+    _lib.check(L.pcgc_range_encode(sym.ctypes.data, sym.size, cdf.ctypes.data, rows, N, precision, out.ctypes.data, cap, C.byref(ln)))
+    return out[:ln.value].tobytes()
+
+
+def range_decode(data: bytes, n: int, cdf: np.ndarray, precision: int = 16) -> np.ndarray:
+    L = _lib.lib()
+    cdf = np.ascontiguousarray(cdf, dtype=np.int32)
+    rows, N = cdf.shape[0], cdf.shape[1] - 1
+    buf = np.frombuffer(bytes(data), np.uint8) if len(data) else np.zeros(1, np.uint8)
+    sym = np.empty(n, np.int16)
+    _lib.check(L.pcgc_range_decode(buf.ctypes.data, len(data), n, cdf.ctypes.data, rows, N, precision, sym.ctypes.data))
+    return sym
+
+
+def range_encode_intervals_batch(iv: np.ndarray, threads: int = 0):
+    """iv uint32/int32 [B,E] (host) -> list of B byte strings."""
+    L = _lib.lib()
+    iv = np.ascontiguousarray(iv)
+    B, E = iv.shape
+    stride = 2 * E + 64
+    out = np.empty((B, stride), np.uint8)
+    lens = np.empty(B, np.int64)
+    _lib.check(L.pcgc_range_encode_intervals_batch(iv.ctypes.data, B, E, 16, out.ctypes.data, stride, lens.ctypes.data, threads))
+    return [out[b, :lens[b]].tobytes() for b in range(B)]
+
+
+def range_decode_rows_batch(strings, E: int, rows: np.ndarray, row_offset: np.ndarray, minmax: np.ndarray,
+                            threads: int = 0) -> np.ndarray:
+    """-> int16 [B,E] symbols (0-based; add min_v)."""
+    L = _lib.lib()
+    B = len(strings)
+    bufs = [np.frombuffer(bytes(s), np.uint8) if len(s) else np.zeros(1, np.uint8) for s in strings]
+    ptrs = (C.c_void_p * B)(*[b.ctypes.data for b in bufs])
+    nbytes = np.array([len(s) for s in strings], np.int64)
+    rows = np.ascontiguousarray(rows)
+    row_offset = np.ascontiguousarray(row_offset, dtype=np.int64)
+    minmax = np.ascontiguousarray(minmax, dtype=np.int32)
+    sym = np.empty((B, E), np.int16)
+    _lib.check(L.pcgc_range_decode_rows_batch(ptrs, nbytes.ctypes.data, B, E, rows.ctypes.data, row_offset.ctypes.data,
+                                              minmax.ctypes.data, 16, sym.ctypes.data, threads))
+    return sym

@@ -1,0 +1,142 @@
+"""Host part of libpcgc_b200.so (range coder, 16-bit CDF normaliser) against the oracle.  CPU only:
+these entry points take no ctx and need no GPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import coder
+from oracle.entropy import SymmetricConditionalOracle
+from pcgcv1_b200 import _lib, runtime
+
+
+def _lib_cdf(pmf, precision=16):
+    L = _lib.lib()
+    pmf = np.ascontiguousarray(pmf, np.float32)
+    out = np.empty((pmf.shape[0], pmf.shape[1] + 1), np.int32)
+    rc = L.pcgc_pmf_to_quantized_cdf(pmf.ctypes.data, pmf.shape[0], pmf.shape[1], precision, out.ctypes.data)
+    assert rc == 0
+    return out
+
+
+def test_oracle_c_equals_python_definition():
+    rng = np.random.default_rng(3)
+    for _ in range(60):
+        n, rows = int(rng.integers(2, 20)), int(rng.integers(1, 4))
+        pmf = rng.random((rows, n)).astype(np.float32) ** int(rng.integers(1, 6))
+        pmf = np.maximum(pmf / pmf.sum(-1, keepdims=True) * rng.choice([1.0, 0.99, 1.01]), 1e-9).astype(np.float32)
+        a = coder.pmf_to_quantized_cdf(pmf, 16, force_python=True)
+        assert np.array_equal(a, coder.pmf_to_quantized_cdf(pmf, 16))
+        cnt = int(rng.integers(0, 300))
+        sym = rng.integers(0, n, cnt).astype(np.int16)
+        idx = rng.integers(0, rows, cnt).astype(np.int32)
+        s = coder.range_encode(sym, a, idx, force_python=True)
+        assert s == coder.range_encode(sym, a, idx)
+        assert np.array_equal(coder.range_decode(s, cnt, a, idx, force_python=True), sym)
+        assert np.array_equal(coder.range_decode(s, cnt, a, idx), sym)
+
+
+def test_normaliser_equals_greedy_definition():
+    """Water-filling normaliser == step-by-step greedy of the oracle, incl. large deficits."""
+    rng = np.random.default_rng(0)
+    for _ in range(150):
+        n, rows = int(rng.integers(2, 64)), int(rng.integers(1, 6))
+        pmf = rng.random((rows, n)).astype(np.float32) ** int(rng.integers(1, 10))
+        pmf /= pmf.sum(-1, keepdims=True)
+        pmf = np.maximum(pmf * rng.choice([1.0, 0.97, 0.9, 0.5, 0.2, 1.02]), 1e-9).astype(np.float32)
+        ref = coder.pmf_to_quantized_cdf(pmf, 16)
+        out = _lib_cdf(pmf)
+        assert np.array_equal(ref, out)
+        assert (out[:, 0] == 0).all() and (out[:, -1] == 65536).all() and (np.diff(out, axis=-1) >= 1).all()
+
+
+@pytest.mark.parametrize("N", [2, 5, 13, 31, 64])
+def test_normaliser_on_laplace_rows(N):
+    rng = np.random.default_rng(N)
+    loc = rng.normal(0, 2, 200).astype(np.float32)
+    sc = (np.abs(rng.normal(0, 1, 200)) + 1e-3).astype(np.float32)
+    sc[:4] = [1e-9, 1e-4, 30.0, 1000.0]
+    mn = -(N // 2)
+    pmf = SymmetricConditionalOracle().pmf(loc, sc, mn, mn + N - 1)
+    assert np.array_equal(coder.pmf_to_quantized_cdf(pmf, 16), _lib_cdf(pmf))
+
+
+def test_single_symbol_alphabet_is_rejected():
+    L = _lib.lib()
+    pmf = np.ones((1, 1), np.float32)
+    out = np.empty((1, 2), np.int32)
+    assert L.pcgc_pmf_to_quantized_cdf(pmf.ctypes.data, 1, 1, 16, out.ctypes.data) == -2     # BAD_RANGE
+    with pytest.raises(ValueError):
+        coder.pmf_to_quantized_cdf(pmf, 16)
+
+
+def test_range_coder_bytes_equal_oracle_and_round_trip():
+    rng = np.random.default_rng(1)
+    for _ in range(80):
+        n, rows = int(rng.integers(2, 33)), int(rng.integers(1, 9))
+        pmf = rng.random((rows, n)).astype(np.float32) ** 3
+        pmf = np.maximum(pmf / pmf.sum(-1, keepdims=True), 1e-9).astype(np.float32)
+        cdf = coder.pmf_to_quantized_cdf(pmf, 16)
+        cnt = int(rng.integers(0, 3000))
+        sym = rng.integers(0, n, cnt).astype(np.int16)
+        idx = (np.arange(cnt) % rows).astype(np.int32)
+        s = runtime.range_encode(sym, cdf)
+        assert s == coder.range_encode(sym, cdf, idx)
+        assert np.array_equal(runtime.range_decode(s, cnt, cdf), sym)
+
+
+def test_carry_propagation_stress():
+    """Skewed tables force long 0xFFFF runs and carries through the delayed word."""
+    rng = np.random.default_rng(2)
+    for hi_first in (False, True):
+        v = np.array([65533, 1, 1, 1] if hi_first else [1, 1, 1, 65533])
+        cdf = np.concatenate([[0], np.cumsum(v)]).astype(np.int32)[None]
+        top = 0 if hi_first else 3
+        for _ in range(40):
+            cnt = int(rng.integers(1, 4000))
+            sym = np.where(rng.random(cnt) < 0.999, top, rng.integers(0, 4, cnt)).astype(np.int16)
+            s = runtime.range_encode(sym, cdf)
+            assert s == coder.range_encode(sym, cdf, np.zeros(cnt, np.int32), force_python=True)
+            assert np.array_equal(runtime.range_decode(s, cnt, cdf), sym)
+
+
+def test_interval_and_row_entry_points_batch():
+    """The per-element forms used by the conditional model: intervals in, uint16 rows out."""
+    rng = np.random.default_rng(5)
+    B, E = 5, 777
+    mm = np.array([[-3, 4], [0, 1], [-15, 15], [-1, 1], [2, 9]], np.int32)
+    sc_or = SymmetricConditionalOracle()
+    ivs = np.zeros((B, E), np.uint32)
+    syms = []
+    rows_all, off = [], [0]
+    for b in range(B):
+        N = mm[b, 1] - mm[b, 0] + 1
+        loc = rng.normal((mm[b, 0] + mm[b, 1]) / 2, 1.5, E).astype(np.float32)
+        scale = (np.abs(rng.normal(0, 1, E)) + 0.01).astype(np.float32)
+        cdf = coder.pmf_to_quantized_cdf(sc_or.pmf(loc, scale, int(mm[b, 0]), int(mm[b, 1])), 16)
+        sym = rng.integers(0, N, E)
+        lower = cdf[np.arange(E), sym].astype(np.uint32)
+        width = (cdf[np.arange(E), sym + 1] - cdf[np.arange(E), sym]).astype(np.uint32)
+        ivs[b] = lower | ((width - 1) << 16)
+        syms.append(sym)
+        rows_all.append(cdf[:, :N].astype(np.uint16).reshape(-1))
+        off.append(off[-1] + E * N)
+        # bytes equal the oracle's
+        ref = coder.range_encode(sym.astype(np.int16), cdf, np.arange(E, dtype=np.int32))
+        assert runtime.range_encode_intervals_batch(ivs[b:b + 1], 1)[0] == ref
+    strings = runtime.range_encode_intervals_batch(ivs, 3)
+    dec = runtime.range_decode_rows_batch(strings, E, np.concatenate(rows_all), np.array(off, np.int64), mm, 3)
+    for b in range(B):
+        assert np.array_equal(dec[b], syms[b])
+
+
+def test_coded_size_close_to_entropy():
+    rng = np.random.default_rng(7)
+    pmf = np.array([[0.5, 0.25, 0.125, 0.125]], np.float32)
+    cdf = coder.pmf_to_quantized_cdf(pmf, 16)
+    n = 20000
+    sym = rng.choice(4, n, p=pmf[0]).astype(np.int16)
+    s = runtime.range_encode(sym, cdf)
+    ideal_bits = -np.log2(pmf[0][sym]).sum()
+    assert len(s) * 8 <= ideal_bits + 64
+    assert len(s) * 8 >= ideal_bits - 64
