@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Benchmark of the per-cube compress+decompress hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = hyper-mode encode + decode of every 64^3 cube of the synthetic vox10 cloud (BASELINE
+config 1: ~190 cubes, ~790 k points, model_voxception, rho = 1, seeded synthetic weights) on each GPU
+(cubes are independent: weak scaling, no data-path collective).
+
+* ``value``  : cubes/s with the occupancy cubes already resident in HBM -- every GPU kernel of the
+               path (analysis, hyper encoder, z quantisation, hyper decoder, Laplace quantise +
+               likelihood + bits + min/max, per-element CDF intervals; then on the decode side hyper
+               decoder, per-element CDF rows, synthesis, top-k classification).  The host range coder
+               (the reference's sequential tail) is not in ``value``; it is in ``e2e``.
+* ``e2e``    : the same metric through the public API (transform.compress_hyper ->
+               transform.decompress_hyper -> select_voxels) with HOST buffers: pinned uint8 cubes in,
+               byte strings + headers between, float32 masks out; H2D/D2H copies and the multi-threaded
+               host range coder inside the timed region.
+* ``roofline``: the dominant kernel group of the timed region, from per-launch CUDA events recorded by
+               the library on its stream (pcgc_profile_enable).
+* ``cpu_baseline``: the oracle (kind "port": the TF-1.13 reference cannot run offline) on a bounded
+               sample of the same cubes, driven one cube per call like the reference's tf.map_fn.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "hyper-mode encode+decode throughput of 64^3 cubes"
+UNIT = "cubes/s"
+GFLOP_PER_CUBE = 21.5675            # A+HE+HD (encode) + HD+S (decode)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------ CPU baseline
+def cpu_path_one_cube(oracle_mods, w, parts, cube_u8, num_points):
+    """The reference's per-cube hyper path restated by the oracle (transform.py:91-259, process.py:54-66)."""
+    nets, entropy, topk, W = oracle_mods
+    x = cube_u8.astype(np.float32)[None]
+    y = nets.run_net("voxception", "analysis", x, parts["analysis_transform"])
+    z = nets.run_net("voxception", "hyper_encoder", y, parts["hyper_encoder"])
+    z_hat, _ = parts["eb"](z)
+    loc, scale = nets.run_net("voxception", "hyper_decoder", z_hat, parts["hyper_decoder"])
+    scale = np.maximum(scale, np.float32(1e-9))
+    z_str, z_min, z_max = parts["eb"].compress(z)
+    sc = parts["sc"]
+    y_str, y_min, y_max = sc.compress(y, loc, scale)
+    # decode
+    z_dec = parts["eb"].decompress(z_str, z_min, z_max, z.shape)
+    loc2, scale2 = nets.run_net("voxception", "hyper_decoder", z_dec, parts["hyper_decoder"])
+    scale2 = np.maximum(scale2, np.float32(1e-9))
+    y_dec = sc.decompress(y_str, loc2, scale2, y_min, y_max, y.shape)
+    logits = nets.run_net("voxception", "synthesis", y_dec, parts["synthesis_transform"])
+    mask = topk.select_voxels(logits, [num_points], 1.0)
+    return len(y_str) + len(z_str), int(mask.sum())
+
+
+def run_cpu(cubes, nums, n_cubes, threads):
+    import torch
+    from oracle import build as obuild, entropy, nets, topk
+    from pcgcv1_b200 import weights as W
+    obuild.build()
+    torch.set_num_threads(threads)
+    w = W.synthetic_weights("voxception")
+    parts = {k: W.net_weights(w, k) for k in ("analysis_transform", "synthesis_transform", "hyper_encoder", "hyper_decoder")}
+    parts["eb"] = entropy.EntropyBottleneckOracle(W.net_weights(w, "estimator"))
+    parts["sc"] = entropy.SymmetricConditionalOracle()
+    mods = (nets, entropy, topk, W)
+    t0 = time.perf_counter()
+    for i in range(n_cubes):
+        cpu_path_one_cube(mods, w, parts, cubes[i % len(cubes)], int(nums[i % len(cubes)]))
+    return n_cubes / (time.perf_counter() - t0)
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def finish(self):
+        self._stop.set()
+        self.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def device_step(codec, st):
+    """All GPU kernels of encode + decode on device-resident inputs (no host coder)."""
+    import torch
+    B = st["B"]
+    y = codec.analysis(st["cubes"])
+    z = codec.hyper_encode(y)
+    z_hat, _, _, _ = codec.factorized(0, z, want_p=True, want_bits=True)
+    loc, scale = codec.hyper_decode(z_hat, 1e-9)
+    y2, l2, s2 = y.reshape(B, -1), loc.reshape(B, -1), scale.reshape(B, -1)
+    y_hat, _, _, mm = codec.laplace(y2, l2, s2, want_p=True, want_bits=True)
+    codec.laplace_intervals(y_hat, l2, s2, mm)
+    # decode side: headers (min/max) come from the stream, z_hat / y_hat from the range decoder
+    loc_d, scale_d = codec.hyper_decode(z_hat, 1e-9)
+    codec.laplace_cdf(loc_d.reshape(B, -1), scale_d.reshape(B, -1), st["minmax_host"])
+    logits = codec.synthesis(y_hat.reshape(y.shape))
+    mask, _, cnt = codec.topk(logits, st["ks"])
+    return mask, cnt
+
+
+def e2e_step(st):
+    from pcgcv1_b200 import transform
+    from pcgcv1_b200.dataprocess import inout_points
+    from pcgcv1_b200.models import model_voxception
+    out = transform.compress_hyper(st["cubes_host"], model_voxception, "")
+    host = [o.numpy() for o in out]
+    xs = transform.decompress_hyper(*host, model_voxception, "")
+    mask = inout_points.select_voxels(xs, st["nums"], 1.0, codec=st["codec"])
+    return host, mask
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from pcgcv1_b200 import runtime, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    cubes, pos, nums = synthetic.workload(args.workload, seed=0, max_cubes=args.cubes)
+    B = len(cubes)
+    codec = runtime.get_codec("voxception", "", local)
+    pinned = torch.from_numpy(cubes).pin_memory()
+    st = {"B": B, "codec": codec, "nums": nums, "cubes_host": pinned, "cubes": pinned.to(codec.dev),
+          "ks": torch.from_numpy(nums.astype(np.int32)).to(codec.dev)}
+    # stream headers for the device-resident decode leg (what a decoder reads from .strings_head)
+    y = codec.analysis(st["cubes"])
+    loc, scale = codec.hyper_decode(torch.round(codec.hyper_encode(y)), 1e-9)
+    _, _, _, mm = codec.laplace(y.reshape(B, -1), loc.reshape(B, -1), scale.reshape(B, -1), want_p=False, want_bits=False)
+    st["minmax_host"] = mm.cpu().numpy()
+    del y, loc, scale
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = a.elapsed_time(b)
+        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=codec.dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    # ---- device-resident hot path (value) with per-launch events for the roofline ----
+    for _ in range(args.warmup):
+        device_step(codec, st)
+    codec.profile(True)
+    codec.profile_report()
+    l0 = codec.launch_count()
+    dev_ms, _ = timed(lambda: device_step(codec, st), args.steps, 0)
+    launches = codec.launch_count() - l0
+    prof = codec.profile_report()
+    codec.profile(False)
+    clocks = sampler.finish()
+    # ---- end to end through the public API with host buffers ----
+    runtime.COUNTERS["h2d_bytes"] = runtime.COUNTERS["d2h_bytes"] = 0
+    e2e_steps = max(1, min(args.steps, 3))
+    _, e2e_wall_ms = timed(lambda: e2e_step(st), e2e_steps, 1)
+    h2d = runtime.COUNTERS["h2d_bytes"] // (e2e_steps + 1)
+    d2h = runtime.COUNTERS["d2h_bytes"] // (e2e_steps + 1)
+
+    if world > 1:
+        lt = torch.tensor([launches], dtype=torch.int64, device=codec.dev)
+        dist.all_reduce(lt)
+        launches = int(lt[0])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    value = world * B * args.steps / (dev_ms / 1e3)
+    e2e = world * B * e2e_steps / (e2e_wall_ms / 1e3)
+    points = float(nums.sum())
+    # dominant kernel group
+    prof.sort(key=lambda r: -r["ms"])
+    total_ms = sum(r["ms"] for r in prof)
+    top = prof[0]
+    per_launch_ms = top["ms"] / top["count"]
+    if top["flops"] > 0:
+        ach = top["flops"] / top["count"] / (per_launch_ms * 1e-3) / 1e12
+        roof = {"kernel": top["tag"], "bound": "tensor", "achieved": round(ach, 3), "peak": peaks["bf16_tflops_sustained"],
+                "unit": "TFLOP/s", "frac": round(ach / peaks["bf16_tflops_sustained"], 5), "traffic": None}
+    else:
+        ach = top["bytes"] / top["count"] / (per_launch_ms * 1e-3) / 1e9
+        roof = {"kernel": top["tag"], "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": round(ach / peaks["hbm_gbs"], 5), "traffic": None}
+    roof.update({"peak_source": peaks["source"], "ms_per_launch": round(per_launch_ms, 4), "share_of_step": round(top["ms"] / total_ms, 4)})
+    conv_ms = sum(r["ms"] for r in prof if r["tag"].startswith("conv"))
+    conv_tflops = sum(r["flops"] for r in prof if r["tag"].startswith("conv")) / (conv_ms * 1e-3) / 1e12
+    kernels = [{"tag": r["tag"], "share": round(r["ms"] / total_ms, 4),
+                "achieved": round((r["flops"] / 1e12 if r["flops"] else r["bytes"] / 1e9) / (r["ms"] * 1e-3), 2),
+                "unit": "TFLOP/s" if r["flops"] else "GB/s"} for r in prof[:8]]
+    # ---- CPU baseline (rank 0, N=1 only) ----
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        n_cpu = args.cpu_cubes
+        v = run_cpu(cubes, nums, n_cpu, cores)
+        cpu = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d cubes of the same cloud, one cube per call, torch-CPU fp32 convs + NumPy entropy + C range coder" % n_cpu}
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(dev_ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s synthetic cloud, %d cubes of 64^3 (%d points) per GPU, hyper mode, model_voxception, rho=1.0, "
+                               "seeded synthetic weights" % (args.workload, B, int(points)),
+                   "cubes_per_gpu": B, "points_per_gpu": int(points), "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)",
+                   "conv_engine": os.environ.get("PCGC_ENGINE", "auto")},
+        "points_per_s": round(value * points / B, 1),
+        "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "points_per_s": round(e2e * points / B, 1), "steps": e2e_steps, "host_threads": os.cpu_count()},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+        "conv": {"achieved_tflops": round(conv_tflops, 2), "share_of_step": round(conv_ms / total_ms, 4),
+                 "algorithmic_gflop_per_cube": GFLOP_PER_CUBE,
+                 "frac_of_bf16_sustained": round(conv_tflops / peaks["bf16_tflops_sustained"], 5)},
+        "kernels": kernels, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU path.  TF 1.13 cannot be installed offline, so this is the
+    oracle port driven exactly as transform.py drives TF (one cube per call), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from pcgcv1_b200 import synthetic
+    cubes, pos, nums = synthetic.workload(args.workload, seed=0, max_cubes=args.cubes)
+    cores = os.cpu_count() or 1
+    per_step = args.cpu_cubes
+    for _ in range(min(args.warmup, 1)):
+        run_cpu(cubes, nums, 1, cores)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        run_cpu(cubes[s * per_step:], nums[s * per_step:], per_step, cores)
+    dt = time.perf_counter() - t0
+    v = args.steps * per_step / dt
+    sample = "%d cubes of the %s cloud per step, one cube per call" % (per_step, args.workload)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s synthetic cloud, hyper mode, model_voxception, rho=1.0, seeded synthetic weights" % args.workload,
+                   "note": "TF 1.13 reference not installable offline: CPU oracle port of the same path"},
+        "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="vox10", choices=["vox10", "vox12"])
+    ap.add_argument("--cubes", type=int, default=None, help="limit the number of cubes (debug)")
+    ap.add_argument("--cpu-cubes", type=int, default=6, help="cubes in the CPU baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        import __graft_entry__
+        __graft_entry__.build()
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -68,6 +68,11 @@ int pcgc_set_engine(pcgc_ctx* ctx, int engine);
 /* number of kernels this library has launched on ctx since creation (bench "gpu_launches"). */
 int64_t pcgc_launch_count(const pcgc_ctx* ctx);
 int pcgc_synchronize(pcgc_ctx* ctx);
+/* Measurement aid (bench.py roofline): when on, every kernel launch group is bracketed by CUDA events
+ * on the ctx stream.  pcgc_profile_report synchronises, writes a JSON array of
+ * {"tag","count","ms","flops","bytes"} (algorithmic work per tag) into buf and clears the records. */
+int pcgc_profile_enable(pcgc_ctx* ctx, int on);
+int pcgc_profile_report(pcgc_ctx* ctx, char* buf, int64_t cap);
 
 /* ---- weights (replaces tf.train.Checkpoint.restore, transform.py:36-38,70-72,107-112,214-218) -- */
 /* kernel: HOST float32 in the Keras layout ([k,k,k,Cin,Cout]; Conv3DTranspose [k,k,k,Cout,Cin]),

@@ -33,6 +33,8 @@ SIGNATURES = {
     "pcgc_set_engine": (_i, [_vp, _i]),
     "pcgc_launch_count": (_i64, [_vp]),
     "pcgc_synchronize": (_i, [_vp]),
+    "pcgc_profile_enable": (_i, [_vp, _i]),
+    "pcgc_profile_report": (_i, [_vp, C.c_char_p, _i64]),
     "pcgc_load_conv": (_i, [_vp, _i, C.c_char_p, _vp, C.POINTER(_i64), _vp]),
     "pcgc_load_bottleneck": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "pcgc_analysis": (_i, [_vp, _i, _vp, _i, _i, _vp]),

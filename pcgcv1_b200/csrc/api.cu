@@ -181,6 +181,11 @@ struct pcgc_ctx {
   int32_t* mm_dev = nullptr; size_t mm_cap = 0;
   int64_t* off_dev = nullptr; size_t off_cap = 0;
   int sub_batch = 32;
+  // optional per-launch CUDA-event timing (bench.py roofline): see pcgc_profile_enable
+  bool profiling = false;
+  struct ProfRec { std::string tag; cudaEvent_t a, b; double flops, bytes; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
 };
 
 namespace {
@@ -193,6 +198,24 @@ int fail(pcgc_ctx* c, int code, const char* fmt, ...) {
   va_end(ap);
   if (c) c->err = buf;
   return code;
+}
+
+cudaEvent_t prof_event(pcgc_ctx* c) {
+  cudaEvent_t e = nullptr;
+  if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+  else cudaEventCreate(&e);
+  return e;
+}
+// Brackets the launches issued between begin/end with events on the ctx stream.
+void prof_begin(pcgc_ctx* c, const std::string& tag, double flops, double bytes) {
+  if (!c->profiling) return;
+  pcgc_ctx::ProfRec r{tag, prof_event(c), prof_event(c), flops, bytes};
+  cudaEventRecord(r.a, c->stream);
+  c->prof.push_back(r);
+}
+void prof_end(pcgc_ctx* c) {
+  if (!c->profiling || c->prof.empty()) return;
+  cudaEventRecord(c->prof.back().b, c->stream);
 }
 
 #define CK(call)                                                                              \
@@ -287,21 +310,30 @@ int run_net(pcgc_ctx* ctx, int kind, const float* in_ext, const void* cubes, int
       c.B = nb;
       if (!c.out) return fail(ctx, PCGC_ERR_BAD_ARG, "net %d: missing output pointer", kind);
       bool done = false;
+      char tag[96];
+      const double flops = 2.0 * nb * (double)(s.transposed ? op.in_n : out_n) * (s.transposed ? op.in_n : out_n) *
+                           (s.transposed ? op.in_n : out_n) * s.k * s.k * s.k * s.cin * s.cout;
       if (ctx->engine != PCGC_ENGINE_FFMA && lw.umma.ok && lw.n_classes == 1) {
         c.d = lw.cls[0]; c.tn = out_n;
+        snprintf(tag, sizeof tag, "conv_umma k%d s%d%s c%d->%d n%d", s.k, s.stride, s.transposed ? "T" : "", s.cin, s.cout, op.in_n);
+        prof_begin(ctx, tag, flops, 0);
         cudaError_t e = launch_conv_umma(c, lw.umma, ctx->stream, &ctx->launches);
+        prof_end(ctx);
         if (e == cudaSuccess) done = true;
         else if (e != cudaErrorNotSupported) return fail(ctx, PCGC_ERR_CUDA, "umma conv '%s': %s", s.name.c_str(), cudaGetErrorString(e));
       }
       if (!done) {
         if (ctx->engine == PCGC_ENGINE_UMMA && lw.umma.ok)
           return fail(ctx, PCGC_ERR_CUDA, "umma conv '%s' unavailable", s.name.c_str());
+        snprintf(tag, sizeof tag, "conv_ffma k%d s%d%s c%d->%d n%d", s.k, s.stride, s.transposed ? "T" : "", s.cin, s.cout, op.in_n);
+        prof_begin(ctx, tag, flops, 0);
         for (int k = 0; k < lw.n_classes; ++k) {
           c.d = lw.cls[k];
           c.tn = s.transposed ? op.in_n : out_n;
           cudaError_t e = launch_conv_ffma(c, ctx->stream, &ctx->launches);
           if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "conv '%s': %s", s.name.c_str(), cudaGetErrorString(e));
         }
+        prof_end(ctx);
       }
     }
   }
@@ -354,6 +386,8 @@ void pcgc_destroy(pcgc_ctx* ctx) {
   if (ctx->err_flag) cudaFree(ctx->err_flag);
   if (ctx->mm_dev) cudaFree(ctx->mm_dev);
   if (ctx->off_dev) cudaFree(ctx->off_dev);
+  for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   delete ctx;
 }
 
@@ -372,6 +406,41 @@ int pcgc_set_engine(pcgc_ctx* ctx, int engine) {
 }
 
 int64_t pcgc_launch_count(const pcgc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int pcgc_profile_enable(pcgc_ctx* ctx, int on) {
+  if (!ctx) return PCGC_ERR_BAD_ARG;
+  ctx->profiling = on != 0;
+  return PCGC_OK;
+}
+
+int pcgc_profile_report(pcgc_ctx* ctx, char* buf, int64_t cap) {
+  if (!ctx || !buf || cap < 3) return PCGC_ERR_BAD_ARG;
+  DeviceGuard g(ctx->device);
+  CK(cudaStreamSynchronize(ctx->stream));
+  struct Agg { std::string tag; int count; double ms, flops, bytes; };
+  std::vector<Agg> aggs;
+  for (auto& r : ctx->prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    Agg* a = nullptr;
+    for (auto& x : aggs) if (x.tag == r.tag) { a = &x; break; }
+    if (!a) { aggs.push_back({r.tag, 0, 0, 0, 0}); a = &aggs.back(); }
+    a->count++; a->ms += ms; a->flops += r.flops; a->bytes += r.bytes;
+    ctx->ev_pool.push_back(r.a); ctx->ev_pool.push_back(r.b);
+  }
+  ctx->prof.clear();
+  std::string out = "[";
+  for (size_t i = 0; i < aggs.size(); ++i) {
+    char line[256];
+    snprintf(line, sizeof line, "%s{\"tag\":\"%s\",\"count\":%d,\"ms\":%.6f,\"flops\":%.6e,\"bytes\":%.6e}", i ? "," : "",
+             aggs[i].tag.c_str(), aggs[i].count, aggs[i].ms, aggs[i].flops, aggs[i].bytes);
+    out += line;
+  }
+  out += "]";
+  if ((int64_t)out.size() + 1 > cap) return fail(ctx, PCGC_ERR_OVERFLOW, "profile report needs %zu bytes", out.size() + 1);
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return PCGC_OK;
+}
 
 int pcgc_synchronize(pcgc_ctx* ctx) {
   if (!ctx) return PCGC_ERR_BAD_ARG;
@@ -532,8 +601,10 @@ int pcgc_factorized_quantize_likelihood(pcgc_ctx* ctx, int slot, const float* x_
   if (C != ctx->bn[slot].channels || C % 4) return fail(ctx, PCGC_ERR_BAD_ARG, "channels %d != loaded %d (must be a multiple of 4)", C, ctx->bn[slot].channels);
   if (n_vox == 0) return PCGC_OK;
   int r = ensure_scratch(ctx, 148 * 8 + 8); if (r) return r;
+  prof_begin(ctx, "factorized_quantize_likelihood", 0, 4.0 * n_vox * C * (1 + (x_hat_dev != nullptr) + (p_dev != nullptr)));
   CK(launch_factorized(ctx->bn[slot], x_dev, n_vox, C, likelihood_bound, x_hat_dev, p_dev, bits_dev, minmax_dev,
                        ctx->scratch, ctx->stream, &ctx->launches));
+  prof_end(ctx);
   return PCGC_OK;
 }
 
@@ -562,8 +633,10 @@ int pcgc_laplace_quantize_likelihood(pcgc_ctx* ctx, const float* y_dev, const fl
   DeviceGuard g(ctx->device);
   if (B == 0) return PCGC_OK;
   int r = ensure_scratch(ctx, (size_t)B * 16 + 8); if (r) return r;
+  prof_begin(ctx, "laplace_quantize_likelihood", 0, 4.0 * B * E * (3 + (y_hat_dev != nullptr) + (p_dev != nullptr)));
   CK(launch_laplace(y_dev, loc_dev, scale_dev, B, E, likelihood_bound, y_hat_dev, p_dev, bits_dev, minmax_dev,
                     ctx->scratch, ctx->stream, &ctx->launches));
+  prof_end(ctx);
   return PCGC_OK;
 }
 
@@ -574,8 +647,10 @@ int pcgc_laplace_intervals(pcgc_ctx* ctx, const float* y_hat_dev, const float* l
     return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_laplace_intervals: bad argument (precision must be 16)");
   DeviceGuard g(ctx->device);
   if (B == 0) return PCGC_OK;
+  prof_begin(ctx, "laplace_intervals", 0, 4.0 * B * E * 4);
   CK(launch_laplace_intervals(y_hat_dev, loc_dev, scale_dev, B, E, minmax_dev, likelihood_bound, precision,
                               intervals_dev, ctx->err_flag, ctx->stream, &ctx->launches));
+  prof_end(ctx);
   return check_err_flag(ctx, "pcgc_laplace_intervals");
 }
 
@@ -600,8 +675,10 @@ int pcgc_laplace_cdf(pcgc_ctx* ctx, const float* loc_dev, const float* scale_dev
   }
   CK(cudaMemcpyAsync(ctx->mm_dev, minmax_host, sizeof(int32_t) * 2 * B, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->off_dev, row_offset_host, sizeof(int64_t) * (B + 1), cudaMemcpyHostToDevice, ctx->stream));
+  prof_begin(ctx, "laplace_cdf", 0, 8.0 * B * E + 2.0 * (double)row_offset_host[B]);
   CK(launch_laplace_cdf(loc_dev, scale_dev, B, E, ctx->mm_dev, ctx->off_dev, likelihood_bound, precision, cdf_dev,
                         ctx->err_flag, ctx->stream, &ctx->launches));
+  prof_end(ctx);
   // the host arrays were pageable: make sure the copies are done before the caller reuses them
   return check_err_flag(ctx, "pcgc_laplace_cdf");
 }
@@ -611,7 +688,9 @@ int pcgc_topk_select(pcgc_ctx* ctx, const float* logits_dev, int B, int64_t V, c
   if (!ctx || !logits_dev || !ks_dev || !mask_dev || B < 0 || V <= 0 || V % 4) return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_topk_select: bad argument");
   DeviceGuard g(ctx->device);
   if (B == 0) return PCGC_OK;
+  prof_begin(ctx, "topk_select", 0, 5.0 * B * V);
   CK(launch_topk(logits_dev, B, V, ks_dev, mask_dev, thres_dev, count_dev, ctx->err_flag, ctx->stream, &ctx->launches));
+  prof_end(ctx);
   return check_err_flag(ctx, "pcgc_topk_select");
 }
 

@@ -26,7 +26,7 @@ def select_voxels(vols, points_nums, offset_ratio=1.0, fixed_thres=None, codec=N
         mask, _, _ = c.topk(v, c.to_device(ks))
     else:
         mask, _ = c.threshold(v, float(fixed_thres))
-    return mask.cpu().numpy().astype("float32")
+    return runtime.to_host(mask).astype("float32")
 
 
 def select_voxels_device(codec, logits: torch.Tensor, ks: torch.Tensor):

@@ -51,7 +51,7 @@ class SymmetricConditional:
         B = y.shape[0]
         _, _, bits, _ = self.codec.laplace(y.reshape(B, -1), l.reshape(B, -1), s.reshape(B, -1), self._likelihood_bound,
                                            want_p=False, want_bits=True)
-        return bits.cpu().numpy()
+        return runtime.to_host(bits)
 
     # ---- reference semantics: one string for the whole tensor -----------------------------------
     def compress(self, inputs, loc, scale):
@@ -78,8 +78,8 @@ class SymmetricConditional:
         y2, l2, s2 = ys.reshape(B, -1), locs.reshape(B, -1), scales.reshape(B, -1)
         y_hat, _, _, mm = c.laplace(y2, l2, s2, self._likelihood_bound, want_p=False, want_bits=False)
         iv = c.laplace_intervals(y_hat, l2, s2, mm, self._likelihood_bound)
-        mm_h = mm.cpu().numpy()
-        strings = runtime.range_encode_intervals_batch(iv.cpu().numpy(), threads)
+        mm_h = runtime.to_host(mm)
+        strings = runtime.range_encode_intervals_batch(runtime.to_host(iv), threads)
         return strings, mm_h[:, 0].copy(), mm_h[:, 1].copy()
 
     def decompress_cubes(self, strings, locs, scales, min_vs, max_vs, threads: int = 0):
@@ -90,6 +90,6 @@ class SymmetricConditional:
         E = l2.shape[1]
         mm = np.stack([np.asarray(min_vs, np.int32).reshape(-1), np.asarray(max_vs, np.int32).reshape(-1)], -1)
         rows, off = c.laplace_cdf(l2, s2, mm, self._likelihood_bound)
-        sym = runtime.range_decode_rows_batch(list(strings), E, rows.cpu().numpy(), off, mm, threads)
+        sym = runtime.range_decode_rows_batch(list(strings), E, runtime.to_host(rows), off, mm, threads)
         vals = (sym.astype(np.int32) + mm[:, :1]).astype(np.float32)
         return c.to_device(vals)

@@ -49,7 +49,7 @@ class EntropyBottleneck:
         x = runtime.unwrap(inputs)
         c, slot = self._resolve(x.shape[-1])
         _, _, bits, _ = c.factorized(slot, c.to_device(x, torch.float32), self._likelihood_bound, want_p=False, want_bits=True)
-        return float(bits.cpu()[0])
+        return float(runtime.to_host(bits)[0])
 
     def _get_cdf(self, min_v, max_v):
         """int32 [1, C, N+1] like the reference (entropy_model.py:183-221)."""
@@ -64,10 +64,10 @@ class EntropyBottleneck:
         c, slot = self._resolve(channels)
         xt = c.to_device(x, torch.float32)
         x_hat, _, _, mm = c.factorized(slot, xt, self._likelihood_bound, want_p=False, want_bits=False)
-        mm_h = mm.cpu().numpy()
+        mm_h = runtime.to_host(mm)
         min_v, max_v = int(mm_h[0]), int(mm_h[1])
         cdf = c.factorized_cdf(slot, min_v, max_v, self._likelihood_bound, self._range_coder_precision)
-        sym = (x_hat.cpu().numpy().reshape(-1).astype(np.int32) - min_v).astype(np.int16)
+        sym = (runtime.to_host(x_hat).reshape(-1).astype(np.int32) - min_v).astype(np.int16)
         string = runtime.range_encode(sym, cdf, self._range_coder_precision)
         return runtime.HostResult(string), runtime.HostResult(np.int32(min_v)), runtime.HostResult(np.int32(max_v))
 

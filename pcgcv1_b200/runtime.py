@@ -29,6 +29,17 @@ _TORCH_DTYPES = {torch.uint8: _lib.DTYPE_U8, torch.bool: _lib.DTYPE_U8, torch.fl
                  torch.float64: _lib.DTYPE_F64}
 
 
+# bytes moved across PCIe by the host layer (bench.py e2e accounting)
+COUNTERS = {"h2d_bytes": 0, "d2h_bytes": 0}
+
+
+def to_host(t: torch.Tensor) -> np.ndarray:
+    """Device tensor -> NumPy (counted)."""
+    if t.is_cuda:
+        COUNTERS["d2h_bytes"] += t.numel() * t.element_size()
+    return t.detach().cpu().numpy()
+
+
 def model_name(model) -> str:
     """'voxception' | 'simple' from a model module (test.py:72 importlib seam), a name, or a class."""
     name = model if isinstance(model, str) else getattr(model, "MODEL_NAME", None) or getattr(model, "__name__", "")
@@ -48,7 +59,7 @@ class DeviceResult:
         self.tensor = tensor
 
     def numpy(self) -> np.ndarray:
-        return self.tensor.detach().cpu().numpy()
+        return to_host(self.tensor)
 
     @property
     def shape(self):
@@ -141,6 +152,16 @@ class Codec:
     def launch_count(self) -> int:
         return int(self.lib.pcgc_launch_count(self.ctx))
 
+    def profile(self, on: bool):
+        self._check(self.lib.pcgc_profile_enable(self.ctx, int(on)))
+
+    def profile_report(self):
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        self._stream()
+        self._check(self.lib.pcgc_profile_report(self.ctx, buf, len(buf)))
+        return json.loads(buf.value.decode())
+
     def _load_weights(self):
         w = self.weights
         for (m, net), layers in netspec.NETS.items():
@@ -174,11 +195,14 @@ class Codec:
         """numpy / torch / Result -> contiguous torch tensor on this codec's device."""
         a = unwrap(a)
         if isinstance(a, torch.Tensor):
+            if not a.is_cuda:
+                COUNTERS["h2d_bytes"] += a.numel() * a.element_size()
             t = a.to(self.dev, non_blocking=True)
         else:
             a = np.ascontiguousarray(a)
             if a.dtype == np.bool_:
                 a = a.view(np.uint8)
+            COUNTERS["h2d_bytes"] += a.nbytes
             t = torch.from_numpy(a).to(self.dev, non_blocking=True)
         if dtype is not None and t.dtype != dtype:
             t = t.to(dtype)
