@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(512) conv_ffma_kernel(const FfmaArgs a) {
   const int G = blockDim.y;
   const int CB = G * CT;                         // couts handled by this CTA
   float* s_in = smem;
-  float* s_w = smem + a.cc * a.plane;
+  float* s_w = smem + ((a.cc * a.plane + 3) & ~3);      // 16-byte aligned for the float4 weight reads
 
   const int tid = threadIdx.x;
   const int tx = tid & 7, ty = (tid >> 3) & 7, tzg = tid >> 6;
@@ -174,7 +174,7 @@ static cudaError_t launch_kzs(const FfmaArgs& a, int B, cudaStream_t s) {
     int want = cc >= 2 ? 32 / (cc > 32 ? 32 : cc) : 0;       // plane % 32 == 32/cc -> conflict-free staging
     if (cc >= 2) { while (plane % 32 != want % 32) ++plane; }
     b.plane = plane; b.cc = cc;
-    smem = ((size_t)cc * plane + (size_t)a.ky * a.kx * cc * KZ * CB) * sizeof(float);
+    smem = ((((size_t)cc * plane + 3) & ~(size_t)3) + (size_t)a.ky * a.kx * cc * KZ * CB) * sizeof(float);
     if (smem <= 96 * 1024 || cc == 1) break;
   }
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
