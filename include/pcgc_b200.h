@@ -87,6 +87,13 @@ int pcgc_load_conv(pcgc_ctx* ctx, int net, const char* layer, const float* kerne
 int pcgc_load_bottleneck(pcgc_ctx* ctx, int slot, int channels, const float* matrices, const float* biases,
                          const float* factors);
 
+/* Test hook for the tcgen05 engine: one 3x3x3 stride-1 SAME conv (+bias, optional ReLU) of a float32 NDHWC
+ * batch [B,n,n,n,cin] (cin in {8,16,32,64}, cout <= 64, n in {16,32,64}) with a HOST Keras kernel
+ * [3,3,3,cin,cout]; converts to the engine's split-bf16 format, runs the UMMA kernel, writes float32
+ * [B,n,n,n,cout].  Synchronises.  Compared against a plain FP32 conv in tests/test_gpu_umma.py. */
+int pcgc_debug_conv3_umma(pcgc_ctx* ctx, const float* in_dev, int n, int cin, int cout, const float* kernel_host,
+                          const float* bias_host, int relu, int B, float* out_dev);
+
 /* ---- transforms (dev pointers) --------------------------------------------------------------- */
 /* AnalysisTransform()(x), one call for B cubes instead of tf.map_fn(parallel_iterations=1)
  * (transform.py:42-48,116-122).  cubes: [B,64,64,64,1] of `dtype`; y: [B,16,16,16,16] (voxception)

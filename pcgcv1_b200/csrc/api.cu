@@ -566,6 +566,27 @@ int pcgc_load_bottleneck(pcgc_ctx* ctx, int slot, int channels, const float* mat
   return PCGC_OK;
 }
 
+int pcgc_debug_conv3_umma(pcgc_ctx* ctx, const float* in_dev, int n, int cin, int cout, const float* kernel_host,
+                          const float* bias_host, int relu, int B, float* out_dev) {
+  if (!ctx || !in_dev || !kernel_host || !out_dev || B < 1) return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_debug_conv3_umma: bad argument");
+  DeviceGuard g(ctx->device);
+  UmmaWeights w;
+  cudaError_t e = pack_umma_weights_dense(kernel_host, bias_host, cin, cout, w);
+  if (e != cudaSuccess) return fail(ctx, PCGC_ERR_BAD_ARG, "pack_umma_weights_dense: %s", cudaGetErrorString(e));
+  PmTensor t; t.n = n; t.c = cin; t.B = B;
+  CK(cudaMalloc((void**)&t.p, t.cube_elems() * B * sizeof(__nv_bfloat16)));
+  CK(launch_f32_to_pm(in_dev, cin, 0, t, ctx->stream, &ctx->launches));
+  UmmaCall c; c.in = t; c.epi = UEPI_F32; c.flags = relu ? EPI_RELU : 0; c.out_f32 = out_dev; c.out_cs = cout; c.out_co = 0;
+  c.err = ctx->err_flag;
+  e = launch_conv_umma_pm(c, w, ctx->stream, &ctx->launches);
+  cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+  cudaFree(t.p);
+  free_umma_weights(w);
+  if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "launch_conv_umma_pm: %s", cudaGetErrorString(e));
+  if (e2 != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "conv_umma kernel: %s", cudaGetErrorString(e2));
+  return check_err_flag(ctx, "pcgc_debug_conv3_umma");
+}
+
 int pcgc_analysis(pcgc_ctx* ctx, int net, const void* cubes_dev, int dtype, int B, float* y_dev) {
   if (!ctx || !cubes_dev || !y_dev || (net != PCGC_NET_VOX_ANALYSIS && net != PCGC_NET_SIMPLE_ANALYSIS) || dtype < 0 || dtype > 2)
     return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_analysis: bad argument");

@@ -1,21 +1,63 @@
-// tcgen05 (UMMA) implicit-GEMM convolution engine: interface.  See umma_conv.cu.
+// tcgen05 (UMMA) implicit-GEMM convolution engine: interface.  See umma_conv.cu for the design.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace pcgc {
 
-struct UmmaWeights {
-  bool ok = false;          // layer qualifies and the packed weights are resident
-  int cin = 0, cout = 0;
-  int cin_pad = 0;          // Cin padded to a multiple of 8 (one 16-byte bf16 cell)
-  int n_pad = 0;            // MMA N (couts incl. hi/lo columns, padded to 16)
-  void* packed = nullptr;   // device: bf16 B-operand tiles, see umma_conv.cu
+// Activation format of the tcgen05 engine ("PM": plane-major split-bf16):
+//   bf16 [B][P = 2*C/8][n][n][n][8]   plane p = (c/8)*2 + hl,  hl = 0: hi = bf16(v), 1: lo = bf16(v - hi)
+// Every 16-byte cell holds 8 consecutive channels of one voxel; the x-run of a plane is contiguous,
+// so a TMA box lands in shared memory exactly in the no-swizzle K-major core-matrix layout.
+struct PmTensor {
+  __nv_bfloat16* p = nullptr;
+  int n = 0, c = 0, B = 0;       // grid edge, channels (multiple of 8), batch
+  size_t plane_elems() const { return (size_t)n * n * n * 8; }
+  size_t cube_elems() const { return plane_elems() * (size_t)(2 * c / 8); }
 };
 
-// kernel: HOST float32 [3,3,3,Cin,Cout] (Keras layout).  cudaErrorNotSupported if the shape does not qualify.
+enum UmmaEpilogue : int {
+  UEPI_F32 = 0,     // +bias, [relu|abs|floor] -> float32 NDHWC (external outputs: y, logits)
+  UEPI_PM = 1,      // +bias, relu -> PM
+  UEPI_VRN = 2      // VRN tail: t12 | t22 -> t23 = relu(W23^T t22 + b23); out = relu(x + [t12|t23]) -> PM
+};
+
+struct UmmaWeights {
+  bool ok = false;
+  int cin = 0;              // K per tap as the kernel sees it (8, 16, 32, 64)
+  int n_real = 0;           // real output columns
+  int np = 0;               // n_real padded to a multiple of 16
+  int n_mma = 0;            // MMA pairs per z-slice per 16-channel chunk (27, or 14 for cin == 8)
+  int kchunks = 0;
+  void* packed = nullptr;   // device bf16: [kchunk][n_mma][2*np x 16] canonical no-swizzle K-major tiles
+  float* bias = nullptr;    // device [np] (zero padded)
+  // VRN tail (UEPI_VRN): conv2_3 1x1x1 weights [c4][c2] and bias [c2]
+  float* w23 = nullptr; float* b23 = nullptr; int c4 = 0, c2 = 0;
+};
+
+// dense: HOST float32 [27][cin][n_real] (tap-major, any zero structure already applied), bias [n_real] or null.
+cudaError_t pack_umma_weights_dense(const float* dense, const float* bias, int cin, int n_real, UmmaWeights& out);
+// Compatibility shim used by pcgc_load_conv (single plain layer, Keras [3,3,3,Cin,Cout]).
 cudaError_t pack_umma_weights(const float* kernel, int cin, int cout, UmmaWeights& out);
 void free_umma_weights(UmmaWeights& w);
-// 3x3x3 stride-1 SAME conv.  cudaErrorNotSupported if this call cannot be taken (caller falls back).
+
+struct UmmaCall {
+  PmTensor in;                 // input activations
+  int epi = UEPI_F32;
+  int flags = 0; float floor_v = 0.f;
+  float* out_f32 = nullptr; int out_cs = 0, out_co = 0;     // UEPI_F32
+  PmTensor out;                // UEPI_PM / UEPI_VRN
+  PmTensor res;                // UEPI_VRN: the block input x
+  int* err = nullptr;          // device int, set on device-side timeouts
+};
+
+cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStream_t s, int64_t* launches);
+// float32 NDHWC (channel stride/offset) <-> PM
+cudaError_t launch_f32_to_pm(const float* in, int in_cs, int in_co, const PmTensor& out, cudaStream_t s, int64_t* launches);
+cudaError_t launch_pm_to_f32(const PmTensor& in, float* out, int out_cs, int out_co, cudaStream_t s, int64_t* launches);
+
+// legacy hook kept for api.cu's generic path
 cudaError_t launch_conv_umma(const ConvCall& c, const UmmaWeights& w, cudaStream_t s, int64_t* launches);
 
 }  // namespace pcgc

@@ -1,0 +1,41 @@
+"""The tcgen05 (UMMA) conv engine against a plain PyTorch FP32 conv of the same op, layer shape by layer
+shape, through the C ABI test hook pcgc_debug_conv3_umma.  Tolerance: the split-bf16 scheme drops only the
+x_lo*w_lo term (~2^-17 relative per product); with FP32 accumulation the result must agree with an FP32
+conv to ~2e-5 of the output scale."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+# (grid n, Cin, Cout): every distinct stride-1 3x3x3 shape the engine serves (fused VRN shapes included)
+SHAPES = [(64, 16, 8), (64, 8, 12), (64, 16, 1), (32, 32, 16), (32, 16, 24), (16, 64, 32), (16, 32, 48), (16, 64, 16),
+          (16, 16, 64), (16, 16, 16)]
+
+
+@pytest.mark.parametrize("n,cin,cout", SHAPES)
+def test_umma_conv_vs_torch_fp32(codec, n, cin, cout):
+    g = torch.Generator(device="cpu").manual_seed(n * 1000 + cin * 10 + cout)
+    B = 2
+    x = torch.randn(B, n, n, n, cin, generator=g).relu_()            # post-ReLU like real activations
+    x[:, : n // 2] *= 37.0                                             # mixed magnitudes
+    w = torch.randn(3, 3, 3, cin, cout, generator=g) * (2.0 / (27 * cin)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    xd = x.to(codec.dev)
+    out = torch.empty(B, n, n, n, cout, device=codec.dev)
+    wh, bh = np.ascontiguousarray(w.numpy()), np.ascontiguousarray(b.numpy())
+    codec._stream()
+    rc = codec.lib.pcgc_debug_conv3_umma(codec.ctx, xd.data_ptr(), n, cin, cout, wh.ctypes.data, bh.ctypes.data, 1, B, out.data_ptr())
+    codec._check(rc)
+    ref = torch.nn.functional.conv3d(xd.permute(0, 4, 1, 2, 3).double(), w.to(codec.dev).permute(4, 3, 0, 1, 2).double(),
+                                     b.to(codec.dev).double(), padding=1).relu_().permute(0, 2, 3, 4, 1)
+    err = (out.double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print("n=%d cin=%d cout=%d: max abs err %.3g (scale %.3g, rel %.2g)" % (n, cin, cout, err, scale, err / scale))
+    assert err <= 3e-5 * scale
+    # deterministic
+    out2 = torch.empty_like(out)
+    codec._check(codec.lib.pcgc_debug_conv3_umma(codec.ctx, xd.data_ptr(), n, cin, cout, wh.ctypes.data, bh.ctypes.data, 1, B, out2.data_ptr()))
+    assert torch.equal(out, out2)
