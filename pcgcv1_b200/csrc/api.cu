@@ -38,7 +38,18 @@ struct LayerW {
   int n_classes = 0;
   ConvDesc cls[8];
   float* bias = nullptr;
-  UmmaWeights umma;             // packed bf16 hi/lo weights when the layer qualifies for tcgen05
+  UmmaWeights umma;             // (unused by the generic path)
+  std::vector<float> hk, hb;    // host copies (Keras layout) used to build the fused tcgen05 weights
+};
+
+// Fused tcgen05 program of one voxception transform: per VRN block two kernels
+//   K_a: [conv1_1 | conv2_1@centre tap]            C   -> C/2   (+bias, ReLU)
+//   K_b: blockdiag[conv1_2, conv2_2] + VRN tail    C/2 -> C     (conv2_3 1x1x1, concat, residual, ReLU in the epilogue)
+struct UmmaProgram {
+  bool ready = false;
+  UmmaWeights ka[9], kb[9];
+  UmmaWeights first;            // synthesis: deconv_in (16 -> 64)
+  UmmaWeights last;             // analysis: conv_out (64 -> 16); synthesis: deconv_out (16 -> 1)
 };
 
 struct Net {
@@ -47,6 +58,7 @@ struct Net {
   std::vector<Op> ops;
   int in_n = 0, in_c = 0;       // external input grid / channels
   size_t elems[BUF_COUNT] = {0};   // floats per cube of each internal buffer
+  UmmaProgram up;
   int find(const char* name) const {
     for (size_t i = 0; i < specs.size(); ++i) if (specs[i].name == name) return (int)i;
     return -1;
@@ -262,6 +274,172 @@ int check_err_flag(pcgc_ctx* ctx, const char* what) {
   return PCGC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- tcgen05 program
+int build_umma_program(pcgc_ctx* ctx, int kind) {
+  Net& n = ctx->nets[kind];
+  UmmaProgram& up = n.up;
+  if (up.ready) return PCGC_OK;
+  const bool ana = kind == PCGC_NET_VOX_ANALYSIS;
+  const char* prefix = ana ? "vrn" : "dvrn";
+  const int chans[3] = {ana ? 16 : 64, 32, ana ? 64 : 16};
+  auto L = [&](const std::string& name) -> LayerW& { return n.w[n.find(name.c_str())]; };
+  for (int s = 0; s < 3; ++s)
+    for (int i = 0; i < 3; ++i) {
+      const int C = chans[s], c4 = C / 4, c2 = C / 2, idx = s * 3 + i;
+      const std::string p = std::string(prefix) + std::to_string(s + 1) + "_" + std::to_string(i + 1);
+      LayerW &l11 = L(p + "_conv1_1"), &l12 = L(p + "_conv1_2"), &l21 = L(p + "_conv2_1"), &l22 = L(p + "_conv2_2"), &l23 = L(p + "_conv2_3");
+      // K_a: dense [27][C][c2]
+      std::vector<float> da((size_t)27 * C * c2, 0.f), ba(c2);
+      for (int t = 0; t < 27; ++t) for (int ci = 0; ci < C; ++ci) for (int co = 0; co < c4; ++co)
+        da[((size_t)t * C + ci) * c2 + co] = l11.hk[((size_t)t * C + ci) * c4 + co];
+      for (int ci = 0; ci < C; ++ci) for (int co = 0; co < c4; ++co)
+        da[((size_t)13 * C + ci) * c2 + c4 + co] = l21.hk[(size_t)ci * c4 + co];       // 1x1x1 conv = centre tap
+      for (int co = 0; co < c4; ++co) { ba[co] = l11.hb[co]; ba[c4 + co] = l21.hb[co]; }
+      cudaError_t e = pack_umma_weights_dense(da.data(), ba.data(), C, c2, up.ka[idx]);
+      if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "pack K_a %s: %s", p.c_str(), cudaGetErrorString(e));
+      // K_b: dense [27][c2][c2 + c4], block diagonal
+      const int nb = c2 + c4;
+      std::vector<float> db((size_t)27 * c2 * nb, 0.f), bb(nb);
+      for (int t = 0; t < 27; ++t) for (int ci = 0; ci < c4; ++ci) {
+        for (int co = 0; co < c2; ++co) db[((size_t)t * c2 + ci) * nb + co] = l12.hk[((size_t)t * c4 + ci) * c2 + co];
+        for (int co = 0; co < c4; ++co) db[((size_t)t * c2 + c4 + ci) * nb + c2 + co] = l22.hk[((size_t)t * c4 + ci) * c4 + co];
+      }
+      for (int co = 0; co < c2; ++co) bb[co] = l12.hb[co];
+      for (int co = 0; co < c4; ++co) bb[c2 + co] = l22.hb[co];
+      UmmaWeights& kb = up.kb[idx];
+      e = pack_umma_weights_dense(db.data(), bb.data(), c2, nb, kb);
+      if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "pack K_b %s: %s", p.c_str(), cudaGetErrorString(e));
+      CK(cudaMalloc((void**)&kb.w23, (size_t)c4 * c2 * sizeof(float)));
+      CK(cudaMemcpy(kb.w23, l23.hk.data(), (size_t)c4 * c2 * sizeof(float), cudaMemcpyHostToDevice));
+      CK(cudaMalloc((void**)&kb.b23, c2 * sizeof(float)));
+      CK(cudaMemcpy(kb.b23, l23.hb.data(), c2 * sizeof(float), cudaMemcpyHostToDevice));
+      kb.c4 = c4; kb.c2 = c2;
+    }
+  if (ana) {
+    LayerW& lo = L("conv_out");
+    cudaError_t e = pack_umma_weights_dense(lo.hk.data(), lo.hb.data(), 64, 16, up.last);
+    if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "pack conv_out: %s", cudaGetErrorString(e));
+  } else {
+    LayerW &li = L("deconv_in"), &lo = L("deconv_out");
+    cudaError_t e = pack_umma_weights_dense(li.hk.data(), li.hb.data(), 16, 64, up.first);
+    if (e == cudaSuccess) e = pack_umma_weights_dense(lo.hk.data(), lo.hb.data(), 16, 1, up.last);
+    if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "pack deconv_in/out: %s", cudaGetErrorString(e));
+  }
+  up.ready = true;
+  return PCGC_OK;
+}
+
+// Analysis / synthesis on the tcgen05 engine.  Internal activations are PM split-bf16 (same byte size as
+// float32, so the float workspaces are reused); stride-2 / transposed / Cin=1 layers run on the FP32 CUDA-core
+// kernel reading and writing PM directly.
+int run_vox_umma(pcgc_ctx* ctx, int kind, const float* in_ext, const void* cubes, int cubes_dtype, int B, float* out0) {
+  Net& n = ctx->nets[kind];
+  for (size_t i = 0; i < n.w.size(); ++i)
+    if (!n.w[i].loaded) return fail(ctx, PCGC_ERR_NOT_READY, "net %d: layer '%s' has no weights", kind, n.specs[i].name.c_str());
+  int r = build_umma_program(ctx, kind);
+  if (r) return r;
+  if (B <= 0) return PCGC_OK;
+  const bool ana = kind == PCGC_NET_VOX_ANALYSIS;
+  const int SB = std::min(B, ctx->sub_batch);
+  for (int bi = BUF_X0; bi < BUF_OUT0; ++bi) {
+    size_t e = n.elems[bi];
+    if (bi == BUF_X0) e = std::max(e, (size_t)64 * 64 * 64);
+    if (bi == BUF_T2) continue;                       // t22 never leaves the K_b epilogue
+    if (e) { r = ensure(ctx, &ctx->bufs[bi], &ctx->buf_cap[bi], e * SB); if (r) return r; }
+  }
+  UmmaProgram& up = n.up;
+  auto pm = [&](int buf, int nn, int c, int nb) { PmTensor t; t.p = (__nv_bfloat16*)ctx->bufs[buf]; t.n = nn; t.c = c; t.B = nb; return t; };
+  auto umma = [&](const char* what, const UmmaWeights& w, const PmTensor& in, int epi, int flags, const PmTensor& out, const PmTensor& res,
+                  float* of32, int ocs) -> int {
+    UmmaCall c; c.in = in; c.epi = epi; c.flags = flags; c.out = out; c.res = res; c.out_f32 = of32; c.out_cs = ocs; c.out_co = 0;
+    c.err = ctx->err_flag;
+    char tag[96];
+    snprintf(tag, sizeof tag, "conv_umma %s c%d->%d n%d", what, w.cin, w.n_real, in.n);
+    // algorithmic MACs of the reference layers this kernel stands for
+    double macs;
+    const double vox = (double)in.n * in.n * in.n * in.B;
+    if (epi == UEPI_VRN) { const double c4 = w.c4, c2 = w.c2; macs = vox * (27 * c4 * c2 + 27 * c4 * c4 + c4 * c2); }
+    else if (!strcmp(what, "vrn_a")) { const double C = w.cin, c4 = C / 4; macs = vox * (27 * C * c4 + C * c4); }
+    else macs = vox * 27.0 * w.cin * w.n_real;
+    prof_begin(ctx, tag, 2.0 * macs, 0);
+    cudaError_t e = launch_conv_umma_pm(c, w, ctx->stream, &ctx->launches);
+    prof_end(ctx);
+    if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "%s: %s", tag, cudaGetErrorString(e));
+    return PCGC_OK;
+  };
+  auto ffma = [&](const char* name, const float* in_f32, const PmTensor& in, int in_n, const PmTensor& out) -> int {
+    const int li = n.find(name);
+    const LayerSpec& s = n.specs[li];
+    LayerW& lw = n.w[li];
+    const int out_n = s.transposed ? in_n * s.stride : in_n / s.stride;
+    ConvCall c;
+    c.in = in_f32; c.in_n = in_n; c.in_cs = s.cin; c.in_co = 0;
+    c.out = nullptr; c.out_n = out_n; c.out_cs = s.cout; c.out_co = 0;
+    c.bias = lw.bias; c.res = nullptr; c.res_cs = c.res_co = 0;
+    c.flags = s.relu ? EPI_RELU : 0; c.floor_v = 0.f; c.B = out.B;
+    c.in_pm = in_f32 ? nullptr : in.p; c.out_pm = out.p;
+    char tag[96];
+    snprintf(tag, sizeof tag, "conv_ffma k%d s%d%s c%d->%d n%d", s.k, s.stride, s.transposed ? "T" : "", s.cin, s.cout, in_n);
+    const double tvox = (double)(s.transposed ? in_n : out_n);
+    prof_begin(ctx, tag, 2.0 * out.B * tvox * tvox * tvox * s.k * s.k * s.k * s.cin * s.cout, 0);
+    for (int k = 0; k < lw.n_classes; ++k) {
+      c.d = lw.cls[k];
+      c.tn = s.transposed ? in_n : out_n;
+      cudaError_t e = launch_conv_ffma(c, ctx->stream, &ctx->launches);
+      if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "conv '%s': %s", name, cudaGetErrorString(e));
+    }
+    prof_end(ctx);
+    return PCGC_OK;
+  };
+  const PmTensor none;
+  for (int b0 = 0; b0 < B; b0 += SB) {
+    const int nb = std::min(SB, B - b0);
+    int cur = BUF_A, nxt = BUF_B;
+    auto vrn_stage = [&](int stage, int C, int nn) -> int {
+      for (int i = 0; i < 3; ++i) {
+        const int idx = stage * 3 + i;
+        int rr = umma("vrn_a", up.ka[idx], pm(cur, nn, C, nb), UEPI_PM, EPI_RELU, pm(BUF_T1, nn, C / 2, nb), none, nullptr, 0);
+        if (rr) return rr;
+        rr = umma("vrn_b", up.kb[idx], pm(BUF_T1, nn, C / 2, nb), UEPI_VRN, 0, pm(nxt, nn, C, nb), pm(cur, nn, C, nb), nullptr, 0);
+        if (rr) return rr;
+        std::swap(cur, nxt);
+      }
+      return PCGC_OK;
+    };
+    if (ana) {
+      const size_t in_elems = (size_t)64 * 64 * 64;
+      const size_t esz = cubes_dtype == PCGC_DTYPE_U8 ? 1 : (cubes_dtype == PCGC_DTYPE_F32 ? 4 : 8);
+      CK(launch_u8_to_f32((const char*)cubes + (size_t)b0 * in_elems * esz, cubes_dtype, ctx->bufs[BUF_X0], (int64_t)nb * in_elems,
+                          ctx->stream, &ctx->launches));
+      if ((r = ffma("conv_in", ctx->bufs[BUF_X0], none, 64, pm(cur, 64, 16, nb)))) return r;
+      if ((r = vrn_stage(0, 16, 64))) return r;
+      if ((r = ffma("down_1", nullptr, pm(cur, 64, 16, nb), 64, pm(nxt, 32, 32, nb)))) return r;
+      std::swap(cur, nxt);
+      if ((r = vrn_stage(1, 32, 32))) return r;
+      if ((r = ffma("down_2", nullptr, pm(cur, 32, 32, nb), 32, pm(nxt, 16, 64, nb)))) return r;
+      std::swap(cur, nxt);
+      if ((r = vrn_stage(2, 64, 16))) return r;
+      if ((r = umma("conv_out", up.last, pm(cur, 16, 64, nb), UEPI_F32, 0, none, none, out0 + (size_t)b0 * 16 * 16 * 16 * 16, 16))) return r;
+    } else {
+      // y (float32 NDHWC, 16 channels) -> PM in T1, deconv_in -> cur
+      PmTensor yin = pm(BUF_T1, 16, 16, nb);
+      prof_begin(ctx, "f32_to_pm", 0, 8.0 * nb * 16 * 16 * 16 * 16);
+      CK(launch_f32_to_pm(in_ext + (size_t)b0 * 16 * 16 * 16 * 16, 16, 0, yin, ctx->stream, &ctx->launches));
+      prof_end(ctx);
+      if ((r = umma("deconv_in", up.first, yin, UEPI_PM, EPI_RELU, pm(cur, 16, 64, nb), none, nullptr, 0))) return r;
+      if ((r = vrn_stage(0, 64, 16))) return r;
+      if ((r = ffma("up_1", nullptr, pm(cur, 16, 64, nb), 16, pm(nxt, 32, 32, nb)))) return r;
+      std::swap(cur, nxt);
+      if ((r = vrn_stage(1, 32, 32))) return r;
+      if ((r = ffma("up_2", nullptr, pm(cur, 32, 32, nb), 32, pm(nxt, 64, 16, nb)))) return r;
+      std::swap(cur, nxt);
+      if ((r = vrn_stage(2, 16, 64))) return r;
+      if ((r = umma("deconv_out", up.last, pm(cur, 64, 16, nb), UEPI_F32, 0, none, none, out0 + (size_t)b0 * 64 * 64 * 64, 1))) return r;
+    }
+  }
+  return PCGC_OK;
+}
+
 int run_net(pcgc_ctx* ctx, int kind, const float* in_ext, const void* cubes, int cubes_dtype, int B, float* out0,
             float* out1, float floor_v) {
   Net& n = ctx->nets[kind];
@@ -313,18 +491,7 @@ int run_net(pcgc_ctx* ctx, int kind, const float* in_ext, const void* cubes, int
       char tag[96];
       const double flops = 2.0 * nb * (double)(s.transposed ? op.in_n : out_n) * (s.transposed ? op.in_n : out_n) *
                            (s.transposed ? op.in_n : out_n) * s.k * s.k * s.k * s.cin * s.cout;
-      if (ctx->engine != PCGC_ENGINE_FFMA && lw.umma.ok && lw.n_classes == 1) {
-        c.d = lw.cls[0]; c.tn = out_n;
-        snprintf(tag, sizeof tag, "conv_umma k%d s%d%s c%d->%d n%d", s.k, s.stride, s.transposed ? "T" : "", s.cin, s.cout, op.in_n);
-        prof_begin(ctx, tag, flops, 0);
-        cudaError_t e = launch_conv_umma(c, lw.umma, ctx->stream, &ctx->launches);
-        prof_end(ctx);
-        if (e == cudaSuccess) done = true;
-        else if (e != cudaErrorNotSupported) return fail(ctx, PCGC_ERR_CUDA, "umma conv '%s': %s", s.name.c_str(), cudaGetErrorString(e));
-      }
       if (!done) {
-        if (ctx->engine == PCGC_ENGINE_UMMA && lw.umma.ok)
-          return fail(ctx, PCGC_ERR_CUDA, "umma conv '%s' unavailable", s.name.c_str());
         snprintf(tag, sizeof tag, "conv_ffma k%d s%d%s c%d->%d n%d", s.k, s.stride, s.transposed ? "T" : "", s.cin, s.cout, op.in_n);
         prof_begin(ctx, tag, flops, 0);
         for (int k = 0; k < lw.n_classes; ++k) {
@@ -374,6 +541,10 @@ void pcgc_destroy(pcgc_ctx* ctx) {
   DeviceGuard g(ctx->device);
   cudaDeviceSynchronize();
   for (int i = 0; i < BUF_COUNT; ++i) if (ctx->bufs[i]) cudaFree(ctx->bufs[i]);
+  for (auto& n : ctx->nets) {
+    for (int i = 0; i < 9; ++i) { free_umma_weights(n.up.ka[i]); free_umma_weights(n.up.kb[i]); }
+    free_umma_weights(n.up.first); free_umma_weights(n.up.last);
+  }
   for (auto& n : ctx->nets)
     for (auto& lw : n.w) {
       for (int k = 0; k < lw.n_classes; ++k) if (lw.cls[k].w) cudaFree((void*)lw.cls[k].w);
@@ -445,8 +616,7 @@ int pcgc_profile_report(pcgc_ctx* ctx, char* buf, int64_t cap) {
 int pcgc_synchronize(pcgc_ctx* ctx) {
   if (!ctx) return PCGC_ERR_BAD_ARG;
   DeviceGuard g(ctx->device);
-  CK(cudaStreamSynchronize(ctx->stream));
-  return PCGC_OK;
+  return check_err_flag(ctx, "pcgc_synchronize");      // also surfaces device-side timeouts of the tcgen05 engine
 }
 
 int pcgc_load_conv(pcgc_ctx* ctx, int net, const char* layer, const float* kernel, const int64_t kshape[5],
@@ -464,6 +634,9 @@ int pcgc_load_conv(pcgc_ctx* ctx, int net, const char* layer, const float* kerne
   if ((bias != nullptr) != s.bias) return fail(ctx, PCGC_ERR_BAD_ARG, "layer '%s': use_bias=%d in the reference", layer, (int)s.bias);
   LayerW& lw = n.w[li];
   CK(cudaStreamSynchronize(ctx->stream));
+  lw.hk.assign(kernel, kernel + (size_t)k * k * k * s.cin * s.cout);
+  if (bias) lw.hb.assign(bias, bias + s.cout); else lw.hb.clear();
+  n.up.ready = false;
   for (int c = 0; c < lw.n_classes; ++c) if (lw.cls[c].w) { cudaFree((void*)lw.cls[c].w); lw.cls[c].w = nullptr; }
   if (lw.bias) { cudaFree(lw.bias); lw.bias = nullptr; }
   free_umma_weights(lw.umma);
@@ -520,10 +693,6 @@ int pcgc_load_conv(pcgc_ctx* ctx, int net, const char* layer, const float* kerne
   if (bias) {
     CK(cudaMalloc((void**)&lw.bias, s.cout * sizeof(float)));
     CK(cudaMemcpy(lw.bias, bias, s.cout * sizeof(float), cudaMemcpyHostToDevice));
-  }
-  if (!s.transposed && s.stride == 1 && s.k == 3) {
-    cudaError_t e = pack_umma_weights(kernel, s.cin, s.cout, lw.umma);
-    if (e != cudaSuccess && e != cudaErrorNotSupported) return fail(ctx, PCGC_ERR_CUDA, "pack_umma_weights('%s'): %s", layer, cudaGetErrorString(e));
   }
   lw.loaded = true;
   return PCGC_OK;
@@ -591,6 +760,7 @@ int pcgc_analysis(pcgc_ctx* ctx, int net, const void* cubes_dev, int dtype, int 
   if (!ctx || !cubes_dev || !y_dev || (net != PCGC_NET_VOX_ANALYSIS && net != PCGC_NET_SIMPLE_ANALYSIS) || dtype < 0 || dtype > 2)
     return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_analysis: bad argument");
   DeviceGuard g(ctx->device);
+  if (net == PCGC_NET_VOX_ANALYSIS && ctx->engine != PCGC_ENGINE_FFMA) return run_vox_umma(ctx, net, nullptr, cubes_dev, dtype, B, y_dev);
   return run_net(ctx, net, nullptr, cubes_dev, dtype, B, y_dev, nullptr, 0.f);
 }
 
@@ -598,6 +768,7 @@ int pcgc_synthesis(pcgc_ctx* ctx, int net, const float* y_dev, int B, float* log
   if (!ctx || !y_dev || !logits_dev || (net != PCGC_NET_VOX_SYNTHESIS && net != PCGC_NET_SIMPLE_SYNTHESIS))
     return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_synthesis: bad argument");
   DeviceGuard g(ctx->device);
+  if (net == PCGC_NET_VOX_SYNTHESIS && ctx->engine != PCGC_ENGINE_FFMA) return run_vox_umma(ctx, net, y_dev, nullptr, 0, B, logits_dev);
   return run_net(ctx, net, y_dev, nullptr, 0, B, logits_dev, nullptr, 0.f);
 }
 

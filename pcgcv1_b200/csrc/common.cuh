@@ -35,6 +35,9 @@ struct ConvCall {
   const float* res; int res_cs; int res_co;               // residual (same grid as out) or null
   int flags; float floor_v;
   int B;
+  // optional "PM" split-bf16 plane-major tensors (umma_conv.cuh) instead of the float32 NDHWC in/out
+  const void* in_pm = nullptr;    // bf16 [B][2*cin/8][in_n^3][8]
+  void* out_pm = nullptr;         // bf16 [B][2*cout/8][out_n^3][8]
 };
 
 cudaError_t launch_conv_ffma(const ConvCall& c, cudaStream_t s, int64_t* launches);

@@ -14,6 +14,7 @@
 // This is the exact-FP32 engine: used for layers the tcgen05 engine does not take (stride 2,
 // transposed, 1^3, Cin=1, k=5/9) and as the on-device cross-check for the tcgen05 engine.
 #include "common.cuh"
+#include "pm_format.cuh"
 
 namespace pcgc {
 
@@ -31,6 +32,7 @@ struct FfmaArgs {
   int plane;              // padded floats per staged channel plane
   int ey, ex, exp_;       // brick extents (y, x) and padded x pitch
   int flags; float floor_v;
+  const __nv_bfloat16* in_pm; __nv_bfloat16* out_pm;
 };
 
 template <int KZ, int S, int CT>
@@ -73,7 +75,28 @@ __global__ void __launch_bounds__(512) conv_ffma_kernel(const FfmaArgs a) {
   for (int c0 = 0; c0 < a.cin; c0 += a.cc) {
     const int ccn = min(a.cc, a.cin - c0);
     __syncthreads();
-    // ---- stage the input brick: global NDHWC -> shared channel-planar ----
+    // ---- stage the input brick: global -> shared channel-planar ----
+    if (a.in_pm) {
+      // PM split-bf16 input: groups of 4 channels (half a 16-byte cell), value = hi + lo
+      const size_t pe = (size_t)a.in_n * a.in_n * a.in_n * 8;
+      const __nv_bfloat16* pb = a.in_pm + (size_t)b * (2 * (a.cin / 8)) * pe;
+      const int g4n = a.cc >> 2;
+      for (int i = ltid; i < brick_vox * g4n; i += nthreads) {
+        const int g = i % g4n;
+        int e = i / g4n;
+        const int x = e % a.ex; e /= a.ex;
+        const int y = e % a.ey; const int z = e / a.ey;
+        const int gz = iz0 + z, gy = iy0 + y, gx = ix0 + x;
+        const int c = c0 + 4 * g;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (c < a.cin && (unsigned)gz < (unsigned)a.in_n && (unsigned)gy < (unsigned)a.in_n && (unsigned)gx < (unsigned)a.in_n) {
+          const size_t vox = ((size_t)(gz * a.in_n + gy) * a.in_n + gx) * 8 + (c & 7);
+          load_half_cell_sum(pb + (size_t)(2 * (c >> 3)) * pe + vox, pb + (size_t)(2 * (c >> 3) + 1) * pe + vox, v);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s_in[(4 * g + k) * a.plane + (z * a.ey + y) * a.exp_ + x] = v[k];
+      }
+    } else
     for (int i = ltid; i < brick_vox * a.cc; i += nthreads) {
       const int c = i % a.cc;
       int e = i / a.cc;
@@ -138,6 +161,26 @@ __global__ void __launch_bounds__(512) conv_ffma_kernel(const FfmaArgs a) {
     const int t_z = bz * 8 + tzg * 4 + j;
     const int o_z = t_z * a.ostride + a.oz;
     const size_t vox = (((size_t)b * a.out_n + o_z) * a.out_n + o_y) * a.out_n + o_x;
+    if constexpr (CT == 8) {
+      if (a.out_pm) {
+        const int co0 = co_base + cg * CT;
+        if (co0 < a.cout) {
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float t = acc[j][q];
+            if (a.bias) t += __ldg(a.bias + co0 + q);
+            if (a.flags & EPI_RELU) t = fmaxf(t, 0.f);
+            v[q] = t;
+          }
+          const size_t pe = (size_t)a.out_n * a.out_n * a.out_n * 8;
+          const size_t lv = (((size_t)o_z * a.out_n + o_y) * a.out_n + o_x) * 8;
+          __nv_bfloat16* ob = a.out_pm + ((size_t)b * (2 * (a.cout / 8)) + 2 * (co0 >> 3)) * pe + lv;
+          split_store(ob, ob + pe, v);
+        }
+        continue;
+      }
+    }
     float* op = a.out + vox * a.out_cs + a.out_co;
     const float* rp = a.res ? a.res + vox * a.res_cs + a.res_co : nullptr;
 #pragma unroll
@@ -166,8 +209,9 @@ static cudaError_t launch_kzs(const FfmaArgs& a, int B, cudaStream_t s) {
   FfmaArgs b = a;
   constexpr int EZ = 7 * S + KZ;
   b.ey = 7 * S + a.ky; b.ex = 7 * S + a.kx; b.exp_ = b.ex;
-  // choose the channel chunk so that brick + weights fit a ~96 KB budget
+  // choose the channel chunk so that brick + weights fit a ~96 KB budget (PM inputs: multiples of 4)
   int cc = a.cin < 16 ? a.cin : 16;
+  const int cc_min = a.in_pm ? 4 : 1;
   size_t smem = 0;
   for (;; cc = (cc + 1) / 2) {
     int plane = EZ * b.ey * b.exp_;
@@ -175,7 +219,7 @@ static cudaError_t launch_kzs(const FfmaArgs& a, int B, cudaStream_t s) {
     if (cc >= 2) { while (plane % 32 != want % 32) ++plane; }
     b.plane = plane; b.cc = cc;
     smem = ((((size_t)cc * plane + 3) & ~(size_t)3) + (size_t)a.ky * a.kx * cc * KZ * CB) * sizeof(float);
-    if (smem <= 96 * 1024 || cc == 1) break;
+    if (smem <= 96 * 1024 || cc <= cc_min) break;
   }
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
   const int tiles = a.tn / 8;
@@ -203,6 +247,9 @@ cudaError_t launch_conv_ffma(const ConvCall& c, cudaStream_t s, int64_t* launche
   a.ostride = c.d.ostride; a.oz = c.d.oz; a.oy = c.d.oy; a.ox = c.d.ox;
   a.cin = c.d.cin; a.cout = c.d.cout;
   a.flags = c.flags; a.floor_v = c.floor_v;
+  a.in_pm = (const __nv_bfloat16*)c.in_pm; a.out_pm = (__nv_bfloat16*)c.out_pm;
+  if (a.in_pm && (c.d.cin % 8 != 0)) return cudaErrorInvalidValue;
+  if (a.out_pm && (c.d.cout % 8 != 0 || c.res)) return cudaErrorInvalidValue;
   a.cc = 0; a.plane = 0; a.ey = a.ex = a.exp_ = 0;
   if (c.tn % 8 != 0 || c.B <= 0) return cudaErrorInvalidValue;
   if (launches) ++*launches;

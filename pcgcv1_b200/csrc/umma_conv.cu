@@ -28,6 +28,7 @@
 #include <tuple>
 #include <vector>
 
+#include "pm_format.cuh"
 #include "umma_conv.cuh"
 
 namespace pcgc {
@@ -125,25 +126,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ void split_store(__nv_bfloat16* hi_cell, __nv_bfloat16* lo_cell, const float* v) {
-  __align__(16) __nv_bfloat16 h[8], l[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    h[i] = __float2bfloat16_rn(v[i]);
-    l[i] = __float2bfloat16_rn(v[i] - __bfloat162float(h[i]));
-  }
-  *reinterpret_cast<uint4*>(hi_cell) = *reinterpret_cast<const uint4*>(h);
-  *reinterpret_cast<uint4*>(lo_cell) = *reinterpret_cast<const uint4*>(l);
-}
-__device__ __forceinline__ void load_cell_sum(const __nv_bfloat16* hi_cell, const __nv_bfloat16* lo_cell, float* v) {
-  const uint4 a = __ldg(reinterpret_cast<const uint4*>(hi_cell));
-  const uint4 b = __ldg(reinterpret_cast<const uint4*>(lo_cell));
-  const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&a);
-  const __nv_bfloat16* l = reinterpret_cast<const __nv_bfloat16*>(&b);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __bfloat162float(h[i]) + __bfloat162float(l[i]);
 }
 
 template <int NP, int EPI>

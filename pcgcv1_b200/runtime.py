@@ -149,6 +149,10 @@ class Codec:
     def set_engine(self, engine: int):
         self._check(self.lib.pcgc_set_engine(self.ctx, int(engine)))
 
+    def synchronize(self):
+        self._stream()
+        self._check(self.lib.pcgc_synchronize(self.ctx))
+
     def launch_count(self) -> int:
         return int(self.lib.pcgc_launch_count(self.ctx))
 

@@ -39,3 +39,31 @@ def test_umma_conv_vs_torch_fp32(codec, n, cin, cout):
     out2 = torch.empty_like(out)
     codec._check(codec.lib.pcgc_debug_conv3_umma(codec.ctx, xd.data_ptr(), n, cin, cout, wh.ctypes.data, bh.ctypes.data, 1, B, out2.data_ptr()))
     assert torch.equal(out, out2)
+
+
+def test_engines_agree_on_the_transforms(codec):
+    """tcgen05 engine (fused VRN kernels, split-bf16) vs the exact-FP32 CUDA-core engine on the same cubes."""
+    from pcgcv1_b200 import _lib, synthetic
+    cubes, _ = synthetic.surface_cubes(3, seed=21)
+    x = codec.to_device(cubes)
+    try:
+        codec.set_engine(_lib.ENGINE_FFMA)
+        y_f = codec.analysis(x)
+        g_f = codec.synthesis(torch.round(y_f))
+        codec.set_engine(_lib.ENGINE_AUTO)
+        y_u = codec.analysis(x)
+        g_u = codec.synthesis(torch.round(y_f))
+        codec.synchronize()
+    finally:
+        codec.set_engine(_lib.ENGINE_AUTO)
+    ey = (y_u - y_f).abs().max().item()
+    eg = (g_u - g_f).abs().max().item()
+    agree = (torch.round(y_u) == torch.round(y_f)).float().mean().item()
+    print("analysis |d|max %.3g (|y|max %.3g), synthesis |d|max %.3g (|logit|max %.3g), rounding agreement %.6f"
+          % (ey, y_f.abs().max().item(), eg, g_f.abs().max().item(), agree))
+    assert ey < 1e-3 * max(1.0, y_f.abs().max().item())
+    assert eg < 1e-3 * max(1.0, g_f.abs().max().item())
+    assert agree >= 0.999
+    # bit-reproducible and batch-invariant on the tcgen05 engine too
+    assert torch.equal(y_u, codec.analysis(x))
+    assert torch.equal(y_u[2:3], codec.analysis(x[2:3]))
