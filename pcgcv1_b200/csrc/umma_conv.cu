@@ -22,6 +22,7 @@
 // Deterministic: fixed K order, no atomics, no split-K; the tile shape never depends on the batch.
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <map>
 #include <mutex>
@@ -56,6 +57,7 @@ struct UmmaArgs {
   const __nv_bfloat16* res_pm; int res_planes;
   const float* w23; const float* b23; int c4, c2;
   int* err;
+  int dbg;                   // PCGC_UMMA_DBG bit mask (timing experiments only): 1 skip MMAs, 2 skip the A TMA, 4 skip epilogue
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -128,7 +130,33 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-template <int NP, int EPI>
+// Issues every MMA of one z-slice for one 16-channel chunk.  Fully unrolled: tap offsets are compile-time
+// constants, so each MMA costs two 64-bit adds on the descriptors -- the single issuing thread must not be the
+// bottleneck (the first version recomputed descriptors with integer divisions and ran at ~125 cycles per MMA).
+template <int NP, bool CIN8>
+__device__ __forceinline__ void issue_slice(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t bdesc, bool first) {
+  constexpr uint32_t idesc_full = make_idesc(128, 2 * NP), idesc_half = make_idesc(128, NP);
+  constexpr int NM = CIN8 ? 14 : 27;
+  constexpr uint64_t b_step = (uint64_t)((2 * NP * 32) >> 4);
+#pragma unroll
+  for (int m = 0; m < NM; ++m) {
+    uint64_t add;
+    if (!CIN8) {
+      const int kz = m / 9, ky = (m / 3) % 3, kx = m % 3;
+      add = (uint64_t)((((kz * EYC + ky) * EXC + kx) * CELL) >> 4);
+    } else {
+      const int ta = m == 0 ? 0 : 2 * m - 1, tb = m == 0 ? 1 : 2 * m;
+      const int oa = (((ta / 9) * EYC + (ta / 3) % 3) * EXC + ta % 3) * CELL;
+      const int ob = (((tb / 9) * EYC + (tb / 3) % 3) * EXC + tb % 3) * CELL;
+      add = (uint64_t)(oa >> 4) | ((uint64_t)((ob - oa) >> 4) << 16);      // start offset | LBO (second tap)
+    }
+    const uint64_t bd = bdesc + (uint64_t)m * b_step;
+    umma_f16(d, a_hi + add, bd, idesc_full, (first && m == 0) ? 0u : 1u);   // x_hi * [w_hi | w_lo]
+    umma_f16(d, a_lo + add, bd, idesc_half, 1u);                             // x_lo * w_hi
+  }
+}
+
+template <int NP, int EPI, bool CIN8>
 __global__ void __launch_bounds__(128) conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const UmmaArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* s_a = smem;
@@ -166,37 +194,23 @@ __global__ void __launch_bounds__(128) conv_umma_kernel(const __grid_constant__ 
 
   if (tid == 0) {
     // ------------------------------ TMA producer + MMA issuer (one thread) ------------------------------
-    constexpr uint32_t idesc_full = make_idesc(128, 2 * NP), idesc_half = make_idesc(128, NP);
     const uint32_t brick = smem_u32(s_a), bsm = smem_u32(s_b);
     const uint32_t PL = (uint32_t)a.plane_bytes;
-    const uint32_t b_tile = 2 * NP * 32, b_lbo = 2 * NP * 16;
+    const uint32_t b_lbo = 2 * NP * 16;
+    const uint64_t z_step = (uint64_t)((EYC * EXC * CELL) >> 4);
+    // cin >= 16: K halves are the two 8-channel planes (LBO = 2 planes); cin == 8: LBO is set per tap pair
+    const uint64_t a_hi0 = make_desc(brick, CIN8 ? 0u : 2 * PL, EXC * CELL);
+    const uint64_t a_lo0 = make_desc(brick + PL, CIN8 ? 0u : 2 * PL, EXC * CELL);
+    const uint64_t b0 = make_desc(bsm, b_lbo, 128);
     bool alive = true;
     for (int ch = 0; ch < a.kchunks && alive; ++ch) {
-      mbar_expect_tx(bar_full, (uint32_t)(a.a_bytes + a.b_bytes));
-      tma_load_5d(brick, &tmap, bar_full, (x0 - 1) * 8, y0 - 1, z0 - 1, ch * a.ppc, b);
+      mbar_expect_tx(bar_full, (uint32_t)(((a.dbg & 2) ? 0 : a.a_bytes) + a.b_bytes));
+      if (!(a.dbg & 2)) tma_load_5d(brick, &tmap, bar_full, (x0 - 1) * 8, y0 - 1, z0 - 1, ch * a.ppc, b);
       bulk_load(bsm, reinterpret_cast<const uint8_t*>(a.wpacked) + (size_t)ch * a.b_bytes, (uint32_t)a.b_bytes, bar_full);
       alive = mbar_wait(bar_full, ch & 1, a.err, -101);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int zi = 0; zi < a.zt; ++zi) {
-        const uint32_t d = tmem_base + (uint32_t)(zi * 2 * NP);
-        for (int m = 0; m < a.n_mma; ++m) {
-          uint32_t off, lbo;
-          if (!a.cin8) {
-            const int kz = m / 9, ky = (m / 3) % 3, kx = m % 3;
-            off = (uint32_t)((((zi + kz) * EYC + ky) * EXC + kx) * CELL);
-            lbo = 2 * PL;
-          } else {
-            const int ta = m == 0 ? 0 : 2 * m - 1, tb = m == 0 ? 1 : 2 * m;
-            const uint32_t oa = (uint32_t)((((zi + ta / 9) * EYC + (ta / 3) % 3) * EXC + ta % 3) * CELL);
-            const uint32_t ob = (uint32_t)((((zi + tb / 9) * EYC + (tb / 3) % 3) * EXC + tb % 3) * CELL);
-            off = oa; lbo = ob - oa;
-          }
-          const uint64_t bdesc = make_desc(bsm + (uint32_t)m * b_tile, b_lbo, 128);
-          const uint32_t acc = (ch | m) ? 1u : 0u;
-          umma_f16(d, make_desc(brick + off, lbo, EXC * CELL), bdesc, idesc_full, acc);        // x_hi * [w_hi | w_lo]
-          umma_f16(d, make_desc(brick + PL + off, lbo, EXC * CELL), bdesc, idesc_half, 1u);    // x_lo * w_hi
-        }
-      }
+      if (!(a.dbg & 1)) for (int zi = 0; zi < a.zt; ++zi)
+        issue_slice<NP, CIN8>(tmem_base + (uint32_t)(zi * 2 * NP), a_hi0 + zi * z_step, a_lo0 + zi * z_step, b0, ch == 0);
       if (ch + 1 < a.kchunks) {
         umma_commit(bar_mma);                       // shared memory may be refilled once these MMAs retire
         alive = mbar_wait(bar_mma, ch & 1, a.err, -102);
@@ -211,7 +225,7 @@ __global__ void __launch_bounds__(128) conv_umma_kernel(const __grid_constant__ 
   const int vx = x0 + (tid & 7), vy = y0 + (tid >> 3);
   const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
   const size_t plane_elems = (size_t)a.n * a.n * a.n * 8;
-  for (int zi = 0; zi < a.zt; ++zi) {
+  for (int zi = 0; zi < ((a.dbg & 4) ? 0 : a.zt); ++zi) {
     const int vz = z0 + zi;
     float v[NP];
 #pragma unroll
@@ -337,14 +351,14 @@ int pick_zt(int n, int np, int cin) {
   return zt;
 }
 
-template <int NP>
+template <int NP, bool CIN8>
 cudaError_t launch_np(const CUtensorMap& tm, const UmmaArgs& a, int epi, int grid, size_t smem, cudaStream_t s) {
   cudaError_t e;
-#define PCGC_UL(E)                                                                                              \
-  do {                                                                                                          \
-    e = cudaFuncSetAttribute(conv_umma_kernel<NP, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e != cudaSuccess) return e;                                                                             \
-    conv_umma_kernel<NP, E><<<grid, 128, smem, s>>>(tm, a);                                                     \
+#define PCGC_UL(E)                                                                                                    \
+  do {                                                                                                                \
+    e = cudaFuncSetAttribute(conv_umma_kernel<NP, E, CIN8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return e;                                                                                   \
+    conv_umma_kernel<NP, E, CIN8><<<grid, 128, smem, s>>>(tm, a);                                                     \
   } while (0)
   if (epi == UEPI_F32) PCGC_UL(UEPI_F32);
   else if (epi == UEPI_PM) PCGC_UL(UEPI_PM);
@@ -427,6 +441,7 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
   a.res_pm = c.res.p; a.res_planes = 2 * c.res.c / 8;
   a.w23 = w.w23; a.b23 = w.b23; a.c4 = w.c4; a.c2 = w.c2;
   a.err = c.err;
+  { static const int dbg = getenv("PCGC_UMMA_DBG") ? atoi(getenv("PCGC_UMMA_DBG")) : 0; a.dbg = dbg; }
   if (c.epi == UEPI_VRN && (!w.w23 || w.c2 + w.c4 != w.n_real || c.out.c != 2 * w.c2 || c.res.c != 2 * w.c2)) return cudaErrorInvalidValue;
   if (c.epi == UEPI_PM && (w.n_real % 8 != 0 || c.out.c != w.n_real)) return cudaErrorInvalidValue;
   CUtensorMap tm;
@@ -436,11 +451,15 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
   const size_t smem = (size_t)a.a_bytes + a.b_bytes + 4 * 8 + (w.np + vrn_floats) * sizeof(float) + 16;
   const int grid = (n / TILE_X) * (n / TILE_Y) * (n / a.zt) * c.in.B;
   if (launches) ++*launches;
+  if (a.cin8) {
+    if (w.np != 16) return cudaErrorNotSupported;
+    return launch_np<16, true>(tm, a, c.epi, grid, smem, s);
+  }
   switch (w.np) {
-    case 16: return launch_np<16>(tm, a, c.epi, grid, smem, s);
-    case 32: return launch_np<32>(tm, a, c.epi, grid, smem, s);
-    case 48: return launch_np<48>(tm, a, c.epi, grid, smem, s);
-    case 64: return launch_np<64>(tm, a, c.epi, grid, smem, s);
+    case 16: return launch_np<16, false>(tm, a, c.epi, grid, smem, s);
+    case 32: return launch_np<32, false>(tm, a, c.epi, grid, smem, s);
+    case 48: return launch_np<48, false>(tm, a, c.epi, grid, smem, s);
+    case 64: return launch_np<64, false>(tm, a, c.epi, grid, smem, s);
   }
   return cudaErrorNotSupported;
 }
