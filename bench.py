@@ -15,7 +15,7 @@ config 1: ~190 cubes, ~790 k points, model_voxception, rho = 1, seeded synthetic
                (the reference's sequential tail) is not in ``value``; it is in ``e2e``.
 * ``e2e``    : the same metric through the public API (transform.compress_hyper ->
                transform.decompress_hyper -> select_voxels) with HOST buffers: pinned uint8 cubes in,
-               byte strings + headers between, float32 masks out; H2D/D2H copies and the multi-threaded
+               byte strings + headers between, uint8 occupancy masks out; H2D/D2H copies and the multi-threaded
                host range coder inside the timed region.
 * ``roofline``: the dominant kernel group of the timed region, from per-launch CUDA events recorded by
                the library on its stream (pcgc_profile_enable).
@@ -158,7 +158,7 @@ def e2e_step(st):
     out = transform.compress_hyper(st["cubes_host"], model_voxception, "")
     host = [o.numpy() for o in out]
     xs = transform.decompress_hyper(*host, model_voxception, "")
-    mask = inout_points.select_voxels(xs, st["nums"], 1.0, codec=st["codec"])
+    mask = inout_points.select_voxels(xs, st["nums"], 1.0, codec=st["codec"], dtype="uint8")
     return host, mask
 
 

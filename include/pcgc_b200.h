@@ -179,6 +179,11 @@ int pcgc_range_decode_rows_batch(const uint8_t* const* data, const int64_t* nbyt
                                  const uint16_t* rows, const int64_t* row_offset, const int32_t* minmax,
                                  int precision, int16_t* sym, int threads);
 
+/* Same, writing y_hat = symbol + min_v as float32 [B,E] (conditional_entropy_model.py:196-199). */
+int pcgc_range_decode_rows_batch_f32(const uint8_t* const* data, const int64_t* nbytes, int B, int64_t E,
+                                     const uint16_t* rows, const int64_t* row_offset, const int32_t* minmax,
+                                     int precision, float* y_hat, int threads);
+
 #ifdef __cplusplus
 }
 #endif

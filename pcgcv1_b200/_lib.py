@@ -56,6 +56,7 @@ SIGNATURES = {
     "pcgc_range_decode_rows": (_i, [_vp, _i64, _i64, _vp, _i, _i, _vp]),
     "pcgc_range_encode_intervals_batch": (_i, [_vp, _i, _i64, _i, _vp, _i64, _vp, _i]),
     "pcgc_range_decode_rows_batch": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _i, _vp, _i]),
+    "pcgc_range_decode_rows_batch_f32": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _i, _vp, _i]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -232,4 +232,27 @@ int pcgc_range_decode_rows_batch(const uint8_t* const* data, const int64_t* nbyt
   return rc.load();
 }
 
+/* As pcgc_range_decode_rows_batch, but writes y_hat = symbol + min_v as float32 (what
+ * SymmetricConditional.decompress returns, conditional_entropy_model.py:196-199) so the host layer
+ * can upload it without another pass over the data. */
+int pcgc_range_decode_rows_batch_f32(const uint8_t* const* data, const int64_t* nbytes, int B, int64_t E,
+                                     const uint16_t* rows, const int64_t* row_offset, const int32_t* minmax,
+                                     int precision, float* y_hat, int threads) {
+  if (!data || !nbytes || !rows || !row_offset || !minmax || !y_hat || B < 0) return PCGC_ERR_BAD_ARG;
+  std::atomic<int> rc(PCGC_OK);
+  parallel_for(B, threads, [&](int b) {
+    const int min_v = minmax[2 * b], N = minmax[2 * b + 1] - min_v + 1;
+    Decoder d(data[b], nbytes[b], precision);
+    const uint32_t top = 1u << precision;
+    const uint16_t* base = rows + row_offset[b];
+    float* out = y_hat + (int64_t)b * E;
+    for (int64_t i = 0; i < E; ++i) {
+      const uint16_t* row = base + i * N;
+      const int s = d.decode(N, [row, N, top](int k) { return k == N ? top : (uint32_t)row[k]; });
+      out[i] = (float)(s + min_v);
+    }
+  });
+  return rc.load();
+}
+
 }  // extern "C"

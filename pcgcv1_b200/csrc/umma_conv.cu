@@ -156,18 +156,22 @@ __device__ __forceinline__ void issue_slice(uint32_t d, uint64_t a_hi, uint64_t 
   }
 }
 
+constexpr int EPI_WARPS = 8;                       // warps 0..7: epilogue; warp 8: TMA producer + MMA issuer
+constexpr int UMMA_THREADS = 32 * (EPI_WARPS + 1);
+constexpr int MAX_ZT = 8;
+
 template <int NP, int EPI, bool CIN8>
-__global__ void __launch_bounds__(128) conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const UmmaArgs a) {
+__global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const UmmaArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* s_a = smem;
   uint8_t* s_b = smem + a.a_bytes;
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_b + a.b_bytes);          // 3 mbarriers + the TMEM base address
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 3);
-  float* s_bias = reinterpret_cast<float*>(s_bar + 4);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_b + a.b_bytes);          // full, mma, z-slice[8] mbarriers
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 + MAX_ZT);
+  float* s_bias = reinterpret_cast<float*>(s_bar + 4 + MAX_ZT);            // 96 bytes in: 16-byte aligned (float4 reads)
   float* s_w23 = s_bias + NP;                                              // [c4][c2] then b23[c2] (UEPI_VRN only)
-  const uint32_t bar_full = smem_u32(s_bar), bar_mma = smem_u32(s_bar + 1), bar_done = smem_u32(s_bar + 2);
+  const uint32_t bar_full = smem_u32(s_bar), bar_mma = smem_u32(s_bar + 1), bar_z = smem_u32(s_bar + 2);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // tile coordinates
   const int tx_n = a.n / TILE_X, ty_n = a.n / TILE_Y, tz_n = a.n / a.zt;
   int bid = blockIdx.x;
@@ -177,13 +181,14 @@ __global__ void __launch_bounds__(128) conv_umma_kernel(const __grid_constant__ 
   const int b = bid;
   const int x0 = bx * TILE_X, y0 = by * TILE_Y, z0 = bz * a.zt;
 
-  for (int i = tid; i < NP; i += 128) s_bias[i] = a.bias ? a.bias[i] : 0.f;
-  if (EPI == UEPI_VRN) for (int i = tid; i < a.c4 * a.c2 + a.c2; i += 128) s_w23[i] = i < a.c4 * a.c2 ? a.w23[i] : a.b23[i - a.c4 * a.c2];
+  for (int i = tid; i < NP; i += UMMA_THREADS) s_bias[i] = a.bias ? a.bias[i] : 0.f;
+  if (EPI == UEPI_VRN) for (int i = tid; i < a.c4 * a.c2 + a.c2; i += UMMA_THREADS) s_w23[i] = i < a.c4 * a.c2 ? a.w23[i] : a.b23[i - a.c4 * a.c2];
   if (tid == 0) {
-    mbar_init(bar_full, 1); mbar_init(bar_mma, 1); mbar_init(bar_done, 1);
+    mbar_init(bar_full, 1); mbar_init(bar_mma, 1);
+    for (int i = 0; i < MAX_ZT; ++i) mbar_init(bar_z + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
+  if (warp == EPI_WARPS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(a.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -192,119 +197,127 @@ __global__ void __launch_bounds__(128) conv_umma_kernel(const __grid_constant__ 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *s_tmem;
 
-  if (tid == 0) {
-    // ------------------------------ TMA producer + MMA issuer (one thread) ------------------------------
-    const uint32_t brick = smem_u32(s_a), bsm = smem_u32(s_b);
-    const uint32_t PL = (uint32_t)a.plane_bytes;
-    const uint32_t b_lbo = 2 * NP * 16;
-    const uint64_t z_step = (uint64_t)((EYC * EXC * CELL) >> 4);
-    // cin >= 16: K halves are the two 8-channel planes (LBO = 2 planes); cin == 8: LBO is set per tap pair
-    const uint64_t a_hi0 = make_desc(brick, CIN8 ? 0u : 2 * PL, EXC * CELL);
-    const uint64_t a_lo0 = make_desc(brick + PL, CIN8 ? 0u : 2 * PL, EXC * CELL);
-    const uint64_t b0 = make_desc(bsm, b_lbo, 128);
-    bool alive = true;
-    for (int ch = 0; ch < a.kchunks && alive; ++ch) {
-      mbar_expect_tx(bar_full, (uint32_t)(((a.dbg & 2) ? 0 : a.a_bytes) + a.b_bytes));
-      if (!(a.dbg & 2)) tma_load_5d(brick, &tmap, bar_full, (x0 - 1) * 8, y0 - 1, z0 - 1, ch * a.ppc, b);
-      bulk_load(bsm, reinterpret_cast<const uint8_t*>(a.wpacked) + (size_t)ch * a.b_bytes, (uint32_t)a.b_bytes, bar_full);
-      alive = mbar_wait(bar_full, ch & 1, a.err, -101);
+  if (warp == EPI_WARPS) {
+    if (lane == 0) {
+      // ------------------------------ TMA producer + MMA issuer (one thread) ------------------------------
+      const uint32_t brick = smem_u32(s_a), bsm = smem_u32(s_b);
+      const uint32_t PL = (uint32_t)a.plane_bytes;
+      const uint32_t b_lbo = 2 * NP * 16;
+      const uint64_t z_step = (uint64_t)((EYC * EXC * CELL) >> 4);
+      // cin >= 16: K halves are the two 8-channel planes (LBO = 2 planes); cin == 8: LBO is set per tap pair
+      const uint64_t a_hi0 = make_desc(brick, CIN8 ? 0u : 2 * PL, EXC * CELL);
+      const uint64_t a_lo0 = make_desc(brick + PL, CIN8 ? 0u : 2 * PL, EXC * CELL);
+      const uint64_t b0 = make_desc(bsm, b_lbo, 128);
+      bool alive = true;
+      for (int ch = 0; ch < a.kchunks && alive; ++ch) {
+        mbar_expect_tx(bar_full, (uint32_t)(((a.dbg & 2) ? 0 : a.a_bytes) + a.b_bytes));
+        if (!(a.dbg & 2)) tma_load_5d(brick, &tmap, bar_full, (x0 - 1) * 8, y0 - 1, z0 - 1, ch * a.ppc, b);
+        bulk_load(bsm, reinterpret_cast<const uint8_t*>(a.wpacked) + (size_t)ch * a.b_bytes, (uint32_t)a.b_bytes, bar_full);
+        alive = mbar_wait(bar_full, ch & 1, a.err, -101);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const bool last = ch + 1 == a.kchunks;
+        for (int zi = 0; zi < a.zt; ++zi) {
+          if (!(a.dbg & 1))
+            issue_slice<NP, CIN8>(tmem_base + (uint32_t)(zi * 2 * NP), a_hi0 + zi * z_step, a_lo0 + zi * z_step, b0, ch == 0);
+          if (last) umma_commit(bar_z + 8 * zi);      // slice zi is final: its epilogue overlaps the MMAs of the next slices
+        }
+        if (!last) {
+          umma_commit(bar_mma);                       // shared memory may be refilled once these MMAs retire
+          alive = mbar_wait(bar_mma, ch & 1, a.err, -102);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------ epilogue: 8 warps; warp w reads TMEM lanes 32*(w&3).., z-slices of parity w>>2 ------------------------------
+    const int row = (warp & 3) * 32 + lane;          // M row = TMEM lane = voxel of the 8x16 tile
+    const int vx = x0 + (row & 7), vy = y0 + (row >> 3);
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const size_t plane_elems = (size_t)a.n * a.n * a.n * 8;
+    for (int zi = (warp >> 2); zi < ((a.dbg & 4) ? 0 : a.zt); zi += 2) {
+      mbar_wait(bar_z + 8 * zi, 0, a.err, -103);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (!(a.dbg & 1)) for (int zi = 0; zi < a.zt; ++zi)
-        issue_slice<NP, CIN8>(tmem_base + (uint32_t)(zi * 2 * NP), a_hi0 + zi * z_step, a_lo0 + zi * z_step, b0, ch == 0);
-      if (ch + 1 < a.kchunks) {
-        umma_commit(bar_mma);                       // shared memory may be refilled once these MMAs retire
-        alive = mbar_wait(bar_mma, ch & 1, a.err, -102);
+      const int vz = z0 + zi;
+      float v[NP];
+#pragma unroll
+      for (int j = 0; j < NP / 16; ++j) {
+        float d1[16], d2[16];
+        tmem_ld16(lane_base + (uint32_t)(zi * 2 * NP + j * 16), d1);
+        tmem_ld16(lane_base + (uint32_t)(zi * 2 * NP + NP + j * 16), d2);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[j * 16 + i] = (d1[i] + d2[i]) + s_bias[j * 16 + i];
       }
-    }
-    umma_commit(bar_done);
-  }
-  // ------------------------------ epilogue: all 4 warps, thread t <-> TMEM lane t <-> voxel ------------------------------
-  __syncwarp();
-  mbar_wait(bar_done, 0, a.err, -103);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const int vx = x0 + (tid & 7), vy = y0 + (tid >> 3);
-  const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-  const size_t plane_elems = (size_t)a.n * a.n * a.n * 8;
-  for (int zi = 0; zi < ((a.dbg & 4) ? 0 : a.zt); ++zi) {
-    const int vz = z0 + zi;
-    float v[NP];
+      const size_t vox = ((size_t)vz * a.n + vy) * a.n + vx;
+      if (EPI == UEPI_F32) {
+        float* op = a.out_f32 + ((size_t)b * a.n * a.n * a.n + vox) * a.out_cs + a.out_co;
 #pragma unroll
-    for (int j = 0; j < NP / 16; ++j) {
-      float d1[16], d2[16];
-      tmem_ld16(lane_base + (uint32_t)(zi * 2 * NP + j * 16), d1);
-      tmem_ld16(lane_base + (uint32_t)(zi * 2 * NP + NP + j * 16), d2);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[j * 16 + i] = (d1[i] + d2[i]) + s_bias[j * 16 + i];
-    }
-    const size_t vox = ((size_t)vz * a.n + vy) * a.n + vx;
-    if (EPI == UEPI_F32) {
-      float* op = a.out_f32 + ((size_t)b * a.n * a.n * a.n + vox) * a.out_cs + a.out_co;
-#pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        if (i < a.n_real) {
-          float t = v[i];
-          if (a.flags & EPI_RELU) t = fmaxf(t, 0.f);
-          if (a.flags & EPI_ABS) t = fabsf(t);
-          if (a.flags & EPI_FLOOR) t = fmaxf(t, a.floor_v);
-          op[i] = t;
-        }
-      }
-    } else if (EPI == UEPI_PM) {
-      __nv_bfloat16* ob = a.out_pm + (size_t)b * a.out_planes * plane_elems + vox * 8;
-#pragma unroll
-      for (int c8 = 0; c8 < NP / 8; ++c8) {
-        if (c8 * 8 < a.n_real) {
-          float t[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) t[i] = (a.flags & EPI_RELU) ? fmaxf(v[c8 * 8 + i], 0.f) : v[c8 * 8 + i];
-          split_store(ob + (size_t)(2 * c8) * plane_elems, ob + (size_t)(2 * c8 + 1) * plane_elems, t);
-        }
-      }
-    } else {
-      // Voxception tail.  columns [0,c2) = conv1_2, [c2,c2+c4) = conv2_2 (both ReLU'd), then conv2_3 (1x1x1),
-      // concat, residual add and ReLU (model_voxception.py:62-67).
-      const int c2 = a.c2, c4 = a.c4;
-      const __nv_bfloat16* rb = a.res_pm + (size_t)b * a.res_planes * plane_elems + vox * 8;
-      __nv_bfloat16* ob = a.out_pm + (size_t)b * a.out_planes * plane_elems + vox * 8;
-#pragma unroll
-      for (int i = 0; i < NP; ++i) v[i] = fmaxf(v[i], 0.f);
-      // first half of the output channels: relu(x + t12)
-#pragma unroll
-      for (int c8 = 0; c8 < NP / 8; ++c8) {
-        if (c8 * 8 < c2) {
-          float x[8], t[8];
-          load_cell_sum(rb + (size_t)(2 * c8) * plane_elems, rb + (size_t)(2 * c8 + 1) * plane_elems, x);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) t[i] = fmaxf(x[i] + v[c8 * 8 + i], 0.f);
-          split_store(ob + (size_t)(2 * c8) * plane_elems, ob + (size_t)(2 * c8 + 1) * plane_elems, t);
-        }
-      }
-      // second half: t23 = relu(b23 + t22 . W23), relu(x + t23)
-      for (int j8 = 0; j8 < c2 / 8; ++j8) {
-        float t23[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) t23[i] = s_w23[c4 * c2 + j8 * 8 + i];
-#pragma unroll
-        for (int q = 0; q < NP; ++q) {
-          if (q >= c2 && q < c2 + c4) {
-            const float tq = v[q];
-            const float* wr = s_w23 + (q - c2) * c2 + j8 * 8;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) t23[i] = fmaf(tq, wr[i], t23[i]);
+        for (int i = 0; i < NP; ++i) {
+          if (i < a.n_real) {
+            float t = v[i];
+            if (a.flags & EPI_RELU) t = fmaxf(t, 0.f);
+            if (a.flags & EPI_ABS) t = fabsf(t);
+            if (a.flags & EPI_FLOOR) t = fmaxf(t, a.floor_v);
+            op[i] = t;
           }
         }
-        float x[8], t[8];
-        const int c8 = c2 / 8 + j8;
-        load_cell_sum(rb + (size_t)(2 * c8) * plane_elems, rb + (size_t)(2 * c8 + 1) * plane_elems, x);
+      } else if (EPI == UEPI_PM) {
+        __nv_bfloat16* ob = a.out_pm + (size_t)b * a.out_planes * plane_elems + vox * 8;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) t[i] = fmaxf(x[i] + fmaxf(t23[i], 0.f), 0.f);
-        split_store(ob + (size_t)(2 * c8) * plane_elems, ob + (size_t)(2 * c8 + 1) * plane_elems, t);
+        for (int c8 = 0; c8 < NP / 8; ++c8) {
+          if (c8 * 8 < a.n_real) {
+            float t[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t[i] = (a.flags & EPI_RELU) ? fmaxf(v[c8 * 8 + i], 0.f) : v[c8 * 8 + i];
+            split_store(ob + (size_t)(2 * c8) * plane_elems, ob + (size_t)(2 * c8 + 1) * plane_elems, t);
+          }
+        }
+      } else {
+        // Voxception tail.  columns [0,c2) = conv1_2, [c2,c2+c4) = conv2_2 (both ReLU'd), then conv2_3 (1x1x1),
+        // concat, residual add and ReLU (model_voxception.py:62-67).
+        const int c2 = a.c2, c4 = a.c4;
+        const __nv_bfloat16* rb = a.res_pm + (size_t)b * a.res_planes * plane_elems + vox * 8;
+        __nv_bfloat16* ob = a.out_pm + (size_t)b * a.out_planes * plane_elems + vox * 8;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) v[i] = fmaxf(v[i], 0.f);
+        // first half of the output channels: relu(x + t12)
+#pragma unroll
+        for (int c8 = 0; c8 < NP / 8; ++c8) {
+          if (c8 * 8 < c2) {
+            float x[8], t[8];
+            load_cell_sum(rb + (size_t)(2 * c8) * plane_elems, rb + (size_t)(2 * c8 + 1) * plane_elems, x);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t[i] = fmaxf(x[i] + v[c8 * 8 + i], 0.f);
+            split_store(ob + (size_t)(2 * c8) * plane_elems, ob + (size_t)(2 * c8 + 1) * plane_elems, t);
+          }
+        }
+        // second half: t23 = relu(b23 + t22 . W23), relu(x + t23)
+        for (int j8 = 0; j8 < c2 / 8; ++j8) {
+          float t23[8];
+          const float4* bp = reinterpret_cast<const float4*>(s_w23 + c4 * c2 + j8 * 8);
+          { const float4 b0v = bp[0], b1v = bp[1]; t23[0] = b0v.x; t23[1] = b0v.y; t23[2] = b0v.z; t23[3] = b0v.w; t23[4] = b1v.x; t23[5] = b1v.y; t23[6] = b1v.z; t23[7] = b1v.w; }
+#pragma unroll
+          for (int q = 0; q < NP; ++q) {
+            if (q >= c2 && q < c2 + c4) {
+              const float tq = v[q];
+              const float4* wr = reinterpret_cast<const float4*>(s_w23 + (q - c2) * c2 + j8 * 8);
+              const float4 w0 = wr[0], w1 = wr[1];
+              t23[0] = fmaf(tq, w0.x, t23[0]); t23[1] = fmaf(tq, w0.y, t23[1]); t23[2] = fmaf(tq, w0.z, t23[2]); t23[3] = fmaf(tq, w0.w, t23[3]);
+              t23[4] = fmaf(tq, w1.x, t23[4]); t23[5] = fmaf(tq, w1.y, t23[5]); t23[6] = fmaf(tq, w1.z, t23[6]); t23[7] = fmaf(tq, w1.w, t23[7]);
+            }
+          }
+          float x[8], t[8];
+          const int c8 = c2 / 8 + j8;
+          load_cell_sum(rb + (size_t)(2 * c8) * plane_elems, rb + (size_t)(2 * c8 + 1) * plane_elems, x);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] = fmaxf(x[i] + fmaxf(t23[i], 0.f), 0.f);
+          split_store(ob + (size_t)(2 * c8) * plane_elems, ob + (size_t)(2 * c8 + 1) * plane_elems, t);
+        }
       }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) {
+  if (warp == EPI_WARPS) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
   }
 }
@@ -358,7 +371,7 @@ cudaError_t launch_np(const CUtensorMap& tm, const UmmaArgs& a, int epi, int gri
   do {                                                                                                                \
     e = cudaFuncSetAttribute(conv_umma_kernel<NP, E, CIN8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                                   \
-    conv_umma_kernel<NP, E, CIN8><<<grid, 128, smem, s>>>(tm, a);                                                     \
+    conv_umma_kernel<NP, E, CIN8><<<grid, UMMA_THREADS, smem, s>>>(tm, a);                                                     \
   } while (0)
   if (epi == UEPI_F32) PCGC_UL(UEPI_F32);
   else if (epi == UEPI_PM) PCGC_UL(UEPI_PM);
@@ -448,7 +461,7 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
   cudaError_t e = make_tmap(c.in, a.ez, a.ppc, &tm);
   if (e != cudaSuccess) return e;
   const int vrn_floats = c.epi == UEPI_VRN ? w.c4 * w.c2 + w.c2 : 0;
-  const size_t smem = (size_t)a.a_bytes + a.b_bytes + 4 * 8 + (w.np + vrn_floats) * sizeof(float) + 16;
+  const size_t smem = (size_t)a.a_bytes + a.b_bytes + (4 + MAX_ZT) * 8 + (w.np + vrn_floats) * sizeof(float) + 16;
   const int grid = (n / TILE_X) * (n / TILE_Y) * (n / a.zt) * c.in.B;
   if (launches) ++*launches;
   if (a.cin8) {

@@ -11,10 +11,11 @@ import torch
 from .. import runtime
 
 
-def select_voxels(vols, points_nums, offset_ratio=1.0, fixed_thres=None, codec=None):
+def select_voxels(vols, points_nums, offset_ratio=1.0, fixed_thres=None, codec=None, dtype="float32"):
     """vols [B,S,S,S,1] float32 logits (NumPy, torch or a DeviceResult), points_nums [B]
     -> float32 mask [B,S,S,S,1] of the top ``int(offset_ratio*points_nums[b])`` voxels per cube, ties
-    included (``>=``), as NumPy like the reference."""
+    included (``>=``), as NumPy like the reference.  ``dtype="uint8"`` skips the float32 widening that the
+    reference's own consumer undoes again (voxels2points casts to uint8, inout_points.py:137)."""
     c = codec or runtime.get_codec("voxception", "")
     v = c.to_device(vols, torch.float32)
     B = v.shape[0]
@@ -26,7 +27,8 @@ def select_voxels(vols, points_nums, offset_ratio=1.0, fixed_thres=None, codec=N
         mask, _, _ = c.topk(v, c.to_device(ks))
     else:
         mask, _ = c.threshold(v, float(fixed_thres))
-    return runtime.to_host(mask).astype("float32")
+    m = runtime.to_host(mask, "mask")
+    return m.astype(dtype) if np.dtype(dtype) != m.dtype else m.copy()
 
 
 def select_voxels_device(codec, logits: torch.Tensor, ks: torch.Tensor):

@@ -79,7 +79,7 @@ class SymmetricConditional:
         y_hat, _, _, mm = c.laplace(y2, l2, s2, self._likelihood_bound, want_p=False, want_bits=False)
         iv = c.laplace_intervals(y_hat, l2, s2, mm, self._likelihood_bound)
         mm_h = runtime.to_host(mm)
-        strings = runtime.range_encode_intervals_batch(runtime.to_host(iv), threads)
+        strings = runtime.range_encode_intervals_batch(runtime.to_host(iv, "intervals"), threads)
         return strings, mm_h[:, 0].copy(), mm_h[:, 1].copy()
 
     def decompress_cubes(self, strings, locs, scales, min_vs, max_vs, threads: int = 0):
@@ -90,6 +90,5 @@ class SymmetricConditional:
         E = l2.shape[1]
         mm = np.stack([np.asarray(min_vs, np.int32).reshape(-1), np.asarray(max_vs, np.int32).reshape(-1)], -1)
         rows, off = c.laplace_cdf(l2, s2, mm, self._likelihood_bound)
-        sym = runtime.range_decode_rows_batch(list(strings), E, runtime.to_host(rows), off, mm, threads)
-        vals = (sym.astype(np.int32) + mm[:, :1]).astype(np.float32)
-        return c.to_device(vals)
+        y_hat = runtime.range_decode_rows_batch_f32(list(strings), E, runtime.to_host(rows, "cdf_rows"), off, mm, threads)
+        return c.to_device(y_hat)

@@ -33,11 +33,33 @@ _TORCH_DTYPES = {torch.uint8: _lib.DTYPE_U8, torch.bool: _lib.DTYPE_U8, torch.fl
 COUNTERS = {"h2d_bytes": 0, "d2h_bytes": 0}
 
 
-def to_host(t: torch.Tensor) -> np.ndarray:
-    """Device tensor -> NumPy (counted)."""
-    if t.is_cuda:
-        COUNTERS["d2h_bytes"] += t.numel() * t.element_size()
-    return t.detach().cpu().numpy()
+_PINNED: Dict[tuple, torch.Tensor] = {}
+
+
+def pinned_buffer(tag: str, nbytes: int) -> torch.Tensor:
+    """Reusable page-locked staging buffer (uint8), grown on demand.  One per call-site tag: the returned
+    view is valid until the same tag is requested again."""
+    buf = _PINNED.get(tag)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes * 1.25), 1 << 16), dtype=torch.uint8).pin_memory()
+        _PINNED[tag] = buf
+    return buf
+
+
+def to_host(t: torch.Tensor, tag: str = None) -> np.ndarray:
+    """Device tensor -> NumPy (counted).  With a ``tag`` the copy lands in a reusable pinned buffer and the
+    returned array is a VIEW of it (valid until the next call with the same tag)."""
+    if not t.is_cuda:
+        return t.detach().numpy()
+    nbytes = t.numel() * t.element_size()
+    COUNTERS["d2h_bytes"] += nbytes
+    if tag is None or nbytes < (1 << 16):
+        return t.detach().cpu().numpy()
+    t = t.detach().contiguous()
+    stage = pinned_buffer(tag, nbytes)[:nbytes].view(t.dtype).view(t.shape)
+    stage.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return stage.numpy()
 
 
 def model_name(model) -> str:
@@ -397,6 +419,23 @@ def range_encode_intervals_batch(iv: np.ndarray, threads: int = 0):
     lens = np.empty(B, np.int64)
     _lib.check(L.pcgc_range_encode_intervals_batch(iv.ctypes.data, B, E, 16, out.ctypes.data, stride, lens.ctypes.data, threads))
     return [out[b, :lens[b]].tobytes() for b in range(B)]
+
+
+def range_decode_rows_batch_f32(strings, E: int, rows: np.ndarray, row_offset: np.ndarray, minmax: np.ndarray,
+                                threads: int = 0) -> torch.Tensor:
+    """-> pinned float32 torch tensor [B,E] holding y_hat = symbol + min_v (valid until the next call)."""
+    L = _lib.lib()
+    B = len(strings)
+    bufs = [np.frombuffer(bytes(s), np.uint8) if len(s) else np.zeros(1, np.uint8) for s in strings]
+    ptrs = (C.c_void_p * B)(*[b.ctypes.data for b in bufs])
+    nbytes = np.array([len(s) for s in strings], np.int64)
+    rows = np.ascontiguousarray(rows)
+    row_offset = np.ascontiguousarray(row_offset, dtype=np.int64)
+    minmax = np.ascontiguousarray(minmax, dtype=np.int32)
+    out = pinned_buffer("y_hat_dec", B * E * 4)[:B * E * 4].view(torch.float32).view(B, E)
+    _lib.check(L.pcgc_range_decode_rows_batch_f32(ptrs, nbytes.ctypes.data, B, E, rows.ctypes.data, row_offset.ctypes.data,
+                                                  minmax.ctypes.data, 16, out.data_ptr(), threads))
+    return out
 
 
 def range_decode_rows_batch(strings, E: int, rows: np.ndarray, row_offset: np.ndarray, minmax: np.ndarray,
