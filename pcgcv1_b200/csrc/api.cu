@@ -50,6 +50,8 @@ struct UmmaProgram {
   UmmaWeights ka[9], kb[9];
   UmmaWeights first;            // synthesis: deconv_in (16 -> 64)
   UmmaWeights last;             // analysis: conv_out (64 -> 16); synthesis: deconv_out (16 -> 1)
+  UmmaWeights up[2][2];         // synthesis: up_1 (two class groups), up_2 (one group) as 8-tap parity-class GEMMs
+  int up_groups[2] = {0, 0};
 };
 
 struct Net {
@@ -324,6 +326,41 @@ int build_umma_program(pcgc_ctx* ctx, int kind) {
     cudaError_t e = pack_umma_weights_dense(li.hk.data(), li.hb.data(), 16, 64, up.first);
     if (e == cudaSuccess) e = pack_umma_weights_dense(lo.hk.data(), lo.hb.data(), 16, 1, up.last);
     if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "pack deconv_in/out: %s", cudaGetErrorString(e));
+    // Conv3DTranspose(k3, s2, same): out[2t] = x[t] W[0] + x[t-1] W[2], out[2t+1] = x[t] W[1] per axis.  One GEMM over the
+    // 2x2x2 input window {t-1,t}^3 (brick index 0/1) whose column blocks are the 8 output-parity classes.
+    const char* up_names[2] = {"up_1", "up_2"};
+    for (int u = 0; u < 2; ++u) {
+      LayerW& lu = L(up_names[u]);
+      const LayerSpec& sp = n.specs[n.find(up_names[u])];
+      const int cin = sp.cin, cout = sp.cout;
+      const int groups = (8 * cout) / 128;                  // up_1: 2 groups of 4 classes, up_2: 1 group of 8
+      const int ncls = 8 / groups;
+      up.up_groups[u] = groups;
+      for (int g = 0; g < groups; ++g) {
+        const int N = ncls * cout;
+        std::vector<float> d((size_t)8 * cin * N, 0.f), bb(N);
+        for (int tap = 0; tap < 8; ++tap) {
+          const int idx[3] = {(tap >> 2) & 1, (tap >> 1) & 1, tap & 1};
+          for (int cl = 0; cl < ncls; ++cl) {
+            const int gc = g * ncls + cl;
+            const int r[3] = {(gc >> 2) & 1, (gc >> 1) & 1, gc & 1};
+            int k[3]; bool ok = true;
+            for (int ax = 0; ax < 3; ++ax) {
+              if (r[ax] == 0) k[ax] = idx[ax] ? 0 : 2; else if (idx[ax]) k[ax] = 1; else ok = false;
+            }
+            if (!ok) continue;
+            const float* wk = lu.hk.data() + (((size_t)k[0] * 3 + k[1]) * 3 + k[2]) * cout * cin;     // [cout][cin]
+            for (int ci = 0; ci < cin; ++ci) for (int co = 0; co < cout; ++co)
+              d[((size_t)tap * cin + ci) * N + cl * cout + co] = wk[(size_t)co * cin + ci];
+          }
+        }
+        for (int cl = 0; cl < ncls; ++cl) for (int co = 0; co < cout; ++co) bb[cl * cout + co] = lu.hb[co];
+        UmmaWeights& w = up.up[u][g];
+        e = pack_umma_weights_dense(d.data(), bb.data(), cin, N, w, 8);
+        if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "pack %s: %s", up_names[u], cudaGetErrorString(e));
+        w.up_ncls = ncls; w.up_cls0 = g * ncls; w.up_cout = cout;
+      }
+    }
   }
   up.ready = true;
   return PCGC_OK;
@@ -359,6 +396,7 @@ int run_vox_umma(pcgc_ctx* ctx, int kind, const float* in_ext, const void* cubes
     double macs;
     const double vox = (double)in.n * in.n * in.n * in.B;
     if (epi == UEPI_VRN) { const double c4 = w.c4, c2 = w.c2; macs = vox * (27 * c4 * c2 + 27 * c4 * c4 + c4 * c2); }
+    else if (epi == UEPI_UP) macs = vox * 27.0 * w.cin * w.up_cout * w.up_ncls / 8.0;
     else if (!strcmp(what, "vrn_a")) { const double C = w.cin, c4 = C / 4; macs = vox * (27 * C * c4 + C * c4); }
     else macs = vox * 27.0 * w.cin * w.n_real;
     prof_begin(ctx, tag, 2.0 * macs, 0);
@@ -428,10 +466,12 @@ int run_vox_umma(pcgc_ctx* ctx, int kind, const float* in_ext, const void* cubes
       prof_end(ctx);
       if ((r = umma("deconv_in", up.first, yin, UEPI_PM, EPI_RELU, pm(cur, 16, 64, nb), none, nullptr, 0))) return r;
       if ((r = vrn_stage(0, 64, 16))) return r;
-      if ((r = ffma("up_1", nullptr, pm(cur, 16, 64, nb), 16, pm(nxt, 32, 32, nb)))) return r;
+      for (int g = 0; g < up.up_groups[0]; ++g)
+        if ((r = umma("up_1", up.up[0][g], pm(cur, 16, 64, nb), UEPI_UP, EPI_RELU, pm(nxt, 32, 32, nb), none, nullptr, 0))) return r;
       std::swap(cur, nxt);
       if ((r = vrn_stage(1, 32, 32))) return r;
-      if ((r = ffma("up_2", nullptr, pm(cur, 32, 32, nb), 32, pm(nxt, 64, 16, nb)))) return r;
+      for (int g = 0; g < up.up_groups[1]; ++g)
+        if ((r = umma("up_2", up.up[1][g], pm(cur, 32, 32, nb), UEPI_UP, EPI_RELU, pm(nxt, 64, 16, nb), none, nullptr, 0))) return r;
       std::swap(cur, nxt);
       if ((r = vrn_stage(2, 16, 64))) return r;
       if ((r = umma("deconv_out", up.last, pm(cur, 64, 16, nb), UEPI_F32, 0, none, none, out0 + (size_t)b0 * 64 * 64 * 64, 1))) return r;
@@ -544,6 +584,7 @@ void pcgc_destroy(pcgc_ctx* ctx) {
   for (auto& n : ctx->nets) {
     for (int i = 0; i < 9; ++i) { free_umma_weights(n.up.ka[i]); free_umma_weights(n.up.kb[i]); }
     free_umma_weights(n.up.first); free_umma_weights(n.up.last);
+    for (int u = 0; u < 2; ++u) for (int g = 0; g < 2; ++g) free_umma_weights(n.up.up[u][g]);
   }
   for (auto& n : ctx->nets)
     for (auto& lw : n.w) {

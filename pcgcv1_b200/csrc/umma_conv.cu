@@ -57,6 +57,7 @@ struct UmmaArgs {
   const __nv_bfloat16* res_pm; int res_planes;
   const float* w23; const float* b23; int c4, c2;
   int* err;
+  int up_ncls, up_cls0, up_cout;   // UEPI_UP: classes in this launch, first class, channels per class
   int dbg;                   // PCGC_UMMA_DBG bit mask (timing experiments only): 1 skip MMAs, 2 skip the A TMA, 4 skip epilogue
 };
 
@@ -130,19 +131,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+enum TapMode : int { TAPS_27 = 0, TAPS_27_PAIRED = 1, TAPS_8 = 2 };
+
 // Issues every MMA of one z-slice for one 16-channel chunk.  Fully unrolled: tap offsets are compile-time
 // constants, so each MMA costs two 64-bit adds on the descriptors -- the single issuing thread must not be the
 // bottleneck (the first version recomputed descriptors with integer divisions and ran at ~125 cycles per MMA).
-template <int NP, bool CIN8>
+template <int NP, int TAPS>
 __device__ __forceinline__ void issue_slice(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t bdesc, bool first) {
   constexpr uint32_t idesc_full = make_idesc(128, 2 * NP), idesc_half = make_idesc(128, NP);
-  constexpr int NM = CIN8 ? 14 : 27;
+  constexpr bool CIN8 = TAPS == TAPS_27_PAIRED;
+  constexpr int NM = TAPS == TAPS_27 ? 27 : (TAPS == TAPS_27_PAIRED ? 14 : 8);
   constexpr uint64_t b_step = (uint64_t)((2 * NP * 32) >> 4);
 #pragma unroll
   for (int m = 0; m < NM; ++m) {
     uint64_t add;
-    if (!CIN8) {
+    if (TAPS == TAPS_27) {
       const int kz = m / 9, ky = (m / 3) % 3, kx = m % 3;
+      add = (uint64_t)((((kz * EYC + ky) * EXC + kx) * CELL) >> 4);
+    } else if (TAPS == TAPS_8) {
+      const int kz = m >> 2, ky = (m >> 1) & 1, kx = m & 1;      // brick index 0 = input t-1, 1 = input t
       add = (uint64_t)((((kz * EYC + ky) * EXC + kx) * CELL) >> 4);
     } else {
       const int ta = m == 0 ? 0 : 2 * m - 1, tb = m == 0 ? 1 : 2 * m;
@@ -160,7 +167,7 @@ constexpr int EPI_WARPS = 8;                       // warps 0..7: epilogue; warp
 constexpr int UMMA_THREADS = 32 * (EPI_WARPS + 1);
 constexpr int MAX_ZT = 8;
 
-template <int NP, int EPI, bool CIN8>
+template <int NP, int EPI, int TAPS>
 __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const UmmaArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* s_a = smem;
@@ -171,6 +178,7 @@ __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const __grid_co
   float* s_w23 = s_bias + NP;                                              // [c4][c2] then b23[c2] (UEPI_VRN only)
   const uint32_t bar_full = smem_u32(s_bar), bar_mma = smem_u32(s_bar + 1), bar_z = smem_u32(s_bar + 2);
 
+  constexpr bool CIN8 = TAPS == TAPS_27_PAIRED;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // tile coordinates
   const int tx_n = a.n / TILE_X, ty_n = a.n / TILE_Y, tz_n = a.n / a.zt;
@@ -218,7 +226,7 @@ __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const __grid_co
         const bool last = ch + 1 == a.kchunks;
         for (int zi = 0; zi < a.zt; ++zi) {
           if (!(a.dbg & 1))
-            issue_slice<NP, CIN8>(tmem_base + (uint32_t)(zi * 2 * NP), a_hi0 + zi * z_step, a_lo0 + zi * z_step, b0, ch == 0);
+            issue_slice<NP, TAPS>(tmem_base + (uint32_t)(zi * 2 * NP), a_hi0 + zi * z_step, a_lo0 + zi * z_step, b0, ch == 0);
           if (last) umma_commit(bar_z + 8 * zi);      // slice zi is final: its epilogue overlaps the MMAs of the next slices
         }
         if (!last) {
@@ -238,9 +246,32 @@ __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const __grid_co
       mbar_wait(bar_z + 8 * zi, 0, a.err, -103);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int vz = z0 + zi;
-      float v[NP];
+      if (EPI == UEPI_UP) {
+        // stride-2 transposed conv: column block [cls*cout, (cls+1)*cout) is output voxel 2t + r(cls) (gather form, no atomics)
+        const int on = 2 * a.n;
+        const size_t out_plane = (size_t)on * on * on * 8;
+        __nv_bfloat16* ob = a.out_pm + (size_t)b * a.out_planes * out_plane;
+#pragma unroll 1
+        for (int cls = 0; cls < a.up_ncls; ++cls) {
+          const int gc = a.up_cls0 + cls;
+          const int oz = 2 * vz + ((gc >> 2) & 1), oy = 2 * vy + ((gc >> 1) & 1), ox = 2 * vx + (gc & 1);
+          __nv_bfloat16* oc = ob + (((size_t)oz * on + oy) * on + ox) * 8;
+          for (int j = 0; j < a.up_cout / 16; ++j) {
+            const int col = cls * a.up_cout + j * 16;
+            float d1[16], d2[16], t[16];
+            tmem_ld16(lane_base + (uint32_t)(zi * 2 * NP + col), d1);
+            tmem_ld16(lane_base + (uint32_t)(zi * 2 * NP + NP + col), d2);
 #pragma unroll
-      for (int j = 0; j < NP / 16; ++j) {
+            for (int i = 0; i < 16; ++i) t[i] = fmaxf((d1[i] + d2[i]) + s_bias[col + i], 0.f);
+            split_store(oc + (size_t)(4 * j) * out_plane, oc + (size_t)(4 * j + 1) * out_plane, t);
+            split_store(oc + (size_t)(4 * j + 2) * out_plane, oc + (size_t)(4 * j + 3) * out_plane, t + 8);
+          }
+        }
+        continue;
+      }
+      float v[EPI == UEPI_UP ? 16 : NP];
+#pragma unroll
+      for (int j = 0; j < (EPI == UEPI_UP ? 0 : NP / 16); ++j) {
         float d1[16], d2[16];
         tmem_ld16(lane_base + (uint32_t)(zi * 2 * NP + j * 16), d1);
         tmem_ld16(lane_base + (uint32_t)(zi * 2 * NP + NP + j * 16), d2);
@@ -359,35 +390,37 @@ int pick_zt(int n, int np, int cin) {
   int zt = 8;
   while (zt > 1 && (zt * 2 * np > 256 || zt > n)) zt /= 2;
   const int ppc = cin == 8 ? 2 : 4;
-  auto smem = [&](int z) { return ppc * (z + 2) * EYC * EXC * CELL + (cin == 8 ? 14 : 27) * 2 * np * 32; };
+  const int nm = np == 128 ? 8 : (cin == 8 ? 14 : 27);
+  auto smem = [&](int z) { return ppc * (z + 2) * EYC * EXC * CELL + nm * 2 * np * 32; };
   while (zt > 1 && smem(zt) > 100 * 1024) zt /= 2;
   return zt;
 }
 
-template <int NP, bool CIN8>
-cudaError_t launch_np(const CUtensorMap& tm, const UmmaArgs& a, int epi, int grid, size_t smem, cudaStream_t s) {
-  cudaError_t e;
-#define PCGC_UL(E)                                                                                                    \
-  do {                                                                                                                \
-    e = cudaFuncSetAttribute(conv_umma_kernel<NP, E, CIN8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e != cudaSuccess) return e;                                                                                   \
-    conv_umma_kernel<NP, E, CIN8><<<grid, UMMA_THREADS, smem, s>>>(tm, a);                                                     \
-  } while (0)
-  if (epi == UEPI_F32) PCGC_UL(UEPI_F32);
-  else if (epi == UEPI_PM) PCGC_UL(UEPI_PM);
-  else PCGC_UL(UEPI_VRN);
-#undef PCGC_UL
+template <int NP, int E, int TAPS>
+cudaError_t launch_one(const CUtensorMap& tm, const UmmaArgs& a, int grid, size_t smem, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<NP, E, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  conv_umma_kernel<NP, E, TAPS><<<grid, UMMA_THREADS, smem, s>>>(tm, a);
   return cudaGetLastError();
+}
+
+template <int NP, int TAPS>
+cudaError_t launch_np(const CUtensorMap& tm, const UmmaArgs& a, int epi, int grid, size_t smem, cudaStream_t s) {
+  if (epi == UEPI_F32) return launch_one<NP, UEPI_F32, TAPS>(tm, a, grid, smem, s);
+  if (epi == UEPI_PM) return launch_one<NP, UEPI_PM, TAPS>(tm, a, grid, smem, s);
+  if (epi == UEPI_VRN) return launch_one<NP, UEPI_VRN, TAPS>(tm, a, grid, smem, s);
+  return cudaErrorNotSupported;
 }
 
 }  // namespace
 
-cudaError_t pack_umma_weights_dense(const float* dense, const float* bias, int cin, int n_real, UmmaWeights& out) {
+cudaError_t pack_umma_weights_dense(const float* dense, const float* bias, int cin, int n_real, UmmaWeights& out, int ntaps) {
   free_umma_weights(out);
-  if (!(cin == 8 || cin == 16 || cin == 32 || cin == 64) || n_real < 1 || n_real > 64) return cudaErrorNotSupported;
+  if (!(cin == 8 || cin == 16 || cin == 32 || cin == 64) || n_real < 1 || n_real > 128) return cudaErrorNotSupported;
+  if (!(ntaps == 27 || (ntaps == 8 && cin >= 16))) return cudaErrorNotSupported;
   const int np = (n_real + 15) / 16 * 16;
   const int kchunks = cin == 8 ? 1 : cin / 16;
-  const int n_mma = cin == 8 ? 14 : 27;
+  const int n_mma = ntaps == 8 ? 8 : (cin == 8 ? 14 : 27);
   const size_t tile = (size_t)2 * np * 16;                    // bf16 elements per B tile
   std::vector<__nv_bfloat16> p((size_t)kchunks * n_mma * tile, __float2bfloat16(0.f));
   auto put = [&](size_t tile_idx, int n, int k, float w) {
@@ -418,13 +451,13 @@ cudaError_t pack_umma_weights_dense(const float* dense, const float* bias, int c
   if (e != cudaSuccess) return e;
   e = cudaMemcpy(out.bias, bz.data(), np * sizeof(float), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return e;
-  out.cin = cin; out.n_real = n_real; out.np = np; out.n_mma = n_mma; out.kchunks = kchunks; out.ok = true;
+  out.cin = cin; out.n_real = n_real; out.np = np; out.n_mma = n_mma; out.kchunks = kchunks; out.ntaps = ntaps; out.ok = true;
   return cudaSuccess;
 }
 
 cudaError_t pack_umma_weights(const float* kernel, int cin, int cout, UmmaWeights& out) {
   // Keras [3,3,3,Cin,Cout] is already tap-major dense [27][cin][cout]
-  return pack_umma_weights_dense(kernel, nullptr, cin, cout, out);
+  return pack_umma_weights_dense(kernel, nullptr, cin, cout, out, 27);
 }
 
 void free_umma_weights(UmmaWeights& w) {
@@ -453,10 +486,12 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
   a.out_pm = c.out.p; a.out_planes = 2 * c.out.c / 8;
   a.res_pm = c.res.p; a.res_planes = 2 * c.res.c / 8;
   a.w23 = w.w23; a.b23 = w.b23; a.c4 = w.c4; a.c2 = w.c2;
+  a.up_ncls = w.up_ncls; a.up_cls0 = w.up_cls0; a.up_cout = w.up_cout;
   a.err = c.err;
   { static const int dbg = getenv("PCGC_UMMA_DBG") ? atoi(getenv("PCGC_UMMA_DBG")) : 0; a.dbg = dbg; }
   if (c.epi == UEPI_VRN && (!w.w23 || w.c2 + w.c4 != w.n_real || c.out.c != 2 * w.c2 || c.res.c != 2 * w.c2)) return cudaErrorInvalidValue;
   if (c.epi == UEPI_PM && (w.n_real % 8 != 0 || c.out.c != w.n_real)) return cudaErrorInvalidValue;
+  if (c.epi == UEPI_UP && (w.up_ncls * w.up_cout != w.n_real || w.up_cout % 16 != 0 || c.out.c != w.up_cout || c.out.n != 2 * n)) return cudaErrorInvalidValue;
   CUtensorMap tm;
   cudaError_t e = make_tmap(c.in, a.ez, a.ppc, &tm);
   if (e != cudaSuccess) return e;
@@ -464,15 +499,20 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
   const size_t smem = (size_t)a.a_bytes + a.b_bytes + (4 + MAX_ZT) * 8 + (w.np + vrn_floats) * sizeof(float) + 16;
   const int grid = (n / TILE_X) * (n / TILE_Y) * (n / a.zt) * c.in.B;
   if (launches) ++*launches;
+  if (c.epi == UEPI_UP) {
+    if (w.ntaps != 8 || w.np != 128) return cudaErrorNotSupported;
+    return launch_one<128, UEPI_UP, TAPS_8>(tm, a, grid, smem, s);
+  }
+  if (w.ntaps != 27) return cudaErrorNotSupported;
   if (a.cin8) {
     if (w.np != 16) return cudaErrorNotSupported;
-    return launch_np<16, true>(tm, a, c.epi, grid, smem, s);
+    return launch_np<16, TAPS_27_PAIRED>(tm, a, c.epi, grid, smem, s);
   }
   switch (w.np) {
-    case 16: return launch_np<16, false>(tm, a, c.epi, grid, smem, s);
-    case 32: return launch_np<32, false>(tm, a, c.epi, grid, smem, s);
-    case 48: return launch_np<48, false>(tm, a, c.epi, grid, smem, s);
-    case 64: return launch_np<64, false>(tm, a, c.epi, grid, smem, s);
+    case 16: return launch_np<16, TAPS_27>(tm, a, c.epi, grid, smem, s);
+    case 32: return launch_np<32, TAPS_27>(tm, a, c.epi, grid, smem, s);
+    case 48: return launch_np<48, TAPS_27>(tm, a, c.epi, grid, smem, s);
+    case 64: return launch_np<64, TAPS_27>(tm, a, c.epi, grid, smem, s);
   }
   return cudaErrorNotSupported;
 }

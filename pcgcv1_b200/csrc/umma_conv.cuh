@@ -20,7 +20,8 @@ struct PmTensor {
 enum UmmaEpilogue : int {
   UEPI_F32 = 0,     // +bias, [relu|abs|floor] -> float32 NDHWC (external outputs: y, logits)
   UEPI_PM = 1,      // +bias, relu -> PM
-  UEPI_VRN = 2      // VRN tail: t12 | t22 -> t23 = relu(W23^T t22 + b23); out = relu(x + [t12|t23]) -> PM
+  UEPI_VRN = 2,     // VRN tail: t12 | t22 -> t23 = relu(W23^T t22 + b23); out = relu(x + [t12|t23]) -> PM
+  UEPI_UP = 3       // stride-2 Conv3DTranspose: 8 output-parity classes as column blocks, +bias, relu -> PM on the 2n grid
 };
 
 struct UmmaWeights {
@@ -28,7 +29,9 @@ struct UmmaWeights {
   int cin = 0;              // K per tap as the kernel sees it (8, 16, 32, 64)
   int n_real = 0;           // real output columns
   int np = 0;               // n_real padded to a multiple of 16
-  int n_mma = 0;            // MMA pairs per z-slice per 16-channel chunk (27, or 14 for cin == 8)
+  int n_mma = 0;            // MMA pairs per z-slice per 16-channel chunk (27, 14 for cin == 8, 8 for transposed conv)
+  int ntaps = 27;           // 27 (3x3x3) or 8 ({t-1,t}^3 window of a stride-2 transposed conv)
+  int up_ncls = 0, up_cls0 = 0, up_cout = 0;   // UEPI_UP column layout
   int kchunks = 0;
   void* packed = nullptr;   // device bf16: [kchunk][n_mma][2*np x 16] canonical no-swizzle K-major tiles
   float* bias = nullptr;    // device [np] (zero padded)
@@ -37,7 +40,7 @@ struct UmmaWeights {
 };
 
 // dense: HOST float32 [27][cin][n_real] (tap-major, any zero structure already applied), bias [n_real] or null.
-cudaError_t pack_umma_weights_dense(const float* dense, const float* bias, int cin, int n_real, UmmaWeights& out);
+cudaError_t pack_umma_weights_dense(const float* dense, const float* bias, int cin, int n_real, UmmaWeights& out, int ntaps = 27);
 // Compatibility shim used by pcgc_load_conv (single plain layer, Keras [3,3,3,Cin,Cout]).
 cudaError_t pack_umma_weights(const float* kernel, int cin, int cout, UmmaWeights& out);
 void free_umma_weights(UmmaWeights& w);
