@@ -52,6 +52,7 @@ struct UmmaProgram {
   UmmaWeights last;             // analysis: conv_out (64 -> 16); synthesis: deconv_out (16 -> 1)
   UmmaWeights up[2][2];         // synthesis: up_1 (two class groups), up_2 (one group) as 8-tap parity-class GEMMs
   int up_groups[2] = {0, 0};
+  UmmaWeights down[2];          // analysis: down_1, down_2 as 8-tap GEMMs over the space-to-depth input
 };
 
 struct Net {
@@ -321,6 +322,25 @@ int build_umma_program(pcgc_ctx* ctx, int kind) {
     LayerW& lo = L("conv_out");
     cudaError_t e = pack_umma_weights_dense(lo.hk.data(), lo.hb.data(), 64, 16, up.last);
     if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "pack conv_out: %s", cudaGetErrorString(e));
+    // Conv3D(k3, s2, same) = pads (0,1): out[t] = sum_k in[2t+k] W[k].  On the space-to-depth input X'[t][p*Cin+ci] = in[2t+p][ci]
+    // it is a 2x2x2-tap stride-1 conv (offsets d in {0,1}^3, k = 2d+p, k <= 2) with 8*Cin channels.
+    const char* dn[2] = {"down_1", "down_2"};
+    for (int u = 0; u < 2; ++u) {
+      LayerW& ld = L(dn[u]);
+      const LayerSpec& sp = n.specs[n.find(dn[u])];
+      const int cin = sp.cin, cout = sp.cout, K = 8 * cin;
+      std::vector<float> d((size_t)8 * K * cout, 0.f);
+      for (int tap = 0; tap < 8; ++tap) for (int par = 0; par < 8; ++par) {
+        const int k[3] = {2 * ((tap >> 2) & 1) + ((par >> 2) & 1), 2 * ((tap >> 1) & 1) + ((par >> 1) & 1), 2 * (tap & 1) + (par & 1)};
+        if (k[0] > 2 || k[1] > 2 || k[2] > 2) continue;
+        const float* wk = ld.hk.data() + (((size_t)k[0] * 3 + k[1]) * 3 + k[2]) * cin * cout;       // [cin][cout]
+        for (int ci = 0; ci < cin; ++ci) for (int co = 0; co < cout; ++co)
+          d[((size_t)tap * K + par * cin + ci) * cout + co] = wk[(size_t)ci * cout + co];
+      }
+      e = pack_umma_weights_dense(d.data(), ld.hb.empty() ? nullptr : ld.hb.data(), K, cout, up.down[u], 8);
+      if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "pack %s: %s", dn[u], cudaGetErrorString(e));
+      up.down[u].origin = 0;
+    }
   } else {
     LayerW &li = L("deconv_in"), &lo = L("deconv_out");
     cudaError_t e = pack_umma_weights_dense(li.hk.data(), li.hb.data(), 16, 64, up.first);
@@ -387,8 +407,8 @@ int run_vox_umma(pcgc_ctx* ctx, int kind, const float* in_ext, const void* cubes
   UmmaProgram& up = n.up;
   auto pm = [&](int buf, int nn, int c, int nb) { PmTensor t; t.p = (__nv_bfloat16*)ctx->bufs[buf]; t.n = nn; t.c = c; t.B = nb; return t; };
   auto umma = [&](const char* what, const UmmaWeights& w, const PmTensor& in, int epi, int flags, const PmTensor& out, const PmTensor& res,
-                  float* of32, int ocs) -> int {
-    UmmaCall c; c.in = in; c.epi = epi; c.flags = flags; c.out = out; c.res = res; c.out_f32 = of32; c.out_cs = ocs; c.out_co = 0;
+                  float* of32, int ocs, int s2d = 0) -> int {
+    UmmaCall c; c.out_s2d = s2d; c.in = in; c.epi = epi; c.flags = flags; c.out = out; c.res = res; c.out_f32 = of32; c.out_cs = ocs; c.out_co = 0;
     c.err = ctx->err_flag;
     char tag[96];
     snprintf(tag, sizeof tag, "conv_umma %s c%d->%d n%d", what, w.cin, w.n_real, in.n);
@@ -397,6 +417,7 @@ int run_vox_umma(pcgc_ctx* ctx, int kind, const float* in_ext, const void* cubes
     const double vox = (double)in.n * in.n * in.n * in.B;
     if (epi == UEPI_VRN) { const double c4 = w.c4, c2 = w.c2; macs = vox * (27 * c4 * c2 + 27 * c4 * c4 + c4 * c2); }
     else if (epi == UEPI_UP) macs = vox * 27.0 * w.cin * w.up_cout * w.up_ncls / 8.0;
+    else if (w.ntaps == 8) macs = vox * 27.0 * (w.cin / 8) * w.n_real;
     else if (!strcmp(what, "vrn_a")) { const double C = w.cin, c4 = C / 4; macs = vox * (27 * C * c4 + C * c4); }
     else macs = vox * 27.0 * w.cin * w.n_real;
     prof_begin(ctx, tag, 2.0 * macs, 0);
@@ -433,12 +454,14 @@ int run_vox_umma(pcgc_ctx* ctx, int kind, const float* in_ext, const void* cubes
   for (int b0 = 0; b0 < B; b0 += SB) {
     const int nb = std::min(SB, B - b0);
     int cur = BUF_A, nxt = BUF_B;
-    auto vrn_stage = [&](int stage, int C, int nn) -> int {
+    auto vrn_stage = [&](int stage, int C, int nn, bool s2d_last = false) -> int {
       for (int i = 0; i < 3; ++i) {
         const int idx = stage * 3 + i;
         int rr = umma("vrn_a", up.ka[idx], pm(cur, nn, C, nb), UEPI_PM, EPI_RELU, pm(BUF_T1, nn, C / 2, nb), none, nullptr, 0);
         if (rr) return rr;
-        rr = umma("vrn_b", up.kb[idx], pm(BUF_T1, nn, C / 2, nb), UEPI_VRN, 0, pm(nxt, nn, C, nb), pm(cur, nn, C, nb), nullptr, 0);
+        const bool s2d = s2d_last && i == 2;          // the block feeding a stride-2 conv writes its output space-to-depth
+        rr = umma("vrn_b", up.kb[idx], pm(BUF_T1, nn, C / 2, nb), UEPI_VRN, 0, s2d ? pm(nxt, nn / 2, 8 * C, nb) : pm(nxt, nn, C, nb),
+                  pm(cur, nn, C, nb), nullptr, 0, s2d);
         if (rr) return rr;
         std::swap(cur, nxt);
       }
@@ -450,11 +473,11 @@ int run_vox_umma(pcgc_ctx* ctx, int kind, const float* in_ext, const void* cubes
       CK(launch_u8_to_f32((const char*)cubes + (size_t)b0 * in_elems * esz, cubes_dtype, ctx->bufs[BUF_X0], (int64_t)nb * in_elems,
                           ctx->stream, &ctx->launches));
       if ((r = ffma("conv_in", ctx->bufs[BUF_X0], none, 64, pm(cur, 64, 16, nb)))) return r;
-      if ((r = vrn_stage(0, 16, 64))) return r;
-      if ((r = ffma("down_1", nullptr, pm(cur, 64, 16, nb), 64, pm(nxt, 32, 32, nb)))) return r;
+      if ((r = vrn_stage(0, 16, 64, true))) return r;
+      if ((r = umma("down_1", up.down[0], pm(cur, 32, 128, nb), UEPI_PM, EPI_RELU, pm(nxt, 32, 32, nb), none, nullptr, 0))) return r;
       std::swap(cur, nxt);
-      if ((r = vrn_stage(1, 32, 32))) return r;
-      if ((r = ffma("down_2", nullptr, pm(cur, 32, 32, nb), 32, pm(nxt, 16, 64, nb)))) return r;
+      if ((r = vrn_stage(1, 32, 32, true))) return r;
+      if ((r = umma("down_2", up.down[1], pm(cur, 16, 256, nb), UEPI_PM, EPI_RELU, pm(nxt, 16, 64, nb), none, nullptr, 0))) return r;
       std::swap(cur, nxt);
       if ((r = vrn_stage(2, 64, 16))) return r;
       if ((r = umma("conv_out", up.last, pm(cur, 16, 64, nb), UEPI_F32, 0, none, none, out0 + (size_t)b0 * 16 * 16 * 16 * 16, 16))) return r;
@@ -585,6 +608,7 @@ void pcgc_destroy(pcgc_ctx* ctx) {
     for (int i = 0; i < 9; ++i) { free_umma_weights(n.up.ka[i]); free_umma_weights(n.up.kb[i]); }
     free_umma_weights(n.up.first); free_umma_weights(n.up.last);
     for (int u = 0; u < 2; ++u) for (int g = 0; g < 2; ++g) free_umma_weights(n.up.up[u][g]);
+    free_umma_weights(n.up.down[0]); free_umma_weights(n.up.down[1]);
   }
   for (auto& n : ctx->nets)
     for (auto& lw : n.w) {

@@ -57,6 +57,9 @@ struct UmmaArgs {
   const __nv_bfloat16* res_pm; int res_planes;
   const float* w23; const float* b23; int c4, c2;
   int* err;
+  int origin;                // brick origin relative to the tile: -1 (SAME 3x3x3, transposed) or 0 (stride-2 conv on a space-to-depth input)
+  uint32_t tap_mask[16];     // per 16-channel chunk: taps with non-zero weights (others are skipped)
+  int out_s2d;               // UEPI_VRN: write the output space-to-depth (grid n/2, 8*C channels) for a following stride-2 conv
   int up_ncls, up_cls0, up_cout;   // UEPI_UP: classes in this launch, first class, channels per class
   int dbg;                   // PCGC_UMMA_DBG bit mask (timing experiments only): 1 skip MMAs, 2 skip the A TMA, 4 skip epilogue
 };
@@ -137,7 +140,7 @@ enum TapMode : int { TAPS_27 = 0, TAPS_27_PAIRED = 1, TAPS_8 = 2 };
 // constants, so each MMA costs two 64-bit adds on the descriptors -- the single issuing thread must not be the
 // bottleneck (the first version recomputed descriptors with integer divisions and ran at ~125 cycles per MMA).
 template <int NP, int TAPS>
-__device__ __forceinline__ void issue_slice(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t bdesc, bool first) {
+__device__ __forceinline__ void issue_slice(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t bdesc, bool first, uint32_t mask) {
   constexpr uint32_t idesc_full = make_idesc(128, 2 * NP), idesc_half = make_idesc(128, NP);
   constexpr bool CIN8 = TAPS == TAPS_27_PAIRED;
   constexpr int NM = TAPS == TAPS_27 ? 27 : (TAPS == TAPS_27_PAIRED ? 14 : 8);
@@ -157,6 +160,7 @@ __device__ __forceinline__ void issue_slice(uint32_t d, uint64_t a_hi, uint64_t 
       const int ob = (((tb / 9) * EYC + (tb / 3) % 3) * EXC + tb % 3) * CELL;
       add = (uint64_t)(oa >> 4) | ((uint64_t)((ob - oa) >> 4) << 16);      // start offset | LBO (second tap)
     }
+    if (TAPS == TAPS_8 && !((mask >> m) & 1u) && !(first && m == 0)) continue;   // all-zero weight tile (the first MMA still initialises D)
     const uint64_t bd = bdesc + (uint64_t)m * b_step;
     umma_f16(d, a_hi + add, bd, idesc_full, (first && m == 0) ? 0u : 1u);   // x_hi * [w_hi | w_lo]
     umma_f16(d, a_lo + add, bd, idesc_half, 1u);                             // x_lo * w_hi
@@ -219,14 +223,14 @@ __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const __grid_co
       bool alive = true;
       for (int ch = 0; ch < a.kchunks && alive; ++ch) {
         mbar_expect_tx(bar_full, (uint32_t)(((a.dbg & 2) ? 0 : a.a_bytes) + a.b_bytes));
-        if (!(a.dbg & 2)) tma_load_5d(brick, &tmap, bar_full, (x0 - 1) * 8, y0 - 1, z0 - 1, ch * a.ppc, b);
+        if (!(a.dbg & 2)) tma_load_5d(brick, &tmap, bar_full, (x0 + a.origin) * 8, y0 + a.origin, z0 + a.origin, ch * a.ppc, b);
         bulk_load(bsm, reinterpret_cast<const uint8_t*>(a.wpacked) + (size_t)ch * a.b_bytes, (uint32_t)a.b_bytes, bar_full);
         alive = mbar_wait(bar_full, ch & 1, a.err, -101);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const bool last = ch + 1 == a.kchunks;
         for (int zi = 0; zi < a.zt; ++zi) {
           if (!(a.dbg & 1))
-            issue_slice<NP, TAPS>(tmem_base + (uint32_t)(zi * 2 * NP), a_hi0 + zi * z_step, a_lo0 + zi * z_step, b0, ch == 0);
+            issue_slice<NP, TAPS>(tmem_base + (uint32_t)(zi * 2 * NP), a_hi0 + zi * z_step, a_lo0 + zi * z_step, b0, ch == 0, a.tap_mask[ch & 15]);
           if (last) umma_commit(bar_z + 8 * zi);      // slice zi is final: its epilogue overlaps the MMAs of the next slices
         }
         if (!last) {
@@ -307,7 +311,16 @@ __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const __grid_co
         // concat, residual add and ReLU (model_voxception.py:62-67).
         const int c2 = a.c2, c4 = a.c4;
         const __nv_bfloat16* rb = a.res_pm + (size_t)b * a.res_planes * plane_elems + vox * 8;
+        // normal: plane stride = n^3 cells.  space-to-depth: voxel (z,y,x) channel c -> voxel (z/2,y/2,x/2) of the n/2 grid,
+        // channel p*C + c with p = parity(z,y,x); the tensor then has 8x the planes of 1/8 the size.
+        size_t ops = plane_elems;                         // elements between consecutive output planes
         __nv_bfloat16* ob = a.out_pm + (size_t)b * a.out_planes * plane_elems + vox * 8;
+        if (a.out_s2d) {
+          const int h = a.n >> 1;
+          ops = plane_elems >> 3;
+          const int par = ((vz & 1) << 2) | ((vy & 1) << 1) | (vx & 1);
+          ob = a.out_pm + ((size_t)b * a.out_planes * 8 + (size_t)par * a.out_planes) * ops + ((((size_t)(vz >> 1) * h + (vy >> 1)) * h + (vx >> 1)) * 8);
+        }
 #pragma unroll
         for (int i = 0; i < NP; ++i) v[i] = fmaxf(v[i], 0.f);
         // first half of the output channels: relu(x + t12)
@@ -318,7 +331,7 @@ __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const __grid_co
             load_cell_sum(rb + (size_t)(2 * c8) * plane_elems, rb + (size_t)(2 * c8 + 1) * plane_elems, x);
 #pragma unroll
             for (int i = 0; i < 8; ++i) t[i] = fmaxf(x[i] + v[c8 * 8 + i], 0.f);
-            split_store(ob + (size_t)(2 * c8) * plane_elems, ob + (size_t)(2 * c8 + 1) * plane_elems, t);
+            split_store(ob + (size_t)(2 * c8) * ops, ob + (size_t)(2 * c8 + 1) * ops, t);
           }
         }
         // second half: t23 = relu(b23 + t22 . W23), relu(x + t23)
@@ -341,7 +354,7 @@ __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const __grid_co
           load_cell_sum(rb + (size_t)(2 * c8) * plane_elems, rb + (size_t)(2 * c8 + 1) * plane_elems, x);
 #pragma unroll
           for (int i = 0; i < 8; ++i) t[i] = fmaxf(x[i] + fmaxf(t23[i], 0.f), 0.f);
-          split_store(ob + (size_t)(2 * c8) * plane_elems, ob + (size_t)(2 * c8 + 1) * plane_elems, t);
+          split_store(ob + (size_t)(2 * c8) * ops, ob + (size_t)(2 * c8 + 1) * ops, t);
         }
       }
     }
@@ -416,7 +429,7 @@ cudaError_t launch_np(const CUtensorMap& tm, const UmmaArgs& a, int epi, int gri
 
 cudaError_t pack_umma_weights_dense(const float* dense, const float* bias, int cin, int n_real, UmmaWeights& out, int ntaps) {
   free_umma_weights(out);
-  if (!(cin == 8 || cin == 16 || cin == 32 || cin == 64) || n_real < 1 || n_real > 128) return cudaErrorNotSupported;
+  if (!(cin == 8 || cin == 16 || cin == 32 || cin == 64 || cin == 128 || cin == 256) || n_real < 1 || n_real > 128) return cudaErrorNotSupported;
   if (!(ntaps == 27 || (ntaps == 8 && cin >= 16))) return cudaErrorNotSupported;
   const int np = (n_real + 15) / 16 * 16;
   const int kchunks = cin == 8 ? 1 : cin / 16;
@@ -451,6 +464,17 @@ cudaError_t pack_umma_weights_dense(const float* dense, const float* bias, int c
   if (e != cudaSuccess) return e;
   e = cudaMemcpy(out.bias, bz.data(), np * sizeof(float), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return e;
+  for (int ch = 0; ch < 16; ++ch) {
+    uint32_t mask = 0;
+    if (ch < kchunks)
+      for (int m = 0; m < n_mma && ntaps == 8; ++m) {
+        bool nz = false;
+        for (int k = 0; k < 16 && !nz; ++k)
+          for (int n = 0; n < n_real && !nz; ++n) nz = dense[((size_t)m * cin + ch * 16 + k) * n_real + n] != 0.f;
+        if (nz) mask |= 1u << m;
+      }
+    out.tap_mask[ch] = ntaps == 8 ? mask : 0xFFFFFFFFu;
+  }
   out.cin = cin; out.n_real = n_real; out.np = np; out.n_mma = n_mma; out.kchunks = kchunks; out.ntaps = ntaps; out.ok = true;
   return cudaSuccess;
 }
@@ -483,13 +507,15 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
   a.wpacked = (const __nv_bfloat16*)w.packed; a.bias = w.bias;
   a.n_real = w.n_real; a.flags = c.flags; a.floor_v = c.floor_v;
   a.out_f32 = c.out_f32; a.out_cs = c.out_cs; a.out_co = c.out_co;
-  a.out_pm = c.out.p; a.out_planes = 2 * c.out.c / 8;
+  a.out_pm = c.out.p; a.out_planes = 2 * (c.out_s2d ? c.out.c / 8 : c.out.c) / 8;
   a.res_pm = c.res.p; a.res_planes = 2 * c.res.c / 8;
   a.w23 = w.w23; a.b23 = w.b23; a.c4 = w.c4; a.c2 = w.c2;
   a.up_ncls = w.up_ncls; a.up_cls0 = w.up_cls0; a.up_cout = w.up_cout;
+  a.origin = w.origin; a.out_s2d = c.out_s2d;
+  for (int i = 0; i < 16; ++i) a.tap_mask[i] = w.tap_mask[i];
   a.err = c.err;
   { static const int dbg = getenv("PCGC_UMMA_DBG") ? atoi(getenv("PCGC_UMMA_DBG")) : 0; a.dbg = dbg; }
-  if (c.epi == UEPI_VRN && (!w.w23 || w.c2 + w.c4 != w.n_real || c.out.c != 2 * w.c2 || c.res.c != 2 * w.c2)) return cudaErrorInvalidValue;
+  if (c.epi == UEPI_VRN && (!w.w23 || w.c2 + w.c4 != w.n_real || c.res.c != 2 * w.c2 || c.out.c != (c.out_s2d ? 16 : 2) * w.c2)) return cudaErrorInvalidValue;
   if (c.epi == UEPI_PM && (w.n_real % 8 != 0 || c.out.c != w.n_real)) return cudaErrorInvalidValue;
   if (c.epi == UEPI_UP && (w.up_ncls * w.up_cout != w.n_real || w.up_cout % 16 != 0 || c.out.c != w.up_cout || c.out.n != 2 * n)) return cudaErrorInvalidValue;
   CUtensorMap tm;
@@ -502,6 +528,12 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
   if (c.epi == UEPI_UP) {
     if (w.ntaps != 8 || w.np != 128) return cudaErrorNotSupported;
     return launch_one<128, UEPI_UP, TAPS_8>(tm, a, grid, smem, s);
+  }
+  if (w.ntaps == 8) {                                   // stride-2 conv on a space-to-depth input
+    if (c.epi != UEPI_PM) return cudaErrorNotSupported;
+    if (w.np == 32) return launch_one<32, UEPI_PM, TAPS_8>(tm, a, grid, smem, s);
+    if (w.np == 64) return launch_one<64, UEPI_PM, TAPS_8>(tm, a, grid, smem, s);
+    return cudaErrorNotSupported;
   }
   if (w.ntaps != 27) return cudaErrorNotSupported;
   if (a.cin8) {

@@ -32,6 +32,8 @@ struct UmmaWeights {
   int n_mma = 0;            // MMA pairs per z-slice per 16-channel chunk (27, 14 for cin == 8, 8 for transposed conv)
   int ntaps = 27;           // 27 (3x3x3) or 8 ({t-1,t}^3 window of a stride-2 transposed conv)
   int up_ncls = 0, up_cls0 = 0, up_cout = 0;   // UEPI_UP column layout
+  int origin = -1;          // brick origin vs tile origin: -1 (taps reach t-1) or 0 (stride-2 conv on a space-to-depth input)
+  uint32_t tap_mask[16] = {0};   // per K chunk: taps whose weight tile is non-zero
   int kchunks = 0;
   void* packed = nullptr;   // device bf16: [kchunk][n_mma][2*np x 16] canonical no-swizzle K-major tiles
   float* bias = nullptr;    // device [np] (zero padded)
@@ -52,6 +54,7 @@ struct UmmaCall {
   float* out_f32 = nullptr; int out_cs = 0, out_co = 0;     // UEPI_F32
   PmTensor out;                // UEPI_PM / UEPI_VRN
   PmTensor res;                // UEPI_VRN: the block input x
+  int out_s2d = 0;             // UEPI_VRN: write `out` space-to-depth (out = the n/2-grid, 8*C-channel tensor)
   int* err = nullptr;          // device int, set on device-side timeouts
 };
 
