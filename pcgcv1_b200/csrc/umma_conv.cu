@@ -397,7 +397,7 @@ cudaError_t make_tmap(const PmTensor& t, int ez, int ppc, CUtensorMap* out) {
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-int pick_zt(int n, int np, int cin) {
+int pick_zt(int n, int np, int cin, int epi) {
   // zt accumulators of 2*np columns must fit 512 TMEM columns (256 so two CTAs can share an SM) and the
   // brick + weights should leave room for two CTAs per SM where possible.
   int zt = 8;
@@ -406,6 +406,11 @@ int pick_zt(int n, int np, int cin) {
   const int nm = np == 128 ? 8 : (cin == 8 ? 14 : 27);
   auto smem = [&](int z) { return ppc * (z + 2) * EYC * EXC * CELL + nm * 2 * np * 32; };
   while (zt > 1 && smem(zt) > 100 * 1024) zt /= 2;
+  // MMA-bound kernels (light epilogue) overlap load / MMA / epilogue better with three CTAs per SM (measured on B200:
+  // K_a16 0.676 -> 0.582 ms); the VRN-tail kernels are epilogue/HBM bound and prefer deep z tiles (less halo re-read).
+  if (epi != UEPI_VRN) while (zt > 2 && smem(zt) > 75 * 1024) zt /= 2;
+  static const int force = getenv("PCGC_UMMA_ZT") ? atoi(getenv("PCGC_UMMA_ZT")) : 0;      // tuning experiments
+  if (force > 0 && force < zt) zt = force;
   return zt;
 }
 
@@ -496,7 +501,7 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
   if (!w.ok || c.in.c != w.cin || c.in.n % TILE_Y != 0) return cudaErrorNotSupported;
   const int n = c.in.n;
   UmmaArgs a;
-  a.n = n; a.zt = pick_zt(n, w.np, w.cin); a.ez = a.zt + 2;
+  a.n = n; a.zt = pick_zt(n, w.np, w.cin, c.epi); a.ez = a.zt + 2;
   a.cin8 = w.cin == 8; a.kchunks = w.kchunks; a.ppc = a.cin8 ? 2 : 4; a.n_mma = w.n_mma;
   a.plane_bytes = a.ez * EYC * EXC * CELL;
   a.a_bytes = a.ppc * a.plane_bytes;

@@ -343,3 +343,32 @@ def test_vox10_properties_full_size():
     assert one[0].numpy()[0] == y_strings.numpy()[i]
     mask = inout_points.select_voxels(xs, nums, 1.0, codec=codec)
     assert (mask.reshape(len(c), -1).sum(1) >= nums).all()
+
+
+def test_sharded_codec_world1_equals_transform(codec, cubes):
+    """pcgcv1_b200.sharding (the multi-GPU form) with a one-rank group reproduces transform.py's
+    stream byte for byte and the same voxel masks."""
+    import os, socket
+    import torch.distributed as dist
+    from pcgcv1_b200 import sharding
+    c, nums = cubes
+    created = False
+    if not dist.is_initialized():
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=0, world_size=1)
+        created = True
+    try:
+        local = sharding.GpuLocalCodec("voxception", "")
+        stream = sharding.compress_sharded(c, local)
+        masks = sharding.decompress_sharded(stream, nums, 1.0, local)
+    finally:
+        if created:
+            dist.destroy_process_group()
+    out = transform.compress_hyper(c, model_voxception, "")
+    assert stream["y_strings"] == list(out[0].numpy())
+    assert stream["z_string"] == out[4].numpy() and (stream["z_min"], stream["z_max"]) == (int(out[5]), int(out[6]))
+    xs = transform.decompress_hyper(*[o.numpy() for o in out], model_voxception, "")
+    ref = inout_points.select_voxels(xs, nums, 1.0, codec=codec, dtype="uint8")
+    assert np.array_equal(masks, ref)
