@@ -264,7 +264,7 @@ def run_gpu(args):
     conv_tflops = sum(r["flops"] for r in prof if r["tag"].startswith("conv")) / (conv_ms * 1e-3) / 1e12
     kernels = [{"tag": r["tag"], "share": round(r["ms"] / total_ms, 4),
                 "achieved": round((r["flops"] / 1e12 if r["flops"] else r["bytes"] / 1e9) / (r["ms"] * 1e-3), 2),
-                "unit": "TFLOP/s" if r["flops"] else "GB/s"} for r in prof[:8]]
+                "unit": "TFLOP/s" if r["flops"] else "GB/s"} for r in prof[:16]]
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None
     if world == 1 and not args.no_cpu:

@@ -144,6 +144,10 @@ int pcgc_laplace_cdf(pcgc_ctx* ctx, const float* loc_dev, const float* scale_dev
                      const int32_t* minmax_host, float likelihood_bound, int precision,
                      const int64_t* row_offset_host, uint16_t* cdf_dev);
 
+/* Test hook: the DEVICE copy of the 16-bit normaliser on given pmf rows (device float32 [rows,N], 2 <= N <=
+ * PCGC_MAX_SYMBOLS) -> device int32 cdf [rows,N+1]; must equal pcgc_pmf_to_quantized_cdf bit for bit.  Synchronises. */
+int pcgc_debug_quantize_pmf(pcgc_ctx* ctx, const float* pmf_dev, int64_t rows, int N, int precision, int32_t* cdf_dev);
+
 /* ---- top-k occupancy classification (dataprocess/inout_points.py:147-179) ---------------------- */
 /* select_voxels: per cube k = ks[b] (caller computes int(rho * n_points)); threshold = k-th
  * largest logit; mask = logits >= threshold (ties kept).  k == 0 reproduces the reference's

@@ -47,6 +47,7 @@ SIGNATURES = {
     "pcgc_laplace_quantize_likelihood": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _f, _vp, _vp, _vp, _vp]),
     "pcgc_laplace_intervals": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _vp, _f, _i, _vp]),
     "pcgc_laplace_cdf": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _f, _i, _vp, _vp]),
+    "pcgc_debug_quantize_pmf": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     "pcgc_topk_select": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _vp]),
     "pcgc_threshold_select": (_i, [_vp, _vp, _i, _i64, _f, _vp, _vp]),
     "pcgc_pmf_to_quantized_cdf": (_i, [_vp, _i64, _i, _i, _vp]),

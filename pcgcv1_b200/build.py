@@ -32,7 +32,7 @@ def _deps_mtime() -> float:
 def _compile(src: str, verbose: bool) -> str:
     obj = os.path.join(OBJ, src + ".o")
     cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200)      # a ptxas blow-up must not hang the build
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
     if verbose:

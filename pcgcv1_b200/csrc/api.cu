@@ -940,6 +940,17 @@ int pcgc_laplace_cdf(pcgc_ctx* ctx, const float* loc_dev, const float* scale_dev
   return check_err_flag(ctx, "pcgc_laplace_cdf");
 }
 
+int pcgc_debug_quantize_pmf(pcgc_ctx* ctx, const float* pmf_dev, int64_t rows, int N, int precision, int32_t* cdf_dev) {
+  if (!ctx || !pmf_dev || !cdf_dev || rows < 0 || N < 2 || N > PCGC_MAX_SYMBOLS) return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_debug_quantize_pmf: bad argument");
+  DeviceGuard g(ctx->device);
+  if (rows == 0) return PCGC_OK;
+  if (ctx->mm_cap < 2) { CK(cudaMalloc((void**)&ctx->mm_dev, sizeof(int32_t) * 2)); ctx->mm_cap = 2; }
+  const int32_t mm[2] = {0, N - 1};
+  CK(cudaMemcpyAsync(ctx->mm_dev, mm, sizeof mm, cudaMemcpyHostToDevice, ctx->stream));
+  CK(launch_debug_quantize_pmf(pmf_dev, rows, ctx->mm_dev, precision, cdf_dev, ctx->err_flag, ctx->stream, &ctx->launches));
+  return check_err_flag(ctx, "pcgc_debug_quantize_pmf");
+}
+
 int pcgc_topk_select(pcgc_ctx* ctx, const float* logits_dev, int B, int64_t V, const int32_t* ks_dev, uint8_t* mask_dev,
                      float* thres_dev, int32_t* count_dev) {
   if (!ctx || !logits_dev || !ks_dev || !mask_dev || B < 0 || V <= 0 || V % 4) return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_topk_select: bad argument");

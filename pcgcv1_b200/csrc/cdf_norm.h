@@ -20,17 +20,60 @@
 
 #if defined(__CUDACC__)
 #define PCGC_HD __host__ __device__ __forceinline__
+#define PCGC_HD_NOINLINE static __host__ __device__ __noinline__      // big bodies: keep ptxas compile time sane
 #else
 #define PCGC_HD inline
+#define PCGC_HD_NOINLINE inline
 #endif
 
 namespace pcgc {
 
 PCGC_HD double cdf_gain(double m, int v) { return m * (log2((double)(v + 1)) - log2((double)v)); }
 
-// pmf[n] -> v[n] (counts, sum == 2^precision).  g: scratch double[n].  Returns 0, or -2 if the row
+// Float SCORE used to shortlist candidates: score = cdf_gain(m, v) * 2^precision / log2(e) - 1, a strictly increasing
+// function of the gain.  All large entries have gains within ~1/v of each other, so the gain itself cannot be ranked
+// in float; the score can: with r = m*2^p - v (exact in float) and x = 1/v,
+//     score = (v + r) * ln(1 + x) - 1 = P + r*x*(1 + P),   P = -x/2 + x^2/3 - x^3/4 + ...
+// is evaluated without cancellation (relative error ~3e-7 OF THE SCORE, i.e. ~1e-12 of the gain).  Entries whose
+// scores are within PCGC_SCORE_TOL of the best are re-ranked on the exact double gains, so every decision equals the
+// all-double greedy of the oracle.
+PCGC_HD float cdf_score(float m, int v, float scale) {
+  if (v >= 16) {
+    const float x = 1.0f / (float)v, r = m * scale - (float)v;
+    const float P = x * (-0.5f + x * (1.0f / 3 + x * (-0.25f + x * (0.2f + x * (-1.0f / 6 + x * (1.0f / 7))))));
+    return P + r * x * (1.0f + P);
+  }
+  return (float)((double)m * (double)scale * log1p(1.0 / (double)v) - 1.0);
+}
+#define PCGC_SCORE_TOL(mx) (4e-6f * fabsf(mx) + 1e-9f)
+
+// Largest u >= 1 with cdf_gain(m, u) >= lambda (0 if none), i.e. u <= 1 / (2^(lambda/m) - 1).  Closed form with a short
+// exact check only when the bound is within rounding distance of an integer.
+PCGC_HD_NOINLINE long long cdf_last_u(double m, double lambda) {
+  if (!(m >= lambda)) return 0;                               // gain(m, u) <= gain(m, 1) = m
+  const double t = lambda / m * 0.6931471805599453;          // gain >= lambda  <=>  ln(1 + 1/u) >= t
+  if (t > 0.05) {                                            // u < 20: walk the few candidates exactly
+    long long u = 0;
+    while (u < 32 && cdf_gain(m, (int)(u + 1)) >= lambda) ++u;
+    return u;
+  }
+  // expm1(t) by its series (t <= 0.05: truncation error < 1e-15 relative)
+  const double em1 = t * (1.0 + t * (0.5 + t * (1.0 / 6 + t * (1.0 / 24 + t * (1.0 / 120 + t * (1.0 / 720 + t * (1.0 / 5040)))))));
+  const double U = 1.0 / em1;
+  if (U >= 4.0e9) return 4000000000LL;
+  long long fu = (long long)U;
+  const double frac = U - (double)fu, tol = 1e-9 * U + 1e-9;
+  if (frac < tol) { if (!(cdf_gain(m, (int)fu) >= lambda)) --fu; }
+  else if (1.0 - frac < tol) { if (cdf_gain(m, (int)(fu + 1)) >= lambda) ++fu; }
+  return fu;
+}
+
+// pmf[n] -> v[n] (counts, sum == 2^precision).  g: scratch float[n].  Returns 0, or -2 if the row
 // cannot be shrunk (all ones and n > target).
-PCGC_HD int quantize_pmf_row(const float* pmf, int n, int precision, int32_t* v, double* g) {
+//
+// One loop serves both directions (dir = +1: grow the entry with the largest gain; dir = -1: shrink the entry with
+// the smallest penalty = largest negated gain at v-1) so that the 32 rows of a warp do not serialise two code paths.
+PCGC_HD_NOINLINE int quantize_pmf_row(const float* pmf, int n, int precision, int32_t* v, float* g) {
   const int target = 1 << precision;
   const float scale = (float)target;
   long long sum = 0;
@@ -40,85 +83,76 @@ PCGC_HD int quantize_pmf_row(const float* pmf, int n, int precision, int32_t* v,
     v[i] = q;
     sum += q;
   }
-  if (sum > target) {
-    long long surplus = sum - target;
-    for (int i = 0; i < n; ++i) g[i] = v[i] > 1 ? cdf_gain((double)pmf[i], v[i] - 1) : INFINITY;
-    while (surplus > 0) {
-      int best = -1;
-      double bp = INFINITY;
-      for (int i = 0; i < n; ++i)
-        if (g[i] < bp) { bp = g[i]; best = i; }
-      if (best < 0) return -2;
-      v[best] -= 1;
-      g[best] = v[best] > 1 ? cdf_gain((double)pmf[best], v[best] - 1) : INFINITY;
-      --surplus;
-    }
-    return 0;
-  }
-  long long deficit = target - sum;
-  if (deficit == 0) return 0;
+  long long todo = sum > target ? sum - target : target - sum;
+  if (todo == 0) return 0;
+  const int dir = sum > target ? -1 : 1;
 
-  bool have_gains = false;
-  if (deficit > 2 * n + 8) {
-    // ---- water-filling: continuous solution of gain_i(v) ~ m_i*log2(e)/(v+0.5) == lambda ----
+  // ---- water-filling for large deficits (Laplace tails cut at min_v / max_v: up to thousands of steps) ----
+  // Every increment whose gain is >= lambda is granted at once, for a lambda that admits at most `todo` increments;
+  // per-entry gains are strictly decreasing, so these are exactly the greedy's first picks.  lambda comes from the
+  // continuous solution gain_i(u) ~ m_i*log2(e)/(u + 0.5), aimed a little short so that the pass is feasible.
+  for (int pass = 0; pass < 8 && dir > 0 && todo > 2 * n + 8; ++pass) {
     const double L = 1.4426950408889634;
-    // active set: entries that grow at the solution; iterate a few times.
-    double inv_lambda = 0.0;                 // 1/lambda
-    {
-      double t_act = (double)target, m_act = 0.0;
-      int n_act = n;
-      for (int i = 0; i < n; ++i) m_act += (double)pmf[i];
-      for (int it = 0; it < 4; ++it) {
-        inv_lambda = m_act > 0.0 ? (t_act + 0.5 * n_act) / (L * m_act) : 0.0;
-        double t2 = (double)target, m2 = 0.0;
-        int n2 = 0;
-        for (int i = 0; i < n; ++i) {
-          const double want = (double)pmf[i] * L * inv_lambda - 0.5;
-          if (want >= (double)v[i]) { m2 += (double)pmf[i]; ++n2; } else { t2 -= (double)v[i]; }
-        }
-        if (n2 == n_act && m2 == m_act) break;
-        t_act = t2; m_act = m2; n_act = n2;
-        if (n2 == 0) break;
+    double m_act = 0.0, t_act = (double)target;
+    int n_act = n;
+    for (int i = 0; i < n; ++i) m_act += (double)pmf[i];
+    double inv_lambda = 0.0;
+    for (int it = 0; it < 4 && m_act > 0.0; ++it) {           // active set = entries that grow at the solution
+      const double slack = 2.0 * sqrt((double)n_act / 12.0) + 1.0;
+      inv_lambda = (t_act - slack) / (L * m_act);
+      double t2 = (double)target, m2 = 0.0;
+      int n2 = 0;
+      for (int i = 0; i < n; ++i) {
+        if ((double)pmf[i] * L * inv_lambda >= (double)v[i]) { m2 += (double)pmf[i]; ++n2; } else { t2 -= (double)v[i]; }
       }
+      if (n2 == n_act && m2 == m_act) break;
+      t_act = t2; m_act = m2; n_act = n2;
+      if (n2 == 0) break;
     }
-    double lambda = inv_lambda > 0.0 ? 1.0 / inv_lambda : INFINITY;
-    for (int attempt = 0; attempt < 64 && lambda < INFINITY; ++attempt) {
-      // exact count c_i = #{k >= 0 : gain_i(v_i + k) >= lambda}, gains cached for the final greedy
+    if (!(inv_lambda > 0.0) || n_act == 0) break;
+    double lambda = 1.0 / inv_lambda;
+    bool done = false;
+    for (int attempt = 0; attempt < 8 && !done; ++attempt) {
       long long granted = 0;
-      bool ok = true;
-      for (int i = 0; i < n && ok; ++i) {
-        const double m = (double)pmf[i];
-        double approx = m * L / lambda - 0.5;                 // largest v with gain >= lambda (approx)
-        long long c = approx >= (double)v[i] ? (long long)(approx - (double)v[i]) + 1 : 0;
-        if (c > deficit) c = deficit + 1;
-        while (c > 0 && cdf_gain(m, (int)(v[i] + c - 1)) < lambda) --c;
-        double nxt = cdf_gain(m, (int)(v[i] + c));
-        while (nxt >= lambda) {
-          ++c;
-          if (c > deficit) break;
-          nxt = cdf_gain(m, (int)(v[i] + c));
-        }
-        g[i] = nxt;
-        granted += c;
-        v[i] += (int32_t)c;                                   // undone below if infeasible
-        if (granted > deficit) ok = false;
+      for (int i = 0; i < n; ++i) {
+        long long lu = cdf_last_u((double)pmf[i], lambda);
+        if (lu > 2 * (long long)target) lu = 2 * (long long)target;
+        g[i] = (float)lu;                                     // <= 2^17: exact in float
+        if (lu >= v[i]) granted += lu - v[i] + 1;
       }
-      if (ok) { deficit -= granted; have_gains = true; break; }
-      // infeasible: restore v from pmf and raise lambda slightly
-      for (int i = 0; i < n; ++i) { int q = (int)rintf(pmf[i] * scale); v[i] = q < 1 ? 1 : q; }
-      lambda *= 1.0 + ldexp(1.0, -14 + attempt / 2);
+      if (granted <= todo) {
+        for (int i = 0; i < n; ++i) { const int32_t lu = (int32_t)g[i]; if (lu >= v[i]) v[i] = lu + 1; }
+        todo -= granted;
+        done = true;
+      } else {
+        lambda *= 1.0 + ((double)(granted - todo) + 2.0 * sqrt((double)n_act) + 2.0) / (double)target;
+      }
     }
+    if (!done) break;
   }
-  if (!have_gains)
-    for (int i = 0; i < n; ++i) g[i] = cdf_gain((double)pmf[i], v[i]);
-  while (deficit > 0) {
-    int best = 0;
-    double bg = -INFINITY;
+
+  // scores: dir > 0: gain(v);  dir < 0: -gain(v-1) (= -penalty), entries at 1 can not shrink
+  for (int i = 0; i < n; ++i)
+    g[i] = dir > 0 ? cdf_score(pmf[i], v[i], scale) : (v[i] > 1 ? -cdf_score(pmf[i], v[i] - 1, scale) : -INFINITY);
+  while (todo > 0) {
+    float mx = -INFINITY;
+    for (int i = 0; i < n; ++i) mx = g[i] > mx ? g[i] : mx;
+    if (!(mx > -INFINITY)) return -2;
+    const float thr = mx - PCGC_SCORE_TOL(mx);
+    int best = -1, cand = 0;
     for (int i = 0; i < n; ++i)
-      if (g[i] > bg) { bg = g[i]; best = i; }
-    v[best] += 1;
-    g[best] = cdf_gain((double)pmf[best], v[best]);
-    --deficit;
+      if (g[i] >= thr) { if (cand == 0) best = i; ++cand; }
+    if (cand > 1) {                         // near tie: decide on the exact gains, lowest index first
+      double bs = -INFINITY;
+      for (int i = 0; i < n; ++i)
+        if (g[i] >= thr) {
+          const double e = dir > 0 ? cdf_gain((double)pmf[i], v[i]) : -cdf_gain((double)pmf[i], v[i] - 1);
+          if (e > bs) { bs = e; best = i; }
+        }
+    }
+    v[best] += dir;
+    g[best] = dir > 0 ? cdf_score(pmf[best], v[best], scale) : (v[best] > 1 ? -cdf_score(pmf[best], v[best] - 1, scale) : -INFINITY);
+    --todo;
   }
   return 0;
 }

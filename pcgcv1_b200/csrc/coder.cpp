@@ -138,7 +138,7 @@ int pcgc_pmf_to_quantized_cdf(const float* pmf, int64_t rows, int N, int precisi
   if (!pmf || !cdf || rows < 0 || precision < 1 || precision > 16) return PCGC_ERR_BAD_ARG;
   if (N < 2) return PCGC_ERR_BAD_RANGE;   // upstream: "`pmf` size should be at least 2 in the last axis"
   std::vector<int32_t> v(N);
-  std::vector<double> g(N);
+  std::vector<float> g(N);
   for (int64_t r = 0; r < rows; ++r) {
     if (pcgc::quantize_pmf_row(pmf + r * N, N, precision, v.data(), g.data()) != 0) return PCGC_ERR_BAD_RANGE;
     int32_t* row = cdf + r * (N + 1);

@@ -62,6 +62,8 @@ cudaError_t launch_laplace_intervals(const float* y_hat, const float* loc, const
 cudaError_t launch_laplace_cdf(const float* loc, const float* scale, int B, int64_t E, const int32_t* minmax_dev,
                                const int64_t* row_offset_dev, float bound, int precision, uint16_t* cdf,
                                int* err_flag, cudaStream_t s, int64_t* launches);
+cudaError_t launch_debug_quantize_pmf(const float* pmf, int64_t rows, const int32_t* minmax_dev, int precision,
+                                      int32_t* cdf32, int* err_flag, cudaStream_t s, int64_t* launches);
 // topk.cu
 cudaError_t launch_topk(const float* logits, int B, int64_t V, const int32_t* ks, uint8_t* mask, float* thres,
                         int32_t* count, int* err_flag, cudaStream_t s, int64_t* launches);

@@ -227,44 +227,64 @@ cudaError_t launch_laplace(const float* y, const float* loc, const float* scale,
 }
 
 // ---- per-element quantised CDF rows (SymmetricConditional._get_cdf, :95-124) -------------------
-// One thread per element: pmf over min_v..max_v -> quantize_pmf_row -> cumulative sums.
-template <bool INTERVALS>
+// One thread per element: pmf over min_v..max_v -> quantize_pmf_row (cdf_norm.h, shared with the host) -> cumulative
+// sums.  MODE 0: uint16 rows for the decoder, 1: the interval of the element's own symbol for the encoder,
+// 2: test hook (pmf given, int32 cdf rows out).
+// r01 note: an 8-lanes-per-row variant (all state in registers, shuffle reductions) was measured 2x SLOWER on the real
+// symbol ranges (N = 5..12): most lanes idle and every greedy step pays 9 shuffles.  The cost that mattered was the
+// water-filling pass of the few heavy-tail rows that almost every warp contains; it is now a closed form (cdf_last_u).
+template <int MODE>
 __global__ void __launch_bounds__(128)
 laplace_cdf_kernel(const float* __restrict__ y_hat, const float* __restrict__ loc, const float* __restrict__ scale,
-                   int64_t E, const int32_t* __restrict__ minmax, const int64_t* __restrict__ row_offset, float bound,
-                   int precision, uint32_t* __restrict__ intervals, uint16_t* __restrict__ cdf, int* __restrict__ err) {
+                   const float* __restrict__ pmf_in, int64_t E, const int32_t* __restrict__ minmax,
+                   const int64_t* __restrict__ row_offset, float bound, int precision, uint32_t* __restrict__ intervals,
+                   uint16_t* __restrict__ cdf, int32_t* __restrict__ cdf32, int* __restrict__ err) {
   const int b = blockIdx.y;
   const int min_v = minmax[2 * b], max_v = minmax[2 * b + 1];
   const int N = max_v - min_v + 1;
   if (N < 2 || N > PCGC_MAX_SYMBOLS) { if (threadIdx.x == 0 && blockIdx.x == 0) atomicExch(err, PCGC_ERR_BAD_RANGE); return; }
   float pmf[PCGC_MAX_SYMBOLS];
   int32_t v[PCGC_MAX_SYMBOLS];
-  double g[PCGC_MAX_SYMBOLS];
+  float g[PCGC_MAX_SYMBOLS];
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
     const size_t o = (size_t)b * E + e;
-    const float l = __ldg(loc + o), s = __ldg(scale + o);
-    for (int k = 0; k < N; ++k) pmf[k] = fmaxf(laplace_likelihood((float)(min_v + k), l, s), bound);
+    if (MODE == 2) {
+      for (int k = 0; k < N; ++k) pmf[k] = __ldg(pmf_in + o * N + k);
+    } else {
+      const float l = __ldg(loc + o), s = __ldg(scale + o);
+      for (int k = 0; k < N; ++k) pmf[k] = fmaxf(laplace_likelihood((float)(min_v + k), l, s), bound);
+    }
     if (quantize_pmf_row(pmf, N, precision, v, g) != 0) { atomicExch(err, PCGC_ERR_BAD_RANGE); continue; }
-    if (INTERVALS) {
+    if (MODE == 1) {
       const int sym = (int)__ldg(y_hat + o) - min_v;
       if (sym < 0 || sym >= N) { atomicExch(err, PCGC_ERR_BAD_RANGE); intervals[o] = 0; continue; }
       uint32_t lower = 0;
       for (int k = 0; k < sym; ++k) lower += (uint32_t)v[k];
       intervals[o] = lower | ((uint32_t)(v[sym] - 1) << 16);
-    } else {
+    } else if (MODE == 0) {
       uint16_t* row = cdf + row_offset[b] + (size_t)e * N;
       uint32_t acc = 0;
       for (int k = 0; k < N; ++k) { row[k] = (uint16_t)acc; acc += (uint32_t)v[k]; }
+    } else {
+      int32_t* row = cdf32 + o * (N + 1);
+      int32_t acc = 0;
+      for (int k = 0; k < N; ++k) { row[k] = acc; acc += v[k]; }
+      row[N] = acc;
     }
   }
+}
+
+static inline dim3 cdf_grid(int64_t E, int B) {
+  int64_t gx = (E + 127) / 128;
+  if (gx > 2048) gx = 2048;
+  return dim3((unsigned)gx, (unsigned)B);
 }
 
 cudaError_t launch_laplace_intervals(const float* y_hat, const float* loc, const float* scale, int B, int64_t E,
                                      const int32_t* minmax, float bound, int precision, uint32_t* intervals,
                                      int* err_flag, cudaStream_t s, int64_t* launches) {
-  dim3 grid((unsigned)((E + 127) / 128), (unsigned)B);
-  laplace_cdf_kernel<true><<<grid, 128, 0, s>>>(y_hat, loc, scale, E, minmax, nullptr, bound, precision, intervals,
-                                               nullptr, err_flag);
+  laplace_cdf_kernel<1><<<cdf_grid(E, B), 128, 0, s>>>(y_hat, loc, scale, nullptr, E, minmax, nullptr, bound, precision,
+                                                      intervals, nullptr, nullptr, err_flag);
   if (launches) ++*launches;
   return cudaGetLastError();
 }
@@ -272,9 +292,17 @@ cudaError_t launch_laplace_intervals(const float* y_hat, const float* loc, const
 cudaError_t launch_laplace_cdf(const float* loc, const float* scale, int B, int64_t E, const int32_t* minmax_dev,
                                const int64_t* row_offset_dev, float bound, int precision, uint16_t* cdf,
                                int* err_flag, cudaStream_t s, int64_t* launches) {
-  dim3 grid((unsigned)((E + 127) / 128), (unsigned)B);
-  laplace_cdf_kernel<false><<<grid, 128, 0, s>>>(nullptr, loc, scale, E, minmax_dev, row_offset_dev, bound, precision,
-                                                nullptr, cdf, err_flag);
+  laplace_cdf_kernel<0><<<cdf_grid(E, B), 128, 0, s>>>(nullptr, loc, scale, nullptr, E, minmax_dev, row_offset_dev, bound,
+                                                      precision, nullptr, cdf, nullptr, err_flag);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+// pmf [rows, N] (device) -> int32 cdf [rows, N+1] with the device copy of the normaliser (test hook).  minmax_dev = {0, N-1}.
+cudaError_t launch_debug_quantize_pmf(const float* pmf, int64_t rows, const int32_t* minmax_dev, int precision,
+                                      int32_t* cdf32, int* err_flag, cudaStream_t s, int64_t* launches) {
+  laplace_cdf_kernel<2><<<cdf_grid(rows, 1), 128, 0, s>>>(nullptr, nullptr, nullptr, pmf, rows, minmax_dev, nullptr, 0.f,
+                                                         precision, nullptr, nullptr, cdf32, err_flag);
   if (launches) ++*launches;
   return cudaGetLastError();
 }

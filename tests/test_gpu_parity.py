@@ -372,3 +372,33 @@ def test_sharded_codec_world1_equals_transform(codec, cubes):
     xs = transform.decompress_hyper(*[o.numpy() for o in out], model_voxception, "")
     ref = inout_points.select_voxels(xs, nums, 1.0, codec=codec, dtype="uint8")
     assert np.array_equal(masks, ref)
+
+
+@pytest.mark.parametrize("N", [2, 7, 8, 9, 16, 23, 24, 31, 33, 48, 64])
+def test_device_normaliser_equals_host_bit_for_bit(codec, N):
+    """The sub-warp (8 lanes per row) device normaliser against the host function of the same library (which the CPU
+    tests tie to the oracle's greedy definition): identical on every row, incl. surplus rows, large deficits
+    (water-filling) and exact ties."""
+    rng = np.random.default_rng(100 + N)
+    rows = 4096
+    pmf = rng.random((rows, N)).astype(np.float32) ** rng.integers(1, 9, (rows, 1))
+    pmf /= pmf.sum(-1, keepdims=True)
+    pmf *= rng.choice([1.0, 1.0, 0.999, 0.98, 0.9, 0.5, 0.1, 1.01, 1.2], (rows, 1)).astype(np.float32)
+    pmf = np.maximum(pmf, 1e-9).astype(np.float32)
+    pmf[:8] = 1.0 / N                                   # exact ties
+    pmf[8:16, 1:] = 1e-9; pmf[8:16, 0] = 1.0            # one dominant symbol, the rest at the likelihood bound
+    sc_or = entropy.SymmetricConditionalOracle()
+    mn = -(N // 2)
+    lap = sc_or.pmf(rng.normal(0, 2, 1024).astype(np.float32), (np.abs(rng.normal(0, 1.5, 1024)) + 1e-3).astype(np.float32), mn, mn + N - 1)
+    pmf[16:16 + 1024] = lap
+    pmf = np.ascontiguousarray(pmf)
+    L = codec.lib
+    ref = np.empty((rows, N + 1), np.int32)
+    assert L.pcgc_pmf_to_quantized_cdf(pmf.ctypes.data, rows, N, 16, ref.ctypes.data) == 0
+    d_pmf = codec.to_device(pmf)
+    d_cdf = torch.empty((rows, N + 1), dtype=torch.int32, device=codec.dev)
+    codec._stream()
+    codec._check(L.pcgc_debug_quantize_pmf(codec.ctx, d_pmf.data_ptr(), rows, N, 16, d_cdf.data_ptr()))
+    got = d_cdf.cpu().numpy()
+    bad = (got != ref).any(-1)
+    assert not bad.any(), "first mismatching row %d: %s vs %s" % (np.argmax(bad), np.diff(got[np.argmax(bad)]), np.diff(ref[np.argmax(bad)]))
