@@ -82,6 +82,38 @@ class SymmetricConditional:
         strings = runtime.range_encode_intervals_batch(runtime.to_host(iv, "intervals"), threads)
         return strings, mm_h[:, 0].copy(), mm_h[:, 1].copy()
 
+    # ---- split forms for the software pipeline in transform.py: GPU part now, host coder part later ---------------
+    def encode_begin(self, ys, locs, scales, slot: int):
+        """GPU half of compress_cubes: returns (pinned intervals, copy-done event, minmax host array)."""
+        c = self.codec
+        B = ys.shape[0]
+        y2, l2, s2 = ys.reshape(B, -1), locs.reshape(B, -1), scales.reshape(B, -1)
+        y_hat, _, _, mm = c.laplace(y2, l2, s2, self._likelihood_bound, want_p=False, want_bits=False)
+        iv = c.laplace_intervals(y_hat, l2, s2, mm, self._likelihood_bound)
+        stage, done = runtime.to_host_async(iv, "intervals%d" % slot)
+        return stage, done, runtime.to_host(mm)
+
+    @staticmethod
+    def encode_finish(stage, done, threads: int = 0):
+        done.synchronize()
+        return runtime.range_encode_intervals_batch(stage.numpy(), threads)
+
+    def decode_begin(self, locs, scales, min_vs, max_vs, slot: int):
+        """GPU half of decompress_cubes: per-element CDF rows -> pinned memory (async)."""
+        c = self.codec
+        B = locs.shape[0]
+        l2, s2 = locs.reshape(B, -1), scales.reshape(B, -1)
+        mm = np.stack([np.asarray(min_vs, np.int32).reshape(-1), np.asarray(max_vs, np.int32).reshape(-1)], -1)
+        rows, off = c.laplace_cdf(l2, s2, mm, self._likelihood_bound)
+        stage, done = runtime.to_host_async(rows, "cdf_rows%d" % slot)
+        return stage, done, off, mm, l2.shape[1]
+
+    @staticmethod
+    def decode_finish(strings, stage, done, off, mm, E, slot: int, threads: int = 0):
+        """Host half: -> pinned float32 torch tensor [B, E] of y_hat."""
+        done.synchronize()
+        return runtime.range_decode_rows_batch_f32(list(strings), E, stage.numpy(), off, mm, threads, out_tag="y_hat_dec%d" % slot)
+
     def decompress_cubes(self, strings, locs, scales, min_vs, max_vs, threads: int = 0):
         """-> torch float32 [B, E] on the device."""
         c = self.codec

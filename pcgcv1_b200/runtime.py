@@ -46,6 +46,38 @@ def pinned_buffer(tag: str, nbytes: int) -> torch.Tensor:
     return buf
 
 
+_COPY_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def copy_stream(dev: torch.device) -> "torch.cuda.Stream":
+    """Side stream for D2H copies that overlap the kernels of the next chunk."""
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    s = _COPY_STREAMS.get(idx)
+    if s is None:
+        s = torch.cuda.Stream(device=dev)
+        _COPY_STREAMS[idx] = s
+    return s
+
+
+def to_host_async(t: torch.Tensor, tag: str):
+    """Start a device->pinned copy of ``t`` on the copy stream (ordered after the work already queued on the current
+    stream).  Returns (pinned view as torch tensor, event to synchronise before reading)."""
+    nbytes = t.numel() * t.element_size()
+    COUNTERS["d2h_bytes"] += nbytes
+    t = t.detach().contiguous()
+    stage = pinned_buffer(tag, nbytes)[:nbytes].view(t.dtype).view(t.shape)
+    cs = copy_stream(t.device)
+    ready = torch.cuda.Event()
+    ready.record(torch.cuda.current_stream(t.device))
+    cs.wait_event(ready)
+    t.record_stream(cs)
+    done = torch.cuda.Event()
+    with torch.cuda.stream(cs):
+        stage.copy_(t, non_blocking=True)
+        done.record(cs)
+    return stage, done
+
+
 def to_host(t: torch.Tensor, tag: str = None) -> np.ndarray:
     """Device tensor -> NumPy (counted).  With a ``tag`` the copy lands in a reusable pinned buffer and the
     returned array is a VIEW of it (valid until the next call with the same tag)."""
@@ -422,7 +454,7 @@ def range_encode_intervals_batch(iv: np.ndarray, threads: int = 0):
 
 
 def range_decode_rows_batch_f32(strings, E: int, rows: np.ndarray, row_offset: np.ndarray, minmax: np.ndarray,
-                                threads: int = 0) -> torch.Tensor:
+                                threads: int = 0, out_tag: str = "y_hat_dec") -> torch.Tensor:
     """-> pinned float32 torch tensor [B,E] holding y_hat = symbol + min_v (valid until the next call)."""
     L = _lib.lib()
     B = len(strings)
@@ -432,7 +464,7 @@ def range_decode_rows_batch_f32(strings, E: int, rows: np.ndarray, row_offset: n
     rows = np.ascontiguousarray(rows)
     row_offset = np.ascontiguousarray(row_offset, dtype=np.int64)
     minmax = np.ascontiguousarray(minmax, dtype=np.int32)
-    out = pinned_buffer("y_hat_dec", B * E * 4)[:B * E * 4].view(torch.float32).view(B, E)
+    out = pinned_buffer(out_tag, B * E * 4)[:B * E * 4].view(torch.float32).view(B, E)
     _lib.check(L.pcgc_range_decode_rows_batch_f32(ptrs, nbytes.ctypes.data, B, E, rows.ctypes.data, row_offset.ctypes.data,
                                                   minmax.ctypes.data, 16, out.data_ptr(), threads))
     return out

@@ -83,41 +83,69 @@ def decompress_factorized(strings, min_v, max_v, shape, model, ckpt_dir):
 
 
 # ---------------------------------------------------------------- hyperprior (conditional) model
+# The batch is processed in chunks as a two-stage software pipeline: while the host range coder (worker thread; the C
+# entry points release the GIL and fan out over their own thread pool) works on chunk k, the GPU already runs the
+# transforms of chunk k+1 and a copy stream moves the coder's inputs through rotating pinned buffers.
+_CHUNK = int(os.environ.get("PCGC_CHUNK", "64"))
+_POOL = None
+
+
+def _pool():
+    global _POOL
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=1)
+    return _POOL
+
+
 def compress_hyper(cubes, model, ckpt_dir, decompress=False):
     """cubes [B,64,64,64,1] -> (y_strings[B], y_min_vs[B], y_max_vs[B], y_shape, z_strings, z_min_v,
     z_max_v, z_shape[, x_decodeds])  (transform.py:91-197)."""
     _log("===== Compress =====")
     codec = runtime.get_codec(model, ckpt_dir)
     entropy_bottleneck = _bottleneck(codec, 8)
-    conditional_entropy_model = SymmetricConditional().bind(codec)
-    x = codec.to_device(cubes)
-
+    cem = SymmetricConditional().bind(codec)
+    cubes = runtime.unwrap(cubes)
+    B = cubes.shape[0]
     start = time.time()
-    ys = codec.analysis(x)
-    _log("Analysis Transform", start)
+    jobs, mms, z_hats, keep = [], [], [], []
+    for k, a in enumerate(range(0, B, _CHUNK)):
+        b = min(B, a + _CHUNK)
+        x = codec.to_device(cubes[a:b])
+        ys = codec.analysis(x)
+        zs = codec.hyper_encode(ys)
+        z_hat, _, _, _ = codec.factorized(entropy_bottleneck._slot, zs, want_p=False, want_bits=False)
+        locs, scales = codec.hyper_decode(z_hat, 1e-9)                  # lower_bound = 1e-9, transform.py:145-146
+        if k >= 2:
+            jobs[k - 2] = jobs[k - 2].result()                          # slot k%2 is free once its previous user finished
+        stage, done, mm = cem.encode_begin(ys, locs, scales, k % 2)
+        jobs.append(_pool().submit(cem.encode_finish, stage, done))
+        mms.append(mm)
+        z_hats.append(z_hat)
+        if decompress:
+            keep.append((ys.shape, locs, scales))
+    strings = []
+    for j in jobs:
+        strings += j if isinstance(j, list) else j.result()
+    _log("Analysis + hyper transforms + entropy encode (pipelined)", start)
     start = time.time()
-    zs = codec.hyper_encode(ys)
-    _log("Hyper Encoder", start)
-    z_hats, _, _, _ = codec.factorized(entropy_bottleneck._slot, zs, want_p=False, want_bits=False)
-    start = time.time()
-    locs, scales = codec.hyper_decode(z_hats, 1e-9)                      # lower_bound = 1e-9, transform.py:145-146
-    _log("Hyper Decoder", start)
-    start = time.time()
-    z_strings, z_min_v, z_max_v = entropy_bottleneck.compress(zs)
-    z_shape = runtime.HostResult(np.array(zs.shape, dtype=np.int32))
+    z_all = torch.cat(z_hats) if len(z_hats) > 1 else z_hats[0]
+    z_strings, z_min_v, z_max_v = entropy_bottleneck.compress(z_all)     # one string, global range (entropy_model.py:249-259)
+    z_shape = runtime.HostResult(np.array(z_all.shape, dtype=np.int32))
     _log("Entropy Encode (Hyper)", start)
-    start = time.time()
-    strings, y_min_vs, y_max_vs = conditional_entropy_model.compress_cubes(ys, locs, scales)
-    y_shape = runtime.HostResult(np.array((1,) + tuple(ys.shape[1:]), dtype=np.int64))
-    _log("Entropy Encode", start)
-    out = (runtime.HostResult(_strings_array(strings)), runtime.HostResult(y_min_vs.astype(np.int32)),
-           runtime.HostResult(y_max_vs.astype(np.int32)), y_shape, z_strings, z_min_v, z_max_v, z_shape)
+    mm = np.concatenate(mms) if mms else np.zeros((0, 2), np.int32)
+    y_min_vs, y_max_vs = mm[:, 0].astype(np.int32), mm[:, 1].astype(np.int32)
+    y_shape = runtime.HostResult(np.array((1, 16, 16, 16, 16), dtype=np.int64))
+    out = (runtime.HostResult(_strings_array(strings)), runtime.HostResult(y_min_vs), runtime.HostResult(y_max_vs), y_shape,
+           z_strings, z_min_v, z_max_v, z_shape)
     if decompress:
         start = time.time()
-        y_dec = conditional_entropy_model.decompress_cubes(strings, locs, scales, y_min_vs, y_max_vs)
+        locs = torch.cat([kk[1] for kk in keep])
+        scales = torch.cat([kk[2] for kk in keep])
+        y_dec = cem.decompress_cubes(strings, locs, scales, y_min_vs, y_max_vs)
         _log("Entropy Decode", start)
         start = time.time()
-        x_dec = codec.synthesis(y_dec.reshape(ys.shape))
+        x_dec = codec.synthesis(y_dec.reshape(B, 16, 16, 16, 16))
         _log("Synthesis Transform", start)
         return out + (runtime.DeviceResult(x_dec),)
     return out
@@ -128,25 +156,37 @@ def decompress_hyper(y_strings, y_min_vs, y_max_vs, y_shape, z_strings, z_min_v,
     _log("===== Decompress =====")
     codec = runtime.get_codec(model, ckpt_dir)
     entropy_bottleneck = _bottleneck(codec, 8)
-    conditional_entropy_model = SymmetricConditional().bind(codec)
+    cem = SymmetricConditional().bind(codec)
     z_shape = np.asarray(runtime.unwrap(z_shape)).reshape(-1)
     y_shape = [int(v) for v in np.asarray(runtime.unwrap(y_shape)).reshape(-1)]
-
     start = time.time()
-    zs = entropy_bottleneck.decompress(z_strings, z_min_v, z_max_v, z_shape, z_shape[-1])
+    zs = entropy_bottleneck.decompress(z_strings, z_min_v, z_max_v, z_shape, z_shape[-1]).tensor
     _log("Entropy Decoder (Hyper)", start)
-    start = time.time()
-    locs, scales = codec.hyper_decode(zs.tensor, 1e-9)
-    _log("Hyper Decoder", start)
-    start = time.time()
     strings = _as_list_of_bytes(y_strings)
-    B = locs.shape[0]
+    B = zs.shape[0]
     if len(strings) != B:
         raise ValueError("got %d y strings for %d cubes" % (len(strings), B))
-    ys = conditional_entropy_model.decompress_cubes(strings, locs, scales, np.asarray(runtime.unwrap(y_min_vs)),
-                                                    np.asarray(runtime.unwrap(y_max_vs)))
-    _log("Entropy Decoder", start)
+    mins = np.asarray(runtime.unwrap(y_min_vs)).reshape(-1)
+    maxs = np.asarray(runtime.unwrap(y_max_vs)).reshape(-1)
     start = time.time()
-    xs = codec.synthesis(ys.reshape([B] + y_shape[1:]))
-    _log("Synthesis Transform", start)
+    chunks = [(a, min(B, a + _CHUNK)) for a in range(0, B, _CHUNK)]
+    xs_parts, pending = [], None
+
+    def finish(p):
+        (a, b), job = p
+        y_hat = job.result()                                              # pinned float32 [b-a, E]
+        ys = codec.to_device(y_hat).reshape([b - a] + y_shape[1:])
+        xs_parts.append(codec.synthesis(ys))
+
+    for k, (a, b) in enumerate(chunks):
+        locs, scales = codec.hyper_decode(zs[a:b], 1e-9)
+        stage, done, off, mm, E = cem.decode_begin(locs, scales, mins[a:b], maxs[a:b], k % 2)
+        job = _pool().submit(cem.decode_finish, strings[a:b], stage, done, off, mm, E, k % 2)
+        if pending is not None:
+            finish(pending)                                               # synthesis of chunk k-1 overlaps the host decode of chunk k
+        pending = ((a, b), job)
+    if pending is not None:
+        finish(pending)
+    xs = torch.cat(xs_parts) if len(xs_parts) > 1 else xs_parts[0]
+    _log("Hyper decoder + entropy decode + synthesis (pipelined)", start)
     return runtime.DeviceResult(xs)
