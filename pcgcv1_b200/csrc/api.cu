@@ -282,6 +282,28 @@ int build_umma_program(pcgc_ctx* ctx, int kind) {
   Net& n = ctx->nets[kind];
   UmmaProgram& up = n.up;
   if (up.ready) return PCGC_OK;
+  if (kind == PCGC_NET_HYPER_ENCODER || kind == PCGC_NET_HYPER_DECODER) {
+    auto Lw = [&](const char* name) -> LayerW& { return n.w[n.find(name)]; };
+    cudaError_t e;
+    if (kind == PCGC_NET_HYPER_ENCODER) {
+      LayerW& l = Lw("conv1");
+      e = pack_umma_weights_dense(l.hk.data(), l.hb.data(), 16, 16, up.first);
+    } else {
+      LayerW &l3 = Lw("deconv3"), &l41 = Lw("deconv4_1"), &l42 = Lw("deconv4_2");
+      e = pack_umma_weights_dense(l3.hk.data(), l3.hb.data(), 16, 32, up.first);
+      // the two heads share their input: one GEMM with N = 16 (loc) + 16 (scale)
+      std::vector<float> d((size_t)27 * 32 * 32), bb(32);
+      for (int t = 0; t < 27; ++t) for (int ci = 0; ci < 32; ++ci) for (int co = 0; co < 16; ++co) {
+        d[((size_t)t * 32 + ci) * 32 + co] = l41.hk[((size_t)t * 32 + ci) * 16 + co];
+        d[((size_t)t * 32 + ci) * 32 + 16 + co] = l42.hk[((size_t)t * 32 + ci) * 16 + co];
+      }
+      for (int co = 0; co < 16; ++co) { bb[co] = l41.hb[co]; bb[16 + co] = l42.hb[co]; }
+      if (e == cudaSuccess) e = pack_umma_weights_dense(d.data(), bb.data(), 32, 32, up.last);
+    }
+    if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "pack hyper net %d: %s", kind, cudaGetErrorString(e));
+    up.ready = true;
+    return PCGC_OK;
+  }
   const bool ana = kind == PCGC_NET_VOX_ANALYSIS;
   const char* prefix = ana ? "vrn" : "dvrn";
   const int chans[3] = {ana ? 16 : 64, 32, ana ? 64 : 16};
@@ -503,13 +525,87 @@ int run_vox_umma(pcgc_ctx* ctx, int kind, const float* in_ext, const void* cubes
   return PCGC_OK;
 }
 
+// Hyper encoder / decoder with their 16^3 layers on the tcgen05 engine (conv1; deconv3 and the fused loc|scale heads);
+// the 8^3 layers and the stride-2 / transposed ones stay on the FP32 CUDA-core kernel (a few MMAC per cube).
+int run_hyper_umma(pcgc_ctx* ctx, int kind, const float* in_ext, int B, float* out0, float* out1, float floor_v) {
+  Net& n = ctx->nets[kind];
+  for (size_t i = 0; i < n.w.size(); ++i)
+    if (!n.w[i].loaded) return fail(ctx, PCGC_ERR_NOT_READY, "net %d: layer '%s' has no weights", kind, n.specs[i].name.c_str());
+  int r = build_umma_program(ctx, kind);
+  if (r) return r;
+  if (B <= 0) return PCGC_OK;
+  const int SB = std::min(B, 8 * ctx->sub_batch);
+  const size_t big = (size_t)16 * 16 * 16 * 32;             // largest activation per cube (floats)
+  for (int bi : {BUF_A, BUF_B, BUF_T1}) { r = ensure(ctx, &ctx->bufs[bi], &ctx->buf_cap[bi], big * SB); if (r) return r; }
+  UmmaProgram& up = n.up;
+  auto pm = [&](int buf, int nn, int c, int nb) { PmTensor t; t.p = (__nv_bfloat16*)ctx->bufs[buf]; t.n = nn; t.c = c; t.B = nb; return t; };
+  const PmTensor none;
+  auto ffma = [&](const char* name, const float* in_f32, const PmTensor* in_pm, int in_n, float* out_f32, const PmTensor* out_pm, int nb) -> int {
+    const int li = n.find(name);
+    const LayerSpec& s = n.specs[li];
+    LayerW& lw = n.w[li];
+    const int out_n = s.transposed ? in_n * s.stride : in_n / s.stride;
+    ConvCall c;
+    c.in = in_f32; c.in_n = in_n; c.in_cs = s.cin; c.in_co = 0;
+    c.out = out_f32; c.out_n = out_n; c.out_cs = s.cout; c.out_co = 0;
+    c.bias = lw.bias; c.res = nullptr; c.res_cs = c.res_co = 0;
+    c.flags = s.relu ? EPI_RELU : 0; c.floor_v = 0.f; c.B = nb;
+    c.in_pm = in_pm ? in_pm->p : nullptr; c.out_pm = out_pm ? out_pm->p : nullptr;
+    char tag[96];
+    snprintf(tag, sizeof tag, "conv_ffma k%d s%d%s c%d->%d n%d", s.k, s.stride, s.transposed ? "T" : "", s.cin, s.cout, in_n);
+    const double tvox = (double)(s.transposed ? in_n : out_n);
+    prof_begin(ctx, tag, 2.0 * nb * tvox * tvox * tvox * 27 * s.cin * s.cout, 0);
+    for (int k = 0; k < lw.n_classes; ++k) {
+      c.d = lw.cls[k];
+      c.tn = s.transposed ? in_n : out_n;
+      cudaError_t e = launch_conv_ffma(c, ctx->stream, &ctx->launches);
+      if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "conv '%s': %s", name, cudaGetErrorString(e));
+    }
+    prof_end(ctx);
+    return PCGC_OK;
+  };
+  auto umma = [&](const char* what, const UmmaWeights& w, const PmTensor& in, UmmaCall c) -> int {
+    c.in = in; c.err = ctx->err_flag;
+    char tag[96];
+    snprintf(tag, sizeof tag, "conv_umma %s c%d->%d n%d", what, w.cin, w.n_real, in.n);
+    prof_begin(ctx, tag, 2.0 * in.B * in.n * in.n * in.n * 27.0 * w.cin * w.n_real, 0);
+    cudaError_t e = launch_conv_umma_pm(c, w, ctx->stream, &ctx->launches);
+    prof_end(ctx);
+    if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "%s: %s", tag, cudaGetErrorString(e));
+    return PCGC_OK;
+  };
+  for (int b0 = 0; b0 < B; b0 += SB) {
+    const int nb = std::min(SB, B - b0);
+    if (kind == PCGC_NET_HYPER_ENCODER) {
+      PmTensor yin = pm(BUF_T1, 16, 16, nb), f1 = pm(BUF_A, 16, 16, nb);
+      CK(launch_f32_to_pm(in_ext + (size_t)b0 * 65536, 16, 0, yin, ctx->stream, &ctx->launches));
+      UmmaCall c; c.epi = UEPI_PM; c.flags = EPI_RELU; c.out = f1;
+      if ((r = umma("conv1", up.first, yin, c))) return r;
+      if ((r = ffma("conv2", nullptr, &f1, 16, ctx->bufs[BUF_B], nullptr, nb))) return r;
+      if ((r = ffma("conv3", ctx->bufs[BUF_B], nullptr, 8, out0 + (size_t)b0 * 4096, nullptr, nb))) return r;
+    } else {
+      PmTensor f2 = pm(BUF_B, 16, 16, nb), f3 = pm(BUF_T1, 16, 32, nb);
+      if ((r = ffma("deconv1", in_ext + (size_t)b0 * 4096, nullptr, 8, ctx->bufs[BUF_A], nullptr, nb))) return r;
+      if ((r = ffma("deconv2", ctx->bufs[BUF_A], nullptr, 8, nullptr, &f2, nb))) return r;
+      UmmaCall c; c.epi = UEPI_PM; c.flags = EPI_RELU; c.out = f3;
+      if ((r = umma("deconv3", up.first, f2, c))) return r;
+      UmmaCall h; h.epi = UEPI_F32; h.flags = 0; h.out_f32 = out0 + (size_t)b0 * 65536; h.out_cs = 16; h.out_co = 0;
+      h.out2_f32 = out1 + (size_t)b0 * 65536; h.split = 16; h.flags2 = EPI_ABS | EPI_FLOOR; h.floor_v = floor_v;   // abs (:308) + max(., 1e-9)
+      if ((r = umma("deconv4_1|4_2", up.last, f3, h))) return r;
+    }
+  }
+  return PCGC_OK;
+}
+
 int run_net(pcgc_ctx* ctx, int kind, const float* in_ext, const void* cubes, int cubes_dtype, int B, float* out0,
             float* out1, float floor_v) {
   Net& n = ctx->nets[kind];
   for (size_t i = 0; i < n.w.size(); ++i)
     if (!n.w[i].loaded) return fail(ctx, PCGC_ERR_NOT_READY, "net %d: layer '%s' has no weights", kind, n.specs[i].name.c_str());
   if (B <= 0) return PCGC_OK;
-  const int SB = std::min(B, ctx->sub_batch);
+  // the hyper nets work on 16^3 / 8^3 grids: a 32-cube sub-batch leaves most SMs idle, their activations are tiny
+  const bool small_net = kind == PCGC_NET_HYPER_ENCODER || kind == PCGC_NET_HYPER_DECODER;
+  const int SB = std::min(B, small_net ? 8 * ctx->sub_batch : ctx->sub_batch);
   for (int bi = BUF_X0; bi < BUF_OUT0; ++bi) {
     size_t e = n.elems[bi];
     if (bi == BUF_X0 && cubes) e = std::max(e, (size_t)n.in_n * n.in_n * n.in_n * n.in_c);
@@ -840,12 +936,14 @@ int pcgc_synthesis(pcgc_ctx* ctx, int net, const float* y_dev, int B, float* log
 int pcgc_hyper_encode(pcgc_ctx* ctx, const float* y_dev, int B, float* z_dev) {
   if (!ctx || !y_dev || !z_dev) return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_hyper_encode: bad argument");
   DeviceGuard g(ctx->device);
+  if (ctx->engine != PCGC_ENGINE_FFMA) return run_hyper_umma(ctx, PCGC_NET_HYPER_ENCODER, y_dev, B, z_dev, nullptr, 0.f);
   return run_net(ctx, PCGC_NET_HYPER_ENCODER, y_dev, nullptr, 0, B, z_dev, nullptr, 0.f);
 }
 
 int pcgc_hyper_decode(pcgc_ctx* ctx, const float* z_hat_dev, int B, float scale_floor, float* loc_dev, float* scale_dev) {
   if (!ctx || !z_hat_dev || !loc_dev || !scale_dev) return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_hyper_decode: bad argument");
   DeviceGuard g(ctx->device);
+  if (ctx->engine != PCGC_ENGINE_FFMA) return run_hyper_umma(ctx, PCGC_NET_HYPER_DECODER, z_hat_dev, B, loc_dev, scale_dev, scale_floor);
   return run_net(ctx, PCGC_NET_HYPER_DECODER, z_hat_dev, nullptr, 0, B, loc_dev, scale_dev, scale_floor);
 }
 

@@ -53,6 +53,7 @@ struct UmmaArgs {
   const float* bias;
   int n_real, flags; float floor_v;
   float* out_f32; int out_cs, out_co;
+  float* out2_f32; int split, flags2;      // UEPI_F32: columns >= split go to out2_f32 (stride n_real - split) with flags2
   __nv_bfloat16* out_pm; int out_planes;
   const __nv_bfloat16* res_pm; int res_planes;
   const float* w23; const float* b23; int c4, c2;
@@ -284,15 +285,18 @@ __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const __grid_co
       }
       const size_t vox = ((size_t)vz * a.n + vy) * a.n + vx;
       if (EPI == UEPI_F32) {
-        float* op = a.out_f32 + ((size_t)b * a.n * a.n * a.n + vox) * a.out_cs + a.out_co;
+        const size_t gv = (size_t)b * a.n * a.n * a.n + vox;
+        float* op = a.out_f32 + gv * a.out_cs + a.out_co;
+        float* op2 = a.out2_f32 ? a.out2_f32 + gv * (a.n_real - a.split) : nullptr;
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
           if (i < a.n_real) {
             float t = v[i];
-            if (a.flags & EPI_RELU) t = fmaxf(t, 0.f);
-            if (a.flags & EPI_ABS) t = fabsf(t);
-            if (a.flags & EPI_FLOOR) t = fmaxf(t, a.floor_v);
-            op[i] = t;
+            const int fl = i < a.split ? a.flags : a.flags2;
+            if (fl & EPI_RELU) t = fmaxf(t, 0.f);
+            if (fl & EPI_ABS) t = fabsf(t);
+            if (fl & EPI_FLOOR) t = fmaxf(t, a.floor_v);
+            if (i < a.split) op[i] = t; else op2[i - a.split] = t;
           }
         }
       } else if (EPI == UEPI_PM) {
@@ -512,6 +516,7 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
   a.wpacked = (const __nv_bfloat16*)w.packed; a.bias = w.bias;
   a.n_real = w.n_real; a.flags = c.flags; a.floor_v = c.floor_v;
   a.out_f32 = c.out_f32; a.out_cs = c.out_cs; a.out_co = c.out_co;
+  a.out2_f32 = c.out2_f32; a.split = c.out2_f32 ? c.split : w.n_real; a.flags2 = c.flags2;
   a.out_pm = c.out.p; a.out_planes = 2 * (c.out_s2d ? c.out.c / 8 : c.out.c) / 8;
   a.res_pm = c.res.p; a.res_planes = 2 * c.res.c / 8;
   a.w23 = w.w23; a.b23 = w.b23; a.c4 = w.c4; a.c2 = w.c2;

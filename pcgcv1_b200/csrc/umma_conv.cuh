@@ -52,6 +52,7 @@ struct UmmaCall {
   int epi = UEPI_F32;
   int flags = 0; float floor_v = 0.f;
   float* out_f32 = nullptr; int out_cs = 0, out_co = 0;     // UEPI_F32
+  float* out2_f32 = nullptr; int split = 0, flags2 = 0;     // UEPI_F32: second output for columns >= split (two-headed layers)
   PmTensor out;                // UEPI_PM / UEPI_VRN
   PmTensor res;                // UEPI_VRN: the block input x
   int out_s2d = 0;             // UEPI_VRN: write `out` space-to-depth (out = the n/2-grid, 8*C-channel tensor)
