@@ -53,6 +53,7 @@ struct UmmaProgram {
   UmmaWeights up[2][2];         // synthesis: up_1 (two class groups), up_2 (one group) as 8-tap parity-class GEMMs
   int up_groups[2] = {0, 0};
   UmmaWeights down[2];          // analysis: down_1, down_2 as 8-tap GEMMs over the space-to-depth input
+  float* conv_in_w = nullptr;   // analysis: conv_in weights [27][16] for the dedicated kernel
 };
 
 struct Net {
@@ -492,9 +493,14 @@ int run_vox_umma(pcgc_ctx* ctx, int kind, const float* in_ext, const void* cubes
     if (ana) {
       const size_t in_elems = (size_t)64 * 64 * 64;
       const size_t esz = cubes_dtype == PCGC_DTYPE_U8 ? 1 : (cubes_dtype == PCGC_DTYPE_F32 ? 4 : 8);
-      CK(launch_u8_to_f32((const char*)cubes + (size_t)b0 * in_elems * esz, cubes_dtype, ctx->bufs[BUF_X0], (int64_t)nb * in_elems,
-                          ctx->stream, &ctx->launches));
-      if ((r = ffma("conv_in", ctx->bufs[BUF_X0], none, 64, pm(cur, 64, 16, nb)))) return r;
+      {
+        // conv_in straight from the cube's own dtype into PM (the Keras [3,3,3,1,16] kernel is already [27][16])
+        LayerW& lin = n.w[n.find("conv_in")];
+        prof_begin(ctx, "conv_in_pm c1->16 n64", 2.0 * nb * in_elems * 27 * 16, 0);
+        CK(launch_conv_in_pm((const char*)cubes + (size_t)b0 * in_elems * esz, cubes_dtype, lin.hk.data(), lin.hb.empty() ? nullptr : lin.hb.data(),
+                             ctx->bufs[cur], nb, ctx->stream, &ctx->launches));
+        prof_end(ctx);
+      }
       if ((r = vrn_stage(0, 16, 64, true))) return r;
       if ((r = umma("down_1", up.down[0], pm(cur, 32, 128, nb), UEPI_PM, EPI_RELU, pm(nxt, 32, 32, nb), none, nullptr, 0))) return r;
       std::swap(cur, nxt);
@@ -705,6 +711,7 @@ void pcgc_destroy(pcgc_ctx* ctx) {
     free_umma_weights(n.up.first); free_umma_weights(n.up.last);
     for (int u = 0; u < 2; ++u) for (int g = 0; g < 2; ++g) free_umma_weights(n.up.up[u][g]);
     free_umma_weights(n.up.down[0]); free_umma_weights(n.up.down[1]);
+    if (n.up.conv_in_w) cudaFree(n.up.conv_in_w);
   }
   for (auto& n : ctx->nets)
     for (auto& lw : n.w) {
@@ -798,6 +805,7 @@ int pcgc_load_conv(pcgc_ctx* ctx, int net, const char* layer, const float* kerne
   lw.hk.assign(kernel, kernel + (size_t)k * k * k * s.cin * s.cout);
   if (bias) lw.hb.assign(bias, bias + s.cout); else lw.hb.clear();
   n.up.ready = false;
+  if (n.up.conv_in_w) { cudaFree(n.up.conv_in_w); n.up.conv_in_w = nullptr; }
   for (int c = 0; c < lw.n_classes; ++c) if (lw.cls[c].w) { cudaFree((void*)lw.cls[c].w); lw.cls[c].w = nullptr; }
   if (lw.bias) { cudaFree(lw.bias); lw.bias = nullptr; }
   free_umma_weights(lw.umma);

@@ -41,6 +41,8 @@ struct ConvCall {
 };
 
 cudaError_t launch_conv_ffma(const ConvCall& c, cudaStream_t s, int64_t* launches);
+cudaError_t launch_conv_in_pm(const void* cubes, int dtype, const float* w_host, const float* bias_host, void* out_pm, int B,
+                              cudaStream_t s, int64_t* launches);
 cudaError_t launch_u8_to_f32(const void* in, int dtype, float* out, int64_t n, cudaStream_t s, int64_t* launches);
 
 // entropy.cu

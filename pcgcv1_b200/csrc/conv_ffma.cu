@@ -267,6 +267,78 @@ cudaError_t launch_conv_ffma(const ConvCall& c, cudaStream_t s, int64_t* launche
   }
 }
 
+// ---- conv_in of the voxception analysis transform (model_voxception.py:83-88): 1 -> 16 channels on the 64^3 occupancy grid
+// Reads the cube in its input dtype (uint8 / float32 / float64: no separate conversion pass), applies the 3x3x3 conv +
+// bias + ReLU in FP32 and writes the PM split-bf16 tensor the tcgen05 engine consumes.  CTA tile 4(z) x 8(y) x 64(x);
+// a thread owns two voxels (y and y+4) so every broadcast weight load feeds 8 FMAs; lanes run along x (conflict-free).
+// The 27x16 weights + bias travel as a by-value kernel parameter: they sit in the constant bank and every FFMA takes its
+// weight as a constant operand (no shared-memory weight loads; the first version was LDS.128-bound at 9 TFLOP/s).
+struct ConvInParams { float w[27 * 16]; float b[16]; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) conv_in_pm_kernel(const T* __restrict__ in, const __grid_constant__ ConvInParams prm,
+                                                         __nv_bfloat16* __restrict__ out) {
+  constexpr int N = 64, TZ = 4, TY = 8;
+  __shared__ float s_in[TZ + 2][TY + 2][N + 2];
+  const int tid = threadIdx.x;
+  int bid = blockIdx.x;
+  const int by = bid % (N / TY); bid /= (N / TY);
+  const int bz = bid % (N / TZ); bid /= (N / TZ);
+  const int b = bid;
+  const T* ib = in + (size_t)b * N * N * N;
+  for (int i = tid; i < (TZ + 2) * (TY + 2) * (N + 2); i += 256) {
+    const int x = i % (N + 2), y = (i / (N + 2)) % (TY + 2), z = i / ((N + 2) * (TY + 2));
+    const int gz = bz * TZ + z - 1, gy = by * TY + y - 1, gx = x - 1;
+    float v = 0.f;
+    if ((unsigned)gz < (unsigned)N && (unsigned)gy < (unsigned)N && (unsigned)gx < (unsigned)N) v = (float)ib[((size_t)gz * N + gy) * N + gx];
+    s_in[z][y][x] = v;
+  }
+  __syncthreads();
+  const int x = tid & 63, z = tid >> 6;
+  const size_t pe = (size_t)N * N * N * 8;
+  __nv_bfloat16* ob = out + (size_t)b * 4 * pe;
+#pragma unroll 1
+  for (int yy = 0; yy < 4; ++yy) {
+    float a0[16], a1[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { a0[c] = prm.b[c]; a1[c] = prm.b[c]; }
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+      const int kz = t / 9, ky = (t / 3) % 3, kx = t % 3;
+      const float v0 = s_in[z + kz][yy + ky][x + kx], v1 = s_in[z + kz][yy + 4 + ky][x + kx];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        a0[c] = fmaf(v0, prm.w[t * 16 + c], a0[c]);
+        a1[c] = fmaf(v1, prm.w[t * 16 + c], a1[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { a0[c] = fmaxf(a0[c], 0.f); a1[c] = fmaxf(a1[c], 0.f); }
+    const int gz = bz * TZ + z, gy0 = by * TY + yy, gy1 = gy0 + 4;
+    __nv_bfloat16* o0 = ob + (((size_t)gz * N + gy0) * N + x) * 8;
+    __nv_bfloat16* o1 = ob + (((size_t)gz * N + gy1) * N + x) * 8;
+    split_store(o0, o0 + pe, a0); split_store(o0 + 2 * pe, o0 + 3 * pe, a0 + 8);
+    split_store(o1, o1 + pe, a1); split_store(o1 + 2 * pe, o1 + 3 * pe, a1 + 8);
+  }
+}
+
+// w: HOST float [27][16] tap-major (the Keras [3,3,3,1,16] kernel as is), bias HOST [16] or null.
+cudaError_t launch_conv_in_pm(const void* cubes, int dtype, const float* w_host, const float* bias_host, void* out_pm, int B,
+                              cudaStream_t s, int64_t* launches) {
+  ConvInParams prm;
+  for (int i = 0; i < 27 * 16; ++i) prm.w[i] = w_host[i];
+  for (int i = 0; i < 16; ++i) prm.b[i] = bias_host ? bias_host[i] : 0.f;
+  const int grid = (64 / 8) * (64 / 4) * B;
+  if (launches) ++*launches;
+  switch (dtype) {
+    case PCGC_DTYPE_U8: conv_in_pm_kernel<uint8_t><<<grid, 256, 0, s>>>((const uint8_t*)cubes, prm, (__nv_bfloat16*)out_pm); break;
+    case PCGC_DTYPE_F32: conv_in_pm_kernel<float><<<grid, 256, 0, s>>>((const float*)cubes, prm, (__nv_bfloat16*)out_pm); break;
+    case PCGC_DTYPE_F64: conv_in_pm_kernel<double><<<grid, 256, 0, s>>>((const double*)cubes, prm, (__nv_bfloat16*)out_pm); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
 // ---- input conversion: occupancy cubes of any host dtype -> float32 ---------------------------
 template <typename T>
 __global__ void to_f32_kernel(const T* __restrict__ in, float* __restrict__ out, int64_t n) {
