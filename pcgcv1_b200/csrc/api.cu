@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <string>
@@ -691,6 +692,7 @@ int pcgc_create(pcgc_ctx** out, int device) {
     return PCGC_ERR_CUDA;
   }
   for (int k = 0; k < PCGC_NET_COUNT; ++k) build_net(ctx->nets[k], k);
+  if (const char* sb = getenv("PCGC_SUB_BATCH")) { const int v = atoi(sb); if (v >= 1 && v <= 512) ctx->sub_batch = v; }
   if (cudaMalloc((void**)&ctx->err_flag, sizeof(int)) != cudaSuccess ||
       cudaMemset(ctx->err_flag, 0, sizeof(int)) != cudaSuccess ||
       cudaMalloc((void**)&ctx->pmf_dev, 32 * 512 * sizeof(float)) != cudaSuccess) {

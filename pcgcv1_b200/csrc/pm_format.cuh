@@ -26,6 +26,14 @@ __device__ __forceinline__ void load_cell_sum(const __nv_bfloat16* hi_cell, cons
   for (int i = 0; i < 8; ++i) v[i] = __bfloat162float(h[i]) + __bfloat162float(l[i]);
 }
 
+// hi cell + lo cell already in registers -> 8 float32 values
+__device__ __forceinline__ void cell_sum(const uint4& a, const uint4& b, float* v) {
+  const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&a);
+  const __nv_bfloat16* l = reinterpret_cast<const __nv_bfloat16*>(&b);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __bfloat162float(h[i]) + __bfloat162float(l[i]);
+}
+
 // half a cell (4 channels)
 __device__ __forceinline__ void load_half_cell_sum(const __nv_bfloat16* hi4, const __nv_bfloat16* lo4, float* v) {
   const uint2 a = __ldg(reinterpret_cast<const uint2*>(hi4));

@@ -248,9 +248,22 @@ __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const __grid_co
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const size_t plane_elems = (size_t)a.n * a.n * a.n * 8;
     for (int zi = (warp >> 2); zi < ((a.dbg & 4) ? 0 : a.zt); zi += 2) {
+      const int vz = z0 + zi;
+      // VRN tail: the residual x does not depend on the MMAs -- fetch it BEFORE waiting for the accumulator so the HBM
+      // latency hides behind the tensor work (2*C/8 16-byte cells, C = 2*NP/3*... <= 64 channels)
+      constexpr int RC = EPI == UEPI_VRN ? (NP == 16 ? 2 : (NP == 32 ? 4 : 8)) : 1;      // cells (8 channels) of the residual
+      constexpr bool PREFETCH = EPI == UEPI_VRN && NP == 16;    // wider blocks: the extra live registers cost a CTA per SM (measured)
+      uint4 rhi[PREFETCH ? RC : 1], rlo[PREFETCH ? RC : 1];
+      if (PREFETCH) {
+        const __nv_bfloat16* rp = a.res_pm + (size_t)b * a.res_planes * plane_elems + (((size_t)vz * a.n + vy) * a.n + vx) * 8;
+#pragma unroll
+        for (int c8 = 0; c8 < RC; ++c8) {
+          rhi[c8] = __ldg(reinterpret_cast<const uint4*>(rp + (size_t)(2 * c8) * plane_elems));
+          rlo[c8] = __ldg(reinterpret_cast<const uint4*>(rp + (size_t)(2 * c8 + 1) * plane_elems));
+        }
+      }
       mbar_wait(bar_z + 8 * zi, 0, a.err, -103);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int vz = z0 + zi;
       if (EPI == UEPI_UP) {
         // stride-2 transposed conv: column block [cls*cout, (cls+1)*cout) is output voxel 2t + r(cls) (gather form, no atomics)
         const int on = 2 * a.n;
@@ -332,14 +345,16 @@ __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const __grid_co
         for (int c8 = 0; c8 < NP / 8; ++c8) {
           if (c8 * 8 < c2) {
             float x[8], t[8];
-            load_cell_sum(rb + (size_t)(2 * c8) * plane_elems, rb + (size_t)(2 * c8 + 1) * plane_elems, x);
+            if (PREFETCH) cell_sum(rhi[c8 < RC ? c8 : 0], rlo[c8 < RC ? c8 : 0], x);
+            else load_cell_sum(rb + (size_t)(2 * c8) * plane_elems, rb + (size_t)(2 * c8 + 1) * plane_elems, x);
 #pragma unroll
             for (int i = 0; i < 8; ++i) t[i] = fmaxf(x[i] + v[c8 * 8 + i], 0.f);
             split_store(ob + (size_t)(2 * c8) * ops, ob + (size_t)(2 * c8 + 1) * ops, t);
           }
         }
         // second half: t23 = relu(b23 + t22 . W23), relu(x + t23)
-        for (int j8 = 0; j8 < c2 / 8; ++j8) {
+#pragma unroll
+        for (int j8 = 0; j8 < RC / 2; ++j8) {
           float t23[8];
           const float4* bp = reinterpret_cast<const float4*>(s_w23 + c4 * c2 + j8 * 8);
           { const float4 b0v = bp[0], b1v = bp[1]; t23[0] = b0v.x; t23[1] = b0v.y; t23[2] = b0v.z; t23[3] = b0v.w; t23[4] = b1v.x; t23[5] = b1v.y; t23[6] = b1v.z; t23[7] = b1v.w; }
@@ -354,8 +369,9 @@ __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const __grid_co
             }
           }
           float x[8], t[8];
-          const int c8 = c2 / 8 + j8;
-          load_cell_sum(rb + (size_t)(2 * c8) * plane_elems, rb + (size_t)(2 * c8 + 1) * plane_elems, x);
+          const int c8 = RC / 2 + j8;
+          if (PREFETCH) cell_sum(rhi[PREFETCH ? c8 : 0], rlo[PREFETCH ? c8 : 0], x);
+          else load_cell_sum(rb + (size_t)(2 * c8) * plane_elems, rb + (size_t)(2 * c8 + 1) * plane_elems, x);
 #pragma unroll
           for (int i = 0; i < 8; ++i) t[i] = fmaxf(x[i] + fmaxf(t23[i], 0.f), 0.f);
           split_store(ob + (size_t)(2 * c8) * ops, ob + (size_t)(2 * c8 + 1) * ops, t);
