@@ -90,9 +90,10 @@ int pcgc_load_bottleneck(pcgc_ctx* ctx, int slot, int channels, const float* mat
 /* Test hook for the tcgen05 engine: one 3x3x3 stride-1 SAME conv (+bias, optional ReLU) of a float32 NDHWC
  * batch [B,n,n,n,cin] (cin in {8,16,32,64}, cout <= 64, n in {16,32,64}) with a HOST Keras kernel
  * [3,3,3,cin,cout]; converts to the engine's split-bf16 format, runs the UMMA kernel, writes float32
- * [B,n,n,n,cout].  Synchronises.  Compared against a plain FP32 conv in tests/test_gpu_umma.py. */
+ * [B,n,n,n,cout].  wt = 1 | 2 | 4 selects the y-banded form of the kernel (each M row produces wt output lines).
+ * Synchronises.  Compared against a plain FP32 conv in tests/test_gpu_umma.py. */
 int pcgc_debug_conv3_umma(pcgc_ctx* ctx, const float* in_dev, int n, int cin, int cout, const float* kernel_host,
-                          const float* bias_host, int relu, int B, float* out_dev);
+                          const float* bias_host, int relu, int B, int wt, float* out_dev);
 
 /* ---- transforms (dev pointers) --------------------------------------------------------------- */
 /* AnalysisTransform()(x), one call for B cubes instead of tf.map_fn(parallel_iterations=1)

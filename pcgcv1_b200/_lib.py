@@ -37,7 +37,7 @@ SIGNATURES = {
     "pcgc_profile_report": (_i, [_vp, C.c_char_p, _i64]),
     "pcgc_load_conv": (_i, [_vp, _i, C.c_char_p, _vp, C.POINTER(_i64), _vp]),
     "pcgc_load_bottleneck": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
-    "pcgc_debug_conv3_umma": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
+    "pcgc_debug_conv3_umma": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp]),
     "pcgc_analysis": (_i, [_vp, _i, _vp, _i, _i, _vp]),
     "pcgc_synthesis": (_i, [_vp, _i, _vp, _i, _vp]),
     "pcgc_hyper_encode": (_i, [_vp, _vp, _i, _vp]),

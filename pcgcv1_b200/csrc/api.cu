@@ -322,7 +322,11 @@ int build_umma_program(pcgc_ctx* ctx, int kind) {
       for (int ci = 0; ci < C; ++ci) for (int co = 0; co < c4; ++co)
         da[((size_t)13 * C + ci) * c2 + c4 + co] = l21.hk[(size_t)ci * c4 + co];       // 1x1x1 conv = centre tap
       for (int co = 0; co < c4; ++co) { ba[co] = l11.hb[co]; ba[c4 + co] = l21.hb[co]; }
-      cudaError_t e = pack_umma_weights_dense(da.data(), ba.data(), C, c2, up.ka[idx]);
+      // y-banded MMAs (umma_conv.cu) on the 64^3 and 32^3 grids: 9*(WT+2) A tiles per 128*WT outputs instead of 27*WT
+      static const int wt_env = getenv("PCGC_UMMA_WT") ? atoi(getenv("PCGC_UMMA_WT")) : 2;
+      const int nn = ana ? (64 >> s) : (16 << s);
+      const int wt = (nn >= 32 && wt_env >= 2) ? 2 : 1;
+      cudaError_t e = pack_umma_weights_dense(da.data(), ba.data(), C, c2, up.ka[idx], 27, wt);
       if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "pack K_a %s: %s", p.c_str(), cudaGetErrorString(e));
       // K_b: dense [27][c2][c2 + c4], block diagonal
       const int nb = c2 + c4;
@@ -334,7 +338,7 @@ int build_umma_program(pcgc_ctx* ctx, int kind) {
       for (int co = 0; co < c2; ++co) bb[co] = l12.hb[co];
       for (int co = 0; co < c4; ++co) bb[c2 + co] = l22.hb[co];
       UmmaWeights& kb = up.kb[idx];
-      e = pack_umma_weights_dense(db.data(), bb.data(), c2, nb, kb);
+      e = pack_umma_weights_dense(db.data(), bb.data(), c2, nb, kb, 27, wt);
       if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "pack K_b %s: %s", p.c_str(), cudaGetErrorString(e));
       CK(cudaMalloc((void**)&kb.w23, (size_t)c4 * c2 * sizeof(float)));
       CK(cudaMemcpy(kb.w23, l23.hk.data(), (size_t)c4 * c2 * sizeof(float), cudaMemcpyHostToDevice));
@@ -368,7 +372,7 @@ int build_umma_program(pcgc_ctx* ctx, int kind) {
   } else {
     LayerW &li = L("deconv_in"), &lo = L("deconv_out");
     cudaError_t e = pack_umma_weights_dense(li.hk.data(), li.hb.data(), 16, 64, up.first);
-    if (e == cudaSuccess) e = pack_umma_weights_dense(lo.hk.data(), lo.hb.data(), 16, 1, up.last);
+    if (e == cudaSuccess) e = pack_umma_weights_dense(lo.hk.data(), lo.hb.data(), 16, 1, up.last, 27, (getenv("PCGC_UMMA_WT") && atoi(getenv("PCGC_UMMA_WT")) < 2) ? 1 : 4);
     if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "pack deconv_in/out: %s", cudaGetErrorString(e));
     // Conv3DTranspose(k3, s2, same): out[2t] = x[t] W[0] + x[t-1] W[2], out[2t+1] = x[t] W[1] per axis.  One GEMM over the
     // 2x2x2 input window {t-1,t}^3 (brick index 0/1) whose column blocks are the 8 output-parity classes.
@@ -907,11 +911,11 @@ int pcgc_load_bottleneck(pcgc_ctx* ctx, int slot, int channels, const float* mat
 }
 
 int pcgc_debug_conv3_umma(pcgc_ctx* ctx, const float* in_dev, int n, int cin, int cout, const float* kernel_host,
-                          const float* bias_host, int relu, int B, float* out_dev) {
+                          const float* bias_host, int relu, int B, int wt, float* out_dev) {
   if (!ctx || !in_dev || !kernel_host || !out_dev || B < 1) return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_debug_conv3_umma: bad argument");
   DeviceGuard g(ctx->device);
   UmmaWeights w;
-  cudaError_t e = pack_umma_weights_dense(kernel_host, bias_host, cin, cout, w);
+  cudaError_t e = pack_umma_weights_dense(kernel_host, bias_host, cin, cout, w, 27, wt < 1 ? 1 : wt);
   if (e != cudaSuccess) return fail(ctx, PCGC_ERR_BAD_ARG, "pack_umma_weights_dense: %s", cudaGetErrorString(e));
   PmTensor t; t.n = n; t.c = cin; t.B = B;
   CK(cudaMalloc((void**)&t.p, t.cube_elems() * B * sizeof(__nv_bfloat16)));

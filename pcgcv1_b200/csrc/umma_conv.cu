@@ -137,29 +137,38 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 
 enum TapMode : int { TAPS_27 = 0, TAPS_27_PAIRED = 1, TAPS_8 = 2 };
 
-// Issues every MMA of one z-slice for one 16-channel chunk.  Fully unrolled: tap offsets are compile-time
+// Brick y extent.  WT > 1 is the Y-BANDED form: M row (g, x) stands for WT consecutive output lines y = WT*g + j, the
+// output columns are (j, channel) and the A tiles are indexed by the input line offset d in [0, WT+2) instead of ky
+// (weights W[kz][d - j][kx], zero outside the band).  The same brick then needs 9*(WT+2) A tiles for 128*WT outputs
+// instead of 27*WT -- and the kernels are bound by exactly that: every MMA waits for its 4 KiB A tile from shared
+// memory (ncu r01: sm__pipe_tc_cycles_active 95 %, tensor math 27 %).
+__host__ __device__ constexpr int brick_ey(int wt) { return 16 * wt + 2; }
+
+// Issues every MMA of one z-slice for one 16-channel chunk.  Fully unrolled: tile offsets are compile-time
 // constants, so each MMA costs two 64-bit adds on the descriptors -- the single issuing thread must not be the
 // bottleneck (the first version recomputed descriptors with integer divisions and ran at ~125 cycles per MMA).
-template <int NP, int TAPS>
+template <int NP, int TAPS, int WT>
 __device__ __forceinline__ void issue_slice(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t bdesc, bool first, uint32_t mask) {
   constexpr uint32_t idesc_full = make_idesc(128, 2 * NP), idesc_half = make_idesc(128, NP);
-  constexpr bool CIN8 = TAPS == TAPS_27_PAIRED;
-  constexpr int NM = TAPS == TAPS_27 ? 27 : (TAPS == TAPS_27_PAIRED ? 14 : 8);
+  constexpr int EY = brick_ey(WT);
+  constexpr int NT = 9 * (WT + 2);                               // A tiles (kz, d, kx) of the 3x3x3 modes
+  constexpr int NM = TAPS == TAPS_27 ? NT : (TAPS == TAPS_27_PAIRED ? (NT + 1) / 2 : 8);
   constexpr uint64_t b_step = (uint64_t)((2 * NP * 32) >> 4);
+  auto tile_off = [](int t) { return ((((t / (3 * (WT + 2))) * EY + (t / 3) % (WT + 2)) * EXC + t % 3) * CELL); };
 #pragma unroll
   for (int m = 0; m < NM; ++m) {
     uint64_t add;
     if (TAPS == TAPS_27) {
-      const int kz = m / 9, ky = (m / 3) % 3, kx = m % 3;
-      add = (uint64_t)((((kz * EYC + ky) * EXC + kx) * CELL) >> 4);
+      add = (uint64_t)(tile_off(m) >> 4);
     } else if (TAPS == TAPS_8) {
       const int kz = m >> 2, ky = (m >> 1) & 1, kx = m & 1;      // brick index 0 = input t-1, 1 = input t
-      add = (uint64_t)((((kz * EYC + ky) * EXC + kx) * CELL) >> 4);
+      add = (uint64_t)((((kz * EY + ky) * EXC + kx) * CELL) >> 4);
     } else {
-      const int ta = m == 0 ? 0 : 2 * m - 1, tb = m == 0 ? 1 : 2 * m;
-      const int oa = (((ta / 9) * EYC + (ta / 3) % 3) * EXC + ta % 3) * CELL;
-      const int ob = (((tb / 9) * EYC + (tb / 3) % 3) * EXC + tb % 3) * CELL;
-      add = (uint64_t)(oa >> 4) | ((uint64_t)((ob - oa) >> 4) << 16);      // start offset | LBO (second tap)
+      // Cin == 8: K = 16 spans two tiles (LBO = their address difference).  Odd tile count: tile 0 goes alone
+      // (its partner carries zero weights).
+      const int ta = (NT & 1) ? (m == 0 ? 0 : 2 * m - 1) : 2 * m, tb = (NT & 1) ? (m == 0 ? 1 : 2 * m) : 2 * m + 1;
+      const int oa = tile_off(ta), ob = tile_off(tb);
+      add = (uint64_t)(oa >> 4) | ((uint64_t)((ob - oa) >> 4) << 16);      // start offset | LBO (second tile)
     }
     if (TAPS == TAPS_8 && !((mask >> m) & 1u) && !(first && m == 0)) continue;   // all-zero weight tile (the first MMA still initialises D)
     const uint64_t bd = bdesc + (uint64_t)m * b_step;
@@ -172,7 +181,96 @@ constexpr int EPI_WARPS = 8;                       // warps 0..7: epilogue; warp
 constexpr int UMMA_THREADS = 32 * (EPI_WARPS + 1);
 constexpr int MAX_ZT = 8;
 
-template <int NP, int EPI, int TAPS>
+// Epilogue of ONE output voxel whose NPJ accumulator columns (+bias) are in v[].
+template <int NPJ, int EPI>
+__device__ __forceinline__ void epilogue_voxel(const UmmaArgs& a, float* v, const float* s_w23, int b, int vz, int vy, int vx,
+                                               size_t plane_elems) {
+  const size_t vox = ((size_t)vz * a.n + vy) * a.n + vx;
+  if (EPI == UEPI_F32) {
+    const size_t gv = (size_t)b * a.n * a.n * a.n + vox;
+    float* op = a.out_f32 + gv * a.out_cs + a.out_co;
+    float* op2 = a.out2_f32 ? a.out2_f32 + gv * (a.n_real - a.split) : nullptr;
+#pragma unroll
+    for (int i = 0; i < NPJ; ++i) {
+      if (i < a.n_real) {
+        float t = v[i];
+        const int fl = i < a.split ? a.flags : a.flags2;
+        if (fl & EPI_RELU) t = fmaxf(t, 0.f);
+        if (fl & EPI_ABS) t = fabsf(t);
+        if (fl & EPI_FLOOR) t = fmaxf(t, a.floor_v);
+        if (i < a.split) op[i] = t; else op2[i - a.split] = t;
+      }
+    }
+  } else if (EPI == UEPI_PM) {
+    __nv_bfloat16* ob = a.out_pm + (size_t)b * a.out_planes * plane_elems + vox * 8;
+#pragma unroll
+    for (int c8 = 0; c8 < NPJ / 8; ++c8) {
+      if (c8 * 8 < a.n_real) {
+        float t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = (a.flags & EPI_RELU) ? fmaxf(v[c8 * 8 + i], 0.f) : v[c8 * 8 + i];
+        split_store(ob + (size_t)(2 * c8) * plane_elems, ob + (size_t)(2 * c8 + 1) * plane_elems, t);
+      }
+    }
+  } else if (EPI == UEPI_VRN) {
+    // Voxception tail.  columns [0,c2) = conv1_2, [c2,c2+c4) = conv2_2 (both ReLU'd), then conv2_3 (1x1x1),
+    // concat, residual add and ReLU (model_voxception.py:62-67).
+    constexpr int RC = NPJ == 16 ? 2 : (NPJ == 24 || NPJ == 32 ? 4 : 8);       // residual cells (8 channels each)
+    const int c2 = a.c2, c4 = a.c4;
+    const __nv_bfloat16* rb = a.res_pm + (size_t)b * a.res_planes * plane_elems + vox * 8;
+    // normal: plane stride = n^3 cells.  space-to-depth: voxel (z,y,x) channel c -> voxel (z/2,y/2,x/2) of the n/2 grid,
+    // channel p*C + c with p = parity(z,y,x); the tensor then has 8x the planes of 1/8 the size.
+    size_t ops = plane_elems;                         // elements between consecutive output planes
+    __nv_bfloat16* ob = a.out_pm + (size_t)b * a.out_planes * plane_elems + vox * 8;
+    if (a.out_s2d) {
+      const int h = a.n >> 1;
+      ops = plane_elems >> 3;
+      const int par = ((vz & 1) << 2) | ((vy & 1) << 1) | (vx & 1);
+      ob = a.out_pm + ((size_t)b * a.out_planes * 8 + (size_t)par * a.out_planes) * ops + ((((size_t)(vz >> 1) * h + (vy >> 1)) * h + (vx >> 1)) * 8);
+    }
+    // all residual cells first (independent loads in flight together), then the math, then the stores
+    uint4 rhi[RC], rlo[RC];
+#pragma unroll
+    for (int c8 = 0; c8 < RC; ++c8) {
+      rhi[c8] = __ldg(reinterpret_cast<const uint4*>(rb + (size_t)(2 * c8) * plane_elems));
+      rlo[c8] = __ldg(reinterpret_cast<const uint4*>(rb + (size_t)(2 * c8 + 1) * plane_elems));
+    }
+#pragma unroll
+    for (int i = 0; i < NPJ; ++i) v[i] = fmaxf(v[i], 0.f);
+#pragma unroll
+    for (int c8 = 0; c8 < RC / 2; ++c8) {            // first half of the output channels: relu(x + t12)
+      float x[8], t[8];
+      cell_sum(rhi[c8], rlo[c8], x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t[i] = fmaxf(x[i] + v[c8 * 8 + i], 0.f);
+      split_store(ob + (size_t)(2 * c8) * ops, ob + (size_t)(2 * c8 + 1) * ops, t);
+    }
+#pragma unroll
+    for (int j8 = 0; j8 < RC / 2; ++j8) {            // second half: t23 = relu(b23 + t22 . W23), relu(x + t23)
+      float t23[8];
+      const float4* bp = reinterpret_cast<const float4*>(s_w23 + c4 * c2 + j8 * 8);
+      { const float4 b0v = bp[0], b1v = bp[1]; t23[0] = b0v.x; t23[1] = b0v.y; t23[2] = b0v.z; t23[3] = b0v.w; t23[4] = b1v.x; t23[5] = b1v.y; t23[6] = b1v.z; t23[7] = b1v.w; }
+#pragma unroll
+      for (int q = RC * 4; q < NPJ; ++q) {           // q in [c2, c2 + c4): c2 = RC*4 channels
+        if (q < c2 + c4) {
+          const float tq = v[q];
+          const float4* wr = reinterpret_cast<const float4*>(s_w23 + (q - c2) * c2 + j8 * 8);
+          const float4 w0 = wr[0], w1 = wr[1];
+          t23[0] = fmaf(tq, w0.x, t23[0]); t23[1] = fmaf(tq, w0.y, t23[1]); t23[2] = fmaf(tq, w0.z, t23[2]); t23[3] = fmaf(tq, w0.w, t23[3]);
+          t23[4] = fmaf(tq, w1.x, t23[4]); t23[5] = fmaf(tq, w1.y, t23[5]); t23[6] = fmaf(tq, w1.z, t23[6]); t23[7] = fmaf(tq, w1.w, t23[7]);
+        }
+      }
+      float x[8], t[8];
+      const int c8 = RC / 2 + j8;
+      cell_sum(rhi[c8], rlo[c8], x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t[i] = fmaxf(x[i] + fmaxf(t23[i], 0.f), 0.f);
+      split_store(ob + (size_t)(2 * c8) * ops, ob + (size_t)(2 * c8 + 1) * ops, t);
+    }
+  }
+}
+
+template <int NP, int EPI, int TAPS, int WT>
 __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const UmmaArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* s_a = smem;
@@ -184,15 +282,17 @@ __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const __grid_co
   const uint32_t bar_full = smem_u32(s_bar), bar_mma = smem_u32(s_bar + 1), bar_z = smem_u32(s_bar + 2);
 
   constexpr bool CIN8 = TAPS == TAPS_27_PAIRED;
+  constexpr int EY = brick_ey(WT);
+  constexpr int NPJ = NP / WT;                       // accumulator columns per output line j
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // tile coordinates
-  const int tx_n = a.n / TILE_X, ty_n = a.n / TILE_Y, tz_n = a.n / a.zt;
+  const int tx_n = a.n / TILE_X, ty_n = a.n / (TILE_Y * WT), tz_n = a.n / a.zt;
   int bid = blockIdx.x;
   const int bx = bid % tx_n; bid /= tx_n;
   const int by = bid % ty_n; bid /= ty_n;
   const int bz = bid % tz_n; bid /= tz_n;
   const int b = bid;
-  const int x0 = bx * TILE_X, y0 = by * TILE_Y, z0 = bz * a.zt;
+  const int x0 = bx * TILE_X, y0 = by * TILE_Y * WT, z0 = bz * a.zt;
 
   for (int i = tid; i < NP; i += UMMA_THREADS) s_bias[i] = a.bias ? a.bias[i] : 0.f;
   if (EPI == UEPI_VRN) for (int i = tid; i < a.c4 * a.c2 + a.c2; i += UMMA_THREADS) s_w23[i] = i < a.c4 * a.c2 ? a.w23[i] : a.b23[i - a.c4 * a.c2];
@@ -216,10 +316,11 @@ __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const __grid_co
       const uint32_t brick = smem_u32(s_a), bsm = smem_u32(s_b);
       const uint32_t PL = (uint32_t)a.plane_bytes;
       const uint32_t b_lbo = 2 * NP * 16;
-      const uint64_t z_step = (uint64_t)((EYC * EXC * CELL) >> 4);
-      // cin >= 16: K halves are the two 8-channel planes (LBO = 2 planes); cin == 8: LBO is set per tap pair
-      const uint64_t a_hi0 = make_desc(brick, CIN8 ? 0u : 2 * PL, EXC * CELL);
-      const uint64_t a_lo0 = make_desc(brick + PL, CIN8 ? 0u : 2 * PL, EXC * CELL);
+      const uint64_t z_step = (uint64_t)((EY * EXC * CELL) >> 4);
+      // cin >= 16: K halves are the two 8-channel planes (LBO = 2 planes); cin == 8: LBO is set per tile pair.
+      // SBO steps the 16 row groups: WT brick lines apart.
+      const uint64_t a_hi0 = make_desc(brick, CIN8 ? 0u : 2 * PL, WT * EXC * CELL);
+      const uint64_t a_lo0 = make_desc(brick + PL, CIN8 ? 0u : 2 * PL, WT * EXC * CELL);
       const uint64_t b0 = make_desc(bsm, b_lbo, 128);
       bool alive = true;
       for (int ch = 0; ch < a.kchunks && alive; ++ch) {
@@ -231,7 +332,7 @@ __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const __grid_co
         const bool last = ch + 1 == a.kchunks;
         for (int zi = 0; zi < a.zt; ++zi) {
           if (!(a.dbg & 1))
-            issue_slice<NP, TAPS>(tmem_base + (uint32_t)(zi * 2 * NP), a_hi0 + zi * z_step, a_lo0 + zi * z_step, b0, ch == 0, a.tap_mask[ch & 15]);
+            issue_slice<NP, TAPS, WT>(tmem_base + (uint32_t)(zi * 2 * NP), a_hi0 + zi * z_step, a_lo0 + zi * z_step, b0, ch == 0, a.tap_mask[ch & 15]);
           if (last) umma_commit(bar_z + 8 * zi);      // slice zi is final: its epilogue overlaps the MMAs of the next slices
         }
         if (!last) {
@@ -243,25 +344,12 @@ __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const __grid_co
     __syncwarp();
   } else {
     // ------------------------------ epilogue: 8 warps; warp w reads TMEM lanes 32*(w&3).., z-slices of parity w>>2 ------------------------------
-    const int row = (warp & 3) * 32 + lane;          // M row = TMEM lane = voxel of the 8x16 tile
-    const int vx = x0 + (row & 7), vy = y0 + (row >> 3);
+    const int row = (warp & 3) * 32 + lane;          // M row = TMEM lane = (y group, x) of the tile
+    const int vx = x0 + (row & 7), vyb = y0 + WT * (row >> 3);
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const size_t plane_elems = (size_t)a.n * a.n * a.n * 8;
     for (int zi = (warp >> 2); zi < ((a.dbg & 4) ? 0 : a.zt); zi += 2) {
       const int vz = z0 + zi;
-      // VRN tail: the residual x does not depend on the MMAs -- fetch it BEFORE waiting for the accumulator so the HBM
-      // latency hides behind the tensor work (2*C/8 16-byte cells, C = 2*NP/3*... <= 64 channels)
-      constexpr int RC = EPI == UEPI_VRN ? (NP == 16 ? 2 : (NP == 32 ? 4 : 8)) : 1;      // cells (8 channels) of the residual
-      constexpr bool PREFETCH = EPI == UEPI_VRN && NP == 16;    // wider blocks: the extra live registers cost a CTA per SM (measured)
-      uint4 rhi[PREFETCH ? RC : 1], rlo[PREFETCH ? RC : 1];
-      if (PREFETCH) {
-        const __nv_bfloat16* rp = a.res_pm + (size_t)b * a.res_planes * plane_elems + (((size_t)vz * a.n + vy) * a.n + vx) * 8;
-#pragma unroll
-        for (int c8 = 0; c8 < RC; ++c8) {
-          rhi[c8] = __ldg(reinterpret_cast<const uint4*>(rp + (size_t)(2 * c8) * plane_elems));
-          rlo[c8] = __ldg(reinterpret_cast<const uint4*>(rp + (size_t)(2 * c8 + 1) * plane_elems));
-        }
-      }
       mbar_wait(bar_z + 8 * zi, 0, a.err, -103);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (EPI == UEPI_UP) {
@@ -272,7 +360,7 @@ __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const __grid_co
 #pragma unroll 1
         for (int cls = 0; cls < a.up_ncls; ++cls) {
           const int gc = a.up_cls0 + cls;
-          const int oz = 2 * vz + ((gc >> 2) & 1), oy = 2 * vy + ((gc >> 1) & 1), ox = 2 * vx + (gc & 1);
+          const int oz = 2 * vz + ((gc >> 2) & 1), oy = 2 * vyb + ((gc >> 1) & 1), ox = 2 * vx + (gc & 1);
           __nv_bfloat16* oc = ob + (((size_t)oz * on + oy) * on + ox) * 8;
           for (int j = 0; j < a.up_cout / 16; ++j) {
             const int col = cls * a.up_cout + j * 16;
@@ -296,87 +384,9 @@ __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const __grid_co
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[j * 16 + i] = (d1[i] + d2[i]) + s_bias[j * 16 + i];
       }
-      const size_t vox = ((size_t)vz * a.n + vy) * a.n + vx;
-      if (EPI == UEPI_F32) {
-        const size_t gv = (size_t)b * a.n * a.n * a.n + vox;
-        float* op = a.out_f32 + gv * a.out_cs + a.out_co;
-        float* op2 = a.out2_f32 ? a.out2_f32 + gv * (a.n_real - a.split) : nullptr;
 #pragma unroll
-        for (int i = 0; i < NP; ++i) {
-          if (i < a.n_real) {
-            float t = v[i];
-            const int fl = i < a.split ? a.flags : a.flags2;
-            if (fl & EPI_RELU) t = fmaxf(t, 0.f);
-            if (fl & EPI_ABS) t = fabsf(t);
-            if (fl & EPI_FLOOR) t = fmaxf(t, a.floor_v);
-            if (i < a.split) op[i] = t; else op2[i - a.split] = t;
-          }
-        }
-      } else if (EPI == UEPI_PM) {
-        __nv_bfloat16* ob = a.out_pm + (size_t)b * a.out_planes * plane_elems + vox * 8;
-#pragma unroll
-        for (int c8 = 0; c8 < NP / 8; ++c8) {
-          if (c8 * 8 < a.n_real) {
-            float t[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) t[i] = (a.flags & EPI_RELU) ? fmaxf(v[c8 * 8 + i], 0.f) : v[c8 * 8 + i];
-            split_store(ob + (size_t)(2 * c8) * plane_elems, ob + (size_t)(2 * c8 + 1) * plane_elems, t);
-          }
-        }
-      } else {
-        // Voxception tail.  columns [0,c2) = conv1_2, [c2,c2+c4) = conv2_2 (both ReLU'd), then conv2_3 (1x1x1),
-        // concat, residual add and ReLU (model_voxception.py:62-67).
-        const int c2 = a.c2, c4 = a.c4;
-        const __nv_bfloat16* rb = a.res_pm + (size_t)b * a.res_planes * plane_elems + vox * 8;
-        // normal: plane stride = n^3 cells.  space-to-depth: voxel (z,y,x) channel c -> voxel (z/2,y/2,x/2) of the n/2 grid,
-        // channel p*C + c with p = parity(z,y,x); the tensor then has 8x the planes of 1/8 the size.
-        size_t ops = plane_elems;                         // elements between consecutive output planes
-        __nv_bfloat16* ob = a.out_pm + (size_t)b * a.out_planes * plane_elems + vox * 8;
-        if (a.out_s2d) {
-          const int h = a.n >> 1;
-          ops = plane_elems >> 3;
-          const int par = ((vz & 1) << 2) | ((vy & 1) << 1) | (vx & 1);
-          ob = a.out_pm + ((size_t)b * a.out_planes * 8 + (size_t)par * a.out_planes) * ops + ((((size_t)(vz >> 1) * h + (vy >> 1)) * h + (vx >> 1)) * 8);
-        }
-#pragma unroll
-        for (int i = 0; i < NP; ++i) v[i] = fmaxf(v[i], 0.f);
-        // first half of the output channels: relu(x + t12)
-#pragma unroll
-        for (int c8 = 0; c8 < NP / 8; ++c8) {
-          if (c8 * 8 < c2) {
-            float x[8], t[8];
-            if (PREFETCH) cell_sum(rhi[c8 < RC ? c8 : 0], rlo[c8 < RC ? c8 : 0], x);
-            else load_cell_sum(rb + (size_t)(2 * c8) * plane_elems, rb + (size_t)(2 * c8 + 1) * plane_elems, x);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) t[i] = fmaxf(x[i] + v[c8 * 8 + i], 0.f);
-            split_store(ob + (size_t)(2 * c8) * ops, ob + (size_t)(2 * c8 + 1) * ops, t);
-          }
-        }
-        // second half: t23 = relu(b23 + t22 . W23), relu(x + t23)
-#pragma unroll
-        for (int j8 = 0; j8 < RC / 2; ++j8) {
-          float t23[8];
-          const float4* bp = reinterpret_cast<const float4*>(s_w23 + c4 * c2 + j8 * 8);
-          { const float4 b0v = bp[0], b1v = bp[1]; t23[0] = b0v.x; t23[1] = b0v.y; t23[2] = b0v.z; t23[3] = b0v.w; t23[4] = b1v.x; t23[5] = b1v.y; t23[6] = b1v.z; t23[7] = b1v.w; }
-#pragma unroll
-          for (int q = 0; q < NP; ++q) {
-            if (q >= c2 && q < c2 + c4) {
-              const float tq = v[q];
-              const float4* wr = reinterpret_cast<const float4*>(s_w23 + (q - c2) * c2 + j8 * 8);
-              const float4 w0 = wr[0], w1 = wr[1];
-              t23[0] = fmaf(tq, w0.x, t23[0]); t23[1] = fmaf(tq, w0.y, t23[1]); t23[2] = fmaf(tq, w0.z, t23[2]); t23[3] = fmaf(tq, w0.w, t23[3]);
-              t23[4] = fmaf(tq, w1.x, t23[4]); t23[5] = fmaf(tq, w1.y, t23[5]); t23[6] = fmaf(tq, w1.z, t23[6]); t23[7] = fmaf(tq, w1.w, t23[7]);
-            }
-          }
-          float x[8], t[8];
-          const int c8 = RC / 2 + j8;
-          if (PREFETCH) cell_sum(rhi[PREFETCH ? c8 : 0], rlo[PREFETCH ? c8 : 0], x);
-          else load_cell_sum(rb + (size_t)(2 * c8) * plane_elems, rb + (size_t)(2 * c8 + 1) * plane_elems, x);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) t[i] = fmaxf(x[i] + fmaxf(t23[i], 0.f), 0.f);
-          split_store(ob + (size_t)(2 * c8) * ops, ob + (size_t)(2 * c8 + 1) * ops, t);
-        }
-      }
+      for (int j = 0; j < WT; ++j)
+        epilogue_voxel<NPJ, (EPI == UEPI_UP ? UEPI_F32 : EPI)>(a, v + (EPI == UEPI_UP ? 0 : j * NPJ), s_w23, b, vz, vyb + j, vx, plane_elems);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -404,27 +414,27 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-cudaError_t make_tmap(const PmTensor& t, int ez, int ppc, CUtensorMap* out) {
+cudaError_t make_tmap(const PmTensor& t, int ey, int ez, int ppc, CUtensorMap* out) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return cudaErrorNotSupported;
   const cuuint64_t n = (cuuint64_t)t.n, planes = (cuuint64_t)(2 * t.c / 8);
   cuuint64_t gdim[5] = {n * 8, n, n, planes, (cuuint64_t)t.B};
   cuuint64_t gstride[4] = {n * 16, n * n * 16, n * n * n * 16, planes * n * n * n * 16};
-  cuuint32_t box[5] = {(cuuint32_t)(EXC * 8), (cuuint32_t)EYC, (cuuint32_t)ez, (cuuint32_t)ppc, 1};
+  cuuint32_t box[5] = {(cuuint32_t)(EXC * 8), (cuuint32_t)ey, (cuuint32_t)ez, (cuuint32_t)ppc, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)t.p, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-int pick_zt(int n, int np, int cin, int epi) {
+int pick_zt(int n, int np, int cin, int epi, int wt, int n_mma) {
   // zt accumulators of 2*np columns must fit 512 TMEM columns (256 so two CTAs can share an SM) and the
   // brick + weights should leave room for two CTAs per SM where possible.
   int zt = 8;
   while (zt > 1 && (zt * 2 * np > 256 || zt > n)) zt /= 2;
   const int ppc = cin == 8 ? 2 : 4;
-  const int nm = np == 128 ? 8 : (cin == 8 ? 14 : 27);
-  auto smem = [&](int z) { return ppc * (z + 2) * EYC * EXC * CELL + nm * 2 * np * 32; };
+  const int nm = n_mma;
+  auto smem = [&](int z) { return ppc * (z + 2) * brick_ey(wt) * EXC * CELL + nm * 2 * np * 32; };
   while (zt > 1 && smem(zt) > 100 * 1024) zt /= 2;
   // MMA-bound kernels (light epilogue) overlap load / MMA / epilogue better with three CTAs per SM (measured on B200:
   // K_a16 0.676 -> 0.582 ms); the VRN-tail kernels are epilogue/HBM bound and prefer deep z tiles (less halo re-read).
@@ -434,79 +444,109 @@ int pick_zt(int n, int np, int cin, int epi) {
   return zt;
 }
 
-template <int NP, int E, int TAPS>
+template <int NP, int E, int TAPS, int WT>
 cudaError_t launch_one(const CUtensorMap& tm, const UmmaArgs& a, int grid, size_t smem, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<NP, E, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<NP, E, TAPS, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  conv_umma_kernel<NP, E, TAPS><<<grid, UMMA_THREADS, smem, s>>>(tm, a);
+  conv_umma_kernel<NP, E, TAPS, WT><<<grid, UMMA_THREADS, smem, s>>>(tm, a);
   return cudaGetLastError();
 }
 
 template <int NP, int TAPS>
 cudaError_t launch_np(const CUtensorMap& tm, const UmmaArgs& a, int epi, int grid, size_t smem, cudaStream_t s) {
-  if (epi == UEPI_F32) return launch_one<NP, UEPI_F32, TAPS>(tm, a, grid, smem, s);
-  if (epi == UEPI_PM) return launch_one<NP, UEPI_PM, TAPS>(tm, a, grid, smem, s);
-  if (epi == UEPI_VRN) return launch_one<NP, UEPI_VRN, TAPS>(tm, a, grid, smem, s);
+  if (epi == UEPI_F32) return launch_one<NP, UEPI_F32, TAPS, 1>(tm, a, grid, smem, s);
+  if (epi == UEPI_PM) return launch_one<NP, UEPI_PM, TAPS, 1>(tm, a, grid, smem, s);
+  if (epi == UEPI_VRN) return launch_one<NP, UEPI_VRN, TAPS, 1>(tm, a, grid, smem, s);
+  return cudaErrorNotSupported;
+}
+
+// y-banded instantiations (only the shapes the layer programs use + their float32 test forms)
+cudaError_t launch_banded(const CUtensorMap& tm, const UmmaArgs& a, int np, int epi, bool paired, int wt, int grid, size_t smem, cudaStream_t s) {
+  if (wt == 2 && !paired) {
+    if (np == 16 && epi == UEPI_PM) return launch_one<16, UEPI_PM, TAPS_27, 2>(tm, a, grid, smem, s);        // K_a16
+    if (np == 16 && epi == UEPI_F32) return launch_one<16, UEPI_F32, TAPS_27, 2>(tm, a, grid, smem, s);
+    if (np == 32 && epi == UEPI_PM) return launch_one<32, UEPI_PM, TAPS_27, 2>(tm, a, grid, smem, s);        // K_a32
+    if (np == 32 && epi == UEPI_F32) return launch_one<32, UEPI_F32, TAPS_27, 2>(tm, a, grid, smem, s);
+    if (np == 48 && epi == UEPI_VRN) return launch_one<48, UEPI_VRN, TAPS_27, 2>(tm, a, grid, smem, s);      // K_b32
+    if (np == 48 && epi == UEPI_F32) return launch_one<48, UEPI_F32, TAPS_27, 2>(tm, a, grid, smem, s);
+  }
+  if (wt == 2 && paired) {
+    if (np == 32 && epi == UEPI_VRN) return launch_one<32, UEPI_VRN, TAPS_27_PAIRED, 2>(tm, a, grid, smem, s);   // K_b16
+    if (np == 32 && epi == UEPI_F32) return launch_one<32, UEPI_F32, TAPS_27_PAIRED, 2>(tm, a, grid, smem, s);
+  }
+  if (wt == 4 && !paired && np == 16 && epi == UEPI_F32) return launch_one<16, UEPI_F32, TAPS_27, 4>(tm, a, grid, smem, s);   // deconv_out
   return cudaErrorNotSupported;
 }
 
 }  // namespace
 
-cudaError_t pack_umma_weights_dense(const float* dense, const float* bias, int cin, int n_real, UmmaWeights& out, int ntaps) {
+cudaError_t pack_umma_weights_dense(const float* dense, const float* bias, int cin, int n_real, UmmaWeights& out, int ntaps, int wt) {
   free_umma_weights(out);
   if (!(cin == 8 || cin == 16 || cin == 32 || cin == 64 || cin == 128 || cin == 256) || n_real < 1 || n_real > 128) return cudaErrorNotSupported;
   if (!(ntaps == 27 || (ntaps == 8 && cin >= 16))) return cudaErrorNotSupported;
-  const int np = (n_real + 15) / 16 * 16;
+  if (!(wt == 1 || ((wt == 2 || wt == 4) && ntaps == 27))) return cudaErrorNotSupported;
+  // columns: n = j * npj + co  (j = output line within the band, co < n_real <= npj); np = wt * npj is a multiple of 16
+  const int unit = 16 / wt;
+  const int npj = (n_real + unit - 1) / unit * unit;
+  const int np = wt * npj;
+  if (np > 128) return cudaErrorNotSupported;
   const int kchunks = cin == 8 ? 1 : cin / 16;
-  const int n_mma = ntaps == 8 ? 8 : (cin == 8 ? 14 : 27);
+  const int nt = ntaps == 8 ? 8 : 9 * (wt + 2);                 // A tiles per chunk: (kz, d, kx), d = input line offset
+  const int n_mma = (ntaps == 27 && cin == 8) ? (nt + 1) / 2 : nt;
   const size_t tile = (size_t)2 * np * 16;                    // bf16 elements per B tile
   std::vector<__nv_bfloat16> p((size_t)kchunks * n_mma * tile, __float2bfloat16(0.f));
+  std::vector<uint8_t> nz((size_t)kchunks * n_mma, 0);
   auto put = [&](size_t tile_idx, int n, int k, float w) {
+    if (w == 0.f) return;
     const __nv_bfloat16 hi = __float2bfloat16_rn(w);
     const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
     auto at = [&](int row) { return tile_idx * tile + (size_t)(k / 8) * (2 * np * 8) + (size_t)(row / 8) * 64 + (row % 8) * 8 + (k % 8); };
     p[at(n)] = hi;
     p[at(np + n)] = lo;
+    nz[tile_idx] = 1;
+  };
+  // value of A tile t, input channel ci -> column (j, co)
+  auto weight = [&](int t, int ci, int j, int co) -> float {
+    if (ntaps == 8) return j == 0 ? dense[((size_t)t * cin + ci) * n_real + co] : 0.f;
+    const int kz = t / (3 * (wt + 2)), d = (t / 3) % (wt + 2), kx = t % 3, ky = d - j;
+    if (ky < 0 || ky > 2) return 0.f;
+    return dense[((size_t)((kz * 3 + ky) * 3 + kx) * cin + ci) * n_real + co];
   };
   for (int ch = 0; ch < kchunks; ++ch)
     for (int m = 0; m < n_mma; ++m)
       for (int k = 0; k < 16; ++k) {
-        int tap, ci;
-        if (cin == 8) {
-          const int ta = m == 0 ? 0 : 2 * m - 1, tb = m == 0 ? -1 : 2 * m;
-          tap = k < 8 ? ta : tb; ci = k % 8;
-        } else { tap = m; ci = ch * 16 + k; }
-        if (tap < 0) continue;
-        for (int n = 0; n < n_real; ++n) put((size_t)ch * n_mma + m, n, k, dense[((size_t)tap * cin + ci) * n_real + n]);
+        int t, ci;
+        if (ntaps == 27 && cin == 8) {
+          const int ta = (nt & 1) ? (m == 0 ? 0 : 2 * m - 1) : 2 * m, tb = (nt & 1) ? (m == 0 ? -1 : 2 * m) : 2 * m + 1;
+          t = k < 8 ? ta : tb; ci = k % 8;
+        } else { t = m; ci = ch * 16 + k; }
+        if (t < 0) continue;
+        for (int j = 0; j < wt; ++j)
+          for (int co = 0; co < n_real; ++co) put((size_t)ch * n_mma + m, j * npj + co, k, weight(t, ci, j, co));
       }
   cudaError_t e = cudaMalloc(&out.packed, p.size() * sizeof(__nv_bfloat16));
   if (e != cudaSuccess) return e;
   e = cudaMemcpy(out.packed, p.data(), p.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return e;
   std::vector<float> bz(np, 0.f);
-  if (bias) for (int i = 0; i < n_real; ++i) bz[i] = bias[i];
+  if (bias) for (int j = 0; j < wt; ++j) for (int i = 0; i < n_real; ++i) bz[j * npj + i] = bias[i];
   e = cudaMalloc((void**)&out.bias, np * sizeof(float));
   if (e != cudaSuccess) return e;
   e = cudaMemcpy(out.bias, bz.data(), np * sizeof(float), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return e;
   for (int ch = 0; ch < 16; ++ch) {
     uint32_t mask = 0;
-    if (ch < kchunks)
-      for (int m = 0; m < n_mma && ntaps == 8; ++m) {
-        bool nz = false;
-        for (int k = 0; k < 16 && !nz; ++k)
-          for (int n = 0; n < n_real && !nz; ++n) nz = dense[((size_t)m * cin + ch * 16 + k) * n_real + n] != 0.f;
-        if (nz) mask |= 1u << m;
-      }
+    if (ch < kchunks && ntaps == 8)
+      for (int m = 0; m < n_mma; ++m) if (nz[(size_t)ch * n_mma + m]) mask |= 1u << m;
     out.tap_mask[ch] = ntaps == 8 ? mask : 0xFFFFFFFFu;
   }
-  out.cin = cin; out.n_real = n_real; out.np = np; out.n_mma = n_mma; out.kchunks = kchunks; out.ntaps = ntaps; out.ok = true;
+  out.cin = cin; out.n_real = n_real; out.np = np; out.npj = npj; out.wt = wt; out.n_mma = n_mma; out.kchunks = kchunks; out.ntaps = ntaps; out.ok = true;
   return cudaSuccess;
 }
 
 cudaError_t pack_umma_weights(const float* kernel, int cin, int cout, UmmaWeights& out) {
   // Keras [3,3,3,Cin,Cout] is already tap-major dense [27][cin][cout]
-  return pack_umma_weights_dense(kernel, nullptr, cin, cout, out, 27);
+  return pack_umma_weights_dense(kernel, nullptr, cin, cout, out, 27, 1);
 }
 
 void free_umma_weights(UmmaWeights& w) {
@@ -518,12 +558,12 @@ void free_umma_weights(UmmaWeights& w) {
 }
 
 cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStream_t s, int64_t* launches) {
-  if (!w.ok || c.in.c != w.cin || c.in.n % TILE_Y != 0) return cudaErrorNotSupported;
+  if (!w.ok || c.in.c != w.cin || c.in.n % (TILE_Y * w.wt) != 0) return cudaErrorNotSupported;
   const int n = c.in.n;
   UmmaArgs a;
-  a.n = n; a.zt = pick_zt(n, w.np, w.cin, c.epi); a.ez = a.zt + 2;
+  a.n = n; a.zt = pick_zt(n, w.np, w.cin, c.epi, w.wt, w.n_mma); a.ez = a.zt + 2;
   a.cin8 = w.cin == 8; a.kchunks = w.kchunks; a.ppc = a.cin8 ? 2 : 4; a.n_mma = w.n_mma;
-  a.plane_bytes = a.ez * EYC * EXC * CELL;
+  a.plane_bytes = a.ez * brick_ey(w.wt) * EXC * CELL;
   a.a_bytes = a.ppc * a.plane_bytes;
   a.b_bytes = w.n_mma * 2 * w.np * 32;
   int cols = 32;
@@ -542,23 +582,24 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
   a.err = c.err;
   { static const int dbg = getenv("PCGC_UMMA_DBG") ? atoi(getenv("PCGC_UMMA_DBG")) : 0; a.dbg = dbg; }
   if (c.epi == UEPI_VRN && (!w.w23 || w.c2 + w.c4 != w.n_real || c.res.c != 2 * w.c2 || c.out.c != (c.out_s2d ? 16 : 2) * w.c2)) return cudaErrorInvalidValue;
-  if (c.epi == UEPI_PM && (w.n_real % 8 != 0 || c.out.c != w.n_real)) return cudaErrorInvalidValue;
+  if (c.epi == UEPI_PM && (w.n_real % 8 != 0 || c.out.c != w.n_real || w.npj % 8 != 0)) return cudaErrorInvalidValue;
   if (c.epi == UEPI_UP && (w.up_ncls * w.up_cout != w.n_real || w.up_cout % 16 != 0 || c.out.c != w.up_cout || c.out.n != 2 * n)) return cudaErrorInvalidValue;
   CUtensorMap tm;
-  cudaError_t e = make_tmap(c.in, a.ez, a.ppc, &tm);
+  cudaError_t e = make_tmap(c.in, brick_ey(w.wt), a.ez, a.ppc, &tm);
   if (e != cudaSuccess) return e;
   const int vrn_floats = c.epi == UEPI_VRN ? w.c4 * w.c2 + w.c2 : 0;
   const size_t smem = (size_t)a.a_bytes + a.b_bytes + (4 + MAX_ZT) * 8 + (w.np + vrn_floats) * sizeof(float) + 16;
-  const int grid = (n / TILE_X) * (n / TILE_Y) * (n / a.zt) * c.in.B;
+  const int grid = (n / TILE_X) * (n / (TILE_Y * w.wt)) * (n / a.zt) * c.in.B;
   if (launches) ++*launches;
+  if (w.wt > 1) return launch_banded(tm, a, w.np, c.epi, a.cin8 != 0, w.wt, grid, smem, s);
   if (c.epi == UEPI_UP) {
     if (w.ntaps != 8 || w.np != 128) return cudaErrorNotSupported;
-    return launch_one<128, UEPI_UP, TAPS_8>(tm, a, grid, smem, s);
+    return launch_one<128, UEPI_UP, TAPS_8, 1>(tm, a, grid, smem, s);
   }
   if (w.ntaps == 8) {                                   // stride-2 conv on a space-to-depth input
     if (c.epi != UEPI_PM) return cudaErrorNotSupported;
-    if (w.np == 32) return launch_one<32, UEPI_PM, TAPS_8>(tm, a, grid, smem, s);
-    if (w.np == 64) return launch_one<64, UEPI_PM, TAPS_8>(tm, a, grid, smem, s);
+    if (w.np == 32) return launch_one<32, UEPI_PM, TAPS_8, 1>(tm, a, grid, smem, s);
+    if (w.np == 64) return launch_one<64, UEPI_PM, TAPS_8, 1>(tm, a, grid, smem, s);
     return cudaErrorNotSupported;
   }
   if (w.ntaps != 27) return cudaErrorNotSupported;

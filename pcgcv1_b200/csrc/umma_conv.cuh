@@ -28,7 +28,9 @@ struct UmmaWeights {
   bool ok = false;
   int cin = 0;              // K per tap as the kernel sees it (8, 16, 32, 64)
   int n_real = 0;           // real output columns
-  int np = 0;               // n_real padded to a multiple of 16
+  int np = 0;               // accumulator columns per pass: wt * npj, a multiple of 16
+  int wt = 1;               // y-band width: each M row produces wt consecutive output lines (columns (j, channel))
+  int npj = 0;              // columns per output line (n_real padded so that wt*npj % 16 == 0)
   int n_mma = 0;            // MMA pairs per z-slice per 16-channel chunk (27, 14 for cin == 8, 8 for transposed conv)
   int ntaps = 27;           // 27 (3x3x3) or 8 ({t-1,t}^3 window of a stride-2 transposed conv)
   int up_ncls = 0, up_cls0 = 0, up_cout = 0;   // UEPI_UP column layout
@@ -42,7 +44,7 @@ struct UmmaWeights {
 };
 
 // dense: HOST float32 [27][cin][n_real] (tap-major, any zero structure already applied), bias [n_real] or null.
-cudaError_t pack_umma_weights_dense(const float* dense, const float* bias, int cin, int n_real, UmmaWeights& out, int ntaps = 27);
+cudaError_t pack_umma_weights_dense(const float* dense, const float* bias, int cin, int n_real, UmmaWeights& out, int ntaps = 27, int wt = 1);
 // Compatibility shim used by pcgc_load_conv (single plain layer, Keras [3,3,3,Cin,Cout]).
 cudaError_t pack_umma_weights(const float* kernel, int cin, int cout, UmmaWeights& out);
 void free_umma_weights(UmmaWeights& w);

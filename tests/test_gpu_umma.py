@@ -11,12 +11,14 @@ import torch
 pytestmark = pytest.mark.gpu
 
 # (grid n, Cin, Cout): every distinct stride-1 3x3x3 shape the engine serves (fused VRN shapes included)
-SHAPES = [(64, 16, 8), (64, 8, 12), (64, 16, 1), (32, 32, 16), (32, 16, 24), (16, 64, 32), (16, 32, 48), (16, 64, 16),
-          (16, 16, 64), (16, 16, 16)]
+# (grid n, Cin, Cout, WT): WT > 1 = the y-banded form (each M row produces WT output lines)
+SHAPES = [(64, 16, 8, 1), (64, 8, 12, 1), (64, 16, 1, 1), (32, 32, 16, 1), (32, 16, 24, 1), (16, 64, 32, 1), (16, 32, 48, 1), (16, 64, 16, 1),
+          (16, 16, 64, 1), (16, 16, 16, 1),
+          (64, 16, 8, 2), (64, 8, 12, 2), (64, 16, 1, 4), (32, 32, 16, 2), (32, 16, 24, 2)]
 
 
-@pytest.mark.parametrize("n,cin,cout", SHAPES)
-def test_umma_conv_vs_torch_fp32(codec, n, cin, cout):
+@pytest.mark.parametrize("n,cin,cout,wt", SHAPES)
+def test_umma_conv_vs_torch_fp32(codec, n, cin, cout, wt):
     g = torch.Generator(device="cpu").manual_seed(n * 1000 + cin * 10 + cout)
     B = 2
     x = torch.randn(B, n, n, n, cin, generator=g).relu_()            # post-ReLU like real activations
@@ -27,17 +29,17 @@ def test_umma_conv_vs_torch_fp32(codec, n, cin, cout):
     out = torch.empty(B, n, n, n, cout, device=codec.dev)
     wh, bh = np.ascontiguousarray(w.numpy()), np.ascontiguousarray(b.numpy())
     codec._stream()
-    rc = codec.lib.pcgc_debug_conv3_umma(codec.ctx, xd.data_ptr(), n, cin, cout, wh.ctypes.data, bh.ctypes.data, 1, B, out.data_ptr())
+    rc = codec.lib.pcgc_debug_conv3_umma(codec.ctx, xd.data_ptr(), n, cin, cout, wh.ctypes.data, bh.ctypes.data, 1, B, wt, out.data_ptr())
     codec._check(rc)
     ref = torch.nn.functional.conv3d(xd.permute(0, 4, 1, 2, 3).double(), w.to(codec.dev).permute(4, 3, 0, 1, 2).double(),
                                      b.to(codec.dev).double(), padding=1).relu_().permute(0, 2, 3, 4, 1)
     err = (out.double() - ref).abs().max().item()
     scale = ref.abs().max().item()
-    print("n=%d cin=%d cout=%d: max abs err %.3g (scale %.3g, rel %.2g)" % (n, cin, cout, err, scale, err / scale))
+    print("n=%d cin=%d cout=%d wt=%d: max abs err %.3g (scale %.3g, rel %.2g)" % (n, cin, cout, wt, err, scale, err / scale))
     assert err <= 3e-5 * scale
     # deterministic
     out2 = torch.empty_like(out)
-    codec._check(codec.lib.pcgc_debug_conv3_umma(codec.ctx, xd.data_ptr(), n, cin, cout, wh.ctypes.data, bh.ctypes.data, 1, B, out2.data_ptr()))
+    codec._check(codec.lib.pcgc_debug_conv3_umma(codec.ctx, xd.data_ptr(), n, cin, cout, wh.ctypes.data, bh.ctypes.data, 1, B, wt, out2.data_ptr()))
     assert torch.equal(out, out2)
 
 
