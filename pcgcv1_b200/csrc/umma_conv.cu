@@ -24,6 +24,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -58,6 +59,8 @@ struct UmmaArgs {
   const __nv_bfloat16* res_pm; int res_planes;
   const float* w23; const float* b23; int c4, c2;
   int* err;
+  int nsets;                 // TMEM accumulator sets (2: ping-pong between tiles, 1 when the columns do not allow it)
+  int batch;                 // cubes in this launch (tiles = per-cube tiles * batch; the grid is persistent)
   int origin;                // brick origin relative to the tile: -1 (SAME 3x3x3, transposed) or 0 (stride-2 conv on a space-to-depth input)
   uint32_t tap_mask[16];     // per 16-channel chunk: taps with non-zero weights (others are skipped)
   int out_s2d;               // UEPI_VRN: write the output space-to-depth (grid n/2, 8*C channels) for a following stride-2 conv
@@ -75,7 +78,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 // Bounded wait: a descriptor / byte-count bug must not hang the GPU.  Returns false on timeout.
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
-  for (uint32_t it = 0; it < (1u << 24); ++it) {
+  for (uint32_t it = 0; it < (1u << 21); ++it) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -270,35 +273,40 @@ __device__ __forceinline__ void epilogue_voxel(const UmmaArgs& a, float* v, cons
   }
 }
 
+// PERSISTENT kernel: a CTA allocates TMEM, initialises its mbarriers, stages bias / 1x1x1 weights and (single-chunk
+// layers) the B tiles ONCE, then walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The r01 timing experiments showed
+// that per-CTA set-up + the 27 KB weight reload was ~40 % of the non-persistent kernel (0.23 of 0.58 ms for K_a16).
+// Two TMEM accumulator sets alternate between tiles, so the MMAs of tile i+1 overlap the epilogue of tile i; the A brick
+// is single-buffered (its TMA is issued as soon as the previous tile's MMAs retire) and 2-3 co-resident CTAs per SM cover
+// each other's load latency.
+//   barriers: full (TMA landed), mma (all MMAs of the tile/chunk retired: brick reusable), z[set][slice] (accumulator
+//   slice final), tmem_free[set] (8 epilogue warps done with the set).
+// min-blocks: the unrolled issue loop otherwise inflates the register count (88 vs 55) and costs the third CTA per SM
 template <int NP, int EPI, int TAPS, int WT>
-__global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const UmmaArgs a) {
+__global__ void __launch_bounds__(UMMA_THREADS, (NP <= 16 ? 3 : (NP <= 32 ? 2 : 1))) conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const UmmaArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* s_a = smem;
   uint8_t* s_b = smem + a.a_bytes;
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_b + a.b_bytes);          // full, mma, z-slice[8] mbarriers
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 + MAX_ZT);
-  float* s_bias = reinterpret_cast<float*>(s_bar + 4 + MAX_ZT);            // 96 bytes in: 16-byte aligned (float4 reads)
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_b + a.b_bytes);          // full, mma, tmem_free[2], z[2][8]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 4 + 2 * MAX_ZT);
+  float* s_bias = reinterpret_cast<float*>(s_bar + 6 + 2 * MAX_ZT);        // 16-byte aligned (float4 reads)
   float* s_w23 = s_bias + NP;                                              // [c4][c2] then b23[c2] (UEPI_VRN only)
-  const uint32_t bar_full = smem_u32(s_bar), bar_mma = smem_u32(s_bar + 1), bar_z = smem_u32(s_bar + 2);
+  const uint32_t bar_full = smem_u32(s_bar), bar_mma = smem_u32(s_bar + 1), bar_free = smem_u32(s_bar + 2), bar_z = smem_u32(s_bar + 4);
 
   constexpr bool CIN8 = TAPS == TAPS_27_PAIRED;
   constexpr int EY = brick_ey(WT);
   constexpr int NPJ = NP / WT;                       // accumulator columns per output line j
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // tile coordinates
   const int tx_n = a.n / TILE_X, ty_n = a.n / (TILE_Y * WT), tz_n = a.n / a.zt;
-  int bid = blockIdx.x;
-  const int bx = bid % tx_n; bid /= tx_n;
-  const int by = bid % ty_n; bid /= ty_n;
-  const int bz = bid % tz_n; bid /= tz_n;
-  const int b = bid;
-  const int x0 = bx * TILE_X, y0 = by * TILE_Y * WT, z0 = bz * a.zt;
+  const int total_tiles = tx_n * ty_n * tz_n * a.batch;
+  const uint32_t set_cols = (uint32_t)(a.zt * 2 * NP);
 
   for (int i = tid; i < NP; i += UMMA_THREADS) s_bias[i] = a.bias ? a.bias[i] : 0.f;
   if (EPI == UEPI_VRN) for (int i = tid; i < a.c4 * a.c2 + a.c2; i += UMMA_THREADS) s_w23[i] = i < a.c4 * a.c2 ? a.w23[i] : a.b23[i - a.c4 * a.c2];
   if (tid == 0) {
     mbar_init(bar_full, 1); mbar_init(bar_mma, 1);
-    for (int i = 0; i < MAX_ZT; ++i) mbar_init(bar_z + 8 * i, 1);
+    mbar_init(bar_free, EPI_WARPS); mbar_init(bar_free + 8, EPI_WARPS);
+    for (int i = 0; i < 2 * MAX_ZT; ++i) mbar_init(bar_z + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == EPI_WARPS) {
@@ -322,22 +330,38 @@ __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const __grid_co
       const uint64_t a_hi0 = make_desc(brick, CIN8 ? 0u : 2 * PL, WT * EXC * CELL);
       const uint64_t a_lo0 = make_desc(brick + PL, CIN8 ? 0u : 2 * PL, WT * EXC * CELL);
       const uint64_t b0 = make_desc(bsm, b_lbo, 128);
+      const bool b_resident = a.kchunks == 1;          // weights loaded once per CTA
       bool alive = true;
-      for (int ch = 0; ch < a.kchunks && alive; ++ch) {
-        mbar_expect_tx(bar_full, (uint32_t)(((a.dbg & 2) ? 0 : a.a_bytes) + a.b_bytes));
-        if (!(a.dbg & 2)) tma_load_5d(brick, &tmap, bar_full, (x0 + a.origin) * 8, y0 + a.origin, z0 + a.origin, ch * a.ppc, b);
-        bulk_load(bsm, reinterpret_cast<const uint8_t*>(a.wpacked) + (size_t)ch * a.b_bytes, (uint32_t)a.b_bytes, bar_full);
-        alive = mbar_wait(bar_full, ch & 1, a.err, -101);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const bool last = ch + 1 == a.kchunks;
-        for (int zi = 0; zi < a.zt; ++zi) {
-          if (!(a.dbg & 1))
-            issue_slice<NP, TAPS, WT>(tmem_base + (uint32_t)(zi * 2 * NP), a_hi0 + zi * z_step, a_lo0 + zi * z_step, b0, ch == 0, a.tap_mask[ch & 15]);
-          if (last) umma_commit(bar_z + 8 * zi);      // slice zi is final: its epilogue overlaps the MMAs of the next slices
-        }
-        if (!last) {
-          umma_commit(bar_mma);                       // shared memory may be refilled once these MMAs retire
-          alive = mbar_wait(bar_mma, ch & 1, a.err, -102);
+      uint32_t n_full = 0, n_mma = 0;                  // completed phases of bar_full / bar_mma
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles && alive; tile += gridDim.x, ++it) {
+        int r = tile;
+        const int bx = r % tx_n; r /= tx_n;
+        const int by = r % ty_n; r /= ty_n;
+        const int bz = r % tz_n; r /= tz_n;
+        const int b = r;
+        const int x0 = bx * TILE_X, y0 = by * TILE_Y * WT, z0 = bz * a.zt;
+        const int set = it % a.nsets, use = it / a.nsets;          // use-th time this accumulator set is filled
+        for (int ch = 0; ch < a.kchunks && alive; ++ch) {
+          const bool load_b = !b_resident || it == 0;
+          if (it > 0 || ch > 0) { alive = mbar_wait(bar_mma, (n_mma - 1) & 1, a.err, -102); if (!alive) break; }   // brick (and B) free
+          mbar_expect_tx(bar_full, (uint32_t)(((a.dbg & 2) ? 0 : a.a_bytes) + (load_b ? a.b_bytes : 0)));
+          if (!(a.dbg & 2)) tma_load_5d(brick, &tmap, bar_full, (x0 + a.origin) * 8, y0 + a.origin, z0 + a.origin, ch * a.ppc, b);
+          if (load_b) bulk_load(bsm, reinterpret_cast<const uint8_t*>(a.wpacked) + (size_t)ch * a.b_bytes, (uint32_t)a.b_bytes, bar_full);
+          if (ch == 0 && use >= 1) { alive = mbar_wait(bar_free + 8 * set, (use - 1) & 1, a.err, -104); if (!alive) break; }   // epilogue of the set's previous tile done
+          alive = mbar_wait(bar_full, n_full & 1, a.err, -101);
+          ++n_full;
+          if (!alive) break;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const bool last = ch + 1 == a.kchunks;
+          for (int zi = 0; zi < a.zt; ++zi) {
+            if (!(a.dbg & 1))
+              issue_slice<NP, TAPS, WT>(tmem_base + set * set_cols + (uint32_t)(zi * 2 * NP), a_hi0 + zi * z_step, a_lo0 + zi * z_step, b0, ch == 0,
+                                        a.tap_mask[ch & 15]);
+            if (last) umma_commit(bar_z + 8 * (set * MAX_ZT + zi));      // slice final: its epilogue overlaps the following MMAs
+          }
+          umma_commit(bar_mma);                       // brick reusable once these MMAs retire
+          ++n_mma;
         }
       }
     }
@@ -345,48 +369,65 @@ __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const __grid_co
   } else {
     // ------------------------------ epilogue: 8 warps; warp w reads TMEM lanes 32*(w&3).., z-slices of parity w>>2 ------------------------------
     const int row = (warp & 3) * 32 + lane;          // M row = TMEM lane = (y group, x) of the tile
-    const int vx = x0 + (row & 7), vyb = y0 + WT * (row >> 3);
-    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const size_t plane_elems = (size_t)a.n * a.n * a.n * 8;
-    for (int zi = (warp >> 2); zi < ((a.dbg & 4) ? 0 : a.zt); zi += 2) {
-      const int vz = z0 + zi;
-      mbar_wait(bar_z + 8 * zi, 0, a.err, -103);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (EPI == UEPI_UP) {
-        // stride-2 transposed conv: column block [cls*cout, (cls+1)*cout) is output voxel 2t + r(cls) (gather form, no atomics)
-        const int on = 2 * a.n;
-        const size_t out_plane = (size_t)on * on * on * 8;
-        __nv_bfloat16* ob = a.out_pm + (size_t)b * a.out_planes * out_plane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      int r = tile;
+      const int bx = r % tx_n; r /= tx_n;
+      const int by = r % ty_n; r /= ty_n;
+      const int bz = r % tz_n; r /= tz_n;
+      const int b = r;
+      const int x0 = bx * TILE_X, y0 = by * TILE_Y * WT, z0 = bz * a.zt;
+      const int set = it % a.nsets, use = it / a.nsets;
+      const int vx = x0 + (row & 7), vyb = y0 + WT * (row >> 3);
+      const uint32_t lane_base = tmem_base + set * set_cols + ((uint32_t)((warp & 3) * 32) << 16);
+      for (int zi = (warp >> 2); zi < ((a.dbg & 4) ? 0 : a.zt); zi += 2) {
+        const int vz = z0 + zi;
+        if (!mbar_wait(bar_z + 8 * (set * MAX_ZT + zi), use & 1, a.err, -103)) break;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (EPI == UEPI_UP) {
+          // stride-2 transposed conv: column block [cls*cout, (cls+1)*cout) is output voxel 2t + r(cls) (gather form, no atomics)
+          const int on = 2 * a.n;
+          const size_t out_plane = (size_t)on * on * on * 8;
+          __nv_bfloat16* ob = a.out_pm + (size_t)b * a.out_planes * out_plane;
 #pragma unroll 1
-        for (int cls = 0; cls < a.up_ncls; ++cls) {
-          const int gc = a.up_cls0 + cls;
-          const int oz = 2 * vz + ((gc >> 2) & 1), oy = 2 * vyb + ((gc >> 1) & 1), ox = 2 * vx + (gc & 1);
-          __nv_bfloat16* oc = ob + (((size_t)oz * on + oy) * on + ox) * 8;
-          for (int j = 0; j < a.up_cout / 16; ++j) {
-            const int col = cls * a.up_cout + j * 16;
-            float d1[16], d2[16], t[16];
-            tmem_ld16(lane_base + (uint32_t)(zi * 2 * NP + col), d1);
-            tmem_ld16(lane_base + (uint32_t)(zi * 2 * NP + NP + col), d2);
+          for (int cls = 0; cls < a.up_ncls; ++cls) {
+            const int gc = a.up_cls0 + cls;
+            const int oz = 2 * vz + ((gc >> 2) & 1), oy = 2 * vyb + ((gc >> 1) & 1), ox = 2 * vx + (gc & 1);
+            __nv_bfloat16* oc = ob + (((size_t)oz * on + oy) * on + ox) * 8;
+            for (int j = 0; j < a.up_cout / 16; ++j) {
+              const int col = cls * a.up_cout + j * 16;
+              float d1[16], d2[16], t[16];
+              tmem_ld16(lane_base + (uint32_t)(zi * 2 * NP + col), d1);
+              tmem_ld16(lane_base + (uint32_t)(zi * 2 * NP + NP + col), d2);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) t[i] = fmaxf((d1[i] + d2[i]) + s_bias[col + i], 0.f);
-            split_store(oc + (size_t)(4 * j) * out_plane, oc + (size_t)(4 * j + 1) * out_plane, t);
-            split_store(oc + (size_t)(4 * j + 2) * out_plane, oc + (size_t)(4 * j + 3) * out_plane, t + 8);
+              for (int i = 0; i < 16; ++i) t[i] = fmaxf((d1[i] + d2[i]) + s_bias[col + i], 0.f);
+              split_store(oc + (size_t)(4 * j) * out_plane, oc + (size_t)(4 * j + 1) * out_plane, t);
+              split_store(oc + (size_t)(4 * j + 2) * out_plane, oc + (size_t)(4 * j + 3) * out_plane, t + 8);
+            }
           }
+          continue;
         }
-        continue;
+        float v[EPI == UEPI_UP ? 16 : NP];
+#pragma unroll
+        for (int j = 0; j < (EPI == UEPI_UP ? 0 : NP / 16); ++j) {
+          float d1[16], d2[16];
+          tmem_ld16(lane_base + (uint32_t)(zi * 2 * NP + j * 16), d1);
+          tmem_ld16(lane_base + (uint32_t)(zi * 2 * NP + NP + j * 16), d2);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[j * 16 + i] = (d1[i] + d2[i]) + s_bias[j * 16 + i];
+        }
+#pragma unroll
+        for (int j = 0; j < WT; ++j)
+          epilogue_voxel<NPJ, (EPI == UEPI_UP ? UEPI_F32 : EPI)>(a, v + (EPI == UEPI_UP ? 0 : j * NPJ), s_w23, b, vz, vyb + j, vx, plane_elems);
       }
-      float v[EPI == UEPI_UP ? 16 : NP];
-#pragma unroll
-      for (int j = 0; j < (EPI == UEPI_UP ? 0 : NP / 16); ++j) {
-        float d1[16], d2[16];
-        tmem_ld16(lane_base + (uint32_t)(zi * 2 * NP + j * 16), d1);
-        tmem_ld16(lane_base + (uint32_t)(zi * 2 * NP + NP + j * 16), d2);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[j * 16 + i] = (d1[i] + d2[i]) + s_bias[j * 16 + i];
-      }
-#pragma unroll
-      for (int j = 0; j < WT; ++j)
-        epilogue_voxel<NPJ, (EPI == UEPI_UP ? UEPI_F32 : EPI)>(a, v + (EPI == UEPI_UP ? 0 : j * NPJ), s_w23, b, vz, vyb + j, vx, plane_elems);
+      // A warp without a slice of its own (zt == 1: warps 4..7) must not run ahead of the MMAs: its arrival for a LATER use
+      // of the set would otherwise complete the current phase early.  Pace it on the tile's last slice.
+      if ((warp >> 2) >= a.zt) mbar_wait(bar_z + 8 * (set * MAX_ZT + a.zt - 1), use & 1, a.err, -105);
+      // this warp is done reading the accumulator set of tile `it`: hand it back to the MMA issuer
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_free + 8 * set) : "memory");
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -427,18 +468,20 @@ cudaError_t make_tmap(const PmTensor& t, int ey, int ez, int ppc, CUtensorMap* o
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-int pick_zt(int n, int np, int cin, int epi, int wt, int n_mma) {
+int pick_zt(int n, int np, int cin, int epi, int wt, int n_mma, int kchunks) {
   // zt accumulators of 2*np columns must fit 512 TMEM columns (256 so two CTAs can share an SM) and the
   // brick + weights should leave room for two CTAs per SM where possible.
   int zt = 8;
-  while (zt > 1 && (zt * 2 * np > 256 || zt > n)) zt /= 2;
+  while (zt > 1 && (zt * 2 * np > 256 || zt > n)) zt /= 2;          // one accumulator set within 256 TMEM columns
   const int ppc = cin == 8 ? 2 : 4;
   const int nm = n_mma;
   auto smem = [&](int z) { return ppc * (z + 2) * brick_ey(wt) * EXC * CELL + nm * 2 * np * 32; };
   while (zt > 1 && smem(zt) > 100 * 1024) zt /= 2;
   // MMA-bound kernels (light epilogue) overlap load / MMA / epilogue better with three CTAs per SM (measured on B200:
   // K_a16 0.676 -> 0.582 ms); the VRN-tail kernels are epilogue/HBM bound and prefer deep z tiles (less halo re-read).
-  if (epi != UEPI_VRN) while (zt > 2 && smem(zt) > 75 * 1024) zt /= 2;
+  static const int three = getenv("PCGC_UMMA_3CTA") ? atoi(getenv("PCGC_UMMA_3CTA")) : 1;          // tuning experiments
+  // (multi-chunk kernels re-load a brick per chunk and are L2-bound on the halo: they keep the deeper z tile)
+  if (epi != UEPI_VRN && three && kchunks == 1) while (zt > 2 && smem(zt) > 75 * 1024) zt /= 2;
   static const int force = getenv("PCGC_UMMA_ZT") ? atoi(getenv("PCGC_UMMA_ZT")) : 0;      // tuning experiments
   if (force > 0 && force < zt) zt = force;
   return zt;
@@ -561,14 +604,11 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
   if (!w.ok || c.in.c != w.cin || c.in.n % (TILE_Y * w.wt) != 0) return cudaErrorNotSupported;
   const int n = c.in.n;
   UmmaArgs a;
-  a.n = n; a.zt = pick_zt(n, w.np, w.cin, c.epi, w.wt, w.n_mma); a.ez = a.zt + 2;
+  a.n = n; a.zt = pick_zt(n, w.np, w.cin, c.epi, w.wt, w.n_mma, w.kchunks); a.ez = a.zt + 2;
   a.cin8 = w.cin == 8; a.kchunks = w.kchunks; a.ppc = a.cin8 ? 2 : 4; a.n_mma = w.n_mma;
   a.plane_bytes = a.ez * brick_ey(w.wt) * EXC * CELL;
   a.a_bytes = a.ppc * a.plane_bytes;
   a.b_bytes = w.n_mma * 2 * w.np * 32;
-  int cols = 32;
-  while (cols < a.zt * 2 * w.np) cols *= 2;
-  a.tmem_cols = cols;
   a.wpacked = (const __nv_bfloat16*)w.packed; a.bias = w.bias;
   a.n_real = w.n_real; a.flags = c.flags; a.floor_v = c.floor_v;
   a.out_f32 = c.out_f32; a.out_cs = c.out_cs; a.out_co = c.out_co;
@@ -588,8 +628,20 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
   cudaError_t e = make_tmap(c.in, brick_ey(w.wt), a.ez, a.ppc, &tm);
   if (e != cudaSuccess) return e;
   const int vrn_floats = c.epi == UEPI_VRN ? w.c4 * w.c2 + w.c2 : 0;
-  const size_t smem = (size_t)a.a_bytes + a.b_bytes + (4 + MAX_ZT) * 8 + (w.np + vrn_floats) * sizeof(float) + 16;
-  const int grid = (n / TILE_X) * (n / (TILE_Y * w.wt)) * (n / a.zt) * c.in.B;
+  const size_t smem = (size_t)a.a_bytes + a.b_bytes + (6 + 2 * MAX_ZT) * 8 + (w.np + vrn_floats) * sizeof(float) + 16;
+  const int tiles = (n / TILE_X) * (n / (TILE_Y * w.wt)) * (n / a.zt) * c.in.B;
+  a.batch = c.in.B;
+  // persistent grid: as many CTAs as fit (shared memory / TMEM columns), each walks tiles with stride gridDim.x.
+  // Two accumulator sets (MMAs of tile i+1 overlap the epilogue of tile i) when the 512 TMEM columns allow it.
+  int per_sm = std::max(1, std::min((int)(227 * 1024 / (smem + 1024)), 3));
+  auto pow2 = [](int v) { int c = 32; while (c < v) c *= 2; return c; };
+  a.nsets = pow2(2 * a.zt * 2 * w.np) * per_sm <= 512 ? 2 : 1;
+  const int cols = pow2(a.nsets * a.zt * 2 * w.np);
+  a.tmem_cols = cols;
+  per_sm = std::max(1, std::min(per_sm, 512 / cols));
+  static const int sms = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
+  static const int persist = getenv("PCGC_UMMA_PERSIST") ? atoi(getenv("PCGC_UMMA_PERSIST")) : 1;  // 0: one tile per CTA
+  const int grid = persist ? std::min(tiles, sms * per_sm) : tiles;
   if (launches) ++*launches;
   if (w.wt > 1) return launch_banded(tm, a, w.np, c.epi, a.cin8 != 0, w.wt, grid, smem, s);
   if (c.epi == UEPI_UP) {

@@ -1,3 +1,4 @@
 #!/bin/bash
-timeout 600 python -m pytest tests/test_gpu_umma.py -m gpu -q 2>&1 | tail -3
-timeout 300 python tools/bench_conv.py 64 2>&1 | tail -14
+timeout 120 python -m pytest tests/test_gpu_umma.py -m gpu -q -x 2>&1 | tail -4
+timeout 60 python tools/bench_conv.py 64 2>&1 | tail -14
+PCGC_UMMA_WT=2 timeout 60 python tools/bench_conv.py 64 2>&1 | tail -14 | head -7
