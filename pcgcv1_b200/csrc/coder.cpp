@@ -99,7 +99,21 @@ struct Decoder {
       const int mid = (lo + hi) >> 1;
       if (size * (uint64_t)cdf(mid) > offset) hi = mid; else lo = mid + 1;
     }
-    const int s = lo - 1;
+    return narrow(lo - 1, size, cdf);
+  }
+  // Same search through one division: size*c > offset  <=>  c > floor(offset/size); find(t) returns the symbol s with
+  // cdf(s) <= t < cdf(s+1).
+  template <typename Find, typename CdfAt>
+  inline int decode_at(Find find, CdfAt cdf) {
+    const uint64_t size = (uint64_t)size_minus1 + 1;
+    const uint64_t offset = (((uint64_t)(uint32_t)(value - base) + 1) << precision) - 1;
+    uint64_t t = offset / size;
+    const uint64_t top = ((uint64_t)1 << precision) - 1;
+    if (t > top) t = top;                         // only a corrupt stream gets here
+    return narrow(find((uint32_t)t), size, cdf);
+  }
+  template <typename CdfAt>
+  inline int narrow(const int s, const uint64_t size, CdfAt cdf) {
     const uint32_t a = (uint32_t)((size * (uint64_t)cdf(s)) >> precision);
     const uint32_t b = (uint32_t)(((size * (uint64_t)cdf(s + 1)) >> precision) - 1);
     base += a;
@@ -170,12 +184,30 @@ int pcgc_range_encode(const int16_t* sym, int64_t n, const int32_t* cdf, int cdf
 
 int pcgc_range_decode(const uint8_t* data, int64_t nbytes, int64_t n, const int32_t* cdf, int cdf_rows, int N,
                       int precision, int16_t* sym) {
-  if ((!data && nbytes) || !cdf || !sym || cdf_rows < 1 || N < 1) return PCGC_ERR_BAD_ARG;
+  if ((!data && nbytes) || !cdf || !sym || cdf_rows < 1 || N < 1 || precision < 1 || precision > 16) return PCGC_ERR_BAD_ARG;
   Decoder d(data, nbytes, precision);
+  // The rows are shared by n / cdf_rows symbols each, so a coarse table per row pays: start[r][t >> sh] is the symbol whose
+  // interval holds the first value of the bucket; a short, well-predicted scan finishes the search.
+  const int sh = precision > 8 ? precision - 8 : 0;
+  std::vector<uint16_t> start((size_t)cdf_rows * 256);
+  for (int r = 0; r < cdf_rows; ++r) {
+    const int32_t* row = cdf + (int64_t)r * (N + 1);
+    int s = 0;
+    for (int q = 0; q < 256; ++q) {
+      const int32_t t = q << sh;
+      while (s + 1 < N && row[s + 1] <= t) ++s;
+      start[(size_t)r * 256 + q] = (uint16_t)s;
+    }
+  }
   int r = 0;
   for (int64_t i = 0; i < n; ++i) {
     const int32_t* row = cdf + (int64_t)r * (N + 1);
-    sym[i] = (int16_t)d.decode(N, [row](int k) { return (uint32_t)row[k]; });
+    const uint16_t* st = start.data() + (size_t)r * 256;
+    sym[i] = (int16_t)d.decode_at([row, st, sh, N](uint32_t t) {
+      int s = st[t >> sh];
+      while (s + 1 < N && (uint32_t)row[s + 1] <= t) ++s;
+      return s;
+    }, [row](int k) { return (uint32_t)row[k]; });
     if (++r == cdf_rows) r = 0;
   }
   return PCGC_OK;
@@ -203,7 +235,12 @@ int pcgc_range_decode_rows(const uint8_t* data, int64_t nbytes, int64_t n, const
   const uint32_t top = 1u << precision;
   for (int64_t i = 0; i < n; ++i) {
     const uint16_t* row = rows + i * N;
-    sym[i] = (int16_t)d.decode(N, [row, N, top](int k) { return k == N ? top : (uint32_t)row[k]; });
+    // symbol = number of interior boundaries row[1..N-1] that are <= t (branch-free; the rows are short)
+    sym[i] = (int16_t)d.decode_at([row, N](uint32_t t) {
+      int s = 0;
+      for (int k = 1; k < N; ++k) s += (uint32_t)row[k] <= t;
+      return s;
+    }, [row, N, top](int k) { return k == N ? top : (uint32_t)row[k]; });
   }
   return PCGC_OK;
 }
@@ -248,7 +285,11 @@ int pcgc_range_decode_rows_batch_f32(const uint8_t* const* data, const int64_t* 
     float* out = y_hat + (int64_t)b * E;
     for (int64_t i = 0; i < E; ++i) {
       const uint16_t* row = base + i * N;
-      const int s = d.decode(N, [row, N, top](int k) { return k == N ? top : (uint32_t)row[k]; });
+      const int s = d.decode_at([row, N](uint32_t t) {
+        int c = 0;
+        for (int k = 1; k < N; ++k) c += (uint32_t)row[k] <= t;
+        return c;
+      }, [row, N, top](int k) { return k == N ? top : (uint32_t)row[k]; });
       out[i] = (float)(s + min_v);
     }
   });

@@ -56,9 +56,9 @@ class EntropyBottleneck:
         c, slot = self._resolve(self._codec.bn_channels[self._slot] if self._slot is not None else 8)
         return c.factorized_cdf(slot, int(min_v), int(max_v), self._likelihood_bound, self._range_coder_precision)[None]
 
-    def compress(self, inputs):
-        """-> (string, min_v, max_v): ONE string over the whole tensor with a global symbol range
-        (entropy_model.py:223-261)."""
+    def compress_begin(self, inputs):
+        """GPU half of ``compress``: quantise, global symbol range, per-channel CDF; returns what the host range coder
+        needs so that the caller can run it on a worker thread."""
         x = runtime.unwrap(inputs)
         channels = x.shape[-1]
         c, slot = self._resolve(channels)
@@ -68,7 +68,16 @@ class EntropyBottleneck:
         min_v, max_v = int(mm_h[0]), int(mm_h[1])
         cdf = c.factorized_cdf(slot, min_v, max_v, self._likelihood_bound, self._range_coder_precision)
         sym = (runtime.to_host(x_hat).reshape(-1).astype(np.int32) - min_v).astype(np.int16)
-        string = runtime.range_encode(sym, cdf, self._range_coder_precision)
+        return sym, cdf, min_v, max_v
+
+    def compress_finish(self, sym, cdf):
+        return runtime.range_encode(sym, cdf, self._range_coder_precision)
+
+    def compress(self, inputs):
+        """-> (string, min_v, max_v): ONE string over the whole tensor with a global symbol range
+        (entropy_model.py:223-261)."""
+        sym, cdf, min_v, max_v = self.compress_begin(inputs)
+        string = self.compress_finish(sym, cdf)
         return runtime.HostResult(string), runtime.HostResult(np.int32(min_v)), runtime.HostResult(np.int32(max_v))
 
     def decompress(self, strings, min_v, max_v, shape, channels=None):

@@ -88,6 +88,7 @@ def decompress_factorized(strings, min_v, max_v, shape, model, ckpt_dir):
 # transforms of chunk k+1 and a copy stream moves the coder's inputs through rotating pinned buffers.
 _CHUNK = int(os.environ.get("PCGC_CHUNK", "64"))
 _POOL = None
+_POOL_Z = None
 
 
 def _pool():
@@ -96,6 +97,15 @@ def _pool():
         from concurrent.futures import ThreadPoolExecutor
         _POOL = ThreadPoolExecutor(max_workers=1)
     return _POOL
+
+
+def _pool_z():
+    """Second worker: the single hyper-latent string (one sequential range coder) is coded beside the per-cube jobs."""
+    global _POOL_Z
+    if _POOL_Z is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL_Z = ThreadPoolExecutor(max_workers=1)
+    return _POOL_Z
 
 
 def compress_hyper(cubes, model, ckpt_dir, decompress=False):
@@ -109,30 +119,39 @@ def compress_hyper(cubes, model, ckpt_dir, decompress=False):
     B = cubes.shape[0]
     start = time.time()
     jobs, mms, z_hats, keep = [], [], [], []
-    for k, a in enumerate(range(0, B, _CHUNK)):
-        b = min(B, a + _CHUNK)
+    chunks = [(a, min(B, a + _CHUNK)) for a in range(0, B, _CHUNK)]
+    z_job = None
+    for k, (a, b) in enumerate(chunks):
         x = codec.to_device(cubes[a:b])
         ys = codec.analysis(x)
         zs = codec.hyper_encode(ys)
         z_hat, _, _, _ = codec.factorized(entropy_bottleneck._slot, zs, want_p=False, want_bits=False)
+        z_hats.append(z_hat)
+        if k == len(chunks) - 1:
+            # every z_hat exists now: start the ONE hyper string (global range, entropy_model.py:249-259) on its own worker so
+            # that it is coded while the GPU finishes this chunk and the per-cube coder runs.
+            z_all = torch.cat(z_hats) if len(z_hats) > 1 else z_hats[0]
+            sym, cdf, z_min, z_max = entropy_bottleneck.compress_begin(z_all)
+            z_job = _pool_z().submit(entropy_bottleneck.compress_finish, sym, cdf)
         locs, scales = codec.hyper_decode(z_hat, 1e-9)                  # lower_bound = 1e-9, transform.py:145-146
         if k >= 2:
             jobs[k - 2] = jobs[k - 2].result()                          # slot k%2 is free once its previous user finished
         stage, done, mm = cem.encode_begin(ys, locs, scales, k % 2)
         jobs.append(_pool().submit(cem.encode_finish, stage, done))
         mms.append(mm)
-        z_hats.append(z_hat)
         if decompress:
             keep.append((ys.shape, locs, scales))
     strings = []
     for j in jobs:
         strings += j if isinstance(j, list) else j.result()
-    _log("Analysis + hyper transforms + entropy encode (pipelined)", start)
-    start = time.time()
-    z_all = torch.cat(z_hats) if len(z_hats) > 1 else z_hats[0]
-    z_strings, z_min_v, z_max_v = entropy_bottleneck.compress(z_all)     # one string, global range (entropy_model.py:249-259)
+    if z_job is None:                                                   # B == 0
+        z_all = torch.zeros((0, 8, 8, 8, 8), device=codec.dev)
+        z_strings, z_min_v, z_max_v = entropy_bottleneck.compress(z_all)
+    else:
+        z_strings = runtime.HostResult(z_job.result())
+        z_min_v, z_max_v = runtime.HostResult(np.int32(z_min)), runtime.HostResult(np.int32(z_max))
     z_shape = runtime.HostResult(np.array(z_all.shape, dtype=np.int32))
-    _log("Entropy Encode (Hyper)", start)
+    _log("Analysis + hyper transforms + entropy encode (pipelined)", start)
     mm = np.concatenate(mms) if mms else np.zeros((0, 2), np.int32)
     y_min_vs, y_max_vs = mm[:, 0].astype(np.int32), mm[:, 1].astype(np.int32)
     y_shape = runtime.HostResult(np.array((1, 16, 16, 16, 16), dtype=np.int64))
