@@ -189,6 +189,35 @@ int pcgc_range_decode_rows_batch_f32(const uint8_t* const* data, const int64_t* 
                                      const uint16_t* rows, const int64_t* row_offset, const int32_t* minmax,
                                      int precision, float* y_hat, int threads);
 
+/* ---- point-cloud I/O either side of the codec ----------------------- */
+/* load_ply_data (dataprocess/inout_points.py:8-28): every line of the ASCII text whose first three single-space
+ * separated tokens parse as floats is a point, truncated to int32; other lines (header, comments) are skipped.
+ * xyz: HOST int32 [cap,3]; *n = points found (set even when PCGC_ERR_OVERFLOW says cap was too small).  A line with a
+ * numeric first token but fewer than three tokens returns PCGC_ERR_CORRUPT (the reference raises IndexError there). */
+int pcgc_ply_parse(const char* text, int64_t nbytes, int32_t* xyz, int64_t cap, int64_t* n, int threads);
+/* write_ply_data (inout_points.py:30-46) for integer coordinates: header + "x y z\n" per point, byte-identical to the
+ * reference's output.  out: HOST buffer of at least 160 + 36*n bytes. */
+int pcgc_ply_format(const int32_t* xyz, int64_t n, char* out, int64_t cap, int64_t* len, int threads);
+/* The cube partition of load_points (inout_points.py:50-90): cube = point // cube_size, local = point % cube_size, cubes
+ * with fewer than min_num points dropped (a single-point cube counts as 3, the reference's 1-D shape quirk), kept cubes
+ * ordered by x + y*step + z*step^2 with step = max kept cube coordinate + 1, file order inside a cube.
+ * Outputs (HOST, caller-allocated): local_sorted int16 [local_cap,3] (points of the kept cubes, grouped in sorted cube
+ * order; local_cap = n suffices unless negative coordinates make the reference repeat a cube -- PCGC_ERR_OVERFLOW then
+ * reports the needed size in *n_points), cube_pos_seen int64 [n,3] (kept cubes in first-appearance order = the reference's cube_positions
+ * return value), cube_pos_sorted int64 [n,3], counts_sorted int64 [n], *n_cubes, *n_points. */
+int pcgc_partition_points(const int32_t* xyz, int64_t n, int cube_size, int min_num, int16_t* local_sorted, int64_t local_cap,
+                          int64_t* cube_pos_seen, int64_t* cube_pos_sorted, int64_t* counts_sorted, int64_t* n_cubes,
+                          int64_t* n_points);
+/* points2voxels (inout_points.py:116-132) on the device: local_dev int16 [n,3] grouped per cube, offsets_host int64
+ * [B+1] -> cubes_dev uint8 [B,S,S,S] (0/1).  Coordinates outside [0,S) return an error (the reference raises
+ * IndexError).  Synchronises (error flag). */
+int pcgc_voxelize(pcgc_ctx* ctx, const int16_t* local_dev, const int64_t* offsets_host, int B, int S, uint8_t* cubes_dev);
+/* voxels2points (inout_points.py:134-143) on the device: mask_dev uint8 [B,S,S,S] -> counts_dev int32 [B], points_dev
+ * int16 [cap,3] (non-zero voxels as (d,h,w), lexicographic per cube, cubes in order = np.where order) and *total_dev
+ * (int64, may exceed cap: only the first cap points are written).  S must be a multiple of 16.  Does not synchronise. */
+int pcgc_extract_points(pcgc_ctx* ctx, const uint8_t* mask_dev, int B, int S, int32_t* counts_dev, int16_t* points_dev,
+                        int64_t cap, int64_t* total_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,7 @@ NET_VOX_ANALYSIS, NET_VOX_SYNTHESIS, NET_HYPER_ENCODER, NET_HYPER_DECODER, NET_S
 DTYPE_U8, DTYPE_F32, DTYPE_F64 = range(3)
 ENGINE_AUTO, ENGINE_FFMA, ENGINE_UMMA = range(3)
 MAX_SYMBOLS = 64
+ERR_BAD_ARG, ERR_BAD_RANGE, ERR_CUDA, ERR_OOM, ERR_NOT_READY, ERR_OVERFLOW, ERR_CORRUPT = -1, -2, -3, -4, -5, -6, -7
 ERR_NAMES = {0: "OK", -1: "BAD_ARG", -2: "BAD_RANGE", -3: "CUDA", -4: "OOM", -5: "NOT_READY", -6: "OVERFLOW", -7: "CORRUPT"}
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
@@ -58,6 +59,11 @@ SIGNATURES = {
     "pcgc_range_encode_intervals_batch": (_i, [_vp, _i, _i64, _i, _vp, _i64, _vp, _i]),
     "pcgc_range_decode_rows_batch": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _i, _vp, _i]),
     "pcgc_range_decode_rows_batch_f32": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _i, _vp, _i]),
+    "pcgc_ply_parse": (_i, [_vp, _i64, _vp, _i64, _vp, _i]),
+    "pcgc_ply_format": (_i, [_vp, _i64, _vp, _i64, _vp, _i]),
+    "pcgc_partition_points": (_i, [_vp, _i64, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "pcgc_voxelize": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "pcgc_extract_points": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i64, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

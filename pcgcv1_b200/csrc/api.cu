@@ -197,6 +197,7 @@ struct pcgc_ctx {
   int* err_flag = nullptr;          // device int
   int32_t* mm_dev = nullptr; size_t mm_cap = 0;
   int64_t* off_dev = nullptr; size_t off_cap = 0;
+  int64_t* chunk_dev = nullptr; size_t chunk_cap = 0;   // voxelize / extract workspace
   int sub_batch = 32;
   // optional per-launch CUDA-event timing (bench.py roofline): see pcgc_profile_enable
   bool profiling = false;
@@ -733,6 +734,7 @@ void pcgc_destroy(pcgc_ctx* ctx) {
   if (ctx->err_flag) cudaFree(ctx->err_flag);
   if (ctx->mm_dev) cudaFree(ctx->mm_dev);
   if (ctx->off_dev) cudaFree(ctx->off_dev);
+  if (ctx->chunk_dev) cudaFree(ctx->chunk_dev);
   for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   delete ctx;
@@ -1082,6 +1084,40 @@ int pcgc_threshold_select(pcgc_ctx* ctx, const float* logits_dev, int B, int64_t
   DeviceGuard g(ctx->device);
   if (B == 0) return PCGC_OK;
   CK(launch_threshold(logits_dev, B, V, thres, mask_dev, count_dev, ctx->stream, &ctx->launches));
+  return PCGC_OK;
+}
+
+int pcgc_voxelize(pcgc_ctx* ctx, const int16_t* local_dev, const int64_t* offsets_host, int B, int S, uint8_t* cubes_dev) {
+  if (!ctx || !offsets_host || !cubes_dev || B < 0 || S < 1 || S > 1024) return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_voxelize: bad argument");
+  DeviceGuard g(ctx->device);
+  if (B == 0) return PCGC_OK;
+  const int64_t n = offsets_host[B];
+  if (n < 0 || (n > 0 && !local_dev)) return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_voxelize: bad offsets");
+  if (ctx->chunk_cap < (size_t)(B + 1)) {
+    if (ctx->chunk_dev) { CK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->chunk_dev); ctx->chunk_dev = nullptr; ctx->chunk_cap = 0; }
+    CK(cudaMalloc((void**)&ctx->chunk_dev, sizeof(int64_t) * (size_t)(B + 1))); ctx->chunk_cap = (size_t)(B + 1);
+  }
+  CK(cudaMemcpyAsync(ctx->chunk_dev, offsets_host, sizeof(int64_t) * (size_t)(B + 1), cudaMemcpyHostToDevice, ctx->stream));
+  prof_begin(ctx, "voxelize", 0, 6.0 * n + (double)B * S * S * S);
+  CK(launch_voxelize(local_dev, ctx->chunk_dev, B, S, n, cubes_dev, ctx->err_flag, ctx->stream, &ctx->launches));
+  prof_end(ctx);
+  return check_err_flag(ctx, "pcgc_voxelize");
+}
+
+int pcgc_extract_points(pcgc_ctx* ctx, const uint8_t* mask_dev, int B, int S, int32_t* counts_dev, int16_t* points_dev, int64_t cap,
+                        int64_t* total_dev) {
+  if (!ctx || !mask_dev || !counts_dev || !total_dev || (!points_dev && cap) || B < 0 || cap < 0 || S < 16 || S % 16 || S > 1024)
+    return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_extract_points: bad argument (S must be a multiple of 16)");
+  DeviceGuard g(ctx->device);
+  if (B == 0) { CK(cudaMemsetAsync(total_dev, 0, sizeof(int64_t), ctx->stream)); return PCGC_OK; }
+  const size_t n_chunks = (size_t)B * ((size_t)S * S * S / 4096);
+  if (ctx->chunk_cap < n_chunks) {
+    if (ctx->chunk_dev) { CK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->chunk_dev); ctx->chunk_dev = nullptr; ctx->chunk_cap = 0; }
+    CK(cudaMalloc((void**)&ctx->chunk_dev, sizeof(int64_t) * n_chunks)); ctx->chunk_cap = n_chunks;
+  }
+  prof_begin(ctx, "extract_points", 0, 2.0 * B * S * S * S);
+  CK(launch_extract_points(mask_dev, B, S, ctx->chunk_dev, counts_dev, points_dev, cap, total_dev, ctx->stream, &ctx->launches));
+  prof_end(ctx);
   return PCGC_OK;
 }
 

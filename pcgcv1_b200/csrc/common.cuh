@@ -72,4 +72,10 @@ cudaError_t launch_topk(const float* logits, int B, int64_t V, const int32_t* ks
 cudaError_t launch_threshold(const float* logits, int B, int64_t V, float thres, uint8_t* mask, int32_t* count,
                              cudaStream_t s, int64_t* launches);
 
+// voxelize.cu
+cudaError_t launch_voxelize(const int16_t* local, const int64_t* offsets, int B, int S, int64_t n, uint8_t* cubes, int* err,
+                            cudaStream_t s, int64_t* launches);
+cudaError_t launch_extract_points(const uint8_t* mask, int B, int S, int64_t* chunk_ws, int32_t* counts, int16_t* points, int64_t cap,
+                                  int64_t* total, cudaStream_t s, int64_t* launches);
+
 }  // namespace pcgc

@@ -1,0 +1,264 @@
+// Host point-cloud I/O of libpcgc_b200.so -- SURVEY.md section 8(f) rank 1: the callers either side of the codec path.
+// Replaces the line-by-line Python of dataprocess/inout_points.py: load_ply_data (:8-28), write_ply_data (:30-46) and the
+// dict + np.vstack cube partition of load_points (:50-90).  Same results (values, order, filtering quirks), different
+// algorithms: a chunk-parallel ASCII parser, a hash + counting-sort partition, a batched integer formatter.
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/pcgc_b200.h"
+
+namespace {
+
+inline bool is_ws(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; }
+
+// Python float(token) for the spellings that occur in PLY files: optional whitespace around, sign, decimal digits, '.',
+// exponent, inf/infinity/nan.  Returns false where float() raises ValueError (empty token, words, hex).
+bool parse_float(const char* b, const char* e, double* out) {
+  while (b < e && is_ws(*b)) ++b;
+  while (e > b && is_ws(e[-1])) --e;
+  if (b == e) return false;
+  // fast path: [+-]digits[.digits]
+  const char* p = b;
+  bool neg = false;
+  if (*p == '+' || *p == '-') { neg = *p == '-'; ++p; }
+  if (p < e && ((*p >= '0' && *p <= '9') || *p == '.')) {
+    uint64_t ip = 0; int nd = 0;
+    while (p < e && *p >= '0' && *p <= '9' && nd < 18) { ip = ip * 10 + (uint64_t)(*p - '0'); ++p; ++nd; }
+    if (p == e && nd > 0) { *out = neg ? -(double)ip : (double)ip; return true; }
+  }
+  // general path through strtod on a bounded copy; reject what Python rejects (hex floats, partial parses)
+  char tmp[64];
+  const size_t len = (size_t)(e - b);
+  if (len >= sizeof tmp) return false;
+  for (size_t i = 0; i < len; ++i) { if (b[i] == 'x' || b[i] == 'X' || b[i] == 'p' || b[i] == 'P' || b[i] == '(') return false; tmp[i] = b[i]; }
+  tmp[len] = 0;
+  char* endp = nullptr;
+  const double v = strtod(tmp, &endp);
+  if (endp != tmp + len) return false;
+  *out = v;
+  return true;
+}
+
+inline int32_t to_i32(double v) {                       // numpy float64 -> int32 cast on x86 (truncation; INT_MIN when out of range)
+  if (!(v > -2147483649.0 && v < 2147483648.0)) return INT32_MIN;
+  return (int32_t)v;
+}
+
+// One line [b, e) (without the '\n').  1 = point, 0 = skipped (ValueError in the reference), -1 = IndexError in the reference.
+int parse_line(const char* b, const char* e, int32_t* xyz) {
+  double v[3];
+  const char* p = b;
+  for (int k = 0; k < 3; ++k) {
+    const char* q = (const char*)memchr(p, ' ', (size_t)(e - p));
+    const char* te = q ? q : e;
+    // the last token of a line carries the '\n' in Python; float() strips it -- same as stripping here
+    if (!parse_float(p, te, &v[k])) return 0;
+    p = te + 1;
+    if (!q && k < 2) {
+      // no further token: wordslist[k+1] raises IndexError -- but only if the earlier tokens parsed (they did)
+      return -1;
+    }
+  }
+  xyz[0] = to_i32(v[0]); xyz[1] = to_i32(v[1]); xyz[2] = to_i32(v[2]);
+  return 1;
+}
+
+template <typename F>
+void run_threads(int n, F f) {
+  if (n <= 1) { f(0); return; }
+  std::vector<std::thread> th;
+  th.reserve(n);
+  for (int t = 0; t < n; ++t) th.emplace_back(f, t);
+  for (auto& x : th) x.join();
+}
+
+int pick_threads(int threads, int64_t work, int64_t grain) {
+  int hw = (int)std::thread::hardware_concurrency();
+  if (hw <= 0) hw = 1;
+  if (threads <= 0 || threads > hw) threads = hw;
+  const int64_t by_work = std::max<int64_t>(1, work / grain);
+  return (int)std::min<int64_t>(threads, by_work);
+}
+
+inline int64_t floordiv(int64_t a, int64_t b) { int64_t q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
+inline int64_t floormod(int64_t a, int64_t b) { return a - floordiv(a, b) * b; }
+
+}  // namespace
+
+extern "C" {
+
+int pcgc_ply_parse(const char* text, int64_t nbytes, int32_t* xyz, int64_t cap, int64_t* n, int threads) {
+  if ((!text && nbytes) || !n || nbytes < 0 || (!xyz && cap)) return PCGC_ERR_BAD_ARG;
+  const int T = pick_threads(threads, nbytes, 1 << 20);
+  // chunk boundaries on line starts
+  std::vector<int64_t> start(T + 1);
+  start[0] = 0; start[T] = nbytes;
+  for (int t = 1; t < T; ++t) {
+    int64_t p = nbytes * t / T;
+    if (p < start[t - 1]) p = start[t - 1];
+    const char* q = (const char*)memchr(text + p, '\n', (size_t)(nbytes - p));
+    start[t] = q ? (q - text) + 1 : nbytes;
+  }
+  std::vector<std::vector<int32_t>> part(T);
+  std::atomic<int> rc(PCGC_OK);
+  run_threads(T, [&](int t) {
+    std::vector<int32_t>& out = part[t];
+    out.reserve((size_t)((start[t + 1] - start[t]) / 8));
+    const char* p = text + start[t];
+    const char* end = text + start[t + 1];
+    while (p < end) {
+      const char* q = (const char*)memchr(p, '\n', (size_t)(end - p));
+      const char* le = q ? q : end;
+      int32_t v[3];
+      const int r = parse_line(p, le, v);
+      if (r == 1) { out.push_back(v[0]); out.push_back(v[1]); out.push_back(v[2]); }
+      else if (r < 0) { rc.store(PCGC_ERR_CORRUPT); return; }
+      p = le + 1;
+    }
+  });
+  if (rc.load() != PCGC_OK) return rc.load();
+  int64_t total = 0;
+  for (auto& v : part) total += (int64_t)v.size() / 3;
+  *n = total;
+  if (total > cap) return PCGC_ERR_OVERFLOW;
+  int64_t off = 0;
+  for (auto& v : part) { if (!v.empty()) memcpy(xyz + off, v.data(), v.size() * sizeof(int32_t)); off += (int64_t)v.size(); }
+  return PCGC_OK;
+}
+
+int pcgc_ply_format(const int32_t* xyz, int64_t n, char* out, int64_t cap, int64_t* len, int threads) {
+  if ((!xyz && n) || !out || !len || n < 0) return PCGC_ERR_BAD_ARG;
+  char head[160];
+  const int hl = snprintf(head, sizeof head,
+                          "ply\nformat ascii 1.0\nelement vertex %lld\nproperty float x\nproperty float y\nproperty float z\nend_header\n",
+                          (long long)n);
+  if (cap < hl + n * 36) return PCGC_ERR_OVERFLOW;      // 3 x (sign + 10 digits) + separators
+  memcpy(out, head, (size_t)hl);
+  const int T = pick_threads(threads, n, 1 << 16);
+  // pass 1: each thread formats its slice into a private buffer; pass 2: concatenate in order
+  std::vector<std::vector<char>> part(T);
+  run_threads(T, [&](int t) {
+    const int64_t a = n * t / T, b = n * (t + 1) / T;
+    std::vector<char>& buf = part[t];
+    buf.resize((size_t)(b - a) * 36);
+    char* w = buf.data();
+    for (int64_t i = a; i < b; ++i) {
+      for (int k = 0; k < 3; ++k) {
+        int64_t v = xyz[3 * i + k];
+        if (v < 0) { *w++ = '-'; v = -v; }
+        char d[12]; int nd = 0;
+        do { d[nd++] = (char)('0' + v % 10); v /= 10; } while (v);
+        while (nd) *w++ = d[--nd];
+        *w++ = k < 2 ? ' ' : '\n';
+      }
+    }
+    buf.resize((size_t)(w - buf.data()));
+  });
+  int64_t off = hl;
+  for (auto& v : part) { if (!v.empty()) memcpy(out + off, v.data(), v.size()); off += (int64_t)v.size(); }
+  *len = off;
+  return PCGC_OK;
+}
+
+int pcgc_partition_points(const int32_t* xyz, int64_t n, int cube_size, int min_num, int16_t* local_sorted, int64_t local_cap,
+                          int64_t* cube_pos_seen, int64_t* cube_pos_sorted, int64_t* counts_sorted, int64_t* n_cubes,
+                          int64_t* n_points) {
+  if ((!xyz && n) || n < 0 || cube_size < 1 || cube_size > 32767 || !local_sorted || !cube_pos_seen || !cube_pos_sorted ||
+      !counts_sorted || !n_cubes || !n_points)
+    return PCGC_ERR_BAD_ARG;
+  // 1. cube id per point in first-seen order (the reference's dict insertion order)
+  struct Key { int64_t x, y, z; bool operator==(const Key& o) const { return x == o.x && y == o.y && z == o.z; } };
+  struct KeyHash { size_t operator()(const Key& k) const { uint64_t h = (uint64_t)k.x * 0x9E3779B97F4A7C15ull; h ^= (uint64_t)k.y + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); h ^= (uint64_t)k.z + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); return (size_t)h; } };
+  std::unordered_map<Key, int64_t, KeyHash> ids;
+  ids.reserve(4096);
+  std::vector<Key> keys;
+  std::vector<int64_t> cnt;
+  std::vector<int32_t> pid((size_t)n);
+  Key last{0, 0, 0}; int64_t last_id = -1;
+  for (int64_t i = 0; i < n; ++i) {
+    const Key k{floordiv(xyz[3 * i], cube_size), floordiv(xyz[3 * i + 1], cube_size), floordiv(xyz[3 * i + 2], cube_size)};
+    int64_t id;
+    if (last_id >= 0 && k == last) id = last_id;
+    else {
+      auto it = ids.find(k);
+      if (it == ids.end()) { id = (int64_t)keys.size(); ids.emplace(k, id); keys.push_back(k); cnt.push_back(0); }
+      else id = it->second;
+      last = k; last_id = id;
+    }
+    pid[(size_t)i] = (int32_t)id;
+    ++cnt[(size_t)id];
+  }
+  // 2. min_num filter.  A cube with ONE point is a 1-D array of 3 numbers in the reference, so its shape[0] is 3 (:71).
+  const int64_t nc_all = (int64_t)keys.size();
+  std::vector<int64_t> kept;                              // ids in first-seen order
+  std::vector<char> is_kept((size_t)nc_all, 0);
+  for (int64_t c = 0; c < nc_all; ++c) {
+    const int64_t shape0 = cnt[(size_t)c] == 1 ? 3 : cnt[(size_t)c];
+    if (shape0 >= min_num) { kept.push_back(c); is_kept[(size_t)c] = 1; }
+  }
+  const int64_t nc = (int64_t)kept.size();
+  *n_cubes = nc;
+  if (nc == 0) { *n_points = 0; return PCGC_OK; }
+  int64_t mx = INT64_MIN;
+  for (int64_t j = 0; j < nc; ++j) {
+    const Key& k = keys[(size_t)kept[(size_t)j]];
+    cube_pos_seen[3 * j] = k.x; cube_pos_seen[3 * j + 1] = k.y; cube_pos_seen[3 * j + 2] = k.z;
+    mx = std::max(mx, std::max(k.x, std::max(k.y, k.z)));
+  }
+  // 3. order: n = x + y*step + z*step^2 ascending, decoded back with floor mod / floor div (:79-86)
+  const int64_t step = mx + 1;
+  if (step == 0) return PCGC_ERR_BAD_RANGE;
+  std::vector<int64_t> lin((size_t)nc);
+  for (int64_t j = 0; j < nc; ++j) lin[(size_t)j] = cube_pos_seen[3 * j] + cube_pos_seen[3 * j + 1] * step + cube_pos_seen[3 * j + 2] * step * step;
+  std::sort(lin.begin(), lin.end());
+  // sorted slot j -> cube id.  With negative cube coordinates the decode can land on another (kept) cube -- the reference
+  // then repeats that cube's points -- or on a missing one (KeyError); both are mirrored.
+  std::vector<int64_t> id_of_slot((size_t)nc);
+  int64_t total = 0;
+  for (int64_t j = 0; j < nc; ++j) {
+    const int64_t v = lin[(size_t)j];
+    const Key k{floormod(v, step), floormod(floordiv(v, step), step), floordiv(floordiv(v, step), step)};
+    auto it = ids.find(k);
+    if (it == ids.end() || !is_kept[(size_t)it->second]) return PCGC_ERR_BAD_RANGE;
+    id_of_slot[(size_t)j] = it->second;
+    cube_pos_sorted[3 * j] = k.x; cube_pos_sorted[3 * j + 1] = k.y; cube_pos_sorted[3 * j + 2] = k.z;
+    counts_sorted[j] = cnt[(size_t)it->second];
+    total += cnt[(size_t)it->second];
+  }
+  *n_points = total;
+  if (total > local_cap) return PCGC_ERR_OVERFLOW;         // *n_points tells the caller what to allocate
+  // 4. group the local coordinates per cube id (file order inside a cube, like the np.vstack chain), then lay the groups
+  //    out in sorted slot order
+  std::vector<int64_t> gstart((size_t)nc_all + 1, 0);
+  for (int64_t c = 0; c < nc_all; ++c) gstart[(size_t)c + 1] = gstart[(size_t)c] + (is_kept[(size_t)c] ? cnt[(size_t)c] : 0);
+  std::vector<int16_t> grouped((size_t)gstart[(size_t)nc_all] * 3);
+  {
+    std::vector<int64_t> cursor(gstart.begin(), gstart.end() - 1);
+    for (int64_t i = 0; i < n; ++i) {
+      const int32_t c = pid[(size_t)i];
+      if (!is_kept[(size_t)c]) continue;
+      const int64_t o = cursor[(size_t)c]++;
+      grouped[3 * o] = (int16_t)floormod(xyz[3 * i], cube_size);
+      grouped[3 * o + 1] = (int16_t)floormod(xyz[3 * i + 1], cube_size);
+      grouped[3 * o + 2] = (int16_t)floormod(xyz[3 * i + 2], cube_size);
+    }
+  }
+  int64_t o = 0;
+  for (int64_t j = 0; j < nc; ++j) {
+    const int64_t c = id_of_slot[(size_t)j];
+    memcpy(local_sorted + 3 * o, grouped.data() + 3 * gstart[(size_t)c], (size_t)cnt[(size_t)c] * 3 * sizeof(int16_t));
+    o += cnt[(size_t)c];
+  }
+  return PCGC_OK;
+}
+
+}  // extern "C"

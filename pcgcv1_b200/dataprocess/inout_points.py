@@ -1,14 +1,133 @@
-"""Drop-in for the hot-path part of ``dataprocess/inout_points.py``: ``select_voxels`` (top-k occupancy
-classification, :147-179), ``voxels2points`` (:134-143) and ``points2voxels`` (:116-132).
+"""Drop-in for ``dataprocess/inout_points.py``: ``select_voxels`` (top-k occupancy classification, :147-179),
+``voxels2points`` (:134-143), ``points2voxels`` (:116-132) on the codec path, and -- SURVEY.md section 8(f) rank 1 -- the
+callers either side of it: ``load_ply_data`` (:8-28), ``write_ply_data`` (:30-46), ``load_points`` (:50-90) and
+``save_points`` (:92-112) with the reference's signatures, return values, ordering and filtering quirks.
 
-``select_voxels`` runs the radix-select kernel of libpcgc_b200.so; the PLY reader/writer and the cube
-partitioner of the same reference file are host I/O outside this path."""
+``select_voxels`` runs the radix-select kernel of libpcgc_b200.so; the PLY parser / writer and the cube partition are the
+library's multithreaded C++ (``csrc/pointio.cpp``) in place of per-line / per-point Python; the ``*_packed`` and
+``*_device`` variants keep points as (array, offsets) and cubes / masks on the GPU so that 6 bytes per point cross PCIe
+instead of 256 KiB - 2 MiB per cube."""
 from __future__ import annotations
+
+import ctypes as C
+import os
 
 import numpy as np
 import torch
 
-from .. import runtime
+from .. import _lib, runtime
+
+
+# ---------------------------------------------------------------- plyfile <--> points
+def load_ply_data(filename):
+    """ASCII .ply -> int32 [n,3]: every line whose first three space-separated tokens are floats (inout_points.py:8-28)."""
+    with open(filename, "rb") as f:
+        data = f.read()
+    L = _lib.lib()
+    cap = data.count(b"\n") + 1
+    xyz = np.empty((cap, 3), np.int32)
+    n = C.c_int64()
+    rc = L.pcgc_ply_parse(data, len(data), xyz.ctypes.data, cap, C.byref(n), 0)
+    if rc == _lib.ERR_CORRUPT:
+        raise IndexError("list index out of range")           # a numeric line with fewer than three tokens (:18)
+    _lib.check(rc)
+    if n.value == 0:
+        return np.array([]).astype(np.int32)                  # what np.array([]) gives the reference
+    return xyz[:n.value].copy() if n.value < cap // 2 else xyz[:n.value]
+
+
+def write_ply_data(filename, points):
+    """[n,3] -> ASCII .ply, byte for byte the reference's file (inout_points.py:30-46)."""
+    points = np.asarray(points)
+    if os.path.exists(filename):
+        os.remove(filename)
+    if points.ndim == 2 and points.shape[1] >= 3 and points.dtype.kind in "iu" and \
+            (points.size == 0 or (points.min() >= -2**31 and points.max() < 2**31)):
+        xyz = np.ascontiguousarray(points[:, :3], dtype=np.int32)
+        cap = 160 + 36 * len(xyz)
+        out = np.empty(cap, np.uint8)
+        ln = C.c_int64()
+        _lib.check(_lib.lib().pcgc_ply_format(xyz.ctypes.data, len(xyz), out.ctypes.data, cap, C.byref(ln), 0))
+        with open(filename, "wb") as f:
+            f.write(memoryview(out[:ln.value]))
+        return
+    # float coordinates (process.py:27-31,74-77): Python's str() of every scalar, like the reference
+    with open(filename, "w") as f:
+        f.write("ply\nformat ascii 1.0\nelement vertex " + str(points.shape[0]) + "\n")
+        f.write("property float x\nproperty float y\nproperty float z\nend_header\n")
+        f.write("".join([str(p[0]) + " " + str(p[1]) + " " + str(p[2]) + "\n" for p in points]))
+
+
+# ---------------------------------------------------------------- plyfile <--> partitioned points
+def partition_points(point_cloud, cube_size=64, min_num=20):
+    """int [n,3] -> (local int16 [m,3] grouped per kept cube in sorted cube order, offsets int64 [B+1],
+    cube_positions [B,3] in first-appearance order (what the reference returns), cube_positions_sorted [B,3])."""
+    xyz = np.ascontiguousarray(np.asarray(point_cloud).reshape(-1, 3), dtype=np.int32)
+    n = len(xyz)
+    seen = np.empty((max(n, 1), 3), np.int64)
+    srt = np.empty((max(n, 1), 3), np.int64)
+    counts = np.empty(max(n, 1), np.int64)
+    nc, npts = C.c_int64(), C.c_int64()
+    cap = max(n, 1)
+    while True:
+        local = np.empty((cap, 3), np.int16)
+        rc = _lib.lib().pcgc_partition_points(xyz.ctypes.data, n, int(cube_size), int(min_num), local.ctypes.data, cap, seen.ctypes.data,
+                                               srt.ctypes.data, counts.ctypes.data, C.byref(nc), C.byref(npts))
+        if rc != _lib.ERR_OVERFLOW:
+            break
+        cap = npts.value                                          # a repeated cube (negative coordinates, see csrc/pointio.cpp)
+    if rc == _lib.ERR_BAD_RANGE:
+        raise KeyError("cube position order cannot be decoded (negative cube coordinates)")
+    _lib.check(rc)
+    B = nc.value
+    offsets = np.zeros(B + 1, np.int64)
+    np.cumsum(counts[:B], out=offsets[1:])
+    return local[:npts.value].copy(), offsets, seen[:B].copy(), srt[:B].copy()
+
+
+def load_points(filename, cube_size=64, min_num=20):
+    """.ply -> (set_points: list of int16 [n_i,3] in sorted cube order, cube_positions [B,3] in first-appearance order)
+    exactly as inout_points.py:50-90 (including the cube_positions order the reference returns)."""
+    local, offsets, seen, _ = partition_points(load_ply_data(filename), cube_size, min_num)
+    if len(seen) == 0:
+        raise ValueError("zero-size array to reduction operation maximum which has no identity")   # cube_positions.max() (:78)
+    set_points = [local[offsets[i]:offsets[i + 1]] for i in range(len(offsets) - 1)]
+    set_points = [p.reshape(3) if len(p) == 1 else p for p in set_points]    # a single point stays 1-D in the reference (:66)
+    return set_points, seen
+
+
+def load_points_packed(filename, cube_size=64, min_num=20):
+    """As load_points but packed: (local int16 [m,3], offsets int64 [B+1], cube_positions [B,3])."""
+    local, offsets, seen, _ = partition_points(load_ply_data(filename), cube_size, min_num)
+    if len(seen) == 0:
+        raise ValueError("zero-size array to reduction operation maximum which has no identity")
+    return local, offsets, seen
+
+
+def _ordered_positions(cube_positions):
+    cube_positions = np.asarray(cube_positions)
+    step = cube_positions.max() + 1
+    n = cube_positions[:, 0:1] + cube_positions[:, 1:2] * step + cube_positions[:, 2:3] * step * step
+    n = np.sort(n, axis=0)
+    return np.concatenate((n % step, (n // step) % step, n // step // step), -1)
+
+
+def save_points(set_points, cube_positions, filename, cube_size=64):
+    """Combine the per-cube points (in sorted cube order) with their cube positions and write the .ply (:92-112)."""
+    ordered = _ordered_positions(cube_positions)
+    parts = [np.asarray(v) + np.array(k) * cube_size for k, v in zip(ordered, set_points)]
+    write_ply_data(filename, np.concatenate(parts).astype("int"))
+
+
+def save_points_packed(points, counts, cube_positions, filename, cube_size=64):
+    """save_points for points packed as one [n,3] array + per-cube counts."""
+    ordered = _ordered_positions(cube_positions)
+    counts = np.asarray(counts).reshape(-1)
+    if len(counts) > len(ordered):
+        counts = counts[:len(ordered)]                           # zip() truncation of the reference
+    m = int(counts.sum())
+    pc = np.asarray(points[:m]).astype(np.int64) + np.repeat(ordered[:len(counts)].astype(np.int64) * cube_size, counts, axis=0)
+    write_ply_data(filename, pc.astype("int"))
 
 
 def select_voxels(vols, points_nums, offset_ratio=1.0, fixed_thres=None, codec=None, dtype="float32"):
@@ -34,6 +153,18 @@ def select_voxels(vols, points_nums, offset_ratio=1.0, fixed_thres=None, codec=N
 def select_voxels_device(codec, logits: torch.Tensor, ks: torch.Tensor):
     """Device-resident form: -> (mask uint8, thres, count) torch tensors."""
     return codec.topk(logits, ks)
+
+
+def points2voxels_device(local, offsets, cube_size=64, codec=None):
+    """Packed points -> DeviceResult of the uint8 occupancy cubes [B,S,S,S,1] on the GPU."""
+    c = codec or runtime.get_codec("voxception", "")
+    return runtime.DeviceResult(c.voxelize(local, offsets, int(cube_size)))
+
+
+def voxels2points_device(mask, codec=None, cap=None):
+    """Device mask (uint8 [B,S,S,S,1]) -> (points int16 [n,3], counts int32 [B]) in voxels2points' order."""
+    c = codec or runtime.get_codec("voxception", "")
+    return c.extract_points(runtime.unwrap(mask), cap)
 
 
 def voxels2points(voxels):

@@ -401,6 +401,46 @@ class Codec:
         return mask, cnt
 
 
+    def voxelize(self, local: np.ndarray, offsets: np.ndarray, S: int = 64) -> torch.Tensor:
+        """points grouped per cube (int16 [n,3], offsets int64 [B+1]) -> uint8 occupancy [B,S,S,S,1] on the device
+        (points2voxels, inout_points.py:116-132)."""
+        local = np.ascontiguousarray(local, dtype=np.int16).reshape(-1, 3)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        B = len(offsets) - 1
+        cubes = torch.empty((B, S, S, S, 1), dtype=torch.uint8, device=self.dev)
+        ld = self.to_device(local) if len(local) else torch.zeros((1, 3), dtype=torch.int16, device=self.dev)
+        self._stream()
+        self._check(self.lib.pcgc_voxelize(self.ctx, ld.data_ptr(), offsets.ctypes.data, B, S, cubes.data_ptr()))
+        return cubes
+
+    def extract_points(self, mask: torch.Tensor, cap: Optional[int] = None):
+        """uint8 mask [B,S,S,S(,1)] on the device -> (points int16 [total,3] NumPy, counts int32 [B] NumPy): the non-zero
+        voxels of every cube in np.where order (voxels2points, inout_points.py:134-143).  ``cap`` = an upper bound of the
+        total when the caller knows one (saves a second pass)."""
+        B, S = mask.shape[0], mask.shape[1]
+        counts = torch.empty(max(B, 1), dtype=torch.int32, device=self.dev)
+        total = torch.empty(1, dtype=torch.int64, device=self.dev)
+        self._stream()
+        for attempt in range(2):
+            n = int(cap) if cap is not None else 0
+            pts = torch.empty((max(n, 1), 3), dtype=torch.int16, device=self.dev)
+            self._check(self.lib.pcgc_extract_points(self.ctx, mask.data_ptr(), B, S, counts.data_ptr(), pts.data_ptr(), n, total.data_ptr()))
+            t = int(to_host(total, "extract_total")[0])
+            if t <= n:
+                break
+            cap = t
+        return to_host(pts[:t], "extract_points").copy(), to_host(counts[:B], "extract_counts").copy()
+
+    def count_voxels(self, cubes: torch.Tensor) -> np.ndarray:
+        """number of non-zero voxels per cube (np.sum(cubes, axis=(1,2,3,4)), process.py:44)."""
+        B, S = cubes.shape[0], cubes.shape[1]
+        counts = torch.empty(max(B, 1), dtype=torch.int32, device=self.dev)
+        total = torch.empty(1, dtype=torch.int64, device=self.dev)
+        self._stream()
+        self._check(self.lib.pcgc_extract_points(self.ctx, cubes.data_ptr(), B, S, counts.data_ptr(), None, 0, total.data_ptr()))
+        return to_host(counts[:B], "extract_counts").copy()
+
+
 _CODECS: Dict[tuple, Codec] = {}
 
 
