@@ -283,7 +283,7 @@ def run_gpu(args):
                    "conv_engine": os.environ.get("PCGC_ENGINE", "auto")},
         "points_per_s": round(value * points / B, 1),
         "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "points_per_s": round(e2e * points / B, 1), "steps": e2e_steps, "host_threads": os.cpu_count()},
+                "points_per_s": round(e2e * points / B, 1), "steps": e2e_steps, "host_threads": runtime.coder_threads()},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
         "conv": {"achieved_tflops": round(conv_tflops, 2), "share_of_step": round(conv_ms / total_ms, 4),
                  "algorithmic_gflop_per_cube": GFLOP_PER_CUBE,

@@ -481,6 +481,17 @@ def range_decode(data: bytes, n: int, cdf: np.ndarray, precision: int = 16) -> n
     return sym
 
 
+def coder_threads() -> int:
+    """Host threads one process gives the per-cube range coder: ``PCGC_CODER_THREADS`` if set, else the cores divided by
+    the processes of this node (torchrun's LOCAL_WORLD_SIZE) so that N ranks do not oversubscribe the host."""
+    env = os.environ.get("PCGC_CODER_THREADS")
+    if env:
+        return max(1, int(env))
+    cores = os.cpu_count() or 1
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+    return max(1, cores // max(1, local_world))
+
+
 def range_encode_intervals_batch(iv: np.ndarray, threads: int = 0):
     """iv uint32/int32 [B,E] (host) -> list of B byte strings."""
     L = _lib.lib()
@@ -489,7 +500,7 @@ def range_encode_intervals_batch(iv: np.ndarray, threads: int = 0):
     stride = 2 * E + 64
     out = np.empty((B, stride), np.uint8)
     lens = np.empty(B, np.int64)
-    _lib.check(L.pcgc_range_encode_intervals_batch(iv.ctypes.data, B, E, 16, out.ctypes.data, stride, lens.ctypes.data, threads))
+    _lib.check(L.pcgc_range_encode_intervals_batch(iv.ctypes.data, B, E, 16, out.ctypes.data, stride, lens.ctypes.data, threads or coder_threads()))
     return [out[b, :lens[b]].tobytes() for b in range(B)]
 
 
@@ -506,7 +517,7 @@ def range_decode_rows_batch_f32(strings, E: int, rows: np.ndarray, row_offset: n
     minmax = np.ascontiguousarray(minmax, dtype=np.int32)
     out = pinned_buffer(out_tag, B * E * 4)[:B * E * 4].view(torch.float32).view(B, E)
     _lib.check(L.pcgc_range_decode_rows_batch_f32(ptrs, nbytes.ctypes.data, B, E, rows.ctypes.data, row_offset.ctypes.data,
-                                                  minmax.ctypes.data, 16, out.data_ptr(), threads))
+                                                  minmax.ctypes.data, 16, out.data_ptr(), threads or coder_threads()))
     return out
 
 
@@ -523,5 +534,5 @@ def range_decode_rows_batch(strings, E: int, rows: np.ndarray, row_offset: np.nd
     minmax = np.ascontiguousarray(minmax, dtype=np.int32)
     sym = np.empty((B, E), np.int16)
     _lib.check(L.pcgc_range_decode_rows_batch(ptrs, nbytes.ctypes.data, B, E, rows.ctypes.data, row_offset.ctypes.data,
-                                              minmax.ctypes.data, 16, sym.ctypes.data, threads))
+                                              minmax.ctypes.data, 16, sym.ctypes.data, threads or coder_threads()))
     return sym
