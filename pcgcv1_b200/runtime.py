@@ -226,6 +226,8 @@ class Codec:
             if m != self.model:
                 continue
             nid = _NET_IDS[(m, net)]
+            if "%s/%s/kernel" % (net, layers[0].name) not in w:
+                continue            # e.g. a factorized-mode checkpoint has no hyper nets; using one then fails with NOT_READY
             for l in layers:
                 k = np.ascontiguousarray(w["%s/%s/kernel" % (net, l.name)], dtype=np.float32)
                 shape = (C.c_int64 * 5)(*k.shape)

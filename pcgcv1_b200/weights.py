@@ -116,8 +116,11 @@ def load(ckpt_dir: str, model: str = "voxception") -> Weights:
         return synthetic_weights(model)
     path = os.path.join(ckpt_dir, "weights.npz")
     if not os.path.exists(path):
+        from . import tf_checkpoint
+        if tf_checkpoint.latest_checkpoint(ckpt_dir) is not None:         # a TF-1.13 checkpoint of the reference
+            return tf_checkpoint.import_checkpoint(ckpt_dir, model)
         raise FileNotFoundError(
-            "%s not found: this build reads weights.npz (keys <net>/<layer>/kernel); TF-1.13 "
-            "TensorBundle checkpoints need converting first (INTEGRATION.md)" % path)
+            "%s not found and no TF checkpoint (*.index) in that directory: this build reads weights.npz "
+            "(keys <net>/<layer>/kernel) or the reference's TF-1.13 checkpoints (pcgcv1_b200/tf_checkpoint.py)" % path)
     with np.load(path) as z:
         return {k: z[k] for k in z.files}
