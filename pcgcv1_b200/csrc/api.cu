@@ -327,7 +327,7 @@ int build_umma_program(pcgc_ctx* ctx, int kind) {
       // measured on B200 (r01 sweep): the banded form pays for K_b at 64^3 (0.396 -> 0.325 ms), not for the other kernels
       static const int wt_env = getenv("PCGC_UMMA_WT") ? atoi(getenv("PCGC_UMMA_WT")) : -1;
       const int nn = ana ? (64 >> s) : (16 << s);
-      const int wt_a = wt_env >= 0 ? ((nn >= 32 && wt_env >= 2) ? 2 : 1) : 1;
+      const int wt_a = wt_env >= 0 ? ((nn >= 32 && wt_env >= 2) ? 2 : 1) : ((umma_stream_mode() && nn == 64) ? 2 : 1);   // K_a: banded only where it streams
       const int wt = wt_env >= 0 ? wt_a : (nn == 64 ? 2 : 1);          // K_b
       cudaError_t e = pack_umma_weights_dense(da.data(), ba.data(), C, c2, up.ka[idx], 27, wt_a);
       if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "pack K_a %s: %s", p.c_str(), cudaGetErrorString(e));
@@ -375,7 +375,8 @@ int build_umma_program(pcgc_ctx* ctx, int kind) {
   } else {
     LayerW &li = L("deconv_in"), &lo = L("deconv_out");
     cudaError_t e = pack_umma_weights_dense(li.hk.data(), li.hb.data(), 16, 64, up.first);
-    if (e == cudaSuccess) e = pack_umma_weights_dense(lo.hk.data(), lo.hb.data(), 16, 1, up.last, 27, (getenv("PCGC_UMMA_WT") && atoi(getenv("PCGC_UMMA_WT")) >= 2) ? 4 : 1);
+    if (e == cudaSuccess) e = pack_umma_weights_dense(lo.hk.data(), lo.hb.data(), 16, 1, up.last, 27,
+                                                          getenv("PCGC_UMMA_WT") ? (atoi(getenv("PCGC_UMMA_WT")) >= 2 ? 4 : 1) : (umma_stream_mode() ? 2 : 1));
     if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "pack deconv_in/out: %s", cudaGetErrorString(e));
     // Conv3DTranspose(k3, s2, same): out[2t] = x[t] W[0] + x[t-1] W[2], out[2t+1] = x[t] W[1] per axis.  One GEMM over the
     // 2x2x2 input window {t-1,t}^3 (brick index 0/1) whose column blocks are the 8 output-parity classes.

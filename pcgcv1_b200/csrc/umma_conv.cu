@@ -66,6 +66,10 @@ struct UmmaArgs {
   int out_s2d;               // UEPI_VRN: write the output space-to-depth (grid n/2, 8*C channels) for a following stride-2 conv
   int up_ncls, up_cls0, up_cout;   // UEPI_UP: classes in this launch, first class, channels per class
   int dbg;                   // PCGC_UMMA_DBG bit mask (timing experiments only): 1 skip MMAs, 2 skip the A TMA, 4 skip epilogue
+  // z-streaming kernel (conv_umma_stream_kernel)
+  int ring, zs, nacc;        // input-slice ring slots, output slices per segment, accumulator slots
+  int slot_bytes;            // bytes of one ring slot = planes * slice_plane
+  int slice_plane;           // bytes of one plane of one z-slice: EY * EXC * CELL
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -122,6 +126,17 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
+}
+// One lane of a fully active warp (CUTLASS' elect_one_sync).  ptxas knows the guarded region runs on a single thread and emits
+// the uniform-datapath tcgen05 instructions directly; behind a plain `lane == 0` it wraps EVERY MMA in an ELECT / BRA.U.ANY loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -185,9 +200,22 @@ constexpr int UMMA_THREADS = 32 * (EPI_WARPS + 1);
 constexpr int MAX_ZT = 8;
 
 // Epilogue of ONE output voxel whose NPJ accumulator columns (+bias) are in v[].
+// Residual cells (8 channels each, hi and lo plane) of one voxel of the Voxception block input.
+template <int RC>
+__device__ __forceinline__ void vrn_load_residual(const UmmaArgs& a, int b, int vz, int vy, int vx, size_t plane_elems, uint4* rhi, uint4* rlo) {
+  const size_t vox = ((size_t)vz * a.n + vy) * a.n + vx;
+  const __nv_bfloat16* rb = a.res_pm + (size_t)b * a.res_planes * plane_elems + vox * 8;
+#pragma unroll
+  for (int c8 = 0; c8 < RC; ++c8) {
+    rhi[c8] = __ldg(reinterpret_cast<const uint4*>(rb + (size_t)(2 * c8) * plane_elems));
+    rlo[c8] = __ldg(reinterpret_cast<const uint4*>(rb + (size_t)(2 * c8 + 1) * plane_elems));
+  }
+}
+template <int NPJ> struct VrnRc { static constexpr int value = NPJ == 16 ? 2 : (NPJ == 24 || NPJ == 32 ? 4 : 8); };
+
 template <int NPJ, int EPI>
 __device__ __forceinline__ void epilogue_voxel(const UmmaArgs& a, float* v, const float* s_w23, int b, int vz, int vy, int vx,
-                                               size_t plane_elems) {
+                                               size_t plane_elems, const uint4* pre_hi = nullptr, const uint4* pre_lo = nullptr) {
   const size_t vox = ((size_t)vz * a.n + vy) * a.n + vx;
   if (EPI == UEPI_F32) {
     const size_t gv = (size_t)b * a.n * a.n * a.n + vox;
@@ -235,8 +263,11 @@ __device__ __forceinline__ void epilogue_voxel(const UmmaArgs& a, float* v, cons
     uint4 rhi[RC], rlo[RC];
 #pragma unroll
     for (int c8 = 0; c8 < RC; ++c8) {
-      rhi[c8] = __ldg(reinterpret_cast<const uint4*>(rb + (size_t)(2 * c8) * plane_elems));
-      rlo[c8] = __ldg(reinterpret_cast<const uint4*>(rb + (size_t)(2 * c8 + 1) * plane_elems));
+      if (pre_hi) { rhi[c8] = pre_hi[c8]; rlo[c8] = pre_lo[c8]; }                  // fetched before the accumulator wait (stream kernel)
+      else {
+        rhi[c8] = __ldg(reinterpret_cast<const uint4*>(rb + (size_t)(2 * c8) * plane_elems));
+        rlo[c8] = __ldg(reinterpret_cast<const uint4*>(rb + (size_t)(2 * c8 + 1) * plane_elems));
+      }
     }
 #pragma unroll
     for (int i = 0; i < NPJ; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -319,7 +350,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, (NP <= 16 ? 3 : (NP <= 32 ? 2 : 
   const uint32_t tmem_base = *s_tmem;
 
   if (warp == EPI_WARPS) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ------------------------------ TMA producer + MMA issuer (one thread) ------------------------------
       const uint32_t brick = smem_u32(s_a), bsm = smem_u32(s_b);
       const uint32_t PL = (uint32_t)a.plane_bytes;
@@ -437,6 +468,203 @@ __global__ void __launch_bounds__(UMMA_THREADS, (NP <= 16 ? 3 : (NP <= 32 ? 2 : 
   }
 }
 
+// Z-STREAMING kernel (r01, third form).  The tile kernel above re-reads every input z-slice (zt+2)/zt times from L2 and holds
+// one single-buffered brick per CTA, so it needs 2-3 co-resident CTAs to hide the brick load and the serial work of its one
+// producer/issuer thread -- which the y-banded forms (larger bricks, more B tiles) cannot afford.  Here ONE CTA per SM walks
+// column segments (b, x tile, y tile, zs output slices) along z with the roles split over warps:
+//   * warp 8 (one lane): TMA producer.  Input z-slices stream through a ring of 8 shared-memory slots, one 5-D TMA box of ONE
+//     slice per slot, as far ahead as the ring allows; every slice is fetched (zs+2)/zs times instead of (zt+2)/zt.
+//   * warps 9-11 (one lane each): MMA issuers.  Output slice O belongs to issuer O % 3, which multiplies the slots of input
+//     slices O, O+1, O+2 (kz = 0, 1, 2: three descriptor bases instead of an address offset) into accumulator slot
+//     O % NACC.  Three issuers keep three independent accumulation chains in the tensor pipe and hide each other's barrier
+//     waits; one output is issued by ONE thread in the tile kernel's tap order, so results are bit-identical to it.
+//   * warps 0-7: epilogue, even / odd outputs; the accumulator slot is released as soon as it is in registers.
+//   * barriers, one phase per use: full[slot] (TMA landed; up to three issuers wait on it), sfree[slot] (count 3: one
+//     tcgen05.commit per reading issuer; the producer supplies the missing arrivals of the halo slices that have fewer than
+//     three readers), afull[acc] (commit after the output's 3 x NTZ tiles), afree[acc] (4 epilogue warps), b (weights, once).
+// Loads and outputs are flat sequences across the CTA's segments, so the ring never drains at a segment boundary.
+constexpr int RING_MAX = 8;                              // ring slots: 8, or 4 where 8 do not fit (power of two: slot = load & (R-1))
+constexpr int STREAM_ISSUERS = 3;
+constexpr int STREAM_THREADS = 32 * (EPI_WARPS + 1 + STREAM_ISSUERS);
+
+// The taps of ONE kz of one output slice: NTZ (d, kx) tiles, two MMAs each.
+template <int NP, bool PAIRED, int WT>
+__device__ __forceinline__ void issue_kz(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t bdesc, bool first) {
+  constexpr uint32_t idesc_full = make_idesc(128, 2 * NP), idesc_half = make_idesc(128, NP);
+  constexpr int NTZ = 3 * (WT + 2);                              // A tiles (d, kx) per kz
+  constexpr uint64_t b_step = (uint64_t)((2 * NP * 32) >> 4);
+  static_assert(!PAIRED || NTZ % 2 == 0, "paired taps must not straddle two z-slices");
+#pragma unroll
+  for (int t = 0; t < (PAIRED ? NTZ / 2 : NTZ); ++t) {
+    uint64_t add;
+    if (!PAIRED) {
+      add = (uint64_t)(((((t / 3) * EXC) + t % 3) * CELL) >> 4);
+    } else {
+      const int ta = 2 * t, tb = 2 * t + 1;
+      const int oa = ((ta / 3) * EXC + ta % 3) * CELL, ob = ((tb / 3) * EXC + tb % 3) * CELL;
+      add = (uint64_t)(oa >> 4) | ((uint64_t)((ob - oa) >> 4) << 16);
+    }
+    const uint64_t bd = bdesc + (uint64_t)t * b_step;
+    umma_f16(d, a_hi + add, bd, idesc_full, (t == 0 && first) ? 0u : 1u);      // x_hi * [w_hi | w_lo]
+    umma_f16(d, a_lo + add, bd, idesc_half, 1u);                               // x_lo * w_hi
+  }
+}
+
+template <int NP, int EPI, bool PAIRED, int WT>
+__global__ void __launch_bounds__(STREAM_THREADS, 1) conv_umma_stream_kernel(const __grid_constant__ CUtensorMap tmap, const UmmaArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* s_a = smem;
+  uint8_t* s_b = smem + (size_t)a.ring * a.slot_bytes;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_b + a.b_bytes);          // full[8], sfree[8], afull[8], afree[8], b
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 4 * 8 + 1);
+  float* s_bias = reinterpret_cast<float*>(s_bar + 4 * 8 + 2);             // 16-byte aligned
+  float* s_w23 = s_bias + NP;
+  const uint32_t bar_full = smem_u32(s_bar), bar_sfree = smem_u32(s_bar + 8), bar_afull = smem_u32(s_bar + 16),
+                 bar_afree = smem_u32(s_bar + 24), bar_b = smem_u32(s_bar + 32);
+  constexpr int NACC = NP <= 32 ? 8 : 4;                         // accumulator slots of 2*NP columns (power of two)
+  constexpr int NACC_SH = NP <= 32 ? 3 : 2;
+  constexpr int NPJ = NP / WT;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ZS = a.zs;
+  const int RMASK = a.ring - 1, RSH = a.ring == 8 ? 3 : 2;
+  const int tx_n = a.n / TILE_X, ty_n = a.n / (TILE_Y * WT), tz_n = a.n / ZS;
+  const int total_segs = tx_n * ty_n * tz_n * a.batch;
+  const int n_my = ((int)blockIdx.x < total_segs) ? (total_segs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int total_outs = n_my * ZS;
+
+  for (int i = tid; i < NP; i += STREAM_THREADS) s_bias[i] = a.bias ? a.bias[i] : 0.f;
+  if (EPI == UEPI_VRN) for (int i = tid; i < a.c4 * a.c2 + a.c2; i += STREAM_THREADS) s_w23[i] = i < a.c4 * a.c2 ? a.w23[i] : a.b23[i - a.c4 * a.c2];
+  if (tid == 0) {
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(bar_full + 8 * i, 1); mbar_init(bar_sfree + 8 * i, 3);
+      mbar_init(bar_afull + 8 * i, 1); mbar_init(bar_afree + 8 * i, EPI_WARPS / 2);
+    }
+    mbar_init(bar_b, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == EPI_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(a.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t ring0 = smem_u32(s_a);
+  const uint32_t SP = (uint32_t)a.slice_plane, SB = (uint32_t)a.slot_bytes;
+
+  if (warp == EPI_WARPS) {
+    if (elect_one() && n_my > 0) {
+      // ------------------------------ TMA producer ------------------------------
+      mbar_expect_tx(bar_b, (uint32_t)a.b_bytes);
+      bulk_load(smem_u32(s_b), a.wpacked, (uint32_t)a.b_bytes, bar_b);
+      int l = 0;
+      bool alive = true;
+      for (int sk = 0; sk < n_my && alive; ++sk) {
+        int r = (int)blockIdx.x + sk * (int)gridDim.x;
+        const int bx = r % tx_n; r /= tx_n;
+        const int by = r % ty_n; r /= ty_n;
+        const int bz = r % tz_n; r /= tz_n;
+        const int cx = (bx * TILE_X + a.origin) * 8, cy = by * TILE_Y * WT + a.origin, cz = bz * ZS + a.origin;
+        for (int k = 0; k < ZS + 2; ++k, ++l) {
+          const int slot = l & RMASK, use = l >> RSH;
+          if (use >= 1 && !mbar_wait(bar_sfree + 8 * slot, (use - 1) & 1, a.err, -112)) { alive = false; break; }
+          mbar_expect_tx(bar_full + 8 * slot, SB);
+          tma_load_5d(ring0 + slot * SB, &tmap, bar_full + 8 * slot, cx, cy, cz + k, 0, r);
+          // halo slices have fewer than three reading outputs: supply the missing releases now
+          const int readers = min(k, ZS - 1) - max(k - 2, 0) + 1;
+          for (int e = readers; e < 3; ++e) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_sfree + 8 * slot) : "memory");
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp > EPI_WARPS) {
+    if (elect_one() && n_my > 0) {
+      // ------------------------------ MMA issuer `me`: outputs O = me, me + 3, ... ------------------------------
+      const int me = warp - EPI_WARPS - 1;
+      constexpr int NTK = PAIRED ? 3 * (WT + 2) / 2 : 3 * (WT + 2);  // B tiles per kz
+      constexpr uint64_t b_step = (uint64_t)((2 * NP * 32) >> 4);
+      const uint64_t b0 = make_desc(smem_u32(s_b), 2 * NP * 16, 128);
+      bool alive = mbar_wait(bar_b, 0, a.err, -110);
+      int sk = 0, o = me;
+      while (o >= ZS) { o -= ZS; ++sk; }
+      for (int O = me; O < total_outs && alive; O += STREAM_ISSUERS) {
+        const int l0 = O + 2 * sk;                              // = sk * (ZS + 2) + o: the slice read with kz = 0
+        const int acc = O & (NACC - 1), ause = O >> NACC_SH;
+        if (ause >= 1) { alive = mbar_wait(bar_afree + 8 * acc, (ause - 1) & 1, a.err, -114); if (!alive) break; }
+        const uint32_t d = tmem_base + (uint32_t)(acc * 2 * NP);
+#pragma unroll
+        for (int kz = 0; kz < 3; ++kz) {
+          const int l = l0 + kz, slot = l & RMASK;
+          alive = mbar_wait(bar_full + 8 * slot, (l >> RSH) & 1, a.err, -111);
+          if (!alive) break;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t base = ring0 + (uint32_t)slot * SB;
+          // cin >= 16: K halves are the two 8-channel planes (LBO = 2 planes); cin == 8: LBO is set per tile pair
+          const uint64_t dh = make_desc(base, PAIRED ? 0u : 2 * SP, WT * EXC * CELL), dl = make_desc(base + SP, PAIRED ? 0u : 2 * SP, WT * EXC * CELL);
+          if (!(a.dbg & 1)) issue_kz<NP, PAIRED, WT>(d, dh, dl, b0 + (uint64_t)(kz * NTK) * b_step, kz == 0);
+          umma_commit(bar_sfree + 8 * slot);                    // this reader is done with the slice once its MMAs retire
+        }
+        if (!alive) break;
+        umma_commit(bar_afull + 8 * acc);
+        o += STREAM_ISSUERS;
+        while (o >= ZS) { o -= ZS; ++sk; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------ epilogue: warps 0-3 take even outputs, 4-7 odd ones ------------------------------
+    const int row = (warp & 3) * 32 + lane;
+    const size_t plane_elems = (size_t)a.n * a.n * a.n * 8;
+    int sk = 0, o = warp >> 2, cur = -1, bx = 0, by = 0, bz = 0, b = 0;
+    while (o >= ZS) { o -= ZS; ++sk; }
+    for (int O = (warp >> 2); O < ((a.dbg & 4) ? 0 : total_outs); O += 2) {
+      if (sk != cur) {
+        int r = (int)blockIdx.x + sk * (int)gridDim.x;
+        bx = r % tx_n; r /= tx_n;
+        by = r % ty_n; r /= ty_n;
+        bz = r % tz_n; r /= tz_n;
+        b = r; cur = sk;
+      }
+      const int vx = bx * TILE_X + (row & 7), vyb = by * TILE_Y * WT + WT * (row >> 3), vz = bz * ZS + o;
+      const int acc = O & (NACC - 1), ause = O >> NACC_SH;
+      // Voxception tail: the block input does not depend on the accumulator -- fetch it while the MMAs still run
+      constexpr int RC = EPI == UEPI_VRN ? VrnRc<NPJ>::value : 1;
+      uint4 rhi[WT][RC], rlo[WT][RC];
+      if (EPI == UEPI_VRN) {
+#pragma unroll
+        for (int j = 0; j < WT; ++j) vrn_load_residual<RC>(a, b, vz, vyb + j, vx, plane_elems, rhi[j], rlo[j]);
+      }
+      if (!mbar_wait(bar_afull + 8 * acc, ause & 1, a.err, -113)) break;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t lane_base = tmem_base + (uint32_t)(acc * 2 * NP) + ((uint32_t)((warp & 3) * 32) << 16);
+      float v[NP];
+#pragma unroll
+      for (int j = 0; j < NP / 16; ++j) {
+        float d1[16], d2[16];
+        tmem_ld16(lane_base + (uint32_t)(j * 16), d1);
+        tmem_ld16(lane_base + (uint32_t)(NP + j * 16), d2);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[j * 16 + i] = (d1[i] + d2[i]) + s_bias[j * 16 + i];
+      }
+      // the accumulator slot is in registers now: hand it back before the (long) epilogue math and stores
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_afree + 8 * acc) : "memory");
+#pragma unroll
+      for (int j = 0; j < WT; ++j)
+        epilogue_voxel<NPJ, EPI>(a, v + j * NPJ, s_w23, b, vz, vyb + j, vx, plane_elems, EPI == UEPI_VRN ? rhi[j] : nullptr, EPI == UEPI_VRN ? rlo[j] : nullptr);
+      o += 2;
+      while (o >= ZS) { o -= ZS; ++sk; }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == EPI_WARPS) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -521,7 +749,48 @@ cudaError_t launch_banded(const CUtensorMap& tm, const UmmaArgs& a, int np, int 
   return cudaErrorNotSupported;
 }
 
+template <int NP, int E, bool PAIRED, int WT>
+cudaError_t launch_stream_one(const CUtensorMap& tm, const UmmaArgs& a, int grid, size_t smem, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(conv_umma_stream_kernel<NP, E, PAIRED, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  conv_umma_stream_kernel<NP, E, PAIRED, WT><<<grid, STREAM_THREADS, smem, s>>>(tm, a);
+  return cudaGetLastError();
+}
+
+// the shapes the layer programs stream (+ their float32 test forms); anything else falls back to the tile kernel
+cudaError_t launch_stream(const CUtensorMap& tm, const UmmaArgs& a, int np, int epi, bool paired, int wt, int grid, size_t smem, cudaStream_t s) {
+  if (!paired && wt == 1) {
+    if (np == 16 && epi == UEPI_PM) return launch_stream_one<16, UEPI_PM, false, 1>(tm, a, grid, smem, s);
+    if (np == 16 && epi == UEPI_F32) return launch_stream_one<16, UEPI_F32, false, 1>(tm, a, grid, smem, s);
+    if (np == 32 && epi == UEPI_VRN) return launch_stream_one<32, UEPI_VRN, false, 1>(tm, a, grid, smem, s);      // K_b32
+    if (np == 32 && epi == UEPI_F32) return launch_stream_one<32, UEPI_F32, false, 1>(tm, a, grid, smem, s);
+    if (np == 64 && epi == UEPI_PM) return launch_stream_one<64, UEPI_PM, false, 1>(tm, a, grid, smem, s);        // deconv_in
+    if (np == 64 && epi == UEPI_F32) return launch_stream_one<64, UEPI_F32, false, 1>(tm, a, grid, smem, s);
+  }
+  if (!paired && wt == 2) {
+    if (np == 16 && epi == UEPI_PM) return launch_stream_one<16, UEPI_PM, false, 2>(tm, a, grid, smem, s);        // K_a16
+    if (np == 16 && epi == UEPI_F32) return launch_stream_one<16, UEPI_F32, false, 2>(tm, a, grid, smem, s);
+  }
+  if (paired && wt == 2) {
+    if (np == 32 && epi == UEPI_VRN) return launch_stream_one<32, UEPI_VRN, true, 2>(tm, a, grid, smem, s);       // K_b16
+    if (np == 32 && epi == UEPI_F32) return launch_stream_one<32, UEPI_F32, true, 2>(tm, a, grid, smem, s);
+  }
+  return cudaErrorNotSupported;
+}
+
+bool stream_shape_ok(int np, int epi, bool paired, int wt) {
+  if (!paired && wt == 1) return ((np == 16 || np == 64) && (epi == UEPI_PM || epi == UEPI_F32)) || (np == 32 && (epi == UEPI_VRN || epi == UEPI_F32));
+  if (!paired && wt == 2) return np == 16 && (epi == UEPI_PM || epi == UEPI_F32);
+  if (paired && wt == 2) return np == 32 && (epi == UEPI_VRN || epi == UEPI_F32);
+  return false;
+}
+
 }  // namespace
+
+int umma_stream_mode() {
+  static const int m = getenv("PCGC_UMMA_STREAM") ? atoi(getenv("PCGC_UMMA_STREAM")) : 1;
+  return m;
+}
 
 cudaError_t pack_umma_weights_dense(const float* dense, const float* bias, int cin, int n_real, UmmaWeights& out, int ntaps, int wt) {
   free_umma_weights(out);
@@ -624,10 +893,41 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
   if (c.epi == UEPI_VRN && (!w.w23 || w.c2 + w.c4 != w.n_real || c.res.c != 2 * w.c2 || c.out.c != (c.out_s2d ? 16 : 2) * w.c2)) return cudaErrorInvalidValue;
   if (c.epi == UEPI_PM && (w.n_real % 8 != 0 || c.out.c != w.n_real || w.npj % 8 != 0)) return cudaErrorInvalidValue;
   if (c.epi == UEPI_UP && (w.up_ncls * w.up_cout != w.n_real || w.up_cout % 16 != 0 || c.out.c != w.up_cout || c.out.n != 2 * n)) return cudaErrorInvalidValue;
+  const int vrn_floats = c.epi == UEPI_VRN ? w.c4 * w.c2 + w.c2 : 0;
+  static const int sm_count = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
+  if (umma_stream_mode() && w.ntaps == 27 && w.kchunks == 1 && n >= 16 && stream_shape_ok(w.np, c.epi, a.cin8 != 0, w.wt)) {
+    // z-streaming kernel: one CTA per SM, ring of input slices, rotating accumulators
+    static const int zs_env = getenv("PCGC_STREAM_ZS") ? atoi(getenv("PCGC_STREAM_ZS")) : 16;
+    static const int ring_env = getenv("PCGC_STREAM_RING") ? atoi(getenv("PCGC_STREAM_RING")) : 0;
+    static const int ctas_env = getenv("PCGC_STREAM_CTAS") ? atoi(getenv("PCGC_STREAM_CTAS")) : 1;
+    a.zs = std::min(n, std::max(1, zs_env));
+    while (n % a.zs) --a.zs;
+    a.slice_plane = brick_ey(w.wt) * EXC * CELL;
+    a.slot_bytes = a.ppc * a.slice_plane;
+    const int per_sm = 1;
+    (void)ctas_env;
+    const size_t fixed = (size_t)a.b_bytes + 34 * 8 + (w.np + vrn_floats) * sizeof(float) + 16;
+    const size_t budget = (size_t)220 * 1024;
+    int ring = (size_t)8 * a.slot_bytes + fixed <= budget ? 8 : ((size_t)4 * a.slot_bytes + fixed <= budget ? 4 : 0);
+    if (ring_env == 4 && ring == 8) ring = 4;
+    const int nacc = w.np <= 32 ? 8 : 4;
+    if (ring >= 4 && nacc >= 2) {
+      a.ring = ring; a.nacc = nacc;
+      int cols = 32; while (cols < nacc * 2 * w.np) cols *= 2;
+      a.tmem_cols = cols;
+      a.batch = c.in.B;
+      CUtensorMap tms;
+      cudaError_t es = make_tmap(c.in, brick_ey(w.wt), 1, a.ppc, &tms);
+      if (es != cudaSuccess) return es;
+      const size_t smem_s = (size_t)ring * a.slot_bytes + fixed;
+      const int segs = (n / TILE_X) * (n / (TILE_Y * w.wt)) * (n / a.zs) * c.in.B;
+      if (launches) ++*launches;
+      return launch_stream(tms, a, w.np, c.epi, a.cin8 != 0, w.wt, std::min(segs, sm_count * per_sm), smem_s, s);
+    }
+  }
   CUtensorMap tm;
   cudaError_t e = make_tmap(c.in, brick_ey(w.wt), a.ez, a.ppc, &tm);
   if (e != cudaSuccess) return e;
-  const int vrn_floats = c.epi == UEPI_VRN ? w.c4 * w.c2 + w.c2 : 0;
   const size_t smem = (size_t)a.a_bytes + a.b_bytes + (6 + 2 * MAX_ZT) * 8 + (w.np + vrn_floats) * sizeof(float) + 16;
   const int tiles = (n / TILE_X) * (n / (TILE_Y * w.wt)) * (n / a.zt) * c.in.B;
   a.batch = c.in.B;
