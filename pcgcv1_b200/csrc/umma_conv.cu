@@ -153,6 +153,37 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// N consecutive accumulator columns of this lane in ONE tcgen05.ld (one TMEM round trip instead of N/16).
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float* v) {
+  static_assert(N == 32 || N == 64, "supported widths");
+  uint32_t r[N];
+  if (N == 32) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+          "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+  } else {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+        "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+          "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+          "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]),
+          "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]),
+          "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr));
+  }
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 enum TapMode : int { TAPS_27 = 0, TAPS_27_PAIRED = 1, TAPS_8 = 2 };
 
 // Brick y extent.  WT > 1 is the Y-BANDED form: M row (g, x) stands for WT consecutive output lines y = WT*g + j, the
@@ -639,13 +670,20 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) conv_umma_stream_kernel(con
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t lane_base = tmem_base + (uint32_t)(acc * 2 * NP) + ((uint32_t)((warp & 3) * 32) << 16);
       float v[NP];
+      if (NP == 16 || NP == 32) {
+        float dd[2 * NP];                                        // [x_hi*w_hi + x_lo*w_hi | x_hi*w_lo] in one TMEM round trip
+        tmem_ld<(NP == 16 || NP == 32) ? 2 * NP : 32>(lane_base, dd);
 #pragma unroll
-      for (int j = 0; j < NP / 16; ++j) {
-        float d1[16], d2[16];
-        tmem_ld16(lane_base + (uint32_t)(j * 16), d1);
-        tmem_ld16(lane_base + (uint32_t)(NP + j * 16), d2);
+        for (int i = 0; i < NP; ++i) v[i] = (dd[i] + dd[NP + i]) + s_bias[i];
+      } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[j * 16 + i] = (d1[i] + d2[i]) + s_bias[j * 16 + i];
+        for (int j = 0; j < NP / 16; ++j) {
+          float d1[16], d2[16];
+          tmem_ld16(lane_base + (uint32_t)(j * 16), d1);
+          tmem_ld16(lane_base + (uint32_t)(NP + j * 16), d2);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[j * 16 + i] = (d1[i] + d2[i]) + s_bias[j * 16 + i];
+        }
       }
       // the accumulator slot is in registers now: hand it back before the (long) epilogue math and stores
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
