@@ -819,7 +819,9 @@ cudaError_t launch_stream(const CUtensorMap& tm, const UmmaArgs& a, int np, int 
 bool stream_shape_ok(int np, int epi, bool paired, int wt) {
   if (!paired && wt == 1) return ((np == 16 || np == 64) && (epi == UEPI_PM || epi == UEPI_F32)) || (np == 32 && (epi == UEPI_VRN || epi == UEPI_F32));
   if (!paired && wt == 2) return np == 16 && (epi == UEPI_PM || epi == UEPI_F32);
-  if (paired && wt == 2) return np == 32 && (epi == UEPI_VRN || epi == UEPI_F32);
+  // K_b16 (Cin = 8, Voxception tail): bound by its epilogue, which 2-3 co-resident CTAs of the tile kernel serve better than the
+  // 8 epilogue warps of one streaming CTA (measured r01: 0.34-0.36 ms tiled vs 0.38-0.39 ms streamed) -> only with PCGC_UMMA_STREAM=2
+  if (paired && wt == 2) return umma_stream_mode() >= 2 && np == 32 && (epi == UEPI_VRN || epi == UEPI_F32);
   return false;
 }
 
