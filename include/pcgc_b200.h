@@ -170,6 +170,11 @@ int pcgc_range_encode(const int16_t* sym, int64_t n, const int32_t* cdf, int cdf
                       uint8_t* out, int64_t cap, int64_t* len);
 int pcgc_range_decode(const uint8_t* data, int64_t nbytes, int64_t n, const int32_t* cdf, int cdf_rows, int N,
                       int precision, int16_t* sym);
+/* As pcgc_range_decode, publishing progress: after every `step` symbols (and at the end) the count of symbols already
+ * written to sym is stored to *progress (release order; -1 on a bad argument), so a second thread can start on the head of
+ * one long string -- decompress_hyper starts the hyper decoder on the first cubes while the rest of z is still decoded. */
+int pcgc_range_decode_progress(const uint8_t* data, int64_t nbytes, int64_t n, const int32_t* cdf, int cdf_rows, int N,
+                               int precision, int16_t* sym, int64_t* progress, int64_t step);
 /* Per-element intervals from pcgc_laplace_intervals -> one string. */
 int pcgc_range_encode_intervals(const uint32_t* intervals, int64_t n, int precision, uint8_t* out, int64_t cap,
                                 int64_t* len);

@@ -55,6 +55,7 @@ SIGNATURES = {
     "pcgc_range_encode": (_i, [_vp, _i64, _vp, _i, _i, _i, _vp, _i64, C.POINTER(_i64)]),
     "pcgc_range_decode": (_i, [_vp, _i64, _i64, _vp, _i, _i, _i, _vp]),
     "pcgc_range_encode_intervals": (_i, [_vp, _i64, _i, _vp, _i64, C.POINTER(_i64)]),
+    "pcgc_range_decode_progress": (_i, [_vp, _i64, _i64, _vp, _i, _i, _i, _vp, _vp, _i64]),
     "pcgc_range_decode_rows": (_i, [_vp, _i64, _i64, _vp, _i, _i, _vp]),
     "pcgc_range_encode_intervals_batch": (_i, [_vp, _i, _i64, _i, _vp, _i64, _vp, _i]),
     "pcgc_range_decode_rows_batch": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _i, _vp, _i]),

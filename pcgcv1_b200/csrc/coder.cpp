@@ -213,6 +213,43 @@ int pcgc_range_decode(const uint8_t* data, int64_t nbytes, int64_t n, const int3
   return PCGC_OK;
 }
 
+/* pcgc_range_decode that publishes its position: after every `step` symbols (and at the end) the number of symbols written
+ * to sym is stored to *progress with release order, so another thread can consume the head of one long string (the hyper
+ * latents of the first cubes) while the tail is still being decoded. */
+int pcgc_range_decode_progress(const uint8_t* data, int64_t nbytes, int64_t n, const int32_t* cdf, int cdf_rows, int N,
+                               int precision, int16_t* sym, int64_t* progress, int64_t step) {
+  if ((!data && nbytes) || !cdf || !sym || !progress || cdf_rows < 1 || N < 1 || precision < 1 || precision > 16 || step < 1) {
+    if (progress) __atomic_store_n(progress, (int64_t)-1, __ATOMIC_RELEASE);
+    return PCGC_ERR_BAD_ARG;
+  }
+  Decoder d(data, nbytes, precision);
+  const int sh = precision > 8 ? precision - 8 : 0;
+  std::vector<uint16_t> start((size_t)cdf_rows * 256);
+  for (int r = 0; r < cdf_rows; ++r) {
+    const int32_t* row = cdf + (int64_t)r * (N + 1);
+    int s = 0;
+    for (int q = 0; q < 256; ++q) {
+      const int32_t t = q << sh;
+      while (s + 1 < N && row[s + 1] <= t) ++s;
+      start[(size_t)r * 256 + q] = (uint16_t)s;
+    }
+  }
+  int r = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int32_t* row = cdf + (int64_t)r * (N + 1);
+    const uint16_t* st = start.data() + (size_t)r * 256;
+    sym[i] = (int16_t)d.decode_at([row, st, sh, N](uint32_t t) {
+      int s = st[t >> sh];
+      while (s + 1 < N && (uint32_t)row[s + 1] <= t) ++s;
+      return s;
+    }, [row](int k) { return (uint32_t)row[k]; });
+    if (++r == cdf_rows) r = 0;
+    if ((i + 1) % step == 0) __atomic_store_n(progress, i + 1, __ATOMIC_RELEASE);
+  }
+  __atomic_store_n(progress, n, __ATOMIC_RELEASE);
+  return PCGC_OK;
+}
+
 int pcgc_range_encode_intervals(const uint32_t* iv, int64_t n, int precision, uint8_t* out, int64_t cap,
                                 int64_t* len) {
   if (!iv || !out || !len) return PCGC_ERR_BAD_ARG;

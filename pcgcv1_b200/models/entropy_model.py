@@ -80,6 +80,26 @@ class EntropyBottleneck:
         string = self.compress_finish(sym, cdf)
         return runtime.HostResult(string), runtime.HostResult(np.int32(min_v)), runtime.HostResult(np.int32(max_v))
 
+    def decompress_progressive(self, strings, min_v, max_v, shape, channels=None):
+        """As ``decompress`` but decoding on a worker thread: returns ``get(a, b)`` -> float32 device tensor of leading-axis
+        slice [a, b) (blocks until those symbols are decoded).  The string is sequential, so the leading slices come first."""
+        strings = runtime.unwrap(strings)
+        if isinstance(strings, np.ndarray):
+            strings = strings.item() if strings.ndim == 0 else strings.tobytes() if strings.dtype != object else strings[0]
+        shape = [int(s) for s in np.asarray(runtime.unwrap(shape)).reshape(-1)]
+        min_v, max_v = int(np.asarray(runtime.unwrap(min_v))), int(np.asarray(runtime.unwrap(max_v)))
+        channels = int(np.asarray(runtime.unwrap(channels))) if channels is not None else shape[-1]
+        c, slot = self._resolve(channels)
+        cdf = c.factorized_cdf(slot, min_v, max_v, self._likelihood_bound, self._range_coder_precision)
+        per = int(np.prod(shape[1:]))
+        dec = runtime.ProgressiveDecode(strings, shape[0] * per, cdf, self._range_coder_precision)
+
+        def get(a, b):
+            sym = dec.wait(b * per)[a * per:b * per]
+            vals = (sym.astype(np.int32) + min_v).astype(np.float32).reshape([b - a] + shape[1:])
+            return c.to_device(vals)
+        return get
+
     def decompress(self, strings, min_v, max_v, shape, channels=None):
         """-> float32 tensor of ``shape`` (entropy_model.py:263-306)."""
         strings = runtime.unwrap(strings)

@@ -473,6 +473,44 @@ def range_encode(sym: np.ndarray, cdf: np.ndarray, precision: int = 16) -> bytes
     return out[:ln.value].tobytes()
 
 
+class ProgressiveDecode:
+    """One long string decoded on a worker thread with its position published (pcgc_range_decode_progress): ``wait(n)``
+    returns once the first ``n`` symbols are in ``sym``."""
+
+    def __init__(self, data: bytes, n: int, cdf: np.ndarray, precision: int = 16, step: int = 1 << 15):
+        self._data = bytes(data)
+        self._buf = np.frombuffer(self._data, np.uint8) if len(self._data) else np.zeros(1, np.uint8)
+        self._cdf = np.ascontiguousarray(cdf, dtype=np.int32)
+        self.n = int(n)
+        self.sym = np.empty(self.n, np.int16)
+        self._progress = C.c_int64(0)
+        self._rc = None
+        rows, N = self._cdf.shape[0], self._cdf.shape[1] - 1
+        L = _lib.lib()
+
+        def run():
+            self._rc = L.pcgc_range_decode_progress(self._buf.ctypes.data, len(self._data), self.n, self._cdf.ctypes.data, rows, N, precision,
+                                                    self.sym.ctypes.data, C.byref(self._progress), int(step))
+        import threading
+        self._thread = threading.Thread(target=run, daemon=True)
+        self._thread.start()
+
+    def wait(self, n: int) -> np.ndarray:
+        n = min(int(n), self.n)
+        import time
+        while self._progress.value < n and self._progress.value >= 0 and self._rc is None:
+            time.sleep(0)                                        # yield; the decoder thread holds no GIL inside the C call
+        if self._progress.value < n:                             # finished (or failed) before reaching n
+            self._thread.join()
+            _lib.check(self._rc if self._rc is not None else 0)
+        return self.sym[:n]
+
+    def finish(self) -> np.ndarray:
+        self._thread.join()
+        _lib.check(self._rc)
+        return self.sym
+
+
 def range_decode(data: bytes, n: int, cdf: np.ndarray, precision: int = 16) -> np.ndarray:
     L = _lib.lib()
     cdf = np.ascontiguousarray(cdf, dtype=np.int32)

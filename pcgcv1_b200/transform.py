@@ -87,6 +87,22 @@ def decompress_factorized(strings, min_v, max_v, shape, model, ckpt_dir):
 # entry points release the GIL and fan out over their own thread pool) works on chunk k, the GPU already runs the
 # transforms of chunk k+1 and a copy stream moves the coder's inputs through rotating pinned buffers.
 _CHUNK = int(os.environ.get("PCGC_CHUNK", "64"))
+_CHUNK_EDGE = int(os.environ.get("PCGC_CHUNK_EDGE", "16"))
+
+
+def _chunks(B, small_first=False, small_last=False):
+    """[a, b) chunk bounds.  The pipeline's exposed latency is one chunk's host-coder round trip at the start of a decode
+    (nothing can be synthesised before the first chunk is decoded) and at the end of an encode (the last chunk's strings):
+    those chunks are small (PCGC_CHUNK_EDGE cubes), the ones in between large (PCGC_CHUNK)."""
+    e = _CHUNK_EDGE if 0 < _CHUNK_EDGE < _CHUNK else 0
+    lo, hi = 0, B
+    head, tail = [], []
+    if small_first and e and B > 2 * e:
+        head.append((0, e)); lo = e
+    if small_last and e and hi - lo > 2 * e:
+        tail.append((hi - e, hi)); hi -= e
+    mid = [(a, min(hi, a + _CHUNK)) for a in range(lo, hi, _CHUNK)]
+    return head + mid + tail
 _POOL = None
 _POOL_Z = None
 
@@ -119,7 +135,7 @@ def compress_hyper(cubes, model, ckpt_dir, decompress=False):
     B = cubes.shape[0]
     start = time.time()
     jobs, mms, z_hats, keep = [], [], [], []
-    chunks = [(a, min(B, a + _CHUNK)) for a in range(0, B, _CHUNK)]
+    chunks = _chunks(B, small_last=True)
     z_job = None
     for k, (a, b) in enumerate(chunks):
         x = codec.to_device(cubes[a:b])
@@ -179,16 +195,17 @@ def decompress_hyper(y_strings, y_min_vs, y_max_vs, y_shape, z_strings, z_min_v,
     z_shape = np.asarray(runtime.unwrap(z_shape)).reshape(-1)
     y_shape = [int(v) for v in np.asarray(runtime.unwrap(y_shape)).reshape(-1)]
     start = time.time()
-    zs = entropy_bottleneck.decompress(z_strings, z_min_v, z_max_v, z_shape, z_shape[-1]).tensor
-    _log("Entropy Decoder (Hyper)", start)
+    # the hyper string decodes on a worker thread; each chunk below waits only for ITS cubes' symbols (they come first)
+    z_get = entropy_bottleneck.decompress_progressive(z_strings, z_min_v, z_max_v, z_shape, z_shape[-1])
+    _log("Entropy Decoder (Hyper) started", start)
     strings = _as_list_of_bytes(y_strings)
-    B = zs.shape[0]
+    B = int(z_shape[0])
     if len(strings) != B:
         raise ValueError("got %d y strings for %d cubes" % (len(strings), B))
     mins = np.asarray(runtime.unwrap(y_min_vs)).reshape(-1)
     maxs = np.asarray(runtime.unwrap(y_max_vs)).reshape(-1)
     start = time.time()
-    chunks = [(a, min(B, a + _CHUNK)) for a in range(0, B, _CHUNK)]
+    chunks = _chunks(B, small_first=True)
     xs_parts, pending = [], None
 
     def finish(p):
@@ -198,7 +215,7 @@ def decompress_hyper(y_strings, y_min_vs, y_max_vs, y_shape, z_strings, z_min_v,
         xs_parts.append(codec.synthesis(ys))
 
     for k, (a, b) in enumerate(chunks):
-        locs, scales = codec.hyper_decode(zs[a:b], 1e-9)
+        locs, scales = codec.hyper_decode(z_get(a, b), 1e-9)
         stage, done, off, mm, E = cem.decode_begin(locs, scales, mins[a:b], maxs[a:b], k % 2)
         job = _pool().submit(cem.decode_finish, strings[a:b], stage, done, off, mm, E, k % 2)
         if pending is not None:
