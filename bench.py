@@ -260,6 +260,19 @@ def run_gpu(args):
         roof = {"kernel": top["tag"], "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": round(ach / peaks["hbm_gbs"], 5), "traffic": None}
     roof.update({"peak_source": peaks["source"], "ms_per_launch": round(per_launch_ms, 4), "share_of_step": round(top["ms"] / total_ms, 4)})
+    # DRAM bytes per launch of that kernel from the committed ncu --set full capture (same launch shape: 32 cubes per launch)
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+            tr = json.load(f).get(top["tag"])
+        if tr:
+            roof["traffic"] = int(tr["dram_bytes_per_launch"])
+            roof["traffic_source"] = tr.get("source", "profiles/r01_ncu_traffic.json")
+            for k in ("sm__pipe_tc_cycles_active_pct", "utchmma_bf16_ops_pct_of_peak", "l1tex_tc_wavefronts_shared_pct_of_peak"):
+                if k in tr:
+                    roof["ncu_" + k] = tr[k]
+    except (OSError, ValueError):
+        pass
+    roof["peak_nominal"] = 2250.0 if roof["unit"] == "TFLOP/s" else 8000.0
     conv_ms = sum(r["ms"] for r in prof if r["tag"].startswith("conv"))
     conv_tflops = sum(r["flops"] for r in prof if r["tag"].startswith("conv")) / (conv_ms * 1e-3) / 1e12
     kernels = [{"tag": r["tag"], "share": round(r["ms"] / total_ms, 4),
