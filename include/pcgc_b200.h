@@ -195,6 +195,9 @@ int pcgc_range_decode_rows_batch_f32(const uint8_t* const* data, const int64_t* 
                                      int precision, float* y_hat, int threads);
 
 /* ---- point-cloud I/O either side of the codec ----------------------- */
+/* Multithreaded memcpy of a large host buffer (a pinned staging buffer -> the NumPy array handed to the caller; first-touch
+ * page faults of the fresh destination are spread over the threads).  No reference counterpart: plumbing of this build. */
+int pcgc_host_copy(void* dst, const void* src, int64_t nbytes, int threads);
 /* load_ply_data (dataprocess/inout_points.py:8-28): every line of the ASCII text whose first three single-space
  * separated tokens parse as floats is a point, truncated to int32; other lines (header, comments) are skipped.
  * xyz: HOST int32 [cap,3]; *n = points found (set even when PCGC_ERR_OVERFLOW says cap was too small).  A line with a

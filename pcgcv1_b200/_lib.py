@@ -60,6 +60,7 @@ SIGNATURES = {
     "pcgc_range_encode_intervals_batch": (_i, [_vp, _i, _i64, _i, _vp, _i64, _vp, _i]),
     "pcgc_range_decode_rows_batch": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _i, _vp, _i]),
     "pcgc_range_decode_rows_batch_f32": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _i, _vp, _i]),
+    "pcgc_host_copy": (_i, [_vp, _vp, _i64, _i]),
     "pcgc_ply_parse": (_i, [_vp, _i64, _vp, _i64, _vp, _i]),
     "pcgc_ply_format": (_i, [_vp, _i64, _vp, _i64, _vp, _i]),
     "pcgc_partition_points": (_i, [_vp, _i64, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),

@@ -96,6 +96,17 @@ inline int64_t floormod(int64_t a, int64_t b) { return a - floordiv(a, b) * b; }
 
 extern "C" {
 
+int pcgc_host_copy(void* dst, const void* src, int64_t nbytes, int threads) {
+  if ((!dst || !src) && nbytes) return PCGC_ERR_BAD_ARG;
+  if (nbytes <= 0) return nbytes == 0 ? PCGC_OK : PCGC_ERR_BAD_ARG;
+  const int T = pick_threads(threads, nbytes, 4 << 20);
+  run_threads(T, [&](int t) {
+    const int64_t a = (nbytes * t / T) & ~(int64_t)63, b = t + 1 == T ? nbytes : ((nbytes * (t + 1) / T) & ~(int64_t)63);
+    if (b > a) memcpy((char*)dst + a, (const char*)src + a, (size_t)(b - a));
+  });
+  return PCGC_OK;
+}
+
 int pcgc_ply_parse(const char* text, int64_t nbytes, int32_t* xyz, int64_t cap, int64_t* n, int threads) {
   if ((!text && nbytes) || !n || nbytes < 0 || (!xyz && cap)) return PCGC_ERR_BAD_ARG;
   const int T = pick_threads(threads, nbytes, 1 << 20);

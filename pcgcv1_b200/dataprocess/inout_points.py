@@ -147,7 +147,7 @@ def select_voxels(vols, points_nums, offset_ratio=1.0, fixed_thres=None, codec=N
     else:
         mask, _ = c.threshold(v, float(fixed_thres))
     m = runtime.to_host(mask, "mask")
-    return m.astype(dtype) if np.dtype(dtype) != m.dtype else m.copy()
+    return m.astype(dtype) if np.dtype(dtype) != m.dtype else runtime.host_copy(m)
 
 
 def select_voxels_device(codec, logits: torch.Tensor, ks: torch.Tensor):

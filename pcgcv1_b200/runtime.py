@@ -94,6 +94,17 @@ def to_host(t: torch.Tensor, tag: str = None) -> np.ndarray:
     return stage.numpy()
 
 
+def host_copy(src: np.ndarray) -> np.ndarray:
+    """Fresh NumPy copy of a (pinned staging) array through the library's multithreaded memcpy."""
+    src = np.ascontiguousarray(src)
+    out = np.empty(src.shape, src.dtype)
+    if src.nbytes < (8 << 20):
+        out[...] = src
+        return out
+    _lib.check(_lib.lib().pcgc_host_copy(out.ctypes.data, src.ctypes.data, src.nbytes, coder_threads()))
+    return out
+
+
 def model_name(model) -> str:
     """'voxception' | 'simple' from a model module (test.py:72 importlib seam), a name, or a class."""
     name = model if isinstance(model, str) else getattr(model, "MODEL_NAME", None) or getattr(model, "__name__", "")
