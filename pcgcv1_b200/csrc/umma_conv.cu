@@ -445,6 +445,14 @@ __global__ void __launch_bounds__(UMMA_THREADS, (NP <= 16 ? 3 : (NP <= 32 ? 2 : 
       const uint32_t lane_base = tmem_base + set * set_cols + ((uint32_t)((warp & 3) * 32) << 16);
       for (int zi = (warp >> 2); zi < ((a.dbg & 4) ? 0 : a.zt); zi += 2) {
         const int vz = z0 + zi;
+        // Voxception tail: the block input does not depend on the accumulator -- fetch it before waiting for the MMAs
+        constexpr int RCP = EPI == UEPI_VRN ? VrnRc<NPJ>::value : 1;
+        constexpr bool PREF = EPI == UEPI_VRN && WT * RCP <= 4;             // register budget: up to 4 cells (32 registers)
+        uint4 rhi[PREF ? WT : 1][RCP], rlo[PREF ? WT : 1][RCP];
+        if (PREF) {
+#pragma unroll
+          for (int j = 0; j < WT; ++j) vrn_load_residual<RCP>(a, b, vz, vyb + j, vx, plane_elems, rhi[j], rlo[j]);
+        }
         if (!mbar_wait(bar_z + 8 * (set * MAX_ZT + zi), use & 1, a.err, -103)) break;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (EPI == UEPI_UP) {
@@ -477,11 +485,18 @@ __global__ void __launch_bounds__(UMMA_THREADS, (NP <= 16 ? 3 : (NP <= 32 ? 2 : 
           tmem_ld16(lane_base + (uint32_t)(zi * 2 * NP + j * 16), d1);
           tmem_ld16(lane_base + (uint32_t)(zi * 2 * NP + NP + j * 16), d2);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[j * 16 + i] = (d1[i] + d2[i]) + s_bias[j * 16 + i];
+          for (int i4 = 0; i4 < 4; ++i4) {                     // bias as 16-byte shared loads (4x fewer LSU wavefronts than scalar reads)
+            const float4 bq = reinterpret_cast<const float4*>(s_bias)[j * 4 + i4];
+            v[j * 16 + 4 * i4 + 0] = (d1[4 * i4 + 0] + d2[4 * i4 + 0]) + bq.x;
+            v[j * 16 + 4 * i4 + 1] = (d1[4 * i4 + 1] + d2[4 * i4 + 1]) + bq.y;
+            v[j * 16 + 4 * i4 + 2] = (d1[4 * i4 + 2] + d2[4 * i4 + 2]) + bq.z;
+            v[j * 16 + 4 * i4 + 3] = (d1[4 * i4 + 3] + d2[4 * i4 + 3]) + bq.w;
+          }
         }
 #pragma unroll
         for (int j = 0; j < WT; ++j)
-          epilogue_voxel<NPJ, (EPI == UEPI_UP ? UEPI_F32 : EPI)>(a, v + (EPI == UEPI_UP ? 0 : j * NPJ), s_w23, b, vz, vyb + j, vx, plane_elems);
+          epilogue_voxel<NPJ, (EPI == UEPI_UP ? UEPI_F32 : EPI)>(a, v + (EPI == UEPI_UP ? 0 : j * NPJ), s_w23, b, vz, vyb + j, vx, plane_elems,
+                                                                  PREF ? rhi[j] : nullptr, PREF ? rlo[j] : nullptr);
       }
       // A warp without a slice of its own (zt == 1: warps 4..7) must not run ahead of the MMAs: its arrival for a LATER use
       // of the set would otherwise complete the current phase early.  Pace it on the tile's last slice.
@@ -674,7 +689,13 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) conv_umma_stream_kernel(con
         float dd[2 * NP];                                        // [x_hi*w_hi + x_lo*w_hi | x_hi*w_lo] in one TMEM round trip
         tmem_ld<(NP == 16 || NP == 32) ? 2 * NP : 32>(lane_base, dd);
 #pragma unroll
-        for (int i = 0; i < NP; ++i) v[i] = (dd[i] + dd[NP + i]) + s_bias[i];
+        for (int i4 = 0; i4 < NP / 4; ++i4) {
+          const float4 bq = reinterpret_cast<const float4*>(s_bias)[i4];
+          v[4 * i4 + 0] = (dd[4 * i4 + 0] + dd[NP + 4 * i4 + 0]) + bq.x;
+          v[4 * i4 + 1] = (dd[4 * i4 + 1] + dd[NP + 4 * i4 + 1]) + bq.y;
+          v[4 * i4 + 2] = (dd[4 * i4 + 2] + dd[NP + 4 * i4 + 2]) + bq.z;
+          v[4 * i4 + 3] = (dd[4 * i4 + 3] + dd[NP + 4 * i4 + 3]) + bq.w;
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < NP / 16; ++j) {
@@ -682,7 +703,13 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) conv_umma_stream_kernel(con
           tmem_ld16(lane_base + (uint32_t)(j * 16), d1);
           tmem_ld16(lane_base + (uint32_t)(NP + j * 16), d2);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[j * 16 + i] = (d1[i] + d2[i]) + s_bias[j * 16 + i];
+          for (int i4 = 0; i4 < 4; ++i4) {                     // bias as 16-byte shared loads (4x fewer LSU wavefronts than scalar reads)
+            const float4 bq = reinterpret_cast<const float4*>(s_bias)[j * 4 + i4];
+            v[j * 16 + 4 * i4 + 0] = (d1[4 * i4 + 0] + d2[4 * i4 + 0]) + bq.x;
+            v[j * 16 + 4 * i4 + 1] = (d1[4 * i4 + 1] + d2[4 * i4 + 1]) + bq.y;
+            v[j * 16 + 4 * i4 + 2] = (d1[4 * i4 + 2] + d2[4 * i4 + 2]) + bq.z;
+            v[j * 16 + 4 * i4 + 3] = (d1[4 * i4 + 3] + d2[4 * i4 + 3]) + bq.w;
+          }
         }
       }
       // the accumulator slot is in registers now: hand it back before the (long) epilogue math and stores
