@@ -769,7 +769,8 @@ int pick_zt(int n, int np, int cin, int epi, int wt, int n_mma, int kchunks) {
   const int ppc = cin == 8 ? 2 : 4;
   const int nm = n_mma;
   auto smem = [&](int z) { return ppc * (z + 2) * brick_ey(wt) * EXC * CELL + nm * 2 * np * 32; };
-  while (zt > 1 && smem(zt) > 100 * 1024) zt /= 2;
+  static const int smem_kb = getenv("PCGC_UMMA_SMEM_KB") ? atoi(getenv("PCGC_UMMA_SMEM_KB")) : 100;      // tuning experiments
+  while (zt > 1 && smem(zt) > smem_kb * 1024) zt /= 2;
   // MMA-bound kernels (light epilogue) overlap load / MMA / epilogue better with three CTAs per SM (measured on B200:
   // K_a16 0.676 -> 0.582 ms); the VRN-tail kernels are epilogue/HBM bound and prefer deep z tiles (less halo re-read).
   static const int three = getenv("PCGC_UMMA_3CTA") ? atoi(getenv("PCGC_UMMA_3CTA")) : 1;          // tuning experiments
