@@ -730,6 +730,168 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) conv_umma_stream_kernel(con
   }
 }
 
+// Z-BANDED streaming kernel (r01, fourth form) for the thin-N layers at 64^3 (K_a16: 8 real columns; deconv_out: 1).  Same roles
+// and ring as conv_umma_stream_kernel, but the MMA is INPUT-slice stationary: one MMA per (d, kx) tile of input slice i carries
+// the three kz taps as column blocks [kz=0 | kz=1 | kz=2] (N = 2*48 then 48), so the 4 KiB A tile -- the operand fetch that
+// bounds these layers -- is read once for the three output slices it feeds instead of three times.  The accumulator slot of
+// input slice i then holds the partial sums P_i[kz] of outputs i, i-1, i-2; the epilogue of output O adds P_O[0] + P_{O+1}[1] +
+// P_{O+2}[2] (+ bias) in registers.  FP32 partial sums are added in a different order than in the tile kernel, so results agree
+// with it to FP32 rounding (not bit for bit); the order is fixed, so the kernel is deterministic.
+//   barriers: full[slot] / sfree[slot] (count 1: one issuer reads a slice), pfull[ts] (partial sums of an input slice complete),
+//   pfree[ts] (count 12 = 3 reading outputs x 4 epilogue warps; the issuer supplies the arrivals of the missing readers of halo
+//   slices), b.  5 TMEM slots of 96 columns.
+constexpr int ZB_NP = 16, ZB_NB = 3 * ZB_NP, ZB_SLOTS = 5;
+
+template <int EPI, int WT>
+__global__ void __launch_bounds__(STREAM_THREADS, 1) conv_umma_zband_kernel(const __grid_constant__ CUtensorMap tmap, const UmmaArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* s_a = smem;
+  uint8_t* s_b = smem + (size_t)a.ring * a.slot_bytes;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_b + a.b_bytes);          // full[8], sfree[8], pfull[8], pfree[8], b
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 4 * 8 + 1);
+  float* s_bias = reinterpret_cast<float*>(s_bar + 4 * 8 + 2);
+  const uint32_t bar_full = smem_u32(s_bar), bar_sfree = smem_u32(s_bar + 8), bar_pfull = smem_u32(s_bar + 16),
+                 bar_pfree = smem_u32(s_bar + 24), bar_b = smem_u32(s_bar + 32);
+  constexpr int NP = ZB_NP, NB = ZB_NB, NPJ = NP / WT;
+  constexpr int NTZ = 3 * (WT + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ZS = a.zs, LPS = ZS + 2;
+  const int RMASK = a.ring - 1, RSH = a.ring == 8 ? 3 : 2;
+  const int tx_n = a.n / TILE_X, ty_n = a.n / (TILE_Y * WT), tz_n = a.n / ZS;
+  const int total_segs = tx_n * ty_n * tz_n * a.batch;
+  const int n_my = ((int)blockIdx.x < total_segs) ? (total_segs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int total_outs = n_my * ZS, total_loads = n_my * LPS;
+
+  for (int i = tid; i < NP; i += STREAM_THREADS) s_bias[i] = a.bias ? a.bias[i] : 0.f;
+  if (tid == 0) {
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(bar_full + 8 * i, 1); mbar_init(bar_sfree + 8 * i, 1);
+      mbar_init(bar_pfull + 8 * i, 1); mbar_init(bar_pfree + 8 * i, 3 * (EPI_WARPS / 2));
+    }
+    mbar_init(bar_b, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == EPI_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(a.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t ring0 = smem_u32(s_a);
+  const uint32_t SP = (uint32_t)a.slice_plane, SB = (uint32_t)a.slot_bytes;
+
+  if (warp == EPI_WARPS) {
+    if (elect_one() && n_my > 0) {
+      // ------------------------------ TMA producer ------------------------------
+      mbar_expect_tx(bar_b, (uint32_t)a.b_bytes);
+      bulk_load(smem_u32(s_b), a.wpacked, (uint32_t)a.b_bytes, bar_b);
+      int l = 0;
+      bool alive = true;
+      for (int sk = 0; sk < n_my && alive; ++sk) {
+        int r = (int)blockIdx.x + sk * (int)gridDim.x;
+        const int bx = r % tx_n; r /= tx_n;
+        const int by = r % ty_n; r /= ty_n;
+        const int bz = r % tz_n; r /= tz_n;
+        const int cx = (bx * TILE_X + a.origin) * 8, cy = by * TILE_Y * WT + a.origin, cz = bz * ZS + a.origin;
+        for (int k = 0; k < LPS; ++k, ++l) {
+          const int slot = l & RMASK, use = l >> RSH;
+          if (use >= 1 && !mbar_wait(bar_sfree + 8 * slot, (use - 1) & 1, a.err, -122)) { alive = false; break; }
+          mbar_expect_tx(bar_full + 8 * slot, SB);
+          tma_load_5d(ring0 + slot * SB, &tmap, bar_full + 8 * slot, cx, cy, cz + k, 0, r);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp > EPI_WARPS) {
+    if (elect_one() && n_my > 0) {
+      // ------------------------------ MMA issuer `me`: input slices l = me, me + 3, ... ------------------------------
+      const int me = warp - EPI_WARPS - 1;
+      constexpr uint32_t idesc_full = make_idesc(128, 2 * NB), idesc_half = make_idesc(128, NB);
+      constexpr uint64_t b_step = (uint64_t)((2 * NB * 32) >> 4);
+      const uint64_t b0 = make_desc(smem_u32(s_b), 2 * NB * 16, 128);
+      bool alive = mbar_wait(bar_b, 0, a.err, -120);
+      int k = me;                                               // position of slice l inside its segment
+      while (k >= LPS) k -= LPS;
+      for (int l = me; l < total_loads && alive; l += STREAM_ISSUERS) {
+        const int slot = l & RMASK, ts = l % ZB_SLOTS, tuse = l / ZB_SLOTS;
+        if (tuse >= 1) { alive = mbar_wait(bar_pfree + 8 * ts, (tuse - 1) & 1, a.err, -124); if (!alive) break; }
+        alive = mbar_wait(bar_full + 8 * slot, (l >> RSH) & 1, a.err, -121);
+        if (!alive) break;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t base = ring0 + (uint32_t)slot * SB;
+        const uint64_t dh = make_desc(base, 2 * SP, WT * EXC * CELL), dl = make_desc(base + SP, 2 * SP, WT * EXC * CELL);
+        const uint32_t d = tmem_base + (uint32_t)(ts * 2 * NB);
+        if (!(a.dbg & 1)) {
+#pragma unroll
+          for (int t = 0; t < NTZ; ++t) {
+            const uint64_t add = (uint64_t)(((((t / 3) * EXC) + t % 3) * CELL) >> 4);
+            const uint64_t bd = b0 + (uint64_t)t * b_step;
+            umma_f16(d, dh + add, bd, idesc_full, t == 0 ? 0u : 1u);       // x_hi * [w_hi(kz 0,1,2) | w_lo(kz 0,1,2)]
+            umma_f16(d, dl + add, bd, idesc_half, 1u);                      // x_lo * w_hi(kz 0,1,2)
+          }
+        }
+        umma_commit(bar_sfree + 8 * slot);
+        umma_commit(bar_pfull + 8 * ts);
+        // halo slices feed fewer than three outputs: supply the epilogue arrivals of the missing readers
+        const int readers = min(k, ZS - 1) - max(k - 2, 0) + 1;
+        for (int e = readers * (EPI_WARPS / 2); e < 3 * (EPI_WARPS / 2); ++e)
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_pfree + 8 * ts) : "memory");
+        k += STREAM_ISSUERS;
+        while (k >= LPS) k -= LPS;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------ epilogue: warps 0-3 take even outputs, 4-7 odd ones ------------------------------
+    const int row = (warp & 3) * 32 + lane;
+    const size_t plane_elems = (size_t)a.n * a.n * a.n * 8;
+    int sk = 0, o = warp >> 2, cur = -1, bx = 0, by = 0, bz = 0, b = 0;
+    while (o >= ZS) { o -= ZS; ++sk; }
+    for (int O = (warp >> 2); O < ((a.dbg & 4) ? 0 : total_outs); O += 2) {
+      if (sk != cur) {
+        int r = (int)blockIdx.x + sk * (int)gridDim.x;
+        bx = r % tx_n; r /= tx_n;
+        by = r % ty_n; r /= ty_n;
+        bz = r % tz_n; r /= tz_n;
+        b = r; cur = sk;
+      }
+      const int vx = bx * TILE_X + (row & 7), vyb = by * TILE_Y * WT + WT * (row >> 3), vz = bz * ZS + o;
+      const int l0 = O + 2 * sk;                                // input slice read with kz = 0
+      float v[NP];
+      bool ok = true;
+#pragma unroll
+      for (int kz = 0; kz < 3; ++kz) {
+        const int l = l0 + kz, ts = l % ZB_SLOTS;
+        if (!mbar_wait(bar_pfull + 8 * ts, (l / ZB_SLOTS) & 1, a.err, -123)) { ok = false; break; }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t lane_base = tmem_base + (uint32_t)(ts * 2 * NB + kz * NP) + ((uint32_t)((warp & 3) * 32) << 16);
+        float d1[16], d2[16];
+        tmem_ld16(lane_base, d1);
+        tmem_ld16(lane_base + (uint32_t)NB, d2);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) v[i] = kz == 0 ? (d1[i] + d2[i]) : v[i] + (d1[i] + d2[i]);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_pfree + 8 * ts) : "memory");
+      }
+      if (!ok) break;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) v[i] += s_bias[i];
+#pragma unroll
+      for (int j = 0; j < WT; ++j) epilogue_voxel<NPJ, EPI>(a, v + j * NPJ, nullptr, b, vz, vyb + j, vx, plane_elems);
+      o += 2;
+      while (o >= ZS) { o -= ZS; ++sk; }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == EPI_WARPS) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -908,6 +1070,31 @@ cudaError_t pack_umma_weights_dense(const float* dense, const float* bias, int c
   if (e != cudaSuccess) return e;
   e = cudaMemcpy(out.packed, p.data(), p.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return e;
+  if (ntaps == 27 && cin == 16 && wt == 2 && np == 16) {
+    // z-banded form (conv_umma_zband_kernel): ONE MMA per (d, kx) tile carries the three kz taps as column blocks, so the A tile
+    // of an input slice is fetched once for the three output slices it feeds.  Rows: hi = kz*np + n, lo = 3*np + kz*np + n.
+    const int nb = 3 * np, ntz = 3 * (wt + 2);
+    const size_t tile3 = (size_t)2 * nb * 16;
+    std::vector<__nv_bfloat16> pz((size_t)ntz * tile3, __float2bfloat16(0.f));
+    for (int t = 0; t < ntz; ++t)
+      for (int kz = 0; kz < 3; ++kz)
+        for (int k = 0; k < 16; ++k)
+          for (int j = 0; j < wt; ++j)
+            for (int co = 0; co < n_real; ++co) {
+              const float w = weight(kz * ntz + t, k, j, co);
+              if (w == 0.f) continue;
+              const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+              const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+              auto at3 = [&](int row) { return (size_t)t * tile3 + (size_t)(k / 8) * (2 * nb * 8) + (size_t)(row / 8) * 64 + (row % 8) * 8 + (k % 8); };
+              pz[at3(kz * np + j * npj + co)] = hi;
+              pz[at3(nb + kz * np + j * npj + co)] = lo;
+            }
+    cudaError_t ez = cudaMalloc(&out.packed_zb, pz.size() * sizeof(__nv_bfloat16));
+    if (ez != cudaSuccess) return ez;
+    ez = cudaMemcpy(out.packed_zb, pz.data(), pz.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice);
+    if (ez != cudaSuccess) return ez;
+    out.zb_bytes = (int)(pz.size() * sizeof(__nv_bfloat16));
+  }
   std::vector<float> bz(np, 0.f);
   if (bias) for (int j = 0; j < wt; ++j) for (int i = 0; i < n_real; ++i) bz[j * npj + i] = bias[i];
   e = cudaMalloc((void**)&out.bias, np * sizeof(float));
@@ -931,6 +1118,7 @@ cudaError_t pack_umma_weights(const float* kernel, int cin, int cout, UmmaWeight
 
 void free_umma_weights(UmmaWeights& w) {
   if (w.packed) cudaFree(w.packed);
+  if (w.packed_zb) cudaFree(w.packed_zb);
   if (w.bias) cudaFree(w.bias);
   if (w.w23) cudaFree(w.w23);
   if (w.b23) cudaFree(w.b23);
@@ -963,6 +1151,36 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
   if (c.epi == UEPI_UP && (w.up_ncls * w.up_cout != w.n_real || w.up_cout % 16 != 0 || c.out.c != w.up_cout || c.out.n != 2 * n)) return cudaErrorInvalidValue;
   const int vrn_floats = c.epi == UEPI_VRN ? w.c4 * w.c2 + w.c2 : 0;
   static const int sm_count = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
+  static const int zband = getenv("PCGC_UMMA_ZBAND") ? atoi(getenv("PCGC_UMMA_ZBAND")) : 1;
+  if (zband && umma_stream_mode() && w.packed_zb && w.wt == 2 && w.np == 16 && n >= 32 && (c.epi == UEPI_PM || c.epi == UEPI_F32)) {
+    // z-banded streaming kernel (thin-N layers): the three kz taps are column blocks of one MMA
+    a.zs = std::min(n, 16);
+    a.slice_plane = brick_ey(2) * EXC * CELL;
+    a.slot_bytes = a.ppc * a.slice_plane;
+    a.b_bytes = w.zb_bytes;
+    a.wpacked = (const __nv_bfloat16*)w.packed_zb;
+    const size_t fixed = (size_t)a.b_bytes + 34 * 8 + w.np * sizeof(float) + 16;
+    a.ring = 8; a.nacc = ZB_SLOTS; a.tmem_cols = 512; a.batch = c.in.B;
+    CUtensorMap tmz;
+    cudaError_t ez = make_tmap(c.in, brick_ey(2), 1, a.ppc, &tmz);
+    if (ez != cudaSuccess) return ez;
+    const size_t smem_z = (size_t)a.ring * a.slot_bytes + fixed;
+    const int segs = (n / TILE_X) * (n / (TILE_Y * 2)) * (n / a.zs) * c.in.B;
+    const int grid_z = std::min(segs, sm_count);
+    if (launches) ++*launches;
+    cudaError_t (*fn)(const CUtensorMap&, const UmmaArgs&, int, size_t, cudaStream_t) = nullptr;
+    if (c.epi == UEPI_PM) {
+      ez = cudaFuncSetAttribute(conv_umma_zband_kernel<UEPI_PM, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_z);
+      if (ez != cudaSuccess) return ez;
+      conv_umma_zband_kernel<UEPI_PM, 2><<<grid_z, STREAM_THREADS, smem_z, s>>>(tmz, a);
+    } else {
+      ez = cudaFuncSetAttribute(conv_umma_zband_kernel<UEPI_F32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_z);
+      if (ez != cudaSuccess) return ez;
+      conv_umma_zband_kernel<UEPI_F32, 2><<<grid_z, STREAM_THREADS, smem_z, s>>>(tmz, a);
+    }
+    (void)fn;
+    return cudaGetLastError();
+  }
   if (umma_stream_mode() && w.ntaps == 27 && w.kchunks == 1 && n >= 16 && stream_shape_ok(w.np, c.epi, a.cin8 != 0, w.wt)) {
     // z-streaming kernel: one CTA per SM, ring of input slices, rotating accumulators
     static const int zs_env = getenv("PCGC_STREAM_ZS") ? atoi(getenv("PCGC_STREAM_ZS")) : 16;

@@ -39,6 +39,8 @@ struct UmmaWeights {
   int kchunks = 0;
   void* packed = nullptr;   // device bf16: [kchunk][n_mma][2*np x 16] canonical no-swizzle K-major tiles
   float* bias = nullptr;    // device [np] (zero padded)
+  void* packed_zb = nullptr;   // device bf16, z-banded form (cin 16, wt 2, np 16 only): [12 (d,kx) tiles][2*48 x 16], columns (kz, j, channel)
+  int zb_bytes = 0;
   // VRN tail (UEPI_VRN): conv2_3 1x1x1 weights [c4][c2] and bias [c2]
   float* w23 = nullptr; float* b23 = nullptr; int c4 = 0, c2 = 0;
 };
