@@ -820,16 +820,17 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) conv_umma_zband_kernel(cons
         alive = mbar_wait(bar_full + 8 * slot, (l >> RSH) & 1, a.err, -121);
         if (!alive) break;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t base = ring0 + (uint32_t)slot * SB;
-        const uint64_t dh = make_desc(base, 2 * SP, WT * EXC * CELL), dl = make_desc(base + SP, 2 * SP, WT * EXC * CELL);
         const uint32_t d = tmem_base + (uint32_t)(ts * 2 * NB);
-        if (!(a.dbg & 1)) {
+        for (int ch = 0; ch < a.kchunks && !(a.dbg & 1); ++ch) {            // 16 input channels (4 planes) per chunk
+          const uint32_t base = ring0 + (uint32_t)slot * SB + (uint32_t)ch * 4u * SP;
+          const uint64_t dh = make_desc(base, 2 * SP, WT * EXC * CELL), dl = make_desc(base + SP, 2 * SP, WT * EXC * CELL);
+          const uint64_t bc = b0 + (uint64_t)(ch * NTZ) * b_step;
 #pragma unroll
           for (int t = 0; t < NTZ; ++t) {
             const uint64_t add = (uint64_t)(((((t / 3) * EXC) + t % 3) * CELL) >> 4);
-            const uint64_t bd = b0 + (uint64_t)t * b_step;
-            umma_f16(d, dh + add, bd, idesc_full, t == 0 ? 0u : 1u);       // x_hi * [w_hi(kz 0,1,2) | w_lo(kz 0,1,2)]
-            umma_f16(d, dl + add, bd, idesc_half, 1u);                      // x_lo * w_hi(kz 0,1,2)
+            const uint64_t bd = bc + (uint64_t)t * b_step;
+            umma_f16(d, dh + add, bd, idesc_full, (ch == 0 && t == 0) ? 0u : 1u);   // x_hi * [w_hi(kz 0,1,2) | w_lo(kz 0,1,2)]
+            umma_f16(d, dl + add, bd, idesc_half, 1u);                               // x_lo * w_hi(kz 0,1,2)
           }
         }
         umma_commit(bar_sfree + 8 * slot);
@@ -1070,22 +1071,23 @@ cudaError_t pack_umma_weights_dense(const float* dense, const float* bias, int c
   if (e != cudaSuccess) return e;
   e = cudaMemcpy(out.packed, p.data(), p.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return e;
-  if (ntaps == 27 && cin == 16 && wt == 2 && np == 16) {
+  if (ntaps == 27 && (cin == 16 || cin == 32) && (wt == 1 || wt == 2) && np == 16) {
     // z-banded form (conv_umma_zband_kernel): ONE MMA per (d, kx) tile carries the three kz taps as column blocks, so the A tile
     // of an input slice is fetched once for the three output slices it feeds.  Rows: hi = kz*np + n, lo = 3*np + kz*np + n.
     const int nb = 3 * np, ntz = 3 * (wt + 2);
     const size_t tile3 = (size_t)2 * nb * 16;
-    std::vector<__nv_bfloat16> pz((size_t)ntz * tile3, __float2bfloat16(0.f));
-    for (int t = 0; t < ntz; ++t)
+    std::vector<__nv_bfloat16> pz((size_t)kchunks * ntz * tile3, __float2bfloat16(0.f));
+    for (int ch = 0; ch < kchunks; ++ch)
+     for (int t = 0; t < ntz; ++t)
       for (int kz = 0; kz < 3; ++kz)
         for (int k = 0; k < 16; ++k)
           for (int j = 0; j < wt; ++j)
             for (int co = 0; co < n_real; ++co) {
-              const float w = weight(kz * ntz + t, k, j, co);
+              const float w = weight(kz * ntz + t, ch * 16 + k, j, co);
               if (w == 0.f) continue;
               const __nv_bfloat16 hi = __float2bfloat16_rn(w);
               const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
-              auto at3 = [&](int row) { return (size_t)t * tile3 + (size_t)(k / 8) * (2 * nb * 8) + (size_t)(row / 8) * 64 + (row % 8) * 8 + (k % 8); };
+              auto at3 = [&](int row) { return (size_t)(ch * ntz + t) * tile3 + (size_t)(k / 8) * (2 * nb * 8) + (size_t)(row / 8) * 64 + (row % 8) * 8 + (k % 8); };
               pz[at3(kz * np + j * npj + co)] = hi;
               pz[at3(nb + kz * np + j * npj + co)] = lo;
             }
@@ -1152,34 +1154,34 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
   const int vrn_floats = c.epi == UEPI_VRN ? w.c4 * w.c2 + w.c2 : 0;
   static const int sm_count = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
   static const int zband = getenv("PCGC_UMMA_ZBAND") ? atoi(getenv("PCGC_UMMA_ZBAND")) : 1;
-  if (zband && umma_stream_mode() && w.packed_zb && w.wt == 2 && w.np == 16 && n >= 32 && (c.epi == UEPI_PM || c.epi == UEPI_F32)) {
+  if (zband && umma_stream_mode() && w.packed_zb && w.np == 16 && n >= 32 && (c.epi == UEPI_PM || c.epi == UEPI_F32)) {
     // z-banded streaming kernel (thin-N layers): the three kz taps are column blocks of one MMA
-    a.zs = std::min(n, 16);
-    a.slice_plane = brick_ey(2) * EXC * CELL;
-    a.slot_bytes = a.ppc * a.slice_plane;
-    a.b_bytes = w.zb_bytes;
-    a.wpacked = (const __nv_bfloat16*)w.packed_zb;
-    const size_t fixed = (size_t)a.b_bytes + 34 * 8 + w.np * sizeof(float) + 16;
-    a.ring = 8; a.nacc = ZB_SLOTS; a.tmem_cols = 512; a.batch = c.in.B;
-    CUtensorMap tmz;
-    cudaError_t ez = make_tmap(c.in, brick_ey(2), 1, a.ppc, &tmz);
-    if (ez != cudaSuccess) return ez;
-    const size_t smem_z = (size_t)a.ring * a.slot_bytes + fixed;
-    const int segs = (n / TILE_X) * (n / (TILE_Y * 2)) * (n / a.zs) * c.in.B;
-    const int grid_z = std::min(segs, sm_count);
-    if (launches) ++*launches;
-    cudaError_t (*fn)(const CUtensorMap&, const UmmaArgs&, int, size_t, cudaStream_t) = nullptr;
-    if (c.epi == UEPI_PM) {
-      ez = cudaFuncSetAttribute(conv_umma_zband_kernel<UEPI_PM, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_z);
+    const int z_slice_plane = brick_ey(w.wt) * EXC * CELL, z_slot = a.ppc * w.kchunks * z_slice_plane;
+    const size_t fixed = (size_t)w.zb_bytes + 34 * 8 + w.np * sizeof(float) + 16;
+    const size_t budget = (size_t)220 * 1024;
+    const int z_ring = (size_t)8 * z_slot + fixed <= budget ? 8 : ((size_t)4 * z_slot + fixed <= budget ? 4 : 0);
+    if (z_ring) {
+      a.zs = n >= 64 ? 16 : 8;                                 // enough segments per launch to balance 148 persistent CTAs
+      a.slice_plane = z_slice_plane; a.slot_bytes = z_slot; a.ring = z_ring;
+      a.b_bytes = w.zb_bytes;
+      a.wpacked = (const __nv_bfloat16*)w.packed_zb;
+      a.nacc = ZB_SLOTS; a.tmem_cols = 512; a.batch = c.in.B;
+      CUtensorMap tmz;
+      cudaError_t ez = make_tmap(c.in, brick_ey(w.wt), 1, a.ppc * w.kchunks, &tmz);
       if (ez != cudaSuccess) return ez;
-      conv_umma_zband_kernel<UEPI_PM, 2><<<grid_z, STREAM_THREADS, smem_z, s>>>(tmz, a);
-    } else {
-      ez = cudaFuncSetAttribute(conv_umma_zband_kernel<UEPI_F32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_z);
-      if (ez != cudaSuccess) return ez;
-      conv_umma_zband_kernel<UEPI_F32, 2><<<grid_z, STREAM_THREADS, smem_z, s>>>(tmz, a);
+      const size_t smem_z = (size_t)a.ring * a.slot_bytes + fixed;
+      const int segs = (n / TILE_X) * (n / (TILE_Y * w.wt)) * (n / a.zs) * c.in.B;
+      const int grid_z = std::min(segs, sm_count);
+      if (launches) ++*launches;
+      auto go = [&](auto kern) -> cudaError_t {
+        cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_z);
+        if (e2 != cudaSuccess) return e2;
+        kern<<<grid_z, STREAM_THREADS, smem_z, s>>>(tmz, a);
+        return cudaGetLastError();
+      };
+      if (w.wt == 2) return c.epi == UEPI_PM ? go(conv_umma_zband_kernel<UEPI_PM, 2>) : go(conv_umma_zband_kernel<UEPI_F32, 2>);
+      return c.epi == UEPI_PM ? go(conv_umma_zband_kernel<UEPI_PM, 1>) : go(conv_umma_zband_kernel<UEPI_F32, 1>);
     }
-    (void)fn;
-    return cudaGetLastError();
   }
   if (umma_stream_mode() && w.ntaps == 27 && w.kchunks == 1 && n >= 16 && stream_shape_ok(w.np, c.epi, a.cin8 != 0, w.wt)) {
     // z-streaming kernel: one CTA per SM, ring of input slices, rotating accumulators
