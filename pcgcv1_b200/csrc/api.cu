@@ -328,7 +328,10 @@ int build_umma_program(pcgc_ctx* ctx, int kind) {
       static const int wt_env = getenv("PCGC_UMMA_WT") ? atoi(getenv("PCGC_UMMA_WT")) : -1;
       const int nn = ana ? (64 >> s) : (16 << s);
       const int wt_a = wt_env >= 0 ? ((nn >= 32 && wt_env >= 2) ? 2 : 1) : ((umma_stream_mode() && nn == 64) ? 2 : 1);   // K_a: banded only where it streams
-      const int wt = wt_env >= 0 ? wt_a : (nn == 64 ? 2 : 1);          // K_b
+      // K_b: y-banded tile kernel at 64^3.  Its z-banded form (wt 1, paired taps, 3 epilogue groups) is correct but measured slower
+      // (0.359 vs 0.330 ms per 32 cubes: twice as many 128-voxel outputs, each with its fixed barrier / TMEM round trips) -> opt-in only
+      static const bool kb16_zband = getenv("PCGC_KB16_ZBAND") && atoi(getenv("PCGC_KB16_ZBAND")) != 0;
+      const int wt = wt_env >= 0 ? wt_a : ((nn == 64 && !(kb16_zband && umma_zband_mode())) ? 2 : 1);
       cudaError_t e = pack_umma_weights_dense(da.data(), ba.data(), C, c2, up.ka[idx], 27, wt_a);
       if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "pack K_a %s: %s", p.c_str(), cudaGetErrorString(e));
       // K_b: dense [27][c2][c2 + c4], block diagonal

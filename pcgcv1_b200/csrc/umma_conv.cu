@@ -742,8 +742,10 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) conv_umma_stream_kernel(con
 //   slices), b.  5 TMEM slots of 96 columns.
 constexpr int ZB_NP = 16, ZB_NB = 3 * ZB_NP, ZB_SLOTS = 5;
 
-template <int EPI, int WT>
-__global__ void __launch_bounds__(STREAM_THREADS, 1) conv_umma_zband_kernel(const __grid_constant__ CUtensorMap tmap, const UmmaArgs a) {
+// EG epilogue groups of 4 warps (output O belongs to group O % EG), NI issuer warps (input slice l belongs to issuer l % NI).
+// The Voxception-tail form (K_b16) is bound by its epilogue: it runs 3 groups and 1 issuer; the plain forms 2 and 3.
+template <int EPI, int WT, bool PAIRED, int EG, int NI>
+__global__ void __launch_bounds__(32 * (4 * EG + 1 + NI), 1) conv_umma_zband_kernel(const __grid_constant__ CUtensorMap tmap, const UmmaArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* s_a = smem;
   uint8_t* s_b = smem + (size_t)a.ring * a.slot_bytes;
@@ -754,6 +756,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) conv_umma_zband_kernel(cons
                  bar_pfree = smem_u32(s_bar + 24), bar_b = smem_u32(s_bar + 32);
   constexpr int NP = ZB_NP, NB = ZB_NB, NPJ = NP / WT;
   constexpr int NTZ = 3 * (WT + 2);
+  constexpr int EW = 4 * EG, THREADS = 32 * (EW + 1 + NI);
+  float* s_w23 = s_bias + NP;                                              // [c4][c2] then b23[c2] (UEPI_VRN only)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ZS = a.zs, LPS = ZS + 2;
   const int RMASK = a.ring - 1, RSH = a.ring == 8 ? 3 : 2;
@@ -762,16 +766,17 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) conv_umma_zband_kernel(cons
   const int n_my = ((int)blockIdx.x < total_segs) ? (total_segs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int total_outs = n_my * ZS, total_loads = n_my * LPS;
 
-  for (int i = tid; i < NP; i += STREAM_THREADS) s_bias[i] = a.bias ? a.bias[i] : 0.f;
+  for (int i = tid; i < NP; i += THREADS) s_bias[i] = a.bias ? a.bias[i] : 0.f;
+  if (EPI == UEPI_VRN) for (int i = tid; i < a.c4 * a.c2 + a.c2; i += THREADS) s_w23[i] = i < a.c4 * a.c2 ? a.w23[i] : a.b23[i - a.c4 * a.c2];
   if (tid == 0) {
     for (int i = 0; i < 8; ++i) {
       mbar_init(bar_full + 8 * i, 1); mbar_init(bar_sfree + 8 * i, 1);
-      mbar_init(bar_pfull + 8 * i, 1); mbar_init(bar_pfree + 8 * i, 3 * (EPI_WARPS / 2));
+      mbar_init(bar_pfull + 8 * i, 1); mbar_init(bar_pfree + 8 * i, 12);            // 3 reading outputs x 4 warps
     }
     mbar_init(bar_b, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == EPI_WARPS) {
+  if (warp == EW) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(a.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -782,7 +787,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) conv_umma_zband_kernel(cons
   const uint32_t ring0 = smem_u32(s_a);
   const uint32_t SP = (uint32_t)a.slice_plane, SB = (uint32_t)a.slot_bytes;
 
-  if (warp == EPI_WARPS) {
+  if (warp == EW) {
     if (elect_one() && n_my > 0) {
       // ------------------------------ TMA producer ------------------------------
       mbar_expect_tx(bar_b, (uint32_t)a.b_bytes);
@@ -804,53 +809,69 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) conv_umma_zband_kernel(cons
       }
     }
     __syncwarp();
-  } else if (warp > EPI_WARPS) {
+  } else if (warp > EW) {
     if (elect_one() && n_my > 0) {
-      // ------------------------------ MMA issuer `me`: input slices l = me, me + 3, ... ------------------------------
-      const int me = warp - EPI_WARPS - 1;
+      // ------------------------------ MMA issuer `me`: input slices l = me, me + NI, ... ------------------------------
+      const int me = warp - EW - 1;
       constexpr uint32_t idesc_full = make_idesc(128, 2 * NB), idesc_half = make_idesc(128, NB);
       constexpr uint64_t b_step = (uint64_t)((2 * NB * 32) >> 4);
       const uint64_t b0 = make_desc(smem_u32(s_b), 2 * NB * 16, 128);
       bool alive = mbar_wait(bar_b, 0, a.err, -120);
       int k = me;                                               // position of slice l inside its segment
       while (k >= LPS) k -= LPS;
-      for (int l = me; l < total_loads && alive; l += STREAM_ISSUERS) {
+      for (int l = me; l < total_loads && alive; l += NI) {
         const int slot = l & RMASK, ts = l % ZB_SLOTS, tuse = l / ZB_SLOTS;
         if (tuse >= 1) { alive = mbar_wait(bar_pfree + 8 * ts, (tuse - 1) & 1, a.err, -124); if (!alive) break; }
         alive = mbar_wait(bar_full + 8 * slot, (l >> RSH) & 1, a.err, -121);
         if (!alive) break;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d = tmem_base + (uint32_t)(ts * 2 * NB);
-        for (int ch = 0; ch < a.kchunks && !(a.dbg & 1); ++ch) {            // 16 input channels (4 planes) per chunk
-          const uint32_t base = ring0 + (uint32_t)slot * SB + (uint32_t)ch * 4u * SP;
-          const uint64_t dh = make_desc(base, 2 * SP, WT * EXC * CELL), dl = make_desc(base + SP, 2 * SP, WT * EXC * CELL);
-          const uint64_t bc = b0 + (uint64_t)(ch * NTZ) * b_step;
+        if (PAIRED) {
+          // cin == 8: K = 16 spans a PAIR of (d, kx) tiles (LBO = their address difference); odd tile count: tile 0 goes alone
+          const uint32_t base = ring0 + (uint32_t)slot * SB;
+          const uint64_t dh = make_desc(base, 0u, WT * EXC * CELL), dl = make_desc(base + SP, 0u, WT * EXC * CELL);
+          constexpr int NTP = (NTZ + 1) / 2;
 #pragma unroll
-          for (int t = 0; t < NTZ; ++t) {
-            const uint64_t add = (uint64_t)(((((t / 3) * EXC) + t % 3) * CELL) >> 4);
-            const uint64_t bd = bc + (uint64_t)t * b_step;
-            umma_f16(d, dh + add, bd, idesc_full, (ch == 0 && t == 0) ? 0u : 1u);   // x_hi * [w_hi(kz 0,1,2) | w_lo(kz 0,1,2)]
-            umma_f16(d, dl + add, bd, idesc_half, 1u);                               // x_lo * w_hi(kz 0,1,2)
+          for (int m = 0; m < NTP && !(a.dbg & 1); ++m) {
+            const int ta = (NTZ & 1) ? (m == 0 ? 0 : 2 * m - 1) : 2 * m, tb = (NTZ & 1) ? (m == 0 ? 1 : 2 * m) : 2 * m + 1;
+            const int oa = ((ta / 3) * EXC + ta % 3) * CELL, ob = ((tb / 3) * EXC + tb % 3) * CELL;
+            const uint64_t add = (uint64_t)(oa >> 4) | ((uint64_t)((ob - oa) >> 4) << 16);
+            const uint64_t bd = b0 + (uint64_t)m * b_step;
+            umma_f16(d, dh + add, bd, idesc_full, m == 0 ? 0u : 1u);
+            umma_f16(d, dl + add, bd, idesc_half, 1u);
+          }
+        } else {
+          for (int ch = 0; ch < a.kchunks && !(a.dbg & 1); ++ch) {          // 16 input channels (4 planes) per chunk
+            const uint32_t base = ring0 + (uint32_t)slot * SB + (uint32_t)ch * 4u * SP;
+            const uint64_t dh = make_desc(base, 2 * SP, WT * EXC * CELL), dl = make_desc(base + SP, 2 * SP, WT * EXC * CELL);
+            const uint64_t bc = b0 + (uint64_t)(ch * NTZ) * b_step;
+#pragma unroll
+            for (int t = 0; t < NTZ; ++t) {
+              const uint64_t add = (uint64_t)(((((t / 3) * EXC) + t % 3) * CELL) >> 4);
+              const uint64_t bd = bc + (uint64_t)t * b_step;
+              umma_f16(d, dh + add, bd, idesc_full, (ch == 0 && t == 0) ? 0u : 1u);   // x_hi * [w_hi(kz 0,1,2) | w_lo(kz 0,1,2)]
+              umma_f16(d, dl + add, bd, idesc_half, 1u);                               // x_lo * w_hi(kz 0,1,2)
+            }
           }
         }
         umma_commit(bar_sfree + 8 * slot);
         umma_commit(bar_pfull + 8 * ts);
         // halo slices feed fewer than three outputs: supply the epilogue arrivals of the missing readers
         const int readers = min(k, ZS - 1) - max(k - 2, 0) + 1;
-        for (int e = readers * (EPI_WARPS / 2); e < 3 * (EPI_WARPS / 2); ++e)
+        for (int e = readers * 4; e < 12; ++e)
           asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_pfree + 8 * ts) : "memory");
-        k += STREAM_ISSUERS;
+        k += NI;
         while (k >= LPS) k -= LPS;
       }
     }
     __syncwarp();
   } else {
-    // ------------------------------ epilogue: warps 0-3 take even outputs, 4-7 odd ones ------------------------------
+    // ------------------------------ epilogue: group g = warp / 4 takes outputs O = g, g + EG, ... ------------------------------
     const int row = (warp & 3) * 32 + lane;
     const size_t plane_elems = (size_t)a.n * a.n * a.n * 8;
     int sk = 0, o = warp >> 2, cur = -1, bx = 0, by = 0, bz = 0, b = 0;
     while (o >= ZS) { o -= ZS; ++sk; }
-    for (int O = (warp >> 2); O < ((a.dbg & 4) ? 0 : total_outs); O += 2) {
+    for (int O = (warp >> 2); O < ((a.dbg & 4) ? 0 : total_outs); O += EG) {
       if (sk != cur) {
         int r = (int)blockIdx.x + sk * (int)gridDim.x;
         bx = r % tx_n; r /= tx_n;
@@ -860,6 +881,13 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) conv_umma_zband_kernel(cons
       }
       const int vx = bx * TILE_X + (row & 7), vyb = by * TILE_Y * WT + WT * (row >> 3), vz = bz * ZS + o;
       const int l0 = O + 2 * sk;                                // input slice read with kz = 0
+      // Voxception tail: the block input does not depend on the accumulators -- fetch it while the MMAs still run
+      constexpr int RC = EPI == UEPI_VRN ? VrnRc<NPJ>::value : 1;
+      uint4 rhi[WT][RC], rlo[WT][RC];
+      if (EPI == UEPI_VRN) {
+#pragma unroll
+        for (int j = 0; j < WT; ++j) vrn_load_residual<RC>(a, b, vz, vyb + j, vx, plane_elems, rhi[j], rlo[j]);
+      }
       float v[NP];
       bool ok = true;
 #pragma unroll
@@ -881,14 +909,15 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) conv_umma_zband_kernel(cons
 #pragma unroll
       for (int i = 0; i < NP; ++i) v[i] += s_bias[i];
 #pragma unroll
-      for (int j = 0; j < WT; ++j) epilogue_voxel<NPJ, EPI>(a, v + j * NPJ, nullptr, b, vz, vyb + j, vx, plane_elems);
-      o += 2;
+      for (int j = 0; j < WT; ++j)
+        epilogue_voxel<NPJ, EPI>(a, v + j * NPJ, s_w23, b, vz, vyb + j, vx, plane_elems, EPI == UEPI_VRN ? rhi[j] : nullptr, EPI == UEPI_VRN ? rlo[j] : nullptr);
+      o += EG;
       while (o >= ZS) { o -= ZS; ++sk; }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == EPI_WARPS) {
+  if (warp == EW) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
   }
 }
@@ -1022,6 +1051,10 @@ int umma_stream_mode() {
   static const int m = getenv("PCGC_UMMA_STREAM") ? atoi(getenv("PCGC_UMMA_STREAM")) : 1;
   return m;
 }
+int umma_zband_mode() {
+  static const int m = getenv("PCGC_UMMA_ZBAND") ? atoi(getenv("PCGC_UMMA_ZBAND")) : 1;
+  return m && umma_stream_mode();
+}
 
 cudaError_t pack_umma_weights_dense(const float* dense, const float* bias, int cin, int n_real, UmmaWeights& out, int ntaps, int wt) {
   free_umma_weights(out);
@@ -1071,23 +1104,30 @@ cudaError_t pack_umma_weights_dense(const float* dense, const float* bias, int c
   if (e != cudaSuccess) return e;
   e = cudaMemcpy(out.packed, p.data(), p.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return e;
-  if (ntaps == 27 && (cin == 16 || cin == 32) && (wt == 1 || wt == 2) && np == 16) {
+  if (ntaps == 27 && (cin == 8 || cin == 16 || cin == 32) && (wt == 1 || wt == 2) && np == 16 && !(cin == 8 && wt != 1)) {
     // z-banded form (conv_umma_zband_kernel): ONE MMA per (d, kx) tile carries the three kz taps as column blocks, so the A tile
     // of an input slice is fetched once for the three output slices it feeds.  Rows: hi = kz*np + n, lo = 3*np + kz*np + n.
     const int nb = 3 * np, ntz = 3 * (wt + 2);
     const size_t tile3 = (size_t)2 * nb * 16;
-    std::vector<__nv_bfloat16> pz((size_t)kchunks * ntz * tile3, __float2bfloat16(0.f));
+    const int ntile = cin == 8 ? (ntz + 1) / 2 : ntz;            // cin == 8: K = 16 is a pair of tiles (tile 0 alone when odd)
+    std::vector<__nv_bfloat16> pz((size_t)kchunks * ntile * tile3, __float2bfloat16(0.f));
     for (int ch = 0; ch < kchunks; ++ch)
-     for (int t = 0; t < ntz; ++t)
+     for (int t = 0; t < ntile; ++t)
       for (int kz = 0; kz < 3; ++kz)
         for (int k = 0; k < 16; ++k)
           for (int j = 0; j < wt; ++j)
             for (int co = 0; co < n_real; ++co) {
-              const float w = weight(kz * ntz + t, ch * 16 + k, j, co);
+              int tt = t, ci = ch * 16 + k;
+              if (cin == 8) {
+                const int ta = (ntz & 1) ? (t == 0 ? 0 : 2 * t - 1) : 2 * t, tb = (ntz & 1) ? (t == 0 ? -1 : 2 * t) : 2 * t + 1;
+                tt = k < 8 ? ta : tb; ci = k % 8;
+                if (tt < 0) continue;
+              }
+              const float w = weight(kz * ntz + tt, ci, j, co);
               if (w == 0.f) continue;
               const __nv_bfloat16 hi = __float2bfloat16_rn(w);
               const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
-              auto at3 = [&](int row) { return (size_t)(ch * ntz + t) * tile3 + (size_t)(k / 8) * (2 * nb * 8) + (size_t)(row / 8) * 64 + (row % 8) * 8 + (k % 8); };
+              auto at3 = [&](int row) { return (size_t)(ch * ntile + t) * tile3 + (size_t)(k / 8) * (2 * nb * 8) + (size_t)(row / 8) * 64 + (row % 8) * 8 + (k % 8); };
               pz[at3(kz * np + j * npj + co)] = hi;
               pz[at3(nb + kz * np + j * npj + co)] = lo;
             }
@@ -1153,11 +1193,11 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
   if (c.epi == UEPI_UP && (w.up_ncls * w.up_cout != w.n_real || w.up_cout % 16 != 0 || c.out.c != w.up_cout || c.out.n != 2 * n)) return cudaErrorInvalidValue;
   const int vrn_floats = c.epi == UEPI_VRN ? w.c4 * w.c2 + w.c2 : 0;
   static const int sm_count = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
-  static const int zband = getenv("PCGC_UMMA_ZBAND") ? atoi(getenv("PCGC_UMMA_ZBAND")) : 1;
-  if (zband && umma_stream_mode() && w.packed_zb && w.np == 16 && n >= 32 && (c.epi == UEPI_PM || c.epi == UEPI_F32)) {
+  const int zband = umma_zband_mode();
+  if (zband && umma_stream_mode() && w.packed_zb && w.np == 16 && n >= 32 && (c.epi == UEPI_PM || c.epi == UEPI_F32 || (c.epi == UEPI_VRN && a.cin8))) {
     // z-banded streaming kernel (thin-N layers): the three kz taps are column blocks of one MMA
     const int z_slice_plane = brick_ey(w.wt) * EXC * CELL, z_slot = a.ppc * w.kchunks * z_slice_plane;
-    const size_t fixed = (size_t)w.zb_bytes + 34 * 8 + w.np * sizeof(float) + 16;
+    const size_t fixed = (size_t)w.zb_bytes + 34 * 8 + (w.np + vrn_floats) * sizeof(float) + 16;
     const size_t budget = (size_t)220 * 1024;
     const int z_ring = (size_t)8 * z_slot + fixed <= budget ? 8 : ((size_t)4 * z_slot + fixed <= budget ? 4 : 0);
     if (z_ring) {
@@ -1173,14 +1213,19 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
       const int segs = (n / TILE_X) * (n / (TILE_Y * w.wt)) * (n / a.zs) * c.in.B;
       const int grid_z = std::min(segs, sm_count);
       if (launches) ++*launches;
-      auto go = [&](auto kern) -> cudaError_t {
+      auto go = [&](auto kern, int threads) -> cudaError_t {
         cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_z);
         if (e2 != cudaSuccess) return e2;
-        kern<<<grid_z, STREAM_THREADS, smem_z, s>>>(tmz, a);
+        kern<<<grid_z, threads, smem_z, s>>>(tmz, a);
         return cudaGetLastError();
       };
-      if (w.wt == 2) return c.epi == UEPI_PM ? go(conv_umma_zband_kernel<UEPI_PM, 2>) : go(conv_umma_zband_kernel<UEPI_F32, 2>);
-      return c.epi == UEPI_PM ? go(conv_umma_zband_kernel<UEPI_PM, 1>) : go(conv_umma_zband_kernel<UEPI_F32, 1>);
+      constexpr int T23 = 32 * (4 * 2 + 1 + 3), T31 = 32 * (4 * 3 + 1 + 1);
+      if (a.cin8) {                                            // K_b16: paired taps, Voxception tail, 3 epilogue groups + 1 issuer
+        if (w.wt != 1) return cudaErrorNotSupported;
+        return c.epi == UEPI_VRN ? go(conv_umma_zband_kernel<UEPI_VRN, 1, true, 3, 1>, T31) : go(conv_umma_zband_kernel<UEPI_F32, 1, true, 3, 1>, T31);
+      }
+      if (w.wt == 2) return c.epi == UEPI_PM ? go(conv_umma_zband_kernel<UEPI_PM, 2, false, 2, 3>, T23) : go(conv_umma_zband_kernel<UEPI_F32, 2, false, 2, 3>, T23);
+      return c.epi == UEPI_PM ? go(conv_umma_zband_kernel<UEPI_PM, 1, false, 2, 3>, T23) : go(conv_umma_zband_kernel<UEPI_F32, 1, false, 2, 3>, T23);
     }
   }
   if (umma_stream_mode() && w.ntaps == 27 && w.kchunks == 1 && n >= 16 && stream_shape_ok(w.np, c.epi, a.cin8 != 0, w.wt)) {

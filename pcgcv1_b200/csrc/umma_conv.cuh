@@ -66,6 +66,8 @@ struct UmmaCall {
 cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStream_t s, int64_t* launches);
 // PCGC_UMMA_STREAM: 0 = tile kernel everywhere, 1 = z-streaming kernel for the shapes it covers (umma_conv.cu)
 int umma_stream_mode();
+// PCGC_UMMA_ZBAND (default 1, needs streaming): z-banded kernel for the NP = 16 layers (K_a16, K_a32, K_b16, deconv_out)
+int umma_zband_mode();
 // float32 NDHWC (channel stride/offset) <-> PM
 cudaError_t launch_f32_to_pm(const float* in, int in_cs, int in_co, const PmTensor& out, cudaStream_t s, int64_t* launches);
 cudaError_t launch_pm_to_f32(const PmTensor& in, float* out, int out_cs, int out_co, cudaStream_t s, int64_t* launches);
