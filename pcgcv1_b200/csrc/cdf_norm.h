@@ -28,7 +28,22 @@
 
 namespace pcgc {
 
-PCGC_HD double cdf_gain(double m, int v) { return m * (log2((double)(v + 1)) - log2((double)v)); }
+// log2(v+1) - log2(v) for v = 1..32 and ln(1 + 1/v) for v = 1..15 as constants (hex doubles = what glibc's log2 / log1p give):
+// one source of truth for host and device, and no libm call on paths that only one or two lanes of a warp take at a time
+// (ncu r01: the v < 16 score and the small-u walk of cdf_last_u were 30 percent of the CDF kernels' warp instructions at 1-2
+// active lanes).
+#if defined(__CUDA_ARCH__)
+#define PCGC_TABLE_QUAL __constant__
+#else
+#define PCGC_TABLE_QUAL
+#endif
+static PCGC_TABLE_QUAL const double pcgc_gain_tab[33] = {0x0.0p+0, 0x1.0000000000000p+0, 0x1.2b803473f7ad0p-1, 0x1.a8ff971810a60p-2, 0x1.49a784bcd1b88p-2, 0x1.0d58e42b1da18p-2, 0x1.c775ad8425790p-3, 0x1.8a8980abfbd30p-3, 0x1.5c01a39fbd680p-3, 0x1.374d65d9e6090p-3, 0x1.199b728cb9d10p-3, 0x1.011655c981720p-3, 0x1.d8fea38406fe0p-4, 0x1.b5ecb78443f40p-4, 0x1.97b2b7eafbf20p-4, 0x1.7d60496cfbb40p-4, 0x1.663f6fac91300p-4, 0x1.51c3d792e9a00p-4, 0x1.3f7f8fe0d2300p-4, 0x1.2f1b3bd2f9e40p-4, 0x1.20508f547ee00p-4, 0x1.12e655c4f4c00p-4, 0x1.06ad885e62d00p-4, 0x1.f6fe466940280p-5, 0x1.e275048da0b80p-5, 0x1.cf88427a6d400p-5, 0x1.be094776e7a80p-5, 0x1.add02791a0400p-5, 0x1.9eba920522280p-5, 0x1.90aaddd0d5c00p-5, 0x1.8387463c61d80p-5, 0x1.77394c9d95900p-5, 0x1.6bad3758efd80p-5};
+static PCGC_TABLE_QUAL const double pcgc_ln1p_tab[16] = {0x0.0p+0, 0x1.62e42fefa39efp-1, 0x1.9f323ecbf984cp-2, 0x1.269621134db92p-2, 0x1.c8ff7c79a9a22p-3, 0x1.7565011e49676p-3, 0x1.3bb35a041d2a9p-3, 0x1.1178e8227e47cp-3, 0x1.e27076e2af2e6p-4, 0x1.af8e8210a415dp-4, 0x1.8663f793c46c7p-4, 0x1.64660aa8ce626p-4, 0x1.47dadcbbdba83p-4, 0x1.2f8bd74c5eacfp-4, 0x1.1a9844eb18ef1p-4, 0x1.08598b59e3a06p-4};
+
+PCGC_HD double cdf_gain(double m, int v) {
+  if (v <= 32) return m * pcgc_gain_tab[v];
+  return m * (log2((double)(v + 1)) - log2((double)v));
+}
 
 // Float SCORE used to shortlist candidates: score = cdf_gain(m, v) * 2^precision / log2(e) - 1, a strictly increasing
 // function of the gain.  All large entries have gains within ~1/v of each other, so the gain itself cannot be ranked
@@ -43,7 +58,7 @@ PCGC_HD float cdf_score(float m, int v, float scale) {
     const float P = x * (-0.5f + x * (1.0f / 3 + x * (-0.25f + x * (0.2f + x * (-1.0f / 6 + x * (1.0f / 7))))));
     return P + r * x * (1.0f + P);
   }
-  return (float)((double)m * (double)scale * log1p(1.0 / (double)v) - 1.0);
+  return (float)((double)m * (double)scale * pcgc_ln1p_tab[v] - 1.0);
 }
 #define PCGC_SCORE_TOL(mx) (4e-6f * fabsf(mx) + 1e-9f)
 
@@ -135,14 +150,17 @@ PCGC_HD_NOINLINE int quantize_pmf_row(const float* pmf, int n, int precision, in
   for (int i = 0; i < n; ++i)
     g[i] = dir > 0 ? cdf_score(pmf[i], v[i], scale) : (v[i] > 1 ? -cdf_score(pmf[i], v[i] - 1, scale) : -INFINITY);
   while (todo > 0) {
-    float mx = -INFINITY;
-    for (int i = 0; i < n; ++i) mx = g[i] > mx ? g[i] : mx;
+    // one pass: the best score, its (first) index and the runner-up; only a runner-up within the tolerance needs the exact path
+    float mx = -INFINITY, second = -INFINITY;
+    int best = -1;
+    for (int i = 0; i < n; ++i) {
+      const float gi = g[i];
+      if (gi > mx) { second = mx; mx = gi; best = i; }
+      else if (gi > second) second = gi;
+    }
     if (!(mx > -INFINITY)) return -2;
     const float thr = mx - PCGC_SCORE_TOL(mx);
-    int best = -1, cand = 0;
-    for (int i = 0; i < n; ++i)
-      if (g[i] >= thr) { if (cand == 0) best = i; ++cand; }
-    if (cand > 1) {                         // near tie: decide on the exact gains, lowest index first
+    if (second >= thr) {                    // near tie: decide on the exact gains, lowest index first
       double bs = -INFINITY;
       for (int i = 0; i < n; ++i)
         if (g[i] >= thr) {
