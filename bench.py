@@ -265,7 +265,8 @@ def run_gpu(args):
         with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
             tr = json.load(f).get(top["tag"])
         if tr:
-            roof["traffic"] = int(tr["dram_bytes_per_launch"])
+            per_launch = int(os.environ.get("PCGC_SUB_BATCH", "64"))      # cubes per kernel launch in this run
+            roof["traffic"] = int(tr["dram_bytes_per_launch"] * per_launch / tr.get("cubes_per_launch", per_launch))
             roof["traffic_source"] = tr.get("source", "profiles/r01_ncu_traffic.json")
             for k in ("sm__pipe_tc_cycles_active_pct", "utchmma_bf16_ops_pct_of_peak", "l1tex_tc_wavefronts_shared_pct_of_peak"):
                 if k in tr:
