@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <new>
 #include <atomic>
 #include <thread>
 #include <vector>
@@ -140,6 +141,88 @@ void parallel_for(int n, int threads, F f) {
   for (int t = 0; t < threads; ++t)
     pool.emplace_back([&] { for (int i; (i = next.fetch_add(1)) < n;) f(i); });
   for (auto& th : pool) th.join();
+}
+
+// K independent per-cube streams decoded in ONE loop: the serial dependency chain of a range decoder (division -> search ->
+// interval update -> renormalise, ~60 cycles per symbol) leaves an out-of-order core mostly idle; interleaving K cubes lets it
+// overlap their chains.  Same arithmetic per stream, so the symbols are identical to the one-at-a-time decoder's.
+template <int K, typename OutT, typename Conv>
+void decode_rows_interleaved(const uint8_t* const* data, const int64_t* nbytes, const int* cube, int64_t E, const uint16_t* rows,
+                             const int64_t* row_offset, const int32_t* minmax, int precision, OutT* out, Conv conv) {
+  Decoder* d[K];
+  alignas(Decoder) unsigned char store[K][sizeof(Decoder)];
+  const uint16_t* base[K];
+  OutT* o[K];
+  int N[K], mn[K];
+  for (int j = 0; j < K; ++j) {
+    const int b = cube[j];
+    d[j] = new (store[j]) Decoder(data[b], nbytes[b], precision);
+    mn[j] = minmax[2 * b]; N[j] = minmax[2 * b + 1] - mn[j] + 1;
+    base[j] = rows + row_offset[b];
+    o[j] = out + (int64_t)b * E;
+  }
+  const uint32_t top = 1u << precision;
+  for (int64_t i = 0; i < E; ++i) {
+#pragma GCC unroll 4
+    for (int j = 0; j < K; ++j) {
+      const uint16_t* row = base[j] + i * N[j];
+      const int n = N[j];
+      const int s = d[j]->decode_at([row, n](uint32_t t) {
+        int c = 0;
+        for (int k = 1; k < n; ++k) c += (uint32_t)row[k] <= t;
+        return c;
+      }, [row, n, top](int k) { return k == n ? top : (uint32_t)row[k]; });
+      o[j][i] = conv(s, mn[j]);
+    }
+  }
+}
+
+// The encoder's chain (two multiplies, carry-propagating renormalisation) interleaves the same way.
+template <int K>
+int encode_intervals_interleaved(const uint32_t* iv, const int* cube, int64_t E, int precision, uint8_t* out, int64_t stride, int64_t* lens) {
+  alignas(Encoder) unsigned char store[K][sizeof(Encoder)];
+  Encoder* e[K];
+  const uint32_t* src[K];
+  for (int j = 0; j < K; ++j) {
+    e[j] = new (store[j]) Encoder(out + (int64_t)cube[j] * stride, stride, precision);
+    src[j] = iv + (int64_t)cube[j] * E;
+  }
+  for (int64_t i = 0; i < E; ++i) {
+#pragma GCC unroll 4
+    for (int j = 0; j < K; ++j) {
+      const uint32_t w = src[j][i], lower = w & 0xFFFF;
+      e[j]->encode(lower, lower + (w >> 16) + 1);
+    }
+  }
+  int rc = PCGC_OK;
+  for (int j = 0; j < K; ++j) {
+    const int64_t m = e[j]->finish();
+    if (m < 0) rc = PCGC_ERR_OVERFLOW; else lens[cube[j]] = m;
+  }
+  return rc;
+}
+
+template <typename OutT, typename Conv>
+int decode_rows_batch_impl(const uint8_t* const* data, const int64_t* nbytes, int B, int64_t E, const uint16_t* rows,
+                           const int64_t* row_offset, const int32_t* minmax, int precision, OutT* out, int threads, Conv conv) {
+  // interleave width: as wide as leaves every host thread a group (64 cubes on 16 threads -> 4; 16 cubes -> 1)
+  int hw = (int)std::thread::hardware_concurrency();
+  if (hw <= 0) hw = 1;
+  const int T = (threads <= 0 || threads > hw) ? hw : threads;
+  const int K = std::max(1, std::min(4, B / std::max(1, T)));
+  const int groups = (B + K - 1) / K;
+  parallel_for(groups, threads, [&](int g) {
+    int cube[4];
+    const int n = std::min(K, B - g * K);
+    for (int j = 0; j < n; ++j) cube[j] = g * K + j;
+    switch (n) {
+      case 4: decode_rows_interleaved<4>(data, nbytes, cube, E, rows, row_offset, minmax, precision, out, conv); break;
+      case 3: decode_rows_interleaved<3>(data, nbytes, cube, E, rows, row_offset, minmax, precision, out, conv); break;
+      case 2: decode_rows_interleaved<2>(data, nbytes, cube, E, rows, row_offset, minmax, precision, out, conv); break;
+      default: decode_rows_interleaved<1>(data, nbytes, cube, E, rows, row_offset, minmax, precision, out, conv); break;
+    }
+  });
+  return PCGC_OK;
 }
 
 }  // namespace
@@ -286,8 +369,22 @@ int pcgc_range_encode_intervals_batch(const uint32_t* iv, int B, int64_t E, int 
                                       int64_t stride, int64_t* lens, int threads) {
   if (!iv || !out || !lens || B < 0) return PCGC_ERR_BAD_ARG;
   std::atomic<int> rc(PCGC_OK);
-  parallel_for(B, threads, [&](int b) {
-    int r = pcgc_range_encode_intervals(iv + (int64_t)b * E, E, precision, out + (int64_t)b * stride, stride, lens + b);
+  int hw = (int)std::thread::hardware_concurrency();
+  if (hw <= 0) hw = 1;
+  const int T = (threads <= 0 || threads > hw) ? hw : threads;
+  const int K = std::max(1, std::min(4, B / std::max(1, T)));
+  const int groups = (B + K - 1) / K;
+  parallel_for(groups, threads, [&](int g) {
+    int cube[4];
+    const int n = std::min(K, B - g * K);
+    for (int j = 0; j < n; ++j) cube[j] = g * K + j;
+    int r;
+    switch (n) {
+      case 4: r = encode_intervals_interleaved<4>(iv, cube, E, precision, out, stride, lens); break;
+      case 3: r = encode_intervals_interleaved<3>(iv, cube, E, precision, out, stride, lens); break;
+      case 2: r = encode_intervals_interleaved<2>(iv, cube, E, precision, out, stride, lens); break;
+      default: r = encode_intervals_interleaved<1>(iv, cube, E, precision, out, stride, lens); break;
+    }
     if (r != PCGC_OK) rc.store(r);
   });
   return rc.load();
@@ -297,13 +394,9 @@ int pcgc_range_decode_rows_batch(const uint8_t* const* data, const int64_t* nbyt
                                  const uint16_t* rows, const int64_t* row_offset, const int32_t* minmax,
                                  int precision, int16_t* sym, int threads) {
   if (!data || !nbytes || !rows || !row_offset || !minmax || !sym || B < 0) return PCGC_ERR_BAD_ARG;
-  std::atomic<int> rc(PCGC_OK);
-  parallel_for(B, threads, [&](int b) {
-    const int N = minmax[2 * b + 1] - minmax[2 * b] + 1;
-    int r = pcgc_range_decode_rows(data[b], nbytes[b], E, rows + row_offset[b], N, precision, sym + (int64_t)b * E);
-    if (r != PCGC_OK) rc.store(r);
-  });
-  return rc.load();
+  for (int b = 0; b < B; ++b) if (minmax[2 * b + 1] - minmax[2 * b] + 1 < 1) return PCGC_ERR_BAD_ARG;
+  return decode_rows_batch_impl(data, nbytes, B, E, rows, row_offset, minmax, precision, sym, threads,
+                                [](int s, int) { return (int16_t)s; });
 }
 
 /* As pcgc_range_decode_rows_batch, but writes y_hat = symbol + min_v as float32 (what
@@ -313,24 +406,9 @@ int pcgc_range_decode_rows_batch_f32(const uint8_t* const* data, const int64_t* 
                                      const uint16_t* rows, const int64_t* row_offset, const int32_t* minmax,
                                      int precision, float* y_hat, int threads) {
   if (!data || !nbytes || !rows || !row_offset || !minmax || !y_hat || B < 0) return PCGC_ERR_BAD_ARG;
-  std::atomic<int> rc(PCGC_OK);
-  parallel_for(B, threads, [&](int b) {
-    const int min_v = minmax[2 * b], N = minmax[2 * b + 1] - min_v + 1;
-    Decoder d(data[b], nbytes[b], precision);
-    const uint32_t top = 1u << precision;
-    const uint16_t* base = rows + row_offset[b];
-    float* out = y_hat + (int64_t)b * E;
-    for (int64_t i = 0; i < E; ++i) {
-      const uint16_t* row = base + i * N;
-      const int s = d.decode_at([row, N](uint32_t t) {
-        int c = 0;
-        for (int k = 1; k < N; ++k) c += (uint32_t)row[k] <= t;
-        return c;
-      }, [row, N, top](int k) { return k == N ? top : (uint32_t)row[k]; });
-      out[i] = (float)(s + min_v);
-    }
-  });
-  return rc.load();
+  for (int b = 0; b < B; ++b) if (minmax[2 * b + 1] - minmax[2 * b] + 1 < 1) return PCGC_ERR_BAD_ARG;
+  return decode_rows_batch_impl(data, nbytes, B, E, rows, row_offset, minmax, precision, y_hat, threads,
+                                [](int s, int mn) { return (float)(s + mn); });
 }
 
 }  // extern "C"
