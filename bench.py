@@ -261,17 +261,30 @@ def run_gpu(args):
                 "frac": round(ach / peaks["hbm_gbs"], 5), "traffic": None}
     roof.update({"peak_source": peaks["source"], "ms_per_launch": round(per_launch_ms, 4), "share_of_step": round(top["ms"] / total_ms, 4)})
     # DRAM bytes per launch of that kernel from the committed ncu --set full capture (same launch shape: 32 cubes per launch)
+    tr = None
+    per_launch = int(os.environ.get("PCGC_SUB_BATCH", "64"))          # cubes per kernel launch in this run
     try:
         with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
             tr = json.load(f).get(top["tag"])
         if tr:
-            per_launch = int(os.environ.get("PCGC_SUB_BATCH", "64"))      # cubes per kernel launch in this run
             roof["traffic"] = int(tr["dram_bytes_per_launch"] * per_launch / tr.get("cubes_per_launch", per_launch))
             roof["traffic_source"] = tr.get("source", "profiles/r01_ncu_traffic.json")
             for k in ("sm__pipe_tc_cycles_active_pct", "utchmma_bf16_ops_pct_of_peak", "l1tex_tc_wavefronts_shared_pct_of_peak"):
                 if k in tr:
                     roof["ncu_" + k] = tr[k]
     except (OSError, ValueError):
+        pass
+    # a conv kernel is bounded by whichever roofline it sits closer to: report that one (the other fraction stays beside it)
+    try:
+        if tr and roof["unit"] == "TFLOP/s" and tr.get("algorithmic_bytes_per_launch"):
+            alg = tr["algorithmic_bytes_per_launch"] * per_launch / tr.get("cubes_per_launch", per_launch)
+            gbs = alg / (per_launch_ms * 1e-3) / 1e9
+            hbm_frac = gbs / peaks["hbm_gbs"]
+            if hbm_frac > roof["frac"]:
+                roof.update({"tensor_achieved_tflops": roof["achieved"], "tensor_frac": roof["frac"], "bound": "hbm",
+                             "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(hbm_frac, 5),
+                             "algorithmic_bytes_per_launch": int(alg)})
+    except (NameError, KeyError):
         pass
     roof["peak_nominal"] = 2250.0 if roof["unit"] == "TFLOP/s" else 8000.0
     conv_ms = sum(r["ms"] for r in prof if r["tag"].startswith("conv"))
