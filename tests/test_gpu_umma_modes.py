@@ -1,6 +1,5 @@
-"""The conv engine has two kernels (tile and z-streaming, csrc/umma_conv.cu) selected per shape; PCGC_UMMA_STREAM is read once
-per process, so the other two settings run the shape tests in a subprocess: so the other kernel-selection
-settings run the shape tests in a subprocess."""
+"""The conv engine has three kernels (tile, z-streaming, z-banded; csrc/umma_conv.cu) selected per shape.  PCGC_UMMA_STREAM and
+PCGC_UMMA_ZBAND are read once per process, so the other kernel-selection settings run the shape tests in a subprocess."""
 import os
 import subprocess
 import sys
