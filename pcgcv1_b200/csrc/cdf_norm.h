@@ -60,6 +60,10 @@ PCGC_HD float cdf_score(float m, int v, float scale) {
   }
   return (float)((double)m * (double)scale * pcgc_ln1p_tab[v] - 1.0);
 }
+// deficits above this go through the water-filling pass first (tuning: the greedy loop costs ~2n instructions per step)
+#ifndef PCGC_WATERFILL_MIN
+#define PCGC_WATERFILL_MIN(n) (2 * (n) + 8)
+#endif
 #define PCGC_SCORE_TOL(mx) (4e-6f * fabsf(mx) + 1e-9f)
 
 // Largest u >= 1 with cdf_gain(m, u) >= lambda (0 if none), i.e. u <= 1 / (2^(lambda/m) - 1).  Closed form with a short
@@ -106,7 +110,7 @@ PCGC_HD_NOINLINE int quantize_pmf_row(const float* pmf, int n, int precision, in
   // Every increment whose gain is >= lambda is granted at once, for a lambda that admits at most `todo` increments;
   // per-entry gains are strictly decreasing, so these are exactly the greedy's first picks.  lambda comes from the
   // continuous solution gain_i(u) ~ m_i*log2(e)/(u + 0.5), aimed a little short so that the pass is feasible.
-  for (int pass = 0; pass < 8 && dir > 0 && todo > 2 * n + 8; ++pass) {
+  for (int pass = 0; pass < 8 && dir > 0 && todo > PCGC_WATERFILL_MIN(n); ++pass) {
     const double L = 1.4426950408889634;
     double m_act = 0.0, t_act = (double)target;
     int n_act = n;
