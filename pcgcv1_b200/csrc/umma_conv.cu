@@ -740,11 +740,13 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) conv_umma_stream_kernel(con
 //   barriers: full[slot] / sfree[slot] (count 1: one issuer reads a slice), pfull[ts] (partial sums of an input slice complete),
 //   pfree[ts] (count 12 = 3 reading outputs x 4 epilogue warps; the issuer supplies the arrivals of the missing readers of halo
 //   slices), b.  5 TMEM slots of 96 columns.
-constexpr int ZB_NP = 16, ZB_NB = 3 * ZB_NP, ZB_SLOTS = 5;
+constexpr int ZB_SLOTS = 5;                          // TMEM slots of 96 columns (one per input slice in flight)
 
 // EG epilogue groups of 4 warps (output O belongs to group O % EG), NI issuer warps (input slice l belongs to issuer l % NI).
 // The Voxception-tail form (K_b16) is bound by its epilogue: it runs 3 groups and 1 issuer; the plain forms 2 and 3.
-template <int EPI, int WT, bool PAIRED, int EG, int NI>
+// NPT = accumulator columns per kz block: 16 (hi and lo products in separate column halves, two MMAs per tile) or 32 (SPLIT3:
+// x_hi*w_hi, x_lo*w_hi and x_hi*w_lo are three MMAs into the SAME 96 columns, so that 5 slots still fit the 512 TMEM columns).
+template <int NPT, int EPI, int WT, bool PAIRED, int EG, int NI>
 __global__ void __launch_bounds__(32 * (4 * EG + 1 + NI), 1) conv_umma_zband_kernel(const __grid_constant__ CUtensorMap tmap, const UmmaArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* s_a = smem;
@@ -754,7 +756,9 @@ __global__ void __launch_bounds__(32 * (4 * EG + 1 + NI), 1) conv_umma_zband_ker
   float* s_bias = reinterpret_cast<float*>(s_bar + 4 * 8 + 2);
   const uint32_t bar_full = smem_u32(s_bar), bar_sfree = smem_u32(s_bar + 8), bar_pfull = smem_u32(s_bar + 16),
                  bar_pfree = smem_u32(s_bar + 24), bar_b = smem_u32(s_bar + 32);
-  constexpr int NP = ZB_NP, NB = ZB_NB, NPJ = NP / WT;
+  constexpr int NP = NPT, NB = 3 * NP, NPJ = NP / WT;
+  constexpr bool SPLIT3 = NP == 32;
+  constexpr int SLOT_COLS = SPLIT3 ? NB : 2 * NB;
   constexpr int NTZ = 3 * (WT + 2);
   constexpr int EW = 4 * EG, THREADS = 32 * (EW + 1 + NI);
   float* s_w23 = s_bias + NP;                                              // [c4][c2] then b23[c2] (UEPI_VRN only)
@@ -813,7 +817,7 @@ __global__ void __launch_bounds__(32 * (4 * EG + 1 + NI), 1) conv_umma_zband_ker
     if (elect_one() && n_my > 0) {
       // ------------------------------ MMA issuer `me`: input slices l = me, me + NI, ... ------------------------------
       const int me = warp - EW - 1;
-      constexpr uint32_t idesc_full = make_idesc(128, 2 * NB), idesc_half = make_idesc(128, NB);
+      constexpr uint32_t idesc_full = make_idesc(128, SPLIT3 ? NB : 2 * NB), idesc_half = make_idesc(128, NB);
       constexpr uint64_t b_step = (uint64_t)((2 * NB * 32) >> 4);
       const uint64_t b0 = make_desc(smem_u32(s_b), 2 * NB * 16, 128);
       bool alive = mbar_wait(bar_b, 0, a.err, -120);
@@ -825,7 +829,7 @@ __global__ void __launch_bounds__(32 * (4 * EG + 1 + NI), 1) conv_umma_zband_ker
         alive = mbar_wait(bar_full + 8 * slot, (l >> RSH) & 1, a.err, -121);
         if (!alive) break;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d = tmem_base + (uint32_t)(ts * 2 * NB);
+        const uint32_t d = tmem_base + (uint32_t)(ts * SLOT_COLS);
         if (PAIRED) {
           // cin == 8: K = 16 spans a PAIR of (d, kx) tiles (LBO = their address difference); odd tile count: tile 0 goes alone
           const uint32_t base = ring0 + (uint32_t)slot * SB;
@@ -839,6 +843,7 @@ __global__ void __launch_bounds__(32 * (4 * EG + 1 + NI), 1) conv_umma_zband_ker
             const uint64_t bd = b0 + (uint64_t)m * b_step;
             umma_f16(d, dh + add, bd, idesc_full, m == 0 ? 0u : 1u);
             umma_f16(d, dl + add, bd, idesc_half, 1u);
+            if (SPLIT3) umma_f16(d, dh + add, bd + (uint64_t)NB, idesc_half, 1u);      // x_hi * w_lo (rows NB.. of the B tile)
           }
         } else {
           for (int ch = 0; ch < a.kchunks && !(a.dbg & 1); ++ch) {          // 16 input channels (4 planes) per chunk
@@ -849,8 +854,9 @@ __global__ void __launch_bounds__(32 * (4 * EG + 1 + NI), 1) conv_umma_zband_ker
             for (int t = 0; t < NTZ; ++t) {
               const uint64_t add = (uint64_t)(((((t / 3) * EXC) + t % 3) * CELL) >> 4);
               const uint64_t bd = bc + (uint64_t)t * b_step;
-              umma_f16(d, dh + add, bd, idesc_full, (ch == 0 && t == 0) ? 0u : 1u);   // x_hi * [w_hi(kz 0,1,2) | w_lo(kz 0,1,2)]
+              umma_f16(d, dh + add, bd, idesc_full, (ch == 0 && t == 0) ? 0u : 1u);   // x_hi * [w_hi(kz 0,1,2) | w_lo(kz 0,1,2)]  (SPLIT3: w_hi only)
               umma_f16(d, dl + add, bd, idesc_half, 1u);                               // x_lo * w_hi(kz 0,1,2)
+              if (SPLIT3) umma_f16(d, dh + add, bd + (uint64_t)NB, idesc_half, 1u);    // x_hi * w_lo(kz 0,1,2) into the same columns
             }
           }
         }
@@ -895,12 +901,18 @@ __global__ void __launch_bounds__(32 * (4 * EG + 1 + NI), 1) conv_umma_zband_ker
         const int l = l0 + kz, ts = l % ZB_SLOTS;
         if (!mbar_wait(bar_pfull + 8 * ts, (l / ZB_SLOTS) & 1, a.err, -123)) { ok = false; break; }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t lane_base = tmem_base + (uint32_t)(ts * 2 * NB + kz * NP) + ((uint32_t)((warp & 3) * 32) << 16);
-        float d1[16], d2[16];
-        tmem_ld16(lane_base, d1);
-        tmem_ld16(lane_base + (uint32_t)NB, d2);
+        const uint32_t lane_base = tmem_base + (uint32_t)(ts * SLOT_COLS + kz * NP) + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll
-        for (int i = 0; i < NP; ++i) v[i] = kz == 0 ? (d1[i] + d2[i]) : v[i] + (d1[i] + d2[i]);
+        for (int q = 0; q < NP / 16; ++q) {
+          float d1[16], d2[16];
+          tmem_ld16(lane_base + (uint32_t)(q * 16), d1);
+          if (!SPLIT3) tmem_ld16(lane_base + (uint32_t)(NB + q * 16), d2);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p = SPLIT3 ? d1[i] : (d1[i] + d2[i]);
+            v[q * 16 + i] = kz == 0 ? p : v[q * 16 + i] + p;
+          }
+        }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_pfree + 8 * ts) : "memory");
@@ -1104,7 +1116,7 @@ cudaError_t pack_umma_weights_dense(const float* dense, const float* bias, int c
   if (e != cudaSuccess) return e;
   e = cudaMemcpy(out.packed, p.data(), p.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return e;
-  if (ntaps == 27 && (cin == 8 || cin == 16 || cin == 32) && (wt == 1 || wt == 2) && np == 16 && !(cin == 8 && wt != 1)) {
+  if (ntaps == 27 && (cin == 8 || cin == 16 || cin == 32) && (wt == 1 || wt == 2) && (np == 16 || (np == 32 && cin != 32))) {
     // z-banded form (conv_umma_zband_kernel): ONE MMA per (d, kx) tile carries the three kz taps as column blocks, so the A tile
     // of an input slice is fetched once for the three output slices it feeds.  Rows: hi = kz*np + n, lo = 3*np + kz*np + n.
     const int nb = 3 * np, ntz = 3 * (wt + 2);
@@ -1194,7 +1206,13 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
   const int vrn_floats = c.epi == UEPI_VRN ? w.c4 * w.c2 + w.c2 : 0;
   static const int sm_count = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
   const int zband = umma_zband_mode();
-  if (zband && umma_stream_mode() && w.packed_zb && w.np == 16 && n >= 32 && (c.epi == UEPI_PM || c.epi == UEPI_F32 || (c.epi == UEPI_VRN && a.cin8))) {
+  // 32-column z-banded forms (K_b16, K_b32): correct (tests run them with PCGC_KB_ZBAND=1) but no faster than the tile / streaming
+  // kernels they would replace (r01: K_b16 0.647 vs 0.640 ms, K_b32 0.189 vs 0.166 ms per 64 cubes) -- those layers are bound by
+  // their Voxception-tail epilogue and HBM traffic, not by the MMA count -> opt-in
+  static const bool kb_zband = getenv("PCGC_KB_ZBAND") && atoi(getenv("PCGC_KB_ZBAND")) != 0;
+  const bool zb16 = w.np == 16 && (c.epi == UEPI_PM || c.epi == UEPI_F32 || (c.epi == UEPI_VRN && a.cin8));
+  const bool zb32 = w.np == 32 && kb_zband && (c.epi == UEPI_VRN || c.epi == UEPI_F32) && ((a.cin8 && w.wt == 2) || (!a.cin8 && w.wt == 1 && w.kchunks == 1));
+  if (zband && umma_stream_mode() && w.packed_zb && n >= 32 && (zb16 || zb32)) {
     // z-banded streaming kernel (thin-N layers): the three kz taps are column blocks of one MMA
     const int z_slice_plane = brick_ey(w.wt) * EXC * CELL, z_slot = a.ppc * w.kchunks * z_slice_plane;
     const size_t fixed = (size_t)w.zb_bytes + 34 * 8 + (w.np + vrn_floats) * sizeof(float) + 16;
@@ -1219,13 +1237,18 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
         kern<<<grid_z, threads, smem_z, s>>>(tmz, a);
         return cudaGetLastError();
       };
-      constexpr int T23 = 32 * (4 * 2 + 1 + 3), T31 = 32 * (4 * 3 + 1 + 1);
-      if (a.cin8) {                                            // K_b16: paired taps, Voxception tail, 3 epilogue groups + 1 issuer
-        if (w.wt != 1) return cudaErrorNotSupported;
-        return c.epi == UEPI_VRN ? go(conv_umma_zband_kernel<UEPI_VRN, 1, true, 3, 1>, T31) : go(conv_umma_zband_kernel<UEPI_F32, 1, true, 3, 1>, T31);
+      constexpr int T23 = 32 * (4 * 2 + 1 + 3), T31 = 32 * (4 * 3 + 1 + 1), T41 = 32 * (4 * 4 + 1 + 1), T21 = 32 * (4 * 2 + 1 + 1);
+      if (zb32) {
+        if (a.cin8)                                            // K_b16: paired taps, y-band 2, Voxception tail: 4 epilogue groups + 1 issuer
+          return c.epi == UEPI_VRN ? go(conv_umma_zband_kernel<32, UEPI_VRN, 2, true, 4, 1>, T41) : go(conv_umma_zband_kernel<32, UEPI_F32, 2, true, 4, 1>, T41);
+        return c.epi == UEPI_VRN ? go(conv_umma_zband_kernel<32, UEPI_VRN, 1, false, 2, 1>, T21) : go(conv_umma_zband_kernel<32, UEPI_F32, 1, false, 2, 1>, T21);   // K_b32
       }
-      if (w.wt == 2) return c.epi == UEPI_PM ? go(conv_umma_zband_kernel<UEPI_PM, 2, false, 2, 3>, T23) : go(conv_umma_zband_kernel<UEPI_F32, 2, false, 2, 3>, T23);
-      return c.epi == UEPI_PM ? go(conv_umma_zband_kernel<UEPI_PM, 1, false, 2, 3>, T23) : go(conv_umma_zband_kernel<UEPI_F32, 1, false, 2, 3>, T23);
+      if (a.cin8) {                                            // Cin = 8, 16 columns: paired taps, 3 epilogue groups + 1 issuer
+        if (w.wt != 1) return cudaErrorNotSupported;
+        return c.epi == UEPI_VRN ? go(conv_umma_zband_kernel<16, UEPI_VRN, 1, true, 3, 1>, T31) : go(conv_umma_zband_kernel<16, UEPI_F32, 1, true, 3, 1>, T31);
+      }
+      if (w.wt == 2) return c.epi == UEPI_PM ? go(conv_umma_zband_kernel<16, UEPI_PM, 2, false, 2, 3>, T23) : go(conv_umma_zband_kernel<16, UEPI_F32, 2, false, 2, 3>, T23);
+      return c.epi == UEPI_PM ? go(conv_umma_zband_kernel<16, UEPI_PM, 1, false, 2, 3>, T23) : go(conv_umma_zband_kernel<16, UEPI_F32, 1, false, 2, 3>, T23);
     }
   }
   if (umma_stream_mode() && w.ntaps == 27 && w.kchunks == 1 && n >= 16 && stream_shape_ok(w.np, c.epi, a.cin8 != 0, w.wt)) {
