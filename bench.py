@@ -344,8 +344,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s synthetic cloud, hyper mode, model_voxception, rho=1.0, seeded synthetic weights" % args.workload,
-                   "note": "TF 1.13 reference not installable offline: CPU oracle port of the same path"},
+        # the same workload description as the CUDA arm prints (the step here is a bounded sample of it: see cpu_baseline.sample)
+        "config": {"workload": "%s synthetic cloud, %d cubes of 64^3 (%d points) per GPU, hyper mode, model_voxception, rho=1.0, "
+                               "seeded synthetic weights" % (args.workload, len(cubes), int(nums.sum())),
+                   "cubes_per_gpu": len(cubes), "points_per_gpu": int(nums.sum()),
+                   "note": "TF 1.13 reference not installable offline: CPU oracle port of the same path, one cube per call"},
         "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
