@@ -88,6 +88,7 @@ def decompress_factorized(strings, min_v, max_v, shape, model, ckpt_dir):
 # transforms of chunk k+1 and a copy stream moves the coder's inputs through rotating pinned buffers.
 _CHUNK = int(os.environ.get("PCGC_CHUNK", "64"))
 _CHUNK_EDGE = int(os.environ.get("PCGC_CHUNK_EDGE", "16"))
+_CHUNK_RAMP = bool(int(os.environ.get("PCGC_CHUNK_RAMP", "1")))
 
 
 def _chunks(B, small_first=False, small_last=False):
@@ -99,6 +100,8 @@ def _chunks(B, small_first=False, small_last=False):
     head, tail = [], []
     if small_first and e and B > 2 * e:
         head.append((0, e)); lo = e
+        if _CHUNK_RAMP and 2 * e < _CHUNK and hi - lo > 2 * e + _CHUNK:      # e, 2e, then full chunks: the GPU gets work early
+            head.append((lo, lo + 2 * e)); lo += 2 * e
     if small_last and e and hi - lo > 2 * e:
         tail.append((hi - e, hi)); hi -= e
     mid = [(a, min(hi, a + _CHUNK)) for a in range(lo, hi, _CHUNK)]
