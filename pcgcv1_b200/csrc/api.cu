@@ -847,6 +847,39 @@ int pcgc_load_conv(pcgc_ctx* ctx, int net, const char* layer, const float* kerne
   } else {
     // stride-2 Conv3DTranspose = 8 output-parity classes, each a stride-1 gather conv over the input grid
     const int pb = same_pad_before(k, 2);
+    if (s.cout == 1) {
+      // One output channel (model_simple deconv_3, k9): the 8 classes become the 8 "output channels" of ONE conv over the union
+      // tap box, so the input brick is staged once instead of 8 times and every staged value feeds 8 FMAs instead of 1
+      // (r01: 15.4 ms -> per 64 cubes for this layer alone as 8 single-channel launches).
+      int km[2], q0[2], o0[2], P[2];
+      for (int r = 0; r < 2; ++r) {
+        km[r] = (k - r + 1) / 2;
+        q0[r] = std::max(0, (pb - r + 1) / 2);
+        o0[r] = 2 * q0[r] + r - pb;
+        P[r] = (km[r] - 1) - q0[r];
+      }
+      const int PU = std::max(P[0], P[1]);
+      const int KM = std::max(km[0] + PU - P[0], km[1] + PU - P[1]);
+      lw.n_classes = 1;
+      ConvDesc& d = lw.cls[0];
+      d.kz = d.ky = d.kx = KM; d.stride = 1; d.pz = d.py = d.px = PU;
+      d.ostride = 2; d.oz = d.oy = d.ox = 0; d.cin = s.cin; d.cout = 8;
+      d.class_mode = 1; d.cls_o0[0] = o0[0]; d.cls_o0[1] = o0[1];
+      packed.assign((size_t)KM * KM * KM * s.cin * 8, 0.f);
+      for (int cls = 0; cls < 8; ++cls) {
+        const int r[3] = {(cls >> 2) & 1, (cls >> 1) & 1, cls & 1};
+        for (int jz = 0; jz < km[r[0]]; ++jz) for (int jy = 0; jy < km[r[1]]; ++jy) for (int jx = 0; jx < km[r[2]]; ++jx) {
+          const int uz = jz + PU - P[r[0]], uy = jy + PU - P[r[1]], ux = jx + PU - P[r[2]];
+          const int kz = r[0] + 2 * (km[r[0]] - 1 - jz), ky = r[1] + 2 * (km[r[1]] - 1 - jy), kx = r[2] + 2 * (km[r[2]] - 1 - jx);
+          for (int ci = 0; ci < s.cin; ++ci)
+            packed[((((size_t)uy * KM + ux) * s.cin + ci) * KM + uz) * 8 + cls] = K(kz, ky, kx, ci, 0);
+        }
+      }
+      float* dw = nullptr;
+      CK(cudaMalloc((void**)&dw, packed.size() * sizeof(float)));
+      CK(cudaMemcpy(dw, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+      d.w = dw;
+    } else {
     lw.n_classes = 8;
     for (int cls = 0; cls < 8; ++cls) {
       const int r[3] = {(cls >> 2) & 1, (cls >> 1) & 1, cls & 1};   // parity of (o+pb) per axis z,y,x
@@ -871,6 +904,7 @@ int pcgc_load_conv(pcgc_ctx* ctx, int net, const char* layer, const float* kerne
       CK(cudaMalloc((void**)&dw, packed.size() * sizeof(float)));
       CK(cudaMemcpy(dw, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
       d.w = dw;
+    }
     }
   }
   if (bias) {

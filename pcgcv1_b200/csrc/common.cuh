@@ -22,6 +22,10 @@ struct ConvDesc {
   int oz, oy, ox;        // output offset per axis (parity class)
   int cin, cout;
   const float* w = nullptr;   // device, [KY][KX][Cin][KZ][Cout] fp32
+  // class_mode: the 8 "output channels" are the 8 output-parity classes of a single-channel stride-2 transposed conv sharing one
+  // union tap box; class q = (rz<<2)|(ry<<1)|rx writes output voxel 2t + cls_o0[r] per axis (channel 0, bias[0]).
+  int class_mode = 0;
+  int cls_o0[2] = {0, 0};
 };
 
 enum EpilogueFlags : int { EPI_RELU = 1, EPI_ABS = 2, EPI_RES = 4, EPI_FLOOR = 8 };

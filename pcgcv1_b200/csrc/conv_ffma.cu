@@ -33,6 +33,7 @@ struct FfmaArgs {
   int ey, ex, exp_;       // brick extents (y, x) and padded x pitch
   int flags; float floor_v;
   const __nv_bfloat16* in_pm; __nv_bfloat16* out_pm;
+  int class_mode, cls_o0a, cls_o0b;   // see ConvDesc::class_mode
 };
 
 template <int KZ, int S, int CT>
@@ -181,6 +182,23 @@ __global__ void __launch_bounds__(512) conv_ffma_kernel(const FfmaArgs a) {
         continue;
       }
     }
+    if (a.class_mode) {
+      // the CT = 8 accumulators are the 8 output-parity classes of a single-channel transposed conv
+      if constexpr (CT == 8) {
+        const float bz0 = a.bias ? __ldg(a.bias) : 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int oz = 2 * t_z + (((q >> 2) & 1) ? a.cls_o0b : a.cls_o0a), oy = 2 * t_y + (((q >> 1) & 1) ? a.cls_o0b : a.cls_o0a),
+                    ox = 2 * t_x + ((q & 1) ? a.cls_o0b : a.cls_o0a);
+          float v = acc[j][q] + bz0;
+          if (a.flags & EPI_RELU) v = fmaxf(v, 0.f);
+          if (a.flags & EPI_ABS) v = fabsf(v);
+          if (a.flags & EPI_FLOOR) v = fmaxf(v, a.floor_v);
+          a.out[((((size_t)b * a.out_n + oz) * a.out_n + oy) * a.out_n + ox) * a.out_cs + a.out_co] = v;
+        }
+      }
+      continue;
+    }
     float* op = a.out + vox * a.out_cs + a.out_co;
     const float* rp = a.res ? a.res + vox * a.res_cs + a.res_co : nullptr;
 #pragma unroll
@@ -247,6 +265,8 @@ cudaError_t launch_conv_ffma(const ConvCall& c, cudaStream_t s, int64_t* launche
   a.ostride = c.d.ostride; a.oz = c.d.oz; a.oy = c.d.oy; a.ox = c.d.ox;
   a.cin = c.d.cin; a.cout = c.d.cout;
   a.flags = c.flags; a.floor_v = c.floor_v;
+  a.class_mode = c.d.class_mode; a.cls_o0a = c.d.cls_o0[0]; a.cls_o0b = c.d.cls_o0[1];
+  if (a.class_mode && (c.out_pm || c.res || c.d.cout != 8)) return cudaErrorInvalidValue;
   a.in_pm = (const __nv_bfloat16*)c.in_pm; a.out_pm = (__nv_bfloat16*)c.out_pm;
   if (a.in_pm && (c.d.cin % 8 != 0)) return cudaErrorInvalidValue;
   if (a.out_pm && (c.d.cout % 8 != 0 || c.res)) return cudaErrorInvalidValue;
