@@ -94,3 +94,22 @@ def test_cli_round_trip(tmp_path, monkeypatch, mode, modelname):
     assert len(rec) >= int(points_numbers.sum()) and np.array_equal(rec, want)
     uniq = np.unique(pts, axis=0)
     assert int(points_numbers.sum()) <= len(uniq)
+
+
+def test_cli_round_trip_with_scaling(tmp_path, monkeypatch):
+    """--scale 0.5 (process.py:24-31,72-78): the cloud is down-scaled and de-duplicated before partitioning, the reconstruction is
+    scaled back up and written with float coordinates; the temporary scaling files are removed."""
+    from pcgcv1_b200 import test as cli
+    from pcgcv1_b200.dataprocess import inout_points
+    monkeypatch.chdir(tmp_path)
+    pts = _small_cloud()
+    inout_points.write_ply_data("cloud_vox10.ply", pts)
+    cli.main(["compress", "cloud_vox10.ply", "--scale", "0.5", "--min_num", "20"])
+    cli.main(["decompress", "compressed/cloud_vox10", "--scale", "0.5"])
+    rec = inout_points.load_ply_data("cloud_vox10_rec.ply")
+    down = np.unique(np.round(pts.astype("float32") * 0.5), axis=0)
+    assert 0.5 * len(down) < len(rec) < 1.5 * len(down)
+    assert (rec % 2 == 0).all()                                           # integer grid of the half-scale cloud, scaled by 2
+    lo, hi = pts.min(0) - 130, pts.max(0) + 130                           # random-init weights: anywhere inside the kept 64^3 cubes (x2)
+    assert (rec >= lo).all() and (rec <= hi).all()
+    assert not [f for f in os.listdir(".") if "downscaling" in f or "downsampling" in f]
