@@ -113,3 +113,21 @@ def test_cli_round_trip_with_scaling(tmp_path, monkeypatch):
     lo, hi = pts.min(0) - 130, pts.max(0) + 130                           # random-init weights: anywhere inside the kept 64^3 cubes (x2)
     assert (rec >= lo).all() and (rec <= hi).all()
     assert not [f for f in os.listdir(".") if "downscaling" in f or "downsampling" in f]
+
+
+def test_tf_checkpoint_directory_runs_like_weights_npz(tmp_path, codec):
+    """A directory holding a TensorBundle checkpoint (written here in the reference's object-graph naming) loads through
+    weights.load -> tf_checkpoint and gives bit-identical transforms and strings to the same weights passed directly."""
+    import torch
+    from pcgcv1_b200 import runtime, synthetic, tf_checkpoint, transform, weights
+    from pcgcv1_b200.models import model_voxception
+    w = {k: v for k, v in weights.synthetic_weights("voxception").items() if not k.startswith("estimator_y/")}
+    tf_checkpoint.export_checkpoint(str(tmp_path), w, step=3)
+    assert not os.path.exists(os.path.join(str(tmp_path), "weights.npz"))
+    c, _ = synthetic.surface_cubes(2, seed=4)
+    a = transform.compress_hyper(c, model_voxception, "")
+    b = transform.compress_hyper(c, model_voxception, str(tmp_path))
+    assert [bytes(s) for s in a[0].numpy()] == [bytes(s) for s in b[0].numpy()] and a[4].numpy() == b[4].numpy()
+    xa = transform.decompress_hyper(*[o.numpy() for o in a], model_voxception, "")
+    xb = transform.decompress_hyper(*[o.numpy() for o in b], model_voxception, str(tmp_path))
+    assert torch.equal(xa.tensor, xb.tensor)
