@@ -292,6 +292,10 @@ def run_gpu(args):
     kernels = [{"tag": r["tag"], "share": round(r["ms"] / total_ms, 4),
                 "achieved": round((r["flops"] / 1e12 if r["flops"] else r["bytes"] / 1e9) / (r["ms"] * 1e-3), 2),
                 "unit": "TFLOP/s" if r["flops"] else "GB/s"} for r in prof[:16]]
+    # memory-bound kernels (entropy models, top-k, voxel I/O): achieved algorithmic GB/s against the measured HBM peak, whatever their rank
+    hbm_kernels = [{"tag": r["tag"], "share": round(r["ms"] / total_ms, 4), "achieved_gbs": round(r["bytes"] / 1e9 / (r["ms"] * 1e-3), 1),
+                    "frac_of_hbm_peak": round(r["bytes"] / 1e9 / (r["ms"] * 1e-3) / peaks["hbm_gbs"], 4)}
+                   for r in prof if not r["flops"] and r["bytes"] and r["ms"] > 0]
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -315,7 +319,7 @@ def run_gpu(args):
         "conv": {"achieved_tflops": round(conv_tflops, 2), "share_of_step": round(conv_ms / total_ms, 4),
                  "algorithmic_gflop_per_cube": GFLOP_PER_CUBE,
                  "frac_of_bf16_sustained": round(conv_tflops / peaks["bf16_tflops_sustained"], 5)},
-        "kernels": kernels, "cpu_baseline": cpu,
+        "kernels": kernels, "hbm_kernels": hbm_kernels, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
     if world > 1:
