@@ -20,6 +20,16 @@
 //     Voxception tail (1x1x1 conv2_3, concat, residual add, ReLU: model_voxception.py:62-67) and writes
 //     PM (or float32 NDHWC for external tensors).
 // Deterministic: fixed K order, no atomics, no split-K; the tile shape never depends on the batch.
+//
+// Three kernels share the operand formats, the epilogues and the weight packing below; launch_conv_umma_pm picks per layer shape:
+//   conv_umma_kernel         tile kernel (this description): persistent CTAs, 2-3 per SM, one haloed brick per tile.  Serves the
+//                            multi-chunk layers (Cin >= 32 at 16^3), the stride-2 / transposed forms and K_b16.
+//   conv_umma_stream_kernel  z-streaming: one CTA per SM walks a column of z slices through a ring of shared-memory slots, with
+//                            the TMA producer, three MMA issuers and the epilogue split over warps.  Serves K_b32, deconv_in.
+//   conv_umma_zband_kernel   z-banded streaming: input-slice stationary, the three kz taps are column blocks of one MMA, so an
+//                            A tile is fetched once for the three output slices it feeds.  Serves the 16-column layers (K_a16,
+//                            K_a32, deconv_out), which were bound by exactly that fetch.
+// PCGC_UMMA_STREAM / PCGC_UMMA_ZBAND select among them for experiments; tests/test_gpu_umma_modes.py runs every setting.
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
