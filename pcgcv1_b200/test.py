@@ -1,37 +1,87 @@
-"""Drop-in for the reference's CLI ``test.py`` (:24-115): same positional arguments, flags, defaults, file naming
-(``./compressed/<name>.*``, ``<name>_rec.ply``) and call sequence; the codec underneath is libpcgc_b200.so.
+"""Command line of the codec with the reference's surface (``test.py:24-115``): the same positional arguments, option names,
+defaults and file naming (``./compressed/<name>.*`` on the way in, ``<name>_rec.ply`` on the way out), so scripts written for the
+reference run unchanged:
 
-    python -m pcgcv1_b200.test compress  cloud.ply               --ckpt_dir=... [--mode=hyper|factorized]
-    python -m pcgcv1_b200.test decompress compressed/cloud       --ckpt_dir=...
+    python -m pcgcv1_b200.test compress   cloud.ply          [--mode hyper|factorized] [--modelname models.model_voxception] [--ckpt_dir DIR]
+    python -m pcgcv1_b200.test decompress compressed/cloud   [... the same options ...]
 
-``--modelname`` takes the reference's module paths (``models.model_voxception``, ``models.model_simple``); ``--gpu`` is
-accepted for compatibility -- there is no CPU path (``--gpu 0`` is an error rather than a silent slow run)."""
+``--modelname`` takes the reference's module paths; ``--gpu 0`` is refused instead of silently falling back (there is no CPU path)."""
 from __future__ import annotations
 
 import argparse
 import importlib
 import os
 
+# (flag, type, default, help) -- names and defaults are the reference's (test.py:33-42)
+_OPTIONS = [
+    ("--mode", str, "hyper", "entropy model: 'hyper' (hyperprior + conditional model) or 'factorized'"),
+    ("--modelname", str, "models.model_voxception", "transform module: models.model_voxception or models.model_simple"),
+    ("--ckpt_dir", str, "", "directory with weights.npz or a TF-1.13 checkpoint ('' = seeded synthetic weights)"),
+    ("--scale", float, 1.0, "geometry scaling applied before coding and undone after decoding"),
+    ("--cube_size", int, 64, "edge of the cubes the cloud is partitioned into"),
+    ("--min_num", int, 64, "cubes with fewer points are dropped"),
+    ("--rho", float, 1.0, "output points per input point (top-k classification)"),
+    ("--gpu", int, 1, "kept for compatibility; must be 1"),
+]
+
 
 def parse_args(argv=None):
-    parser = argparse.ArgumentParser(formatter_class=argparse.ArgumentDefaultsHelpFormatter)
-    parser.add_argument("command", choices=["compress", "decompress"],
-                        help="What to do: 'compress' reads a point cloud (.ply format) and writes compressed binary files. "
-                             "'decompress' reads binary files and reconstructs the point cloud (.ply format). "
-                             "input and output filenames need to be provided for the latter. ")
-    parser.add_argument("input", nargs="?", help="Input filename.")
-    parser.add_argument("output", nargs="?", help="Output filename.")
-    parser.add_argument("--mode", type=str, default='hyper', dest="mode", help='factorized entropy model or hyper prior')
-    parser.add_argument("--modelname", default="models.model_voxception", dest="modelname", help="(model_simple, model_voxception)")
-    parser.add_argument("--ckpt_dir", type=str, default='', dest="ckpt_dir", help='checkpoint')
-    parser.add_argument("--scale", type=float, default=1.0, dest="scale", help="scaling factor.")
-    parser.add_argument("--cube_size", type=int, default=64, dest="cube_size", help="size of partitioned cubes.")
-    parser.add_argument("--min_num", type=int, default=64, dest="min_num", help="minimum number of points in a cube.")
-    parser.add_argument("--rho", type=float, default=1.0, dest="rho", help="ratio of the numbers of output points to the number of input points.")
-    parser.add_argument("--gpu", type=int, default=1, dest="gpu", help="use gpu (1) or not (0).")
-    args = parser.parse_args(argv)
+    ap = argparse.ArgumentParser(prog="pcgcv1_b200.test", formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    ap.add_argument("command", choices=["compress", "decompress"], help="compress: .ply -> ./compressed/<name>.*; decompress: the reverse")
+    ap.add_argument("input", nargs="?", help="point cloud (.ply) to compress, or compressed/<name> to decompress")
+    ap.add_argument("output", nargs="?", help="name of the compressed set / of the reconstructed .ply")
+    for flag, typ, default, text in _OPTIONS:
+        ap.add_argument(flag, type=typ, default=default, dest=flag.lstrip("-"), help=text)
+    args = ap.parse_args(argv)
     print(args)
     return args
+
+
+class _Session:
+    """Everything one invocation needs: the model module, its codec and the mode-specific pairs of functions."""
+
+    def __init__(self, args):
+        from . import runtime, transform
+        from .dataprocess import inout_bitstream as ibs
+        name = args.modelname if args.modelname.startswith("pcgcv1_b200.") else "pcgcv1_b200." + args.modelname
+        self.args = args
+        self.model = importlib.import_module(name)
+        self.codec = runtime.get_codec(self.model, args.ckpt_dir)
+        if args.mode == "hyper":
+            self.encode, self.decode = transform.compress_hyper, transform.decompress_hyper
+            self.store, self.fetch = ibs.write_binary_files_hyper, ibs.read_binary_files_hyper
+        elif args.mode == "factorized":
+            self.encode, self.decode = transform.compress_factorized, transform.decompress_factorized
+            self.store, self.fetch = ibs.write_binary_files_factorized, ibs.read_binary_files_factorized
+        else:
+            raise SystemExit("--mode must be 'hyper' or 'factorized'")
+
+    def compress(self):
+        from .process import preprocess
+        a = self.args
+        name = a.output or os.path.split(a.input)[-1][:-4]
+        cubes, cube_positions, points_numbers = preprocess(a.input, a.scale, a.cube_size, a.min_num, codec=self.codec)
+        coded = [v.numpy() for v in self.encode(cubes, self.model, a.ckpt_dir)]
+        if a.mode == "hyper":
+            y_strings, y_min_vs, y_max_vs, y_shape, z_strings, z_min_v, z_max_v, z_shape = coded
+            self.store(name, y_strings, z_strings, points_numbers, cube_positions, y_min_vs, y_max_vs, y_shape, z_min_v, z_max_v, z_shape,
+                       rootdir="./compressed")
+        else:
+            strings, min_v, max_v, shape = coded
+            self.store(name, strings, points_numbers, cube_positions, min_v, max_v, shape, rootdir="./compressed")
+
+    def decompress(self):
+        from .process import postprocess
+        a = self.args
+        rootdir, name = os.path.split(a.input)
+        target = a.output or name + "_rec.ply"
+        if a.mode == "hyper":
+            y_strings, z_strings, points_numbers, cube_positions, y_min_vs, y_max_vs, y_shape, z_min_v, z_max_v, z_shape = self.fetch(name, rootdir)
+            logits = self.decode(y_strings, y_min_vs, y_max_vs, y_shape, z_strings, z_min_v, z_max_v, z_shape, self.model, a.ckpt_dir)
+        else:
+            strings, points_numbers, cube_positions, min_v, max_v, shape = self.fetch(name, rootdir)
+            logits = self.decode(strings, min_v, max_v, shape, self.model, a.ckpt_dir)
+        postprocess(target, logits, points_numbers, cube_positions, a.scale, a.cube_size, a.rho, codec=self.codec)
 
 
 def main(argv=None):
@@ -40,50 +90,8 @@ def main(argv=None):
         raise SystemExit("pcgcv1_b200 has no CPU path (--gpu 0): the codec is the CUDA library")
     if args.cube_size != 64:
         raise SystemExit("the transforms are built for 64^3 cubes (the reference's default and its checkpoints)")
-    from .dataprocess.inout_bitstream import (read_binary_files_factorized, read_binary_files_hyper,
-                                              write_binary_files_factorized, write_binary_files_hyper)
-    from .process import postprocess, preprocess
-    from .transform import compress_factorized, compress_hyper, decompress_factorized, decompress_hyper
-    from . import runtime
-
-    name = args.modelname if args.modelname.startswith("pcgcv1_b200.") else "pcgcv1_b200." + args.modelname
-    model = importlib.import_module(name)
-    codec = runtime.get_codec(model, args.ckpt_dir)
-
-    if args.mode == "factorized":
-        if args.command == "compress":
-            cubes, cube_positions, points_numbers = preprocess(args.input, args.scale, args.cube_size, args.min_num, codec=codec)
-            strings, min_v, max_v, shape = compress_factorized(cubes, model, args.ckpt_dir)
-            if not args.output:
-                args.output = os.path.split(args.input)[-1][:-4]
-            write_binary_files_factorized(args.output, strings.numpy(), points_numbers, cube_positions, min_v.numpy(), max_v.numpy(),
-                                          shape.numpy(), rootdir='./compressed')
-        elif args.command == "decompress":
-            rootdir, filename = os.path.split(args.input)
-            if not args.output:
-                args.output = filename + "_rec.ply"
-            strings_d, points_numbers_d, cube_positions_d, min_v_d, max_v_d, shape_d = read_binary_files_factorized(filename, rootdir)
-            cubes_d = decompress_factorized(strings_d, min_v_d, max_v_d, shape_d, model, args.ckpt_dir)
-            postprocess(args.output, cubes_d, points_numbers_d, cube_positions_d, args.scale, args.cube_size, args.rho, codec=codec)
-
-    if args.mode == "hyper":
-        if args.command == "compress":
-            if not args.output:
-                args.output = os.path.split(args.input)[-1][:-4]
-            cubes, cube_positions, points_numbers = preprocess(args.input, args.scale, args.cube_size, args.min_num, codec=codec)
-            y_strings, y_min_vs, y_max_vs, y_shape, z_strings, z_min_v, z_max_v, z_shape = compress_hyper(cubes, model, args.ckpt_dir)
-            write_binary_files_hyper(args.output, y_strings.numpy(), z_strings.numpy(), points_numbers, cube_positions,
-                                     y_min_vs.numpy(), y_max_vs.numpy(), y_shape.numpy(), z_min_v.numpy(), z_max_v.numpy(),
-                                     z_shape.numpy(), rootdir='./compressed')
-        elif args.command == "decompress":
-            rootdir, filename = os.path.split(args.input)
-            if not args.output:
-                args.output = filename + "_rec.ply"
-            (y_strings_d, z_strings_d, points_numbers_d, cube_positions_d, y_min_vs_d, y_max_vs_d, y_shape_d, z_min_v_d, z_max_v_d,
-             z_shape_d) = read_binary_files_hyper(filename, rootdir)
-            cubes_d = decompress_hyper(y_strings_d, y_min_vs_d, y_max_vs_d, y_shape_d, z_strings_d, z_min_v_d, z_max_v_d, z_shape_d,
-                                       model, args.ckpt_dir)
-            postprocess(args.output, cubes_d, points_numbers_d, cube_positions_d, args.scale, args.cube_size, args.rho, codec=codec)
+    session = _Session(args)
+    getattr(session, args.command)()
 
 
 if __name__ == "__main__":
