@@ -68,6 +68,10 @@ int pcgc_set_engine(pcgc_ctx* ctx, int engine);
 /* number of kernels this library has launched on ctx since creation (bench "gpu_launches"). */
 int64_t pcgc_launch_count(const pcgc_ctx* ctx);
 int pcgc_synchronize(pcgc_ctx* ctx);
+/* Pipelining aid.  Several entry points synchronise the stream only to read the device-side error flag (bad symbol range,
+ * tcgen05 barrier timeout ...).  With deferred checks ON they return right after enqueueing; the caller MUST call
+ * pcgc_synchronize (which reports the flag) before it consumes any result.  Default OFF. */
+int pcgc_set_deferred_checks(pcgc_ctx* ctx, int on);
 /* Measurement aid (bench.py roofline): when on, every kernel launch group is bracketed by CUDA events
  * on the ctx stream.  pcgc_profile_report synchronises, writes a JSON array of
  * {"tag","count","ms","flops","bytes"} (algorithmic work per tag) into buf and clears the records. */
@@ -106,7 +110,8 @@ int pcgc_synthesis(pcgc_ctx* ctx, int net, const float* y_dev, int B, float* log
 int pcgc_hyper_encode(pcgc_ctx* ctx, const float* y_dev, int B, float* z_dev);
 /* HyperDecoder()(z_hat) followed by scales = max(scales, 1e-9) (transform.py:138-146,225-233):
  * z_hat [B,8,8,8,8] -> loc, scale [B,16,16,16,16]; scale = max(|.|, scale_floor).
- * Bit-reproducible across calls, batch sizes and devices of the same type. */
+ * Bit-reproducible across calls, batch sizes, devices of the same type, pcgc_set_engine settings and the PCGC_UMMA_* tuning
+ * switches (one pinned kernel program: the outputs become integer CDF tables on both sides of the stream). */
 int pcgc_hyper_decode(pcgc_ctx* ctx, const float* z_hat_dev, int B, float scale_floor, float* loc_dev,
                       float* scale_dev);
 
@@ -148,6 +153,44 @@ int pcgc_laplace_cdf(pcgc_ctx* ctx, const float* loc_dev, const float* scale_dev
 /* Test hook: the DEVICE copy of the 16-bit normaliser on given pmf rows (device float32 [rows,N], 2 <= N <=
  * PCGC_MAX_SYMBOLS) -> device int32 cdf [rows,N+1]; must equal pcgc_pmf_to_quantized_cdf bit for bit.  Synchronises. */
 int pcgc_debug_quantize_pmf(pcgc_ctx* ctx, const float* pmf_dev, int64_t rows, int N, int precision, int32_t* cdf_dev);
+
+/* "noise" quantisation of the training graph (entropy_model.py:105-107, conditional_entropy_model.py:62-64): when noise = 1
+ * the two *_quantize_likelihood entry points return x + U(-1/2, 1/2) (counter-based Philox4x32-10 keyed by `seed`, element
+ * index as the counter: reproducible, independent of the launch shape) and the likelihood AT that value instead of round(x);
+ * minmax outputs are then meaningless.  noise = 0 (default) is "symbols" = round half to even. */
+int pcgc_set_quantize_mode(pcgc_ctx* ctx, int noise, uint64_t seed);
+/* Test hook (host, no ctx): the four draws of elements 4*v .. 4*v+3 for `seed` as the kernels make them (the conditional
+ * model's launch uses seed + 0x9E3779B97F4A7C15 so that y and z do not share a stream). */
+int pcgc_debug_noise(uint64_t seed, uint64_t v, float* out4);
+
+/* ---- GPU-side range coding of the per-cube strings (models/conditional_entropy_model.py:126-201) ----
+ * All pointers are DEVICE pointers, nothing synchronises; device-side failures (overflow, bad range) set the ctx error flag
+ * that pcgc_synchronize reports.  The strings are byte-identical to the host coder's (same state machine source). */
+/* pcgc_laplace_cdf with device-resident headers: minmax_dev int32[2B], row_offset_dev int64[B+1] (uint16 units);
+ * rows_total = row_offset[B] (only used for the profile's byte count). */
+int pcgc_laplace_cdf_dev(pcgc_ctx* ctx, const float* loc_dev, const float* scale_dev, int B, int64_t E,
+                         const int32_t* minmax_dev, const int64_t* row_offset_dev, double rows_total, float likelihood_bound,
+                         int precision, uint16_t* cdf_dev);
+/* range_encode of B cubes from pcgc_laplace_intervals' output: cube b is coded into scratch_dev + b*stride (stride >= 2*E+64
+ * always suffices), lens_dev[b] receives its length, then the strings are concatenated into packed_dev (capacity cap) with
+ * offsets_dev int64[B+1] (offsets[B] = total bytes). */
+int pcgc_range_encode_intervals_dev(pcgc_ctx* ctx, const uint32_t* intervals_dev, int B, int64_t E, int precision,
+                                    uint8_t* scratch_dev, int64_t stride, int64_t* lens_dev, uint8_t* packed_dev, int64_t cap,
+                                    int64_t* offsets_dev);
+/* range_decode of B cubes: string b = packed_dev[offsets[b] .. offsets[b+1]), rows as written by pcgc_laplace_cdf(_dev),
+ * y_hat_dev float32 [B,E] = symbol + min_v (conditional_entropy_model.py:196-199).  E % 32 == 0; max_n = the largest
+ * N_b = max_v - min_v + 1 of the call (<= PCGC_MAX_SYMBOLS; sizes the shared-memory row window). */
+int pcgc_range_decode_rows_dev(pcgc_ctx* ctx, const uint8_t* packed_dev, const int64_t* offsets_dev, int B, int64_t E,
+                               const uint16_t* rows_dev, const int64_t* row_offset_dev, double rows_total, const int32_t* minmax_dev,
+                               int max_n, int precision, float* y_hat_dev);
+
+/* ---- host twins of the CDF builders (bit-identical tables: det_math.h + cdf_norm.h are shared by host and device) ---------
+ * Interoperability / test aids: a CPU that has (loc, scale) or the bottleneck parameters can build exactly the tables the GPU
+ * coded with, and decode the stream with pcgc_range_decode_rows / pcgc_range_decode.  Not on the product path. */
+int pcgc_host_laplace_cdf(const float* loc, const float* scale, int B, int64_t E, const int32_t* minmax, float likelihood_bound,
+                          int precision, const int64_t* row_offset, uint16_t* rows, int threads);
+int pcgc_factorized_cdf_host(pcgc_ctx* ctx, int slot, int min_v, int max_v, float likelihood_bound, int precision,
+                             int32_t* cdf_host);
 
 /* ---- top-k occupancy classification (dataprocess/inout_points.py:147-179) ---------------------- */
 /* select_voxels: per cube k = ks[b] (caller computes int(rho * n_points)); threshold = k-th

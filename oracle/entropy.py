@@ -32,6 +32,30 @@ def _sigmoid(x):
     return out
 
 
+def philox4x32_10(c0, c1, k0, k1):
+    """Philox4x32-10 (Salmon et al. 2011, Random123) on uint32 arrays: counter (c0, c1, 0, 0), key (k0, k1) -> 4 uint32 arrays.
+    The "noise" quantisation of the CUDA path draws from this generator (csrc/entropy.cu:noise4)."""
+    c = [np.asarray(c0, np.uint64), np.asarray(c1, np.uint64), np.zeros_like(np.asarray(c0, np.uint64)), np.zeros_like(np.asarray(c0, np.uint64))]
+    k0, k1 = np.uint64(k0), np.uint64(k1)
+    M0, M1, W0, W1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0x9E3779B9), np.uint64(0xBB67AE85), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [(p1 >> np.uint64(32)) ^ c[1] ^ k0, p1 & MASK, (p0 >> np.uint64(32)) ^ c[3] ^ k1, p0 & MASK]
+        k0, k1 = (k0 + W0) & MASK, (k1 + W1) & MASK
+    return [x.astype(np.uint32) for x in c]
+
+
+def philox_uniform(seed: int, n: int) -> np.ndarray:
+    """n draws of U[-1/2, 1/2) as float32: element i uses word i % 4 of the block with counter i // 4, key = seed."""
+    v = np.arange((n + 3) // 4, dtype=np.uint64)
+    r = philox4x32_10(v & np.uint64(0xFFFFFFFF), v >> np.uint64(32), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    u = np.stack(r, -1).reshape(-1)[:n]
+    return ((u >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24) - np.float32(0.5)).astype(np.float32)
+
+
+Y_NOISE_SEED_OFFSET = 0x9E3779B97F4A7C15      # the conditional model's stream (api.cu: pcgc_laplace_quantize_likelihood)
+
+
 def tf_round(x):
     """tf.math.round = round half to even (np.rint)."""
     return np.rint(x)
@@ -90,9 +114,9 @@ class EntropyBottleneckOracle:
         p = self._likelihood_cm(x_cm)
         return np.moveaxis(p.reshape((c,) + x.shape[:-1]), 0, -1)
 
-    def __call__(self, x: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
-        """call(inputs, training=False), entropy_model.py:153-181."""
-        x_hat = tf_round(x)
+    def __call__(self, x: np.ndarray, training: bool = False, seed: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+        """call(inputs, training), entropy_model.py:153-181; training=True is the "noise" mode (:105-107)."""
+        x_hat = (x + philox_uniform(seed, x.size).reshape(x.shape).astype(x.dtype)) if training else tf_round(x)
         p = np.maximum(self.likelihood(x_hat), x.dtype.type(self.likelihood_bound))
         return x_hat, p
 
@@ -156,9 +180,9 @@ class SymmetricConditionalOracle:
         return np.abs(self.standardized_cumulative(upper, loc, scale)
                       - self.standardized_cumulative(lower, loc, scale))
 
-    def __call__(self, y, loc, scale):
-        """call(inputs, loc, scale, training=False), conditional_entropy_model.py:71-93."""
-        y_hat = tf_round(y)
+    def __call__(self, y, loc, scale, training: bool = False, seed: int = 0):
+        """call(inputs, loc, scale, training), conditional_entropy_model.py:71-93; training=True = "noise" (:62-64)."""
+        y_hat = (y + philox_uniform((seed + Y_NOISE_SEED_OFFSET) & 0xFFFFFFFFFFFFFFFF, y.size).reshape(y.shape).astype(y.dtype)) if training else tf_round(y)
         p = np.maximum(self.likelihood(y_hat, loc, scale), y.dtype.type(self.likelihood_bound))
         return y_hat, p
 

@@ -60,6 +60,14 @@ SIGNATURES = {
     "pcgc_range_encode_intervals_batch": (_i, [_vp, _i, _i64, _i, _vp, _i64, _vp, _i]),
     "pcgc_range_decode_rows_batch": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _i, _vp, _i]),
     "pcgc_range_decode_rows_batch_f32": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _i, _vp, _i]),
+    "pcgc_set_deferred_checks": (_i, [_vp, _i]),
+    "pcgc_set_quantize_mode": (_i, [_vp, _i, C.c_uint64]),
+    "pcgc_debug_noise": (_i, [C.c_uint64, C.c_uint64, _vp]),
+    "pcgc_laplace_cdf_dev": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, C.c_double, _f, _i, _vp]),
+    "pcgc_range_encode_intervals_dev": (_i, [_vp, _vp, _i, _i64, _i, _vp, _i64, _vp, _vp, _i64, _vp]),
+    "pcgc_range_decode_rows_dev": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, C.c_double, _vp, _i, _i, _vp]),
+    "pcgc_host_laplace_cdf": (_i, [_vp, _vp, _i, _i64, _vp, _f, _i, _vp, _vp, _i]),
+    "pcgc_factorized_cdf_host": (_i, [_vp, _i, _i, _i, _f, _i, _vp]),
     "pcgc_host_copy": (_i, [_vp, _vp, _i64, _i]),
     "pcgc_ply_parse": (_i, [_vp, _i64, _vp, _i64, _vp, _i]),
     "pcgc_ply_format": (_i, [_vp, _i64, _vp, _i64, _vp, _i]),

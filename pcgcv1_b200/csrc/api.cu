@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "det_math.h"
 #include "umma_conv.cuh"
 
 using namespace pcgc;
@@ -189,6 +190,10 @@ struct pcgc_ctx {
   std::string err;
   Net nets[PCGC_NET_COUNT];
   BottleneckDev bn[2];
+  std::vector<float> bn_host[2];    // packed parameters (44 per channel) for the host twin of the pmf (pcgc_factorized_cdf_host)
+  bool deferred_checks = false;     // pcgc_set_deferred_checks
+  int quant_noise = 0;              // pcgc_set_quantize_mode: 0 = "symbols" (round), 1 = "noise" (training)
+  uint64_t quant_seed = 0;
   // workspaces
   float* bufs[BUF_COUNT] = {nullptr};
   size_t buf_cap[BUF_COUNT] = {0};
@@ -269,7 +274,8 @@ int ensure_scratch(pcgc_ctx* ctx, size_t n) {
 // pad-before of TF SAME for an even extent: stride 1 -> (k-1)/2 ; stride 2 -> (k-2)/2
 int same_pad_before(int k, int stride) { return stride == 1 ? (k - 1) / 2 : (k - 2) / 2; }
 
-int check_err_flag(pcgc_ctx* ctx, const char* what) {
+int check_err_flag(pcgc_ctx* ctx, const char* what, bool force = false) {
+  if (ctx->deferred_checks && !force) return PCGC_OK;       // the caller promised a pcgc_synchronize before it consumes results
   int h = 0;
   CK(cudaMemcpyAsync(&h, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -605,9 +611,10 @@ int run_hyper_umma(pcgc_ctx* ctx, int kind, const float* in_ext, int B, float* o
       PmTensor f2 = pm(BUF_B, 16, 16, nb), f3 = pm(BUF_T1, 16, 32, nb);
       if ((r = ffma("deconv1", in_ext + (size_t)b0 * 4096, nullptr, 8, ctx->bufs[BUF_A], nullptr, nb))) return r;
       if ((r = ffma("deconv2", ctx->bufs[BUF_A], nullptr, 8, nullptr, &f2, nb))) return r;
-      UmmaCall c; c.epi = UEPI_PM; c.flags = EPI_RELU; c.out = f3;
+      // pinned kernels: loc / scale feed the integer CDF tables, so the decoder process must reproduce the encoder's bits
+      UmmaCall c; c.epi = UEPI_PM; c.flags = EPI_RELU; c.out = f3; c.pin_tile = true;
       if ((r = umma("deconv3", up.first, f2, c))) return r;
-      UmmaCall h; h.epi = UEPI_F32; h.flags = 0; h.out_f32 = out0 + (size_t)b0 * 65536; h.out_cs = 16; h.out_co = 0;
+      UmmaCall h; h.epi = UEPI_F32; h.pin_tile = true; h.flags = 0; h.out_f32 = out0 + (size_t)b0 * 65536; h.out_cs = 16; h.out_co = 0;
       h.out2_f32 = out1 + (size_t)b0 * 65536; h.split = 16; h.flags2 = EPI_ABS | EPI_FLOOR; h.floor_v = floor_v;   // abs (:308) + max(., 1e-9)
       if ((r = umma("deconv4_1|4_2", up.last, f3, h))) return r;
     }
@@ -798,7 +805,7 @@ int pcgc_profile_report(pcgc_ctx* ctx, char* buf, int64_t cap) {
 int pcgc_synchronize(pcgc_ctx* ctx) {
   if (!ctx) return PCGC_ERR_BAD_ARG;
   DeviceGuard g(ctx->device);
-  return check_err_flag(ctx, "pcgc_synchronize");      // also surfaces device-side timeouts of the tcgen05 engine
+  return check_err_flag(ctx, "pcgc_synchronize", true);      // also surfaces device-side timeouts of the tcgen05 engine
 }
 
 int pcgc_load_conv(pcgc_ctx* ctx, int net, const char* layer, const float* kernel, const int64_t kshape[5],
@@ -949,6 +956,7 @@ int pcgc_load_bottleneck(pcgc_ctx* ctx, int slot, int channels, const float* mat
   CK(cudaMalloc((void**)&bn.params, p.size() * sizeof(float)));
   CK(cudaMemcpy(bn.params, p.data(), p.size() * sizeof(float), cudaMemcpyHostToDevice));
   bn.channels = C;
+  ctx->bn_host[slot] = p;
   return PCGC_OK;
 }
 
@@ -999,8 +1007,9 @@ int pcgc_hyper_encode(pcgc_ctx* ctx, const float* y_dev, int B, float* z_dev) {
 int pcgc_hyper_decode(pcgc_ctx* ctx, const float* z_hat_dev, int B, float scale_floor, float* loc_dev, float* scale_dev) {
   if (!ctx || !z_hat_dev || !loc_dev || !scale_dev) return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_hyper_decode: bad argument");
   DeviceGuard g(ctx->device);
-  if (ctx->engine != PCGC_ENGINE_FFMA) return run_hyper_umma(ctx, PCGC_NET_HYPER_DECODER, z_hat_dev, B, loc_dev, scale_dev, scale_floor);
-  return run_net(ctx, PCGC_NET_HYPER_DECODER, z_hat_dev, nullptr, 0, B, loc_dev, scale_dev, scale_floor);
+  // ONE fixed program whatever pcgc_set_engine / the PCGC_UMMA_* tuning switches say: loc and scale become integer CDF tables,
+  // and a last-bit difference between the encoding and the decoding process desynchronises the range decoder.
+  return run_hyper_umma(ctx, PCGC_NET_HYPER_DECODER, z_hat_dev, B, loc_dev, scale_dev, scale_floor);
 }
 
 int pcgc_factorized_quantize_likelihood(pcgc_ctx* ctx, int slot, const float* x_dev, int64_t n_vox, int C,
@@ -1014,7 +1023,7 @@ int pcgc_factorized_quantize_likelihood(pcgc_ctx* ctx, int slot, const float* x_
   int r = ensure_scratch(ctx, 148 * 8 + 8); if (r) return r;
   prof_begin(ctx, "factorized_quantize_likelihood", 0, 4.0 * n_vox * C * (1 + (x_hat_dev != nullptr) + (p_dev != nullptr)));
   CK(launch_factorized(ctx->bn[slot], x_dev, n_vox, C, likelihood_bound, x_hat_dev, p_dev, bits_dev, minmax_dev,
-                       ctx->scratch, ctx->stream, &ctx->launches));
+                       ctx->scratch, ctx->stream, &ctx->launches, ctx->quant_noise, ctx->quant_seed));
   prof_end(ctx);
   return PCGC_OK;
 }
@@ -1031,8 +1040,9 @@ int pcgc_factorized_cdf(pcgc_ctx* ctx, int slot, int min_v, int max_v, float lik
   CK(launch_factorized_pmf(bn, min_v, max_v, likelihood_bound, ctx->pmf_dev, ctx->stream, &ctx->launches));
   std::vector<float> pmf((size_t)N * bn.channels);
   CK(cudaMemcpyAsync(pmf.data(), ctx->pmf_dev, pmf.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  int r = pcgc_pmf_to_quantized_cdf(pmf.data(), bn.channels, N, precision, cdf_host);
+  int r = check_err_flag(ctx, "pcgc_factorized_cdf (earlier kernels on this stream)", true);     // synchronises; surfaces tcgen05 timeouts of the transforms
+  if (r) return r;
+  r = pcgc_pmf_to_quantized_cdf(pmf.data(), bn.channels, N, precision, cdf_host);
   if (r) return fail(ctx, r, "pmf_to_quantized_cdf failed");
   return PCGC_OK;
 }
@@ -1046,7 +1056,7 @@ int pcgc_laplace_quantize_likelihood(pcgc_ctx* ctx, const float* y_dev, const fl
   int r = ensure_scratch(ctx, (size_t)B * 16 + 8); if (r) return r;
   prof_begin(ctx, "laplace_quantize_likelihood", 0, 4.0 * B * E * (3 + (y_hat_dev != nullptr) + (p_dev != nullptr)));
   CK(launch_laplace(y_dev, loc_dev, scale_dev, B, E, likelihood_bound, y_hat_dev, p_dev, bits_dev, minmax_dev,
-                    ctx->scratch, ctx->stream, &ctx->launches));
+                    ctx->scratch, ctx->stream, &ctx->launches, ctx->quant_noise, ctx->quant_seed + 0x9E3779B97F4A7C15ull));
   prof_end(ctx);
   return PCGC_OK;
 }
@@ -1155,6 +1165,77 @@ int pcgc_extract_points(pcgc_ctx* ctx, const uint8_t* mask_dev, int B, int S, in
   }
   prof_begin(ctx, "extract_points", 0, 2.0 * B * S * S * S);
   CK(launch_extract_points(mask_dev, B, S, ctx->chunk_dev, counts_dev, points_dev, cap, total_dev, ctx->stream, &ctx->launches));
+  prof_end(ctx);
+  return PCGC_OK;
+}
+
+int pcgc_set_deferred_checks(pcgc_ctx* ctx, int on) {
+  if (!ctx) return PCGC_ERR_BAD_ARG;
+  ctx->deferred_checks = on != 0;
+  return PCGC_OK;
+}
+
+int pcgc_set_quantize_mode(pcgc_ctx* ctx, int noise, uint64_t seed) {
+  if (!ctx || noise < 0 || noise > 1) return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_set_quantize_mode: bad argument");
+  ctx->quant_noise = noise; ctx->quant_seed = seed;
+  return PCGC_OK;
+}
+
+int pcgc_factorized_cdf_host(pcgc_ctx* ctx, int slot, int min_v, int max_v, float likelihood_bound, int precision,
+                             int32_t* cdf_host) {
+  if (!ctx || slot < 0 || slot > 1 || !cdf_host) return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_factorized_cdf_host: bad argument");
+  const std::vector<float>& hp = ctx->bn_host[slot];
+  if (hp.empty()) return fail(ctx, PCGC_ERR_NOT_READY, "bottleneck slot %d not loaded", slot);
+  const int C = (int)(hp.size() / 44), N = max_v - min_v + 1;
+  if (N < 2) return fail(ctx, PCGC_ERR_BAD_RANGE, "single-symbol alphabet [%d,%d]", min_v, max_v);
+  std::vector<float> pmf((size_t)C * N);
+  for (int c = 0; c < C; ++c)
+    for (int k = 0; k < N; ++k) pmf[(size_t)c * N + k] = fmaxf(det_bn_likelihood((float)(min_v + k), hp.data() + (size_t)c * 44), likelihood_bound);
+  int r = pcgc_pmf_to_quantized_cdf(pmf.data(), C, N, precision, cdf_host);
+  if (r) return fail(ctx, r, "pmf_to_quantized_cdf failed");
+  return PCGC_OK;
+}
+
+int pcgc_laplace_cdf_dev(pcgc_ctx* ctx, const float* loc_dev, const float* scale_dev, int B, int64_t E,
+                         const int32_t* minmax_dev, const int64_t* row_offset_dev, double rows_total, float likelihood_bound,
+                         int precision, uint16_t* cdf_dev) {
+  if (!ctx || !loc_dev || !scale_dev || !minmax_dev || !row_offset_dev || !cdf_dev || B < 0 || precision != 16)
+    return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_laplace_cdf_dev: bad argument (precision must be 16)");
+  DeviceGuard g(ctx->device);
+  if (B == 0) return PCGC_OK;
+  prof_begin(ctx, "laplace_cdf", 0, 8.0 * B * E + 2.0 * rows_total);
+  CK(launch_laplace_cdf(loc_dev, scale_dev, B, E, minmax_dev, row_offset_dev, likelihood_bound, precision, cdf_dev,
+                        ctx->err_flag, ctx->stream, &ctx->launches));
+  prof_end(ctx);
+  return PCGC_OK;
+}
+
+int pcgc_range_encode_intervals_dev(pcgc_ctx* ctx, const uint32_t* intervals_dev, int B, int64_t E, int precision,
+                                    uint8_t* scratch_dev, int64_t stride, int64_t* lens_dev, uint8_t* packed_dev, int64_t cap,
+                                    int64_t* offsets_dev) {
+  if (!ctx || !intervals_dev || !scratch_dev || !lens_dev || !packed_dev || !offsets_dev || B < 0 || E <= 0 || E % 4 || stride < 2 ||
+      precision < 1 || precision > 16)
+    return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_range_encode_intervals_dev: bad argument");
+  DeviceGuard g(ctx->device);
+  if (B == 0) { CK(cudaMemsetAsync(offsets_dev, 0, sizeof(int64_t), ctx->stream)); return PCGC_OK; }
+  prof_begin(ctx, "range_encode_gpu", 0, 4.0 * B * E);
+  CK(launch_range_encode_intervals(intervals_dev, B, E, precision, scratch_dev, stride, lens_dev, packed_dev, cap, offsets_dev,
+                                   ctx->err_flag, ctx->stream, &ctx->launches));
+  prof_end(ctx);
+  return PCGC_OK;
+}
+
+int pcgc_range_decode_rows_dev(pcgc_ctx* ctx, const uint8_t* packed_dev, const int64_t* offsets_dev, int B, int64_t E,
+                               const uint16_t* rows_dev, const int64_t* row_offset_dev, double rows_total, const int32_t* minmax_dev,
+                               int max_n, int precision, float* y_hat_dev) {
+  if (!ctx || max_n < 1 || max_n > PCGC_MAX_SYMBOLS || !packed_dev || !offsets_dev || !rows_dev || !row_offset_dev || !minmax_dev || !y_hat_dev || B < 0 || E <= 0 || E % 32 ||
+      precision < 1 || precision > 16)
+    return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_range_decode_rows_dev: bad argument (E must be a multiple of 32)");
+  DeviceGuard g(ctx->device);
+  if (B == 0) return PCGC_OK;
+  prof_begin(ctx, "range_decode_gpu", 0, 2.0 * rows_total + 4.0 * B * E);
+  CK(launch_range_decode_rows(packed_dev, offsets_dev, B, E, rows_dev, row_offset_dev, minmax_dev, max_n, precision, y_hat_dev,
+                              ctx->err_flag, ctx->stream, &ctx->launches));
   prof_end(ctx);
   return PCGC_OK;
 }

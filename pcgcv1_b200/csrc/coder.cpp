@@ -18,115 +18,13 @@
 
 #include "../../include/pcgc_b200.h"
 #include "cdf_norm.h"
+#include "det_math.h"
+#include "range_coder.h"
 
 namespace {
 
-struct Encoder {
-  uint64_t base = 0;            // bit 32 holds a carry that has not been propagated yet
-  uint32_t size_minus1 = 0xFFFFFFFFu;
-  bool have_cache = false;
-  uint32_t cache = 0;           // delayed 16-bit word
-  int64_t pending = 0;          // delayed 0xFFFF words following `cache`
-  uint8_t* out;
-  int64_t n = 0, cap;
-  bool overflow = false;
-  int precision;
-
-  Encoder(uint8_t* o, int64_t c, int p) : out(o), cap(c), precision(p) {}
-
-  inline void emit16(uint32_t w) {
-    if (n + 2 > cap) { overflow = true; return; }
-    out[n++] = (uint8_t)(w >> 8);
-    out[n++] = (uint8_t)w;
-  }
-  inline void shift() {
-    const uint32_t carry = (uint32_t)(base >> 32);
-    const uint32_t low32 = (uint32_t)base;
-    if (low32 < 0xFFFF0000u || carry) {
-      if (have_cache) emit16((cache + carry) & 0xFFFF);
-      for (; pending > 0; --pending) emit16((0xFFFF + carry) & 0xFFFF);
-      cache = (low32 >> 16) & 0xFFFF;
-      have_cache = true;
-    } else {
-      ++pending;
-    }
-    base = (uint64_t)(low32 & 0xFFFF) << 16;
-  }
-  inline void encode(uint32_t lower, uint32_t upper) {
-    const uint64_t size = (uint64_t)size_minus1 + 1;
-    const uint32_t a = (uint32_t)((size * lower) >> precision);
-    const uint32_t b = (uint32_t)(((size * upper) >> precision) - 1);
-    base += a;
-    size_minus1 = b - a;
-    if ((size_minus1 >> 16) == 0) {
-      shift();
-      size_minus1 = (size_minus1 << 16) | 0xFFFF;
-    }
-  }
-  inline int64_t finish() {
-    const uint64_t v = (base + 0xFFFF) >> 16;
-    const uint32_t carry = (uint32_t)(v >> 16), word = (uint32_t)(v & 0xFFFF);
-    if (have_cache) emit16((cache + carry) & 0xFFFF);
-    for (; pending > 0; --pending) emit16((0xFFFF + carry) & 0xFFFF);
-    emit16(word);
-    if (overflow) return -1;
-    while (n > 0 && out[n - 1] == 0) --n;
-    return n;
-  }
-};
-
-struct Decoder {
-  const uint8_t* p;
-  int64_t nbytes, pos = 0;
-  uint32_t base = 0, size_minus1 = 0xFFFFFFFFu, value;
-  int precision;
-
-  Decoder(const uint8_t* d, int64_t n, int prec) : p(d), nbytes(n), precision(prec) {
-    value = read16() << 16;
-    value |= read16();
-  }
-  inline uint32_t read16() {
-    uint32_t v = 0;
-    for (int k = 0; k < 2; ++k) { v <<= 8; if (pos < nbytes) v |= p[pos++]; }
-    return v;
-  }
-  // cdf(i) for i in [0, N]; returns the symbol.
-  template <typename CdfAt>
-  inline int decode(int N, CdfAt cdf) {
-    const uint64_t size = (uint64_t)size_minus1 + 1;
-    const uint64_t offset = (((uint64_t)(uint32_t)(value - base) + 1) << precision) - 1;
-    int lo = 1, hi = N;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (size * (uint64_t)cdf(mid) > offset) hi = mid; else lo = mid + 1;
-    }
-    return narrow(lo - 1, size, cdf);
-  }
-  // Same search through one division: size*c > offset  <=>  c > floor(offset/size); find(t) returns the symbol s with
-  // cdf(s) <= t < cdf(s+1).
-  template <typename Find, typename CdfAt>
-  inline int decode_at(Find find, CdfAt cdf) {
-    const uint64_t size = (uint64_t)size_minus1 + 1;
-    const uint64_t offset = (((uint64_t)(uint32_t)(value - base) + 1) << precision) - 1;
-    uint64_t t = offset / size;
-    const uint64_t top = ((uint64_t)1 << precision) - 1;
-    if (t > top) t = top;                         // only a corrupt stream gets here
-    return narrow(find((uint32_t)t), size, cdf);
-  }
-  template <typename CdfAt>
-  inline int narrow(const int s, const uint64_t size, CdfAt cdf) {
-    const uint32_t a = (uint32_t)((size * (uint64_t)cdf(s)) >> precision);
-    const uint32_t b = (uint32_t)(((size * (uint64_t)cdf(s + 1)) >> precision) - 1);
-    base += a;
-    size_minus1 = b - a;
-    if ((size_minus1 >> 16) == 0) {
-      base <<= 16;
-      size_minus1 = (size_minus1 << 16) | 0xFFFF;
-      value = (value << 16) | read16();
-    }
-    return s;
-  }
-};
+using Encoder = pcgc::RangeEncoder;      // range_coder.h: shared with the GPU coder (gpu_coder.cu)
+using Decoder = pcgc::RangeDecoder;
 
 template <typename F>
 void parallel_for(int n, int threads, F f) {
@@ -409,6 +307,37 @@ int pcgc_range_decode_rows_batch_f32(const uint8_t* const* data, const int64_t* 
   for (int b = 0; b < B; ++b) if (minmax[2 * b + 1] - minmax[2 * b] + 1 < 1) return PCGC_ERR_BAD_ARG;
   return decode_rows_batch_impl(data, nbytes, B, E, rows, row_offset, minmax, precision, y_hat, threads,
                                 [](int s, int mn) { return (float)(s + mn); });
+}
+
+/* Host twin of pcgc_laplace_cdf (SymmetricConditional._get_cdf, conditional_entropy_model.py:95-124): the same det_math.h
+ * likelihood and the same cdf_norm.h normaliser as laplace_cdf_kernel, so the rows are bit-identical to the GPU's and a
+ * CPU can decode a GPU-written stream given (loc, scale).  Test / interoperability aid, not on the product path. */
+int pcgc_host_laplace_cdf(const float* loc, const float* scale, int B, int64_t E, const int32_t* minmax, float likelihood_bound,
+                          int precision, const int64_t* row_offset, uint16_t* rows, int threads) {
+  if (!loc || !scale || !minmax || !row_offset || !rows || B < 0 || E < 0 || precision < 1 || precision > 16) return PCGC_ERR_BAD_ARG;
+  for (int b = 0; b < B; ++b) {
+    const int N = minmax[2 * b + 1] - minmax[2 * b] + 1;
+    if (N < 2 || N > PCGC_MAX_SYMBOLS) return PCGC_ERR_BAD_RANGE;
+  }
+  std::atomic<int> rc(PCGC_OK);
+  const int64_t CH = 4096;                                   // elements per job
+  const int64_t per = (E + CH - 1) / CH;
+  parallel_for((int)(B * per), threads, [&](int job) {
+    const int b = (int)(job / per);
+    const int64_t e0 = (job % per) * CH, e1 = std::min(E, e0 + CH);
+    const int min_v = minmax[2 * b], N = minmax[2 * b + 1] - min_v + 1;
+    float pmf[PCGC_MAX_SYMBOLS], g[PCGC_MAX_SYMBOLS];
+    int32_t v[PCGC_MAX_SYMBOLS];
+    for (int64_t e = e0; e < e1; ++e) {
+      const float l = loc[(int64_t)b * E + e], s = scale[(int64_t)b * E + e];
+      for (int k = 0; k < N; ++k) pmf[k] = fmaxf(pcgc::det_laplace_likelihood((float)(min_v + k), l, s), likelihood_bound);
+      if (pcgc::quantize_pmf_row(pmf, N, precision, v, g) != 0) { rc.store(PCGC_ERR_BAD_RANGE); continue; }
+      uint16_t* row = rows + row_offset[b] + e * N;
+      uint32_t acc = 0;
+      for (int k = 0; k < N; ++k) { row[k] = (uint16_t)acc; acc += (uint32_t)v[k]; }
+    }
+  });
+  return rc.load();
 }
 
 }  // extern "C"

@@ -56,12 +56,12 @@ struct BottleneckDev {
 };
 cudaError_t launch_factorized(const BottleneckDev& bn, const float* x, int64_t n_vox, int C, float bound,
                               float* x_hat, float* p, double* bits, int32_t* minmax, double* scratch,
-                              cudaStream_t s, int64_t* launches);
+                              cudaStream_t s, int64_t* launches, int noise = 0, uint64_t seed = 0);
 cudaError_t launch_factorized_pmf(const BottleneckDev& bn, int min_v, int max_v, float bound, float* pmf,
                                   cudaStream_t s, int64_t* launches);
 cudaError_t launch_laplace(const float* y, const float* loc, const float* scale, int B, int64_t E, float bound,
                            float* y_hat, float* p, double* bits, int32_t* minmax, double* scratch,
-                           cudaStream_t s, int64_t* launches);
+                           cudaStream_t s, int64_t* launches, int noise = 0, uint64_t seed = 0);
 cudaError_t launch_laplace_intervals(const float* y_hat, const float* loc, const float* scale, int B, int64_t E,
                                      const int32_t* minmax, float bound, int precision, uint32_t* intervals,
                                      int* err_flag, cudaStream_t s, int64_t* launches);
@@ -70,6 +70,13 @@ cudaError_t launch_laplace_cdf(const float* loc, const float* scale, int B, int6
                                int* err_flag, cudaStream_t s, int64_t* launches);
 cudaError_t launch_debug_quantize_pmf(const float* pmf, int64_t rows, const int32_t* minmax_dev, int precision,
                                       int32_t* cdf32, int* err_flag, cudaStream_t s, int64_t* launches);
+// gpu_coder.cu
+cudaError_t launch_range_encode_intervals(const uint32_t* iv, int B, int64_t E, int precision, uint8_t* scratch, int64_t stride,
+                                          int64_t* lens, uint8_t* packed, int64_t cap, int64_t* offsets, int* err,
+                                          cudaStream_t s, int64_t* launches);
+cudaError_t launch_range_decode_rows(const uint8_t* packed, const int64_t* offsets, int B, int64_t E, const uint16_t* rows,
+                                     const int64_t* row_offset, const int32_t* minmax, int max_n, int precision, float* y_hat, int* err,
+                                     cudaStream_t s, int64_t* launches);
 // topk.cu
 cudaError_t launch_topk(const float* logits, int B, int64_t V, const int32_t* ks, uint8_t* mask, float* thres,
                         int32_t* count, int* err_flag, cudaStream_t s, int64_t* launches);

@@ -2,72 +2,45 @@
 //   factorized:  models/entropy_model.py:72-181  (quantise + per-channel 1-3-3-3-1 density + bits + min/max)
 //   conditional: models/conditional_entropy_model.py:21-124 (quantise + LAPLACE likelihood + bits +
 //                per-cube min/max; per-element quantised CDF rows / symbol intervals for the coder)
-// The arithmetic follows the reference's operation order in FP32 (expf/tanhf, IEEE division; this
-// file must NOT be compiled with --use_fast_math).  Reductions are two-stage with a fixed order
+// The arithmetic follows the reference's operation order in FP32 with the bit-reproducible exp / tanh of det_math.h (shared
+// with the host half of the library; this file must NOT be compiled with --use_fast_math).  Reductions are two-stage with a fixed order
 // (block partials -> one finalising block), min/max use integer atomics: results are reproducible.
 #include <float.h>
 #include <limits.h>
 
 #include "cdf_norm.h"
 #include "common.cuh"
+#include "det_math.h"
 
 namespace pcgc {
 
 constexpr int BN_PARAMS = 44;   // per channel: see api.cu pack_bottleneck()
 
-// _logits_cumulative (entropy_model.py:72-98) for one value and one channel's parameters.
-__device__ __forceinline__ float bn_logits(float x, const float* __restrict__ p) {
-  float h[3], g[3];
+// The likelihood formulas live in det_math.h (bit-reproducible on host and device): _logits_cumulative / _likelihood of
+// entropy_model.py:72-151 and the Laplace cdf / likelihood of conditional_entropy_model.py:21-56.
+__device__ __forceinline__ float bn_likelihood(float xq, const float* __restrict__ p) { return det_bn_likelihood(xq, p); }
+__device__ __forceinline__ float laplace_likelihood(float x, float loc, float scale) { return det_laplace_likelihood(x, loc, scale); }
+
+// "noise" quantisation (entropy_model.py:105-107, conditional_entropy_model.py:62-64): x + U(-1/2, 1/2).  Counter-based
+// Philox4x32-10 keyed by the seed, counter = element index / 4, so the draw of an element does not depend on the launch
+// shape and the oracle (oracle/entropy.py:philox_uniform) reproduces it bit for bit.
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+  uint32_t c[4] = {c0, c1, 0u, 0u};
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {               // layer 0: [3,1]
-    float t = p[j] * x + p[3 + j];
-    h[j] = t + p[6 + j] * tanhf(t);
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
-  const float* q = p + 9;
+  out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+// 4 uniforms in [-1/2, 1/2) for the vector of elements 4*v .. 4*v+3: (top 24 bits) * 2^-24 - 1/2 (exact in float)
+__host__ __device__ __forceinline__ void noise4(uint64_t seed, uint64_t v, float u[4]) {
+  uint32_t r[4];
+  philox4x32_10((uint32_t)v, (uint32_t)(v >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), r);
 #pragma unroll
-  for (int l = 0; l < 2; ++l) {               // layers 1,2: [3,3]
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      float t = q[3 * j] * h[0];
-      t = fmaf(q[3 * j + 1], h[1], t);
-      t = fmaf(q[3 * j + 2], h[2], t);
-      t += q[9 + j];
-      g[j] = t + q[12 + j] * tanhf(t);
-    }
-    h[0] = g[0]; h[1] = g[1]; h[2] = g[2];
-    q += 15;
-  }
-  float t = q[0] * h[0];                      // layer 3: [1,3]
-  t = fmaf(q[1], h[1], t);
-  t = fmaf(q[2], h[2], t);
-  t += q[3];
-  return t + q[4] * tanhf(t);
-}
-
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
-__device__ __forceinline__ float signf_(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
-
-// _likelihood (entropy_model.py:131-139) at an already quantised value.
-__device__ __forceinline__ float bn_likelihood(float xq, const float* __restrict__ p) {
-  const float lower = bn_logits(xq - 0.5f, p);
-  const float upper = bn_logits(xq + 0.5f, p);
-  const float sgn = -signf_(lower + upper);
-  return fabsf(sigmoidf_(sgn * upper) - sigmoidf_(sgn * lower));
-}
-
-// Laplace likelihood (conditional_entropy_model.py:21-56), operation for operation.
-__device__ __forceinline__ float laplace_cdf(float t, float loc, float scale) {
-  const float e = expf(-fabsf(t - loc) / scale);
-  const float c_l = 0.5f * e;
-  const float c_r = 1.0f - 0.5f * e;
-  return (t <= loc) ? c_l : ((t > loc) ? c_r : 0.f);     // NaN -> both masks false -> 0 like the reference
-}
-__device__ __forceinline__ float laplace_likelihood(float x, float loc, float scale) {
-  float upper = x + 0.5f, lower = x - 0.5f;
-  const float sgn = signf_(upper + lower - loc);        // sign(2x - loc): the reference's quirk (:47)
-  upper = -sgn * (upper - loc) + loc;
-  lower = -sgn * (lower - loc) + loc;
-  return fabsf(laplace_cdf(upper, loc, scale) - laplace_cdf(lower, loc, scale));
+  for (int k = 0; k < 4; ++k) u[k] = (float)(r[k] >> 8) * 5.9604644775390625e-8f - 0.5f;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -115,7 +88,7 @@ constexpr int ENT_VEC = 4;
 __global__ void __launch_bounds__(ENT_THREADS)
 factorized_kernel(const float* __restrict__ x, int64_t n, int C, const float* __restrict__ params, float bound,
                   float* __restrict__ x_hat, float* __restrict__ p_out, double* __restrict__ partial,
-                  int32_t* __restrict__ minmax) {
+                  int32_t* __restrict__ minmax, int noise, uint64_t seed) {
   extern __shared__ float s_par[];
   for (int i = threadIdx.x; i < C * BN_PARAMS; i += ENT_THREADS) s_par[i] = params[i];
   __syncthreads();
@@ -126,9 +99,11 @@ factorized_kernel(const float* __restrict__ x, int64_t n, int C, const float* __
     const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + v);
     float xs[4] = {xv.x, xv.y, xv.z, xv.w}, q[4], pr[4];
     const int c0 = (int)((v * ENT_VEC) % C);
+    float u[4] = {0.f, 0.f, 0.f, 0.f};
+    if (noise) noise4(seed, (uint64_t)v, u);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      q[k] = rintf(xs[k]);                                        // tf.math.round: half to even
+      q[k] = noise ? xs[k] + u[k] : rintf(xs[k]);                 // "noise" (:105-107) | tf.math.round: half to even
       pr[k] = fmaxf(bn_likelihood(q[k], s_par + (c0 + k) * BN_PARAMS), bound);
       bits -= (double)log2f(pr[k]);
       const int qi = (int)q[k];
@@ -146,14 +121,14 @@ factorized_kernel(const float* __restrict__ x, int64_t n, int C, const float* __
 
 cudaError_t launch_factorized(const BottleneckDev& bn, const float* x, int64_t n_vox, int C, float bound,
                               float* x_hat, float* p, double* bits, int32_t* minmax, double* scratch,
-                              cudaStream_t s, int64_t* launches) {
+                              cudaStream_t s, int64_t* launches, int noise, uint64_t seed) {
   const int64_t n = n_vox * C;
   if (C % 4 != 0 || C != bn.channels) return cudaErrorInvalidValue;
   int64_t want = (n / ENT_VEC + ENT_THREADS - 1) / ENT_THREADS;
   const int blocks = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
   if (minmax) { init_minmax_kernel<<<1, 32, 0, s>>>(minmax, 1); if (launches) ++*launches; }
   factorized_kernel<<<blocks, ENT_THREADS, C * BN_PARAMS * sizeof(float), s>>>(x, n, C, bn.params, bound, x_hat, p,
-                                                                              bits ? scratch : nullptr, minmax);
+                                                                              bits ? scratch : nullptr, minmax, noise, seed);
   if (launches) ++*launches;
   if (bits) { finalize_bits_kernel<<<1, 32, 0, s>>>(scratch, blocks, bits); if (launches) ++*launches; }
   return cudaGetLastError();
@@ -181,7 +156,7 @@ cudaError_t launch_factorized_pmf(const BottleneckDev& bn, int min_v, int max_v,
 __global__ void __launch_bounds__(ENT_THREADS)
 laplace_kernel(const float* __restrict__ y, const float* __restrict__ loc, const float* __restrict__ scale,
                int64_t E, float bound, float* __restrict__ y_hat, float* __restrict__ p_out,
-               double* __restrict__ partial, int32_t* __restrict__ minmax) {
+               double* __restrict__ partial, int32_t* __restrict__ minmax, int noise, uint64_t seed) {
   const int b = blockIdx.y;
   const size_t base = (size_t)b * E;
   double bits = 0.0;
@@ -193,10 +168,11 @@ laplace_kernel(const float* __restrict__ y, const float* __restrict__ loc, const
     const float4 lv = __ldg(reinterpret_cast<const float4*>(loc) + o);
     const float4 sv = __ldg(reinterpret_cast<const float4*>(scale) + o);
     const float ys[4] = {yv.x, yv.y, yv.z, yv.w}, ls[4] = {lv.x, lv.y, lv.z, lv.w}, ss[4] = {sv.x, sv.y, sv.z, sv.w};
-    float q[4], pr[4];
+    float q[4], pr[4], u[4] = {0.f, 0.f, 0.f, 0.f};
+    if (noise) noise4(seed, (uint64_t)o, u);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      q[k] = rintf(ys[k]);
+      q[k] = noise ? ys[k] + u[k] : rintf(ys[k]);               // "noise" (conditional_entropy_model.py:62-64) | round
       pr[k] = fmaxf(laplace_likelihood(q[k], ls[k], ss[k]), bound);
       bits -= (double)log2f(pr[k]);
       const int qi = (int)q[k];
@@ -214,13 +190,13 @@ laplace_kernel(const float* __restrict__ y, const float* __restrict__ loc, const
 
 cudaError_t launch_laplace(const float* y, const float* loc, const float* scale, int B, int64_t E, float bound,
                            float* y_hat, float* p, double* bits, int32_t* minmax, double* scratch, cudaStream_t s,
-                           int64_t* launches) {
+                           int64_t* launches, int noise, uint64_t seed) {
   if (E % ENT_VEC != 0) return cudaErrorInvalidValue;
   int64_t per = (E / ENT_VEC + ENT_THREADS - 1) / ENT_THREADS;
   if (per > 16) per = 16;                          // 16 blocks x 256 threads x 4 elements x 4 iterations per cube
   if (minmax) { init_minmax_kernel<<<(B + 127) / 128, 128, 0, s>>>(minmax, B); if (launches) ++*launches; }
   dim3 grid((unsigned)per, (unsigned)B);
-  laplace_kernel<<<grid, ENT_THREADS, 0, s>>>(y, loc, scale, E, bound, y_hat, p, bits ? scratch : nullptr, minmax);
+  laplace_kernel<<<grid, ENT_THREADS, 0, s>>>(y, loc, scale, E, bound, y_hat, p, bits ? scratch : nullptr, minmax, noise, seed);
   if (launches) ++*launches;
   if (bits) { finalize_bits_kernel<<<B, 32, 0, s>>>(scratch, (int)per, bits); if (launches) ++*launches; }
   return cudaGetLastError();
@@ -308,3 +284,10 @@ cudaError_t launch_debug_quantize_pmf(const float* pmf, int64_t rows, const int3
 }
 
 }  // namespace pcgc
+
+// Test hook (host): the noise of elements 4*v .. 4*v+3 exactly as the kernels draw it.
+extern "C" int pcgc_debug_noise(uint64_t seed, uint64_t v, float* out4) {
+  if (!out4) return PCGC_ERR_BAD_ARG;
+  pcgc::noise4(seed, v, out4);
+  return PCGC_OK;
+}

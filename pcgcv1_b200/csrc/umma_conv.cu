@@ -1222,7 +1222,7 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
   static const bool kb_zband = getenv("PCGC_KB_ZBAND") && atoi(getenv("PCGC_KB_ZBAND")) != 0;
   const bool zb16 = w.np == 16 && (c.epi == UEPI_PM || c.epi == UEPI_F32 || (c.epi == UEPI_VRN && a.cin8));
   const bool zb32 = w.np == 32 && kb_zband && (c.epi == UEPI_VRN || c.epi == UEPI_F32) && ((a.cin8 && w.wt == 2) || (!a.cin8 && w.wt == 1 && w.kchunks == 1));
-  if (zband && umma_stream_mode() && w.packed_zb && n >= 32 && (zb16 || zb32)) {
+  if (!c.pin_tile && zband && umma_stream_mode() && w.packed_zb && n >= 32 && (zb16 || zb32)) {
     // z-banded streaming kernel (thin-N layers): the three kz taps are column blocks of one MMA
     const int z_slice_plane = brick_ey(w.wt) * EXC * CELL, z_slot = a.ppc * w.kchunks * z_slice_plane;
     const size_t fixed = (size_t)w.zb_bytes + 34 * 8 + (w.np + vrn_floats) * sizeof(float) + 16;
@@ -1261,7 +1261,7 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
       return c.epi == UEPI_PM ? go(conv_umma_zband_kernel<16, UEPI_PM, 1, false, 2, 3>, T23) : go(conv_umma_zband_kernel<16, UEPI_F32, 1, false, 2, 3>, T23);
     }
   }
-  if (umma_stream_mode() && w.ntaps == 27 && w.kchunks == 1 && n >= 16 && stream_shape_ok(w.np, c.epi, a.cin8 != 0, w.wt)) {
+  if (!c.pin_tile && umma_stream_mode() && w.ntaps == 27 && w.kchunks == 1 && n >= 16 && stream_shape_ok(w.np, c.epi, a.cin8 != 0, w.wt)) {
     // z-streaming kernel: one CTA per SM, ring of input slices, rotating accumulators
     static const int zs_env = getenv("PCGC_STREAM_ZS") ? atoi(getenv("PCGC_STREAM_ZS")) : 16;
     static const int ring_env = getenv("PCGC_STREAM_RING") ? atoi(getenv("PCGC_STREAM_RING")) : 0;

@@ -61,6 +61,8 @@ struct UmmaCall {
   PmTensor res;                // UEPI_VRN: the block input x
   int out_s2d = 0;             // UEPI_VRN: write `out` space-to-depth (out = the n/2-grid, 8*C-channel tensor)
   int* err = nullptr;          // device int, set on device-side timeouts
+  bool pin_tile = false;       // always the tile kernel, whatever PCGC_UMMA_STREAM / PCGC_UMMA_ZBAND / PCGC_KB_ZBAND say: the hyper
+                               // decoder's loc / scale must have the same bits in the encoding and the decoding process
 };
 
 cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStream_t s, int64_t* launches);

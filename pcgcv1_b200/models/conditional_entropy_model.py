@@ -36,13 +36,18 @@ class SymmetricConditional:
         c = self.codec
         return (c.to_device(inputs, torch.float32), c.to_device(loc, torch.float32), c.to_device(scale, torch.float32))
 
-    def __call__(self, inputs, loc, scale, training=False):
-        """-> (round(inputs), max(likelihood, bound)) (conditional_entropy_model.py:71-93)."""
-        if training:
-            raise NotImplementedError("noise quantisation (training=True) is not on the codec hot path")
+    def __call__(self, inputs, loc, scale, training=False, seed=0):
+        """-> (quantised inputs, max(likelihood, bound)) (conditional_entropy_model.py:71-93).  ``training=True`` is the
+        reference's "noise" mode (:62-64): inputs + U(-1/2, 1/2) from a Philox stream keyed by ``seed`` (the reference is
+        unseeded), likelihood evaluated at the noisy value."""
         y, l, s = self._dev3(inputs, loc, scale)
-        y_hat, p, _, _ = self.codec.laplace(y.reshape(1, -1), l.reshape(1, -1), s.reshape(1, -1), self._likelihood_bound,
-                                            want_p=True, want_bits=False)
+        c = self.codec
+        c.set_quantize_mode(bool(training), seed)
+        try:
+            y_hat, p, _, _ = c.laplace(y.reshape(1, -1), l.reshape(1, -1), s.reshape(1, -1), self._likelihood_bound,
+                                       want_p=True, want_bits=False)
+        finally:
+            c.set_quantize_mode(False)
         return runtime.DeviceResult(y_hat.reshape(y.shape)), runtime.DeviceResult(p.reshape(y.shape))
 
     def estimate_bits(self, inputs, loc, scale) -> np.ndarray:
@@ -79,7 +84,14 @@ class SymmetricConditional:
         y_hat, _, _, mm = c.laplace(y2, l2, s2, self._likelihood_bound, want_p=False, want_bits=False)
         iv = c.laplace_intervals(y_hat, l2, s2, mm, self._likelihood_bound)
         mm_h = runtime.to_host(mm)
-        strings = runtime.range_encode_intervals_batch(runtime.to_host(iv, "intervals"), threads)
+        if runtime.coder_mode() == "gpu" and B > 0:
+            packed, offsets = self.encode_dev(iv)
+            off = runtime.to_host(offsets)
+            blob = runtime.to_host(packed[:int(off[B])], "enc_bytes")
+            c.synchronize()
+            strings = [blob[off[i]:off[i + 1]].tobytes() for i in range(B)]
+        else:
+            strings = runtime.range_encode_intervals_batch(runtime.to_host(iv, "intervals"), threads)
         return strings, mm_h[:, 0].copy(), mm_h[:, 1].copy()
 
     # ---- split forms for the software pipeline in transform.py: GPU part now, host coder part later ---------------
@@ -114,12 +126,50 @@ class SymmetricConditional:
         done.synchronize()
         return runtime.range_decode_rows_batch_f32(list(strings), E, stage.numpy(), off, mm, threads, out_tag="y_hat_dec%d" % slot)
 
+    # ---- GPU-side coder (csrc/gpu_coder.cu): nothing per-element crosses PCIe ------------------------------------------
+    def intervals_dev(self, ys, locs, scales, iv_out=None, want_likelihoods=False):
+        """Quantise + per-cube range + per-element intervals, all on the device and asynchronous.
+        -> (iv int32 [B,E], minmax int32 [B,2]) device tensors; ``iv_out`` = a [B,E] slice to fill in place."""
+        c = self.codec
+        B = ys.shape[0]
+        y2, l2, s2 = ys.reshape(B, -1), locs.reshape(B, -1), scales.reshape(B, -1)
+        y_hat, _, _, mm = c.laplace(y2, l2, s2, self._likelihood_bound, want_p=want_likelihoods, want_bits=want_likelihoods)
+        iv = c.laplace_intervals(y_hat, l2, s2, mm, self._likelihood_bound, out=iv_out)
+        return iv, mm
+
+    def encode_dev(self, iv):
+        """iv int32 [B,E] on the device -> (packed uint8, offsets int64 [B+1]) device tensors (asynchronous)."""
+        return self.codec.gpu_range_encode(iv)
+
+    def decode_dev(self, packed, offsets, locs, scales, min_vs, max_vs):
+        """Strings b = packed[offsets[b]:offsets[b+1]] (device) -> y_hat float32 [B,E] on the device; CDF rows are built and
+        consumed on the device (asynchronous on the current stream; headers come from the host)."""
+        c = self.codec
+        B = locs.shape[0]
+        l2, s2 = locs.reshape(B, -1), scales.reshape(B, -1)
+        E = l2.shape[1]
+        mm = np.stack([np.asarray(min_vs, np.int32).reshape(-1), np.asarray(max_vs, np.int32).reshape(-1)], -1)
+        n_sym = mm[:, 1] - mm[:, 0] + 1
+        if B and (n_sym.min() < 2 or n_sym.max() > 64):
+            raise runtime._lib.PcgcError(runtime._lib.ERR_BAD_RANGE, "symbol range outside [2, 64] symbols")
+        off = c.row_offsets(mm, E)
+        hdr = np.concatenate([off, mm.reshape(-1).astype(np.int64)])             # one small H2D for both headers
+        hdr_d = c.to_device(hdr)
+        off_d, mm_d = hdr_d[:B + 1], hdr_d[B + 1:].to(torch.int32)
+        rows = c.laplace_cdf_dev(l2, s2, mm_d, off_d, int(off[-1]), self._likelihood_bound)
+        return c.gpu_range_decode(packed, offsets, rows, off_d, int(off[-1]), mm_d, int(n_sym.max()) if B else 2, B, E)
+
     def decompress_cubes(self, strings, locs, scales, min_vs, max_vs, threads: int = 0):
         """-> torch float32 [B, E] on the device."""
         c = self.codec
         B = locs.shape[0]
         l2, s2 = locs.reshape(B, -1), scales.reshape(B, -1)
         E = l2.shape[1]
+        if runtime.coder_mode() == "gpu" and B > 0:
+            packed, offsets = c.upload_strings(list(strings))
+            y_hat = self.decode_dev(packed, offsets, l2, s2, min_vs, max_vs)
+            c.synchronize()
+            return y_hat
         mm = np.stack([np.asarray(min_vs, np.int32).reshape(-1), np.asarray(max_vs, np.int32).reshape(-1)], -1)
         rows, off = c.laplace_cdf(l2, s2, mm, self._likelihood_bound)
         y_hat = runtime.range_decode_rows_batch_f32(list(strings), E, runtime.to_host(rows, "cdf_rows"), off, mm, threads)

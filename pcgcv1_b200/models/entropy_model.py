@@ -33,15 +33,19 @@ class EntropyBottleneck:
             self._slot = self._codec.bottleneck_slot(int(channels))
         return self._codec, self._slot
 
-    def __call__(self, inputs, training=False):
-        """-> (quantised values, likelihoods), both shaped like ``inputs`` (entropy_model.py:153-181)."""
-        if training:
-            raise NotImplementedError("noise quantisation (training=True, entropy_model.py:105-107) is not on the codec hot path")
+    def __call__(self, inputs, training=False, seed=0):
+        """-> (quantised values, likelihoods), both shaped like ``inputs`` (entropy_model.py:153-181).  ``training=True`` is
+        the reference's "noise" mode (:105-107): inputs + U(-1/2, 1/2) from a Philox stream keyed by ``seed`` (the reference
+        is unseeded), likelihood evaluated at the noisy value."""
         x = runtime.unwrap(inputs)
         channels = x.shape[-1]
         c, slot = self._resolve(channels)
         xt = c.to_device(x, torch.float32)
-        x_hat, p, _, _ = c.factorized(slot, xt, self._likelihood_bound, want_p=True, want_bits=False)
+        c.set_quantize_mode(bool(training), seed)
+        try:
+            x_hat, p, _, _ = c.factorized(slot, xt, self._likelihood_bound, want_p=True, want_bits=False)
+        finally:
+            c.set_quantize_mode(False)
         return runtime.DeviceResult(x_hat), runtime.DeviceResult(p)
 
     def estimate_bits(self, inputs) -> float:

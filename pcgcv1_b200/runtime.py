@@ -368,10 +368,10 @@ class Codec:
             p.data_ptr() if want_p else None, bits.data_ptr() if want_bits else None, mm.data_ptr()))
         return y_hat, p, bits, mm
 
-    def laplace_intervals(self, y_hat, loc, scale, mm: torch.Tensor, bound: float = 1e-9) -> torch.Tensor:
+    def laplace_intervals(self, y_hat, loc, scale, mm: torch.Tensor, bound: float = 1e-9, out: torch.Tensor = None) -> torch.Tensor:
         B = y_hat.shape[0]
         E = y_hat.numel() // max(B, 1)
-        iv = torch.empty((B, E), dtype=torch.int32, device=self.dev)     # uint32 payload
+        iv = out if out is not None else torch.empty((B, E), dtype=torch.int32, device=self.dev)     # uint32 payload
         self._stream()
         self._check(self.lib.pcgc_laplace_intervals(self.ctx, y_hat.data_ptr(), loc.data_ptr(), scale.data_ptr(), B, E,
                                                     mm.data_ptr(), bound, 16, iv.data_ptr()))
@@ -390,6 +390,91 @@ class Codec:
         self._check(self.lib.pcgc_laplace_cdf(self.ctx, loc.data_ptr(), scale.data_ptr(), B, E, mm.ctypes.data, bound, 16,
                                               off.ctypes.data, rows.data_ptr()))
         return rows, off
+
+    # -- GPU-side range coder (csrc/gpu_coder.cu) ------------------------------------------------------
+    def coder_stream(self) -> "torch.cuda.Stream":
+        """Side stream of this codec for the (latency-bound, one warp / thread per cube) coder kernels: they run beside the
+        conv kernels of the next chunk instead of between them."""
+        s = getattr(self, "_coder_stream", None)
+        if s is None:
+            s = self._coder_stream = torch.cuda.Stream(device=self.dev)
+        return s
+
+    def deferred_checks(self, on: bool):
+        """Pipelined sections: entry points stop synchronising just to read the device error flag; ``synchronize()`` at the
+        end of the section reports it (and raises)."""
+        self._check(self.lib.pcgc_set_deferred_checks(self.ctx, int(bool(on))))
+
+    def set_quantize_mode(self, noise: bool, seed: int = 0):
+        """"symbols" (round, default) or "noise" (x + U(-1/2, 1/2), seeded Philox) for factorized() / laplace()."""
+        self._check(self.lib.pcgc_set_quantize_mode(self.ctx, int(bool(noise)), int(seed) & 0xFFFFFFFFFFFFFFFF))
+
+    @staticmethod
+    def row_offsets(minmax_host: np.ndarray, E: int) -> np.ndarray:
+        mm = np.ascontiguousarray(minmax_host, dtype=np.int32).reshape(-1, 2)
+        N = (mm[:, 1] - mm[:, 0] + 1).astype(np.int64)
+        off = np.zeros(len(mm) + 1, np.int64)
+        np.cumsum(N * E, out=off[1:])
+        return off
+
+    def laplace_cdf_dev(self, loc, scale, mm_dev: torch.Tensor, off_dev: torch.Tensor, total: int, bound: float = 1e-9):
+        """Per-element CDF rows with device-resident headers; no host synchronisation.  -> rows (uint16 payload) on the device."""
+        B = loc.shape[0]
+        E = loc.numel() // max(B, 1)
+        rows = torch.empty(max(int(total), 1), dtype=torch.int16, device=self.dev)
+        self._stream()
+        self._check(self.lib.pcgc_laplace_cdf_dev(self.ctx, loc.data_ptr(), scale.data_ptr(), B, E, mm_dev.data_ptr(), off_dev.data_ptr(),
+                                                  float(total), bound, 16, rows.data_ptr()))
+        return rows
+
+    def gpu_range_encode(self, iv: torch.Tensor):
+        """iv int32 [B,E] (pcgc_laplace_intervals payload) on the device -> (packed uint8 [cap], offsets int64 [B+1]), both on the
+        device; string b = packed[offsets[b]:offsets[b+1]].  Asynchronous on the current stream."""
+        B, E = iv.shape
+        stride = 2 * E + 64
+        scratch = torch.empty((max(B, 1), stride), dtype=torch.uint8, device=self.dev)
+        packed = torch.empty(max(B, 1) * stride, dtype=torch.uint8, device=self.dev)
+        lens = torch.empty(max(B, 1), dtype=torch.int64, device=self.dev)
+        offsets = torch.empty(B + 1, dtype=torch.int64, device=self.dev)
+        self._stream()
+        self._check(self.lib.pcgc_range_encode_intervals_dev(self.ctx, iv.data_ptr(), B, E, 16, scratch.data_ptr(), stride, lens.data_ptr(),
+                                                             packed.data_ptr(), packed.numel(), offsets.data_ptr()))
+        return packed, offsets
+
+    def gpu_range_decode(self, packed: torch.Tensor, offsets: torch.Tensor, rows: torch.Tensor, off_dev: torch.Tensor, total: int,
+                         mm_dev: torch.Tensor, max_n: int, B: int, E: int) -> torch.Tensor:
+        """-> y_hat float32 [B,E] on the device (symbol + min_v).  Asynchronous on the current stream."""
+        y_hat = torch.empty((B, E), dtype=torch.float32, device=self.dev)
+        self._stream()
+        self._check(self.lib.pcgc_range_decode_rows_dev(self.ctx, packed.data_ptr(), offsets.data_ptr(), B, E, rows.data_ptr(), off_dev.data_ptr(),
+                                                        float(total), mm_dev.data_ptr(), int(max_n), 16, y_hat.data_ptr()))
+        return y_hat
+
+    def upload_strings(self, strings):
+        """list of byte strings -> (packed uint8 device tensor, offsets int64 [B+1] device tensor) in ONE H2D copy."""
+        B = len(strings)
+        lens = np.fromiter((len(s) for s in strings), np.int64, B)
+        off = np.zeros(B + 1, np.int64)
+        np.cumsum(lens, out=off[1:])
+        total = int(off[B])
+        pad = (-total) % 8                                                   # keep the offsets 8-byte aligned inside the buffer
+        n = total + pad + 8 * (B + 1)
+        stage = pinned_buffer("dec_bytes", n)[:n]
+        h = stage.numpy()
+        if total:
+            h[:total] = np.frombuffer(b"".join(bytes(s) for s in strings), np.uint8)
+        h[total + pad:] = off.view(np.uint8)
+        COUNTERS["h2d_bytes"] += n
+        up = stage.to(self.dev, non_blocking=True)
+        return up, up[total + pad:].view(torch.int64)
+
+    def factorized_cdf_host(self, slot: int, min_v: int, max_v: int, bound: float = 1e-9, precision: int = 16) -> np.ndarray:
+        """Host twin of factorized_cdf (same det_math.h density, same normaliser): must be bit-identical to it."""
+        Cc = self.bn_channels[slot]
+        N = int(max_v) - int(min_v) + 1
+        cdf = np.empty((Cc, max(N, 1) + 1), np.int32)
+        self._check(self.lib.pcgc_factorized_cdf_host(self.ctx, slot, int(min_v), int(max_v), bound, precision, cdf.ctypes.data))
+        return cdf
 
     # -- top-k ---------------------------------------------------------------------------------
     def topk(self, logits: torch.Tensor, ks: torch.Tensor):
@@ -530,6 +615,30 @@ def range_decode(data: bytes, n: int, cdf: np.ndarray, precision: int = 16) -> n
     sym = np.empty(n, np.int16)
     _lib.check(L.pcgc_range_decode(buf.ctypes.data, len(data), n, cdf.ctypes.data, rows, N, precision, sym.ctypes.data))
     return sym
+
+
+def host_laplace_cdf(loc: np.ndarray, scale: np.ndarray, minmax: np.ndarray, bound: float = 1e-9, threads: int = 0):
+    """Host twin of Codec.laplace_cdf (bit-identical rows): loc/scale float32 [B,E] -> (rows uint16 flat, row_offset int64 [B+1])."""
+    L = _lib.lib()
+    loc = np.ascontiguousarray(loc, dtype=np.float32)
+    scale = np.ascontiguousarray(scale, dtype=np.float32)
+    B = loc.shape[0]
+    E = loc.size // max(B, 1)
+    mm = np.ascontiguousarray(minmax, dtype=np.int32).reshape(B, 2)
+    off = Codec.row_offsets(mm, E)
+    rows = np.empty(int(off[-1]), np.uint16)
+    _lib.check(L.pcgc_host_laplace_cdf(loc.ctypes.data, scale.ctypes.data, B, E, mm.ctypes.data, bound, 16, off.ctypes.data, rows.ctypes.data,
+                                       threads or coder_threads()))
+    return rows, off
+
+
+def coder_mode() -> str:
+    """Where the per-cube range coder runs: "gpu" (default; csrc/gpu_coder.cu) or "host" (the thread-pool coder of coder.cpp,
+    PCGC_CODER=host).  Both write the same bytes."""
+    m = os.environ.get("PCGC_CODER", "gpu").lower()
+    if m not in ("gpu", "host"):
+        raise ValueError("PCGC_CODER must be 'gpu' or 'host'")
+    return m
 
 
 def coder_threads() -> int:

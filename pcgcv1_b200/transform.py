@@ -127,6 +127,78 @@ def _pool_z():
     return _POOL_Z
 
 
+def encode_on_device(codec, entropy_bottleneck, cem, cubes, keep_side_info=False, want_likelihoods=False):
+    """Every GPU kernel of the hyper encoder for ``cubes`` (host or device resident), enqueued without a host
+    synchronisation: transforms chunk by chunk on the current stream, then ONE range-encoder launch for all cubes on the coder
+    stream.  -> (intervals [B,E], minmax [B,2], [z_hat per chunk], [(loc, scale) per chunk], packed bytes, offsets [B+1]),
+    all device tensors.  The caller owns the synchronisation (codec.synchronize())."""
+    B = cubes.shape[0]
+    E = 16 * 16 * 16 * 16
+    dev = codec.dev
+    main, side = torch.cuda.current_stream(dev), codec.coder_stream()
+    iv_all = torch.empty((B, E), dtype=torch.int32, device=dev)
+    mm_all = torch.empty((B, 2), dtype=torch.int32, device=dev)
+    z_hats, keep = [], []
+    for a, b in _chunks(B):
+        x = codec.to_device(cubes[a:b])
+        ys = codec.analysis(x)
+        zs = codec.hyper_encode(ys)
+        z_hat, _, _, _ = codec.factorized(entropy_bottleneck._slot, zs, want_p=want_likelihoods, want_bits=want_likelihoods)
+        z_hats.append(z_hat)
+        locs, scales = codec.hyper_decode(z_hat, 1e-9)                  # lower_bound = 1e-9, transform.py:145-146
+        _, mm = cem.intervals_dev(ys, locs, scales, iv_out=iv_all[a:b], want_likelihoods=want_likelihoods)
+        mm_all[a:b].copy_(mm)
+        if keep_side_info:
+            keep.append((locs, scales))
+    ready = torch.cuda.Event()
+    ready.record(main)
+    iv_all.record_stream(side)
+    mm_all.record_stream(side)
+    with torch.cuda.stream(side):
+        side.wait_event(ready)
+        packed, offsets = cem.encode_dev(iv_all)
+    return iv_all, mm_all, z_hats, keep, packed, offsets
+
+
+def _compress_hyper_gpu_coder(codec, entropy_bottleneck, cem, cubes, decompress):
+    """compress_hyper with the per-cube strings written ON THE GPU (csrc/gpu_coder.cu).  The chunks only enqueue kernels (no
+    host synchronisation in the loop); the intervals of every cube land in one device buffer and ONE encoder launch codes all
+    strings on the coder stream while this thread range-codes the single hyper string z on the host."""
+    B = cubes.shape[0]
+    dev = codec.dev
+    side = codec.coder_stream()
+    codec.deferred_checks(True)
+    try:
+        iv_all, mm_all, z_hats, keep, packed, offsets = encode_on_device(codec, entropy_bottleneck, cem, cubes, decompress)
+        hdr = runtime.pinned_buffer("enc_hdr", 8 * (B + 1) + 8 * B)
+        off_h = hdr[:8 * (B + 1)].view(torch.int64)
+        mm_h = hdr[8 * (B + 1):8 * (B + 1) + 8 * B].view(torch.int32).view(B, 2)
+        with torch.cuda.stream(side):
+            off_h.copy_(offsets, non_blocking=True)
+            mm_h.copy_(mm_all, non_blocking=True)
+            hdr_done = torch.cuda.Event()
+            hdr_done.record(side)
+        # the ONE hyper string (global range, entropy_model.py:249-259) is coded here on the host beside the GPU encoder
+        z_all = torch.cat(z_hats) if len(z_hats) > 1 else z_hats[0]
+        sym, cdf, z_min, z_max = entropy_bottleneck.compress_begin(z_all)
+        z_string = entropy_bottleneck.compress_finish(sym, cdf)
+        hdr_done.synchronize()
+        off = off_h.numpy().copy()
+        mm = mm_h.numpy().copy()
+        total = int(off[B])
+        stage = runtime.pinned_buffer("enc_bytes", max(total, 1))[:total]
+        with torch.cuda.stream(side):
+            stage.copy_(packed[:total], non_blocking=True)
+        side.synchronize()
+        runtime.COUNTERS["d2h_bytes"] += total + hdr.numel()
+        blob = stage.numpy()
+        strings = [blob[off[i]:off[i + 1]].tobytes() for i in range(B)]
+    finally:
+        codec.deferred_checks(False)
+    codec.synchronize()                                                   # raises if any kernel of the section flagged an error
+    return strings, mm, z_all, z_string, z_min, z_max, keep
+
+
 def compress_hyper(cubes, model, ckpt_dir, decompress=False):
     """cubes [B,64,64,64,1] -> (y_strings[B], y_min_vs[B], y_max_vs[B], y_shape, z_strings, z_min_v,
     z_max_v, z_shape[, x_decodeds])  (transform.py:91-197)."""
@@ -137,6 +209,21 @@ def compress_hyper(cubes, model, ckpt_dir, decompress=False):
     cubes = runtime.unwrap(cubes)
     B = cubes.shape[0]
     start = time.time()
+    if runtime.coder_mode() == "gpu" and B > 0:
+        strings, mm, z_all, z_string, z_min, z_max, keep = _compress_hyper_gpu_coder(codec, entropy_bottleneck, cem, cubes, decompress)
+        _log("Analysis + hyper transforms + entropy encode (GPU coder)", start)
+        y_min_vs, y_max_vs = mm[:, 0].astype(np.int32), mm[:, 1].astype(np.int32)
+        out = (runtime.HostResult(_strings_array(strings)), runtime.HostResult(y_min_vs), runtime.HostResult(y_max_vs),
+               runtime.HostResult(np.array((1, 16, 16, 16, 16), dtype=np.int64)), runtime.HostResult(z_string),
+               runtime.HostResult(np.int32(z_min)), runtime.HostResult(np.int32(z_max)),
+               runtime.HostResult(np.array(z_all.shape, dtype=np.int32)))
+        if decompress:
+            locs = torch.cat([kk[0] for kk in keep])
+            scales = torch.cat([kk[1] for kk in keep])
+            y_dec = cem.decompress_cubes(strings, locs, scales, y_min_vs, y_max_vs)
+            x_dec = codec.synthesis(y_dec.reshape(B, 16, 16, 16, 16))
+            return out + (runtime.DeviceResult(x_dec),)
+        return out
     jobs, mms, z_hats, keep = [], [], [], []
     chunks = _chunks(B, small_last=True)
     z_job = None
@@ -189,6 +276,43 @@ def compress_hyper(cubes, model, ckpt_dir, decompress=False):
     return out
 
 
+def _decompress_hyper_gpu_coder(codec, cem, strings, mins, maxs, y_shape, z_get, chunks, uploaded=None, sync=True):
+    """decompress_hyper with the per-cube strings read ON THE GPU: the strings go up once (a few KB per cube), CDF rows are
+    built and consumed on the device.  Chunk k+1 is decoded on the coder stream while chunk k is synthesised."""
+    dev = codec.dev
+    main, side = torch.cuda.current_stream(dev), codec.coder_stream()
+    packed, offsets = uploaded if uploaded is not None else codec.upload_strings(strings)
+    xs_parts, pending = [], None
+    codec.deferred_checks(True)
+    try:
+        def finish(p):
+            (a, b), y_hat, done = p
+            main.wait_event(done)
+            xs_parts.append(codec.synthesis(y_hat.reshape([b - a] + y_shape[1:])))
+
+        for a, b in chunks:
+            locs, scales = codec.hyper_decode(z_get(a, b), 1e-9)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            for t in (locs, scales, packed, offsets):
+                t.record_stream(side)
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                y_hat = cem.decode_dev(packed, offsets[a:b + 1], locs, scales, mins[a:b], maxs[a:b])
+                done = torch.cuda.Event()
+                done.record(side)
+            y_hat.record_stream(main)
+            if pending is not None:
+                finish(pending)                                            # synthesis of chunk k-1 overlaps the GPU decode of chunk k
+            pending = ((a, b), y_hat, done)
+        finish(pending)
+    finally:
+        codec.deferred_checks(False)
+    if sync:
+        codec.synchronize()                                                # raises if any kernel of the section flagged an error
+    return torch.cat(xs_parts) if len(xs_parts) > 1 else xs_parts[0]
+
+
 def decompress_hyper(y_strings, y_min_vs, y_max_vs, y_shape, z_strings, z_min_v, z_max_v, z_shape, model, ckpt_dir):
     """-> xs [B,64,64,64,1] occupancy logits  (transform.py:200-259)."""
     _log("===== Decompress =====")
@@ -208,7 +332,13 @@ def decompress_hyper(y_strings, y_min_vs, y_max_vs, y_shape, z_strings, z_min_v,
     mins = np.asarray(runtime.unwrap(y_min_vs)).reshape(-1)
     maxs = np.asarray(runtime.unwrap(y_max_vs)).reshape(-1)
     start = time.time()
+    if B == 0:
+        return runtime.DeviceResult(torch.zeros((0, 64, 64, 64, 1), dtype=torch.float32, device=codec.dev))
     chunks = _chunks(B, small_first=True)
+    if runtime.coder_mode() == "gpu":
+        xs = _decompress_hyper_gpu_coder(codec, cem, strings, mins, maxs, y_shape, z_get, chunks)
+        _log("Hyper decoder + entropy decode (GPU coder) + synthesis", start)
+        return runtime.DeviceResult(xs)
     xs_parts, pending = [], None
 
     def finish(p):

@@ -98,22 +98,22 @@ class _ConvBase:
         self.activation, self.use_bias, self.name = activation, use_bias, name
 
     def __call__(self, x):
-        import torch
-        from oracle import nets
-        w = {self.name + "/kernel": WEIGHTS[self.name + "/kernel"]}
+        # direct-definition NumPy convolutions (tests/golden/ref_conv.py): independent of oracle/nets.py, so the goldens pin the
+        # SAME-padding / Conv3DTranspose arithmetic and not only the layer graph
+        import ref_conv
+        kern = WEIGHTS[self.name + "/kernel"]
         has_bias = (self.name + "/bias") in WEIGHTS
         assert has_bias == bool(self.use_bias), "use_bias mismatch for %s" % self.name
-        if has_bias:
-            w[self.name + "/bias"] = WEIGHTS[self.name + "/bias"]
-        assert tuple(WEIGHTS[self.name + "/kernel"].shape[:3]) == tuple(self.k)
-        xt = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        bias = WEIGHTS[self.name + "/bias"] if has_bias else None
+        assert tuple(kern.shape[:3]) == tuple(self.k)
+        x = np.ascontiguousarray(x, dtype=np.float32)
         s = self.s[0]
         if self.transposed:
-            assert WEIGHTS[self.name + "/kernel"].shape[3] == self.filters
-            y = nets.conv3d_transpose_same(xt, w, self.name, stride=s).numpy()
+            assert kern.shape[3] == self.filters
+            y = ref_conv.conv3d_transpose_same(x, kern, bias, stride=s)
         else:
-            assert WEIGHTS[self.name + "/kernel"].shape[4] == self.filters
-            y = nets.conv3d_same(xt, w, self.name, stride=s).numpy()
+            assert kern.shape[4] == self.filters
+            y = ref_conv.conv3d_same(x, kern, bias, stride=s)
         if self.activation is not None:
             y = self.activation(y)
         return y

@@ -1,6 +1,7 @@
 """The oracle against the golden vectors produced by running the reference's own source
 (tests/golden/make_golden.py).  CPU only."""
 import hashlib
+import os
 
 import numpy as np
 import torch
@@ -103,3 +104,29 @@ def test_topk_matches_reference(golden):
     for i in range(5):
         assert mask[i].sum() >= nums[i]
     assert mask.shape == shape
+
+
+def test_oracle_convs_match_the_direct_definition():
+    """oracle/nets.py (torch conv3d + pad / crop rules) against tests/golden/ref_conv.py, which writes every output straight
+    from TensorFlow's documented SAME / conv3d_transpose definitions: all kernel sizes and strides of the two models, odd and
+    even extents, float64 so that only the index arithmetic is compared."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import ref_conv
+    rng = np.random.default_rng(3)
+    for k, s, n in ((3, 1, 6), (3, 1, 5), (1, 1, 4), (3, 2, 8), (3, 2, 6), (5, 2, 8), (9, 2, 8), (5, 2, 4)):
+        ci, co = 3, 4
+        kern = rng.normal(size=(k, k, k, ci, co))
+        bias = rng.normal(size=co)
+        x = rng.normal(size=(2, n, n, n, ci))
+        a = nets.conv3d_same(torch.from_numpy(x), {"c/kernel": kern, "c/bias": bias}, "c", stride=s).numpy()
+        b = ref_conv.conv3d_same(x, kern, bias, stride=s)
+        assert a.shape == b.shape and np.abs(a - b).max() < 1e-12, (k, s, n)
+    for k, n in ((3, 4), (3, 3), (5, 4), (9, 4), (9, 2)):
+        ci, co = 3, 2
+        kern = rng.normal(size=(k, k, k, co, ci))
+        bias = rng.normal(size=co)
+        x = rng.normal(size=(2, n, n, n, ci))
+        a = nets.conv3d_transpose_same(torch.from_numpy(x), {"c/kernel": kern, "c/bias": bias}, "c", stride=2).numpy()
+        b = ref_conv.conv3d_transpose_same(x, kern, bias, stride=2)
+        assert a.shape == b.shape == (2, 2 * n, 2 * n, 2 * n, co) and np.abs(a - b).max() < 1e-12, (k, n)
