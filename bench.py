@@ -144,7 +144,7 @@ def device_step(codec, st):
         # decode side: headers (min/max) and the strings come from the stream, z_hat from the (host) hyper decoder
         z_all = torch_cat(z_hats)
         xs = transform._decompress_hyper_gpu_coder(codec, cem, None, st["mins"], st["maxs"], [1, 16, 16, 16, 16],
-                                                   lambda a, b: z_all[a:b], transform._chunks(st["B"], small_first=True),
+                                                   lambda a, b: z_all[a:b], transform._gpu_decode_chunks(st["B"]),
                                                    uploaded=(st["packed"], st["offsets"]), sync=False)
     finally:
         codec.deferred_checks(False)
@@ -194,6 +194,7 @@ def run_gpu(args):
     st["eb"] = transform._bottleneck(codec, 8)
     st["cem"] = SymmetricConditional().bind(codec)
     _, mm_all, _, _, packed, offsets = transform.encode_on_device(codec, st["eb"], st["cem"], st["cubes"])
+    torch.cuda.synchronize()
     codec.synchronize()
     mm = mm_all.cpu().numpy()
     st["mins"], st["maxs"] = mm[:, 0].copy(), mm[:, 1].copy()

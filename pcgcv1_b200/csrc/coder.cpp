@@ -234,6 +234,16 @@ int pcgc_range_decode_progress(const uint8_t* data, int64_t nbytes, int64_t n, c
 int pcgc_range_encode_intervals(const uint32_t* iv, int64_t n, int precision, uint8_t* out, int64_t cap,
                                 int64_t* len) {
   if (!iv || !out || !len) return PCGC_ERR_BAD_ARG;
+  if (precision == 16) {
+    // the 32-bit state machine the GPU encoder runs (range_coder.h RangeEncoder16); the batch entry point below runs the generic
+    // RangeEncoder -- tests/test_host_coder.py holds the two to the same bytes
+    pcgc::RangeEncoder16 e16(out, cap);
+    for (int64_t i = 0; i < n; ++i) e16.encode_word(iv[i]);
+    const int64_t m16 = e16.finish();
+    if (m16 < 0) return PCGC_ERR_OVERFLOW;
+    *len = m16;
+    return PCGC_OK;
+  }
   Encoder e(out, cap, precision);
   for (int64_t i = 0; i < n; ++i) {
     const uint32_t lower = iv[i] & 0xFFFF;

@@ -10,6 +10,20 @@
 
 namespace pcgc {
 
+// Every kernel of the library asks for the SAME shared-memory / L1 carveout (all shared).  The carveout is per-SM state: a CTA
+// whose kernel prefers another split cannot be placed on an SM until the CTAs resident there have drained, so the coder-stream
+// kernels (tiny, latency-bound) would serialise with the persistent conv kernels of the main stream instead of running beside
+// them (measured r02: the 0.05 ms first kernel of the hyper decoder waited 2-3 ms behind the range encoder).
+template <typename K>
+inline void prefer_shared_carveout(K kernel) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+#define PCGC_CARVEOUT_ONCE(kernel)                                            \
+  do {                                                                        \
+    static const bool once_ = (::pcgc::prefer_shared_carveout(kernel), true); \
+    (void)once_;                                                              \
+  } while (0)
+
 // One convolution as the kernels see it: a stride-S "gather" convolution over an input grid with
 // a (KZ,KY,KX) tap box.  Forward Conv3D layers map 1:1; a stride-2 Conv3DTranspose is split into
 // 8 output-parity classes, each of which is such a convolution over the INPUT grid whose outputs

@@ -245,6 +245,7 @@ static cudaError_t launch_kzs(const FfmaArgs& a, int B, cudaStream_t s) {
   cudaError_t e = cudaSuccess;
 #define PCGC_LAUNCH(CTV)                                                                              \
   do {                                                                                                \
+    prefer_shared_carveout(conv_ffma_kernel<KZ, S, CTV>);                                                   \
     e = cudaFuncSetAttribute(conv_ffma_kernel<KZ, S, CTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                              (int)smem);                                                              \
     if (e == cudaSuccess) { conv_ffma_kernel<KZ, S, CTV><<<grid, block, smem, s>>>(b); e = cudaGetLastError(); } \
@@ -351,7 +352,7 @@ cudaError_t launch_conv_in_pm(const void* cubes, int dtype, const float* w_host,
   const int grid = (64 / 8) * (64 / 4) * B;
   if (launches) ++*launches;
   switch (dtype) {
-    case PCGC_DTYPE_U8: conv_in_pm_kernel<uint8_t><<<grid, 256, 0, s>>>((const uint8_t*)cubes, prm, (__nv_bfloat16*)out_pm); break;
+    case PCGC_DTYPE_U8: PCGC_CARVEOUT_ONCE(conv_in_pm_kernel<uint8_t>); conv_in_pm_kernel<uint8_t><<<grid, 256, 0, s>>>((const uint8_t*)cubes, prm, (__nv_bfloat16*)out_pm); break;
     case PCGC_DTYPE_F32: conv_in_pm_kernel<float><<<grid, 256, 0, s>>>((const float*)cubes, prm, (__nv_bfloat16*)out_pm); break;
     case PCGC_DTYPE_F64: conv_in_pm_kernel<double><<<grid, 256, 0, s>>>((const double*)cubes, prm, (__nv_bfloat16*)out_pm); break;
     default: return cudaErrorInvalidValue;

@@ -126,6 +126,7 @@ cudaError_t launch_factorized(const BottleneckDev& bn, const float* x, int64_t n
   if (C % 4 != 0 || C != bn.channels) return cudaErrorInvalidValue;
   int64_t want = (n / ENT_VEC + ENT_THREADS - 1) / ENT_THREADS;
   const int blocks = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+  PCGC_CARVEOUT_ONCE(init_minmax_kernel); PCGC_CARVEOUT_ONCE(factorized_kernel); PCGC_CARVEOUT_ONCE(finalize_bits_kernel);
   if (minmax) { init_minmax_kernel<<<1, 32, 0, s>>>(minmax, 1); if (launches) ++*launches; }
   factorized_kernel<<<blocks, ENT_THREADS, C * BN_PARAMS * sizeof(float), s>>>(x, n, C, bn.params, bound, x_hat, p,
                                                                               bits ? scratch : nullptr, minmax, noise, seed);
@@ -147,6 +148,7 @@ cudaError_t launch_factorized_pmf(const BottleneckDev& bn, int min_v, int max_v,
                                   cudaStream_t s, int64_t* launches) {
   const int N = max_v - min_v + 1;
   const int tot = bn.channels * N;
+  PCGC_CARVEOUT_ONCE(factorized_pmf_kernel);
   factorized_pmf_kernel<<<(tot + 127) / 128, 128, 0, s>>>(bn.params, bn.channels, min_v, N, bound, pmf);
   if (launches) ++*launches;
   return cudaGetLastError();
@@ -194,6 +196,7 @@ cudaError_t launch_laplace(const float* y, const float* loc, const float* scale,
   if (E % ENT_VEC != 0) return cudaErrorInvalidValue;
   int64_t per = (E / ENT_VEC + ENT_THREADS - 1) / ENT_THREADS;
   if (per > 16) per = 16;                          // 16 blocks x 256 threads x 4 elements x 4 iterations per cube
+  PCGC_CARVEOUT_ONCE(init_minmax_kernel); PCGC_CARVEOUT_ONCE(laplace_kernel); PCGC_CARVEOUT_ONCE(finalize_bits_kernel);
   if (minmax) { init_minmax_kernel<<<(B + 127) / 128, 128, 0, s>>>(minmax, B); if (launches) ++*launches; }
   dim3 grid((unsigned)per, (unsigned)B);
   laplace_kernel<<<grid, ENT_THREADS, 0, s>>>(y, loc, scale, E, bound, y_hat, p, bits ? scratch : nullptr, minmax, noise, seed);
@@ -259,6 +262,7 @@ static inline dim3 cdf_grid(int64_t E, int B) {
 cudaError_t launch_laplace_intervals(const float* y_hat, const float* loc, const float* scale, int B, int64_t E,
                                      const int32_t* minmax, float bound, int precision, uint32_t* intervals,
                                      int* err_flag, cudaStream_t s, int64_t* launches) {
+  PCGC_CARVEOUT_ONCE(laplace_cdf_kernel<1>);
   laplace_cdf_kernel<1><<<cdf_grid(E, B), 128, 0, s>>>(y_hat, loc, scale, nullptr, E, minmax, nullptr, bound, precision,
                                                       intervals, nullptr, nullptr, err_flag);
   if (launches) ++*launches;
@@ -268,6 +272,7 @@ cudaError_t launch_laplace_intervals(const float* y_hat, const float* loc, const
 cudaError_t launch_laplace_cdf(const float* loc, const float* scale, int B, int64_t E, const int32_t* minmax_dev,
                                const int64_t* row_offset_dev, float bound, int precision, uint16_t* cdf,
                                int* err_flag, cudaStream_t s, int64_t* launches) {
+  PCGC_CARVEOUT_ONCE(laplace_cdf_kernel<0>);
   laplace_cdf_kernel<0><<<cdf_grid(E, B), 128, 0, s>>>(nullptr, loc, scale, nullptr, E, minmax_dev, row_offset_dev, bound,
                                                       precision, nullptr, cdf, nullptr, err_flag);
   if (launches) ++*launches;

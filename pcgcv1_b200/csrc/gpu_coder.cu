@@ -6,8 +6,8 @@
 //
 // The state machines are range_coder.h's -- the SAME source as the host coder (coder.cpp) -- so a string written here is
 // byte-identical to pcgc_range_encode_intervals' and decodes with pcgc_range_decode_rows (tests/test_gpu_coder.py).
-//   encode: one THREAD per cube (the encoder is ~20 integer instructions per symbol with one data-dependent branch);
-//           CPW cubes per warp keeps the divergence of that branch small and spreads the cubes over the SMs.
+//   encode: one WARP per cube with the state replicated in every lane: coalesced interval loads handed round by shuffles, a
+//           warp-uniform renormalisation branch, lane 0 stores the words.
 //   decode: one WARP per cube.  The symbol search is lane-parallel: lane k holds cdf[k] of the current symbol's row and
 //           tests size*cdf[k] <= offset; a ballot gives the symbol without a division or a serial scan.  Rows stream
 //           through a double-buffered shared-memory window (cp.async), the next 16-bit word of the string is prefetched.
@@ -20,27 +20,81 @@ namespace pcgc {
 
 namespace {
 
-constexpr int ENC_CPW = 8;            // cubes (= active lanes) per encoder warp
-
+// One WARP per cube, precision 16, state replicated in every lane (RangeEncoder16 of range_coder.h, unrolled for the warp):
+// the lanes fetch 32 intervals with one coalesced load and hand them round by shuffles, the renormalisation branch is
+// warp-uniform (no divergence), lane 0 stores the emitted 16-bit words.  A thread-per-cube form with 4-8 cubes per warp was
+// measured at ~260 cycles per symbol (divergent renormalisation, 64-bit output bookkeeping on the serial chain).
+// Every symbol renormalises at most once and every renormalisation emits at most one word on average, so 2*E + 8 bytes always
+// suffice: the launcher checks the stride once instead of the kernel checking every store.
 __global__ void __launch_bounds__(32)
-range_encode_intervals_kernel(const uint32_t* __restrict__ iv, int B, int64_t E, int precision, uint8_t* __restrict__ out,
-                              int64_t stride, int64_t* __restrict__ lens, int* __restrict__ err) {
+range_encode_intervals_kernel(const uint32_t* __restrict__ iv, int B, int64_t E, uint8_t* __restrict__ out,
+                              int64_t stride, int64_t* __restrict__ lens) {
   const int lane = threadIdx.x;
-  const int b = blockIdx.x * ENC_CPW + lane;
-  if (lane >= ENC_CPW || b >= B) return;
-  RangeEncoder e(out + (size_t)b * stride, stride, precision);
+  const int b = blockIdx.x;
+  const unsigned FULL = 0xffffffffu;
   const uint32_t* src = iv + (size_t)b * E;
-  int64_t i = 0;
-  for (; i + 8 <= E; i += 8) {
-    // the loads do not depend on the coder state: issue a batch, then run the serial chain over it
-    const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(src + i)), w1 = __ldg(reinterpret_cast<const uint4*>(src + i + 4));
-    const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+  uint16_t* o16 = reinterpret_cast<uint16_t*>(out + (size_t)b * stride);          // stride and the buffer are 2-byte aligned
+  uint32_t base = 0, carry = 0, sm1 = 0xFFFFFFFFu, cache = 0, have = 0, pending = 0, n16 = 0;
+  auto emit = [&](uint32_t w) {                                                     // big-endian 16-bit word
+    if (lane == 0) o16[n16] = (uint16_t)(((w & 0xFF) << 8) | ((w >> 8) & 0xFF));
+    ++n16;
+  };
+  const int64_t groups = E / 32;                                                    // E % 32 == 0 (checked by the launcher)
+  // Every lane reads the SAME 32 intervals (8 broadcast 16-byte loads) one group ahead into registers: nothing inside the
+  // 32-symbol loop touches memory or another lane (a shuffle per symbol sat on the serial chain: 186 cycles per symbol).
+  const uint4* src4 = reinterpret_cast<const uint4*>(src);
+  uint4 cur[8], nxt[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { const uint32_t lower = w[k] & 0xFFFF; e.encode(lower, lower + (w[k] >> 16) + 1); }
+  for (int q = 0; q < 8; ++q) cur[q] = __ldg(src4 + q);
+  for (int64_t g = 0; g < groups; ++g) {
+    if (g + 1 < groups) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) nxt[q] = __ldg(src4 + (g + 1) * 8 + q);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const uint4 qv = cur[j >> 2];
+      const uint32_t w = (j & 3) == 0 ? qv.x : ((j & 3) == 1 ? qv.y : ((j & 3) == 2 ? qv.z : qv.w));
+      const uint32_t lower = w & 0xFFFFu, upper = lower + (w >> 16) + 1u;
+      const uint32_t a = (uint32_t)(((uint64_t)sm1 * lower + lower) >> 16);
+      const uint32_t bq = (uint32_t)(((uint64_t)sm1 * upper + upper) >> 16) - 1u;
+      const uint32_t nb = base + a;
+      carry |= (uint32_t)(nb < a);
+      base = nb;
+      const uint32_t t = bq - a;
+      const bool renorm = t < 0x10000u;                                             // warp-uniform
+      sm1 = renorm ? ((t << 16) | 0xFFFFu) : t;                                     // the size chain does not wait for the emission below
+      if (renorm) {
+        if (base < 0xFFFF0000u || carry) {
+          if (have) emit((cache + carry) & 0xFFFF);
+#pragma unroll 1
+          for (; pending > 0; --pending) emit((0xFFFF + carry) & 0xFFFF);
+          cache = base >> 16;
+          have = 1;
+        } else {
+          ++pending;
+        }
+        base <<= 16;
+        carry = 0;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) cur[q] = nxt[q];
   }
-  for (; i < E; ++i) { const uint32_t w = __ldg(src + i), lower = w & 0xFFFF; e.encode(lower, lower + (w >> 16) + 1); }
-  const int64_t m = e.finish();
-  if (m < 0) { atomicExch(err, PCGC_ERR_OVERFLOW); lens[b] = 0; } else lens[b] = m;
+  // finish(): the multiple of 2^16 inside the interval, then drop trailing zero bytes
+  const uint64_t v = (((uint64_t)carry << 32) + base + 0xFFFF) >> 16;
+  const uint32_t c = (uint32_t)(v >> 16), word = (uint32_t)(v & 0xFFFF);
+  if (have) emit((cache + c) & 0xFFFF);
+#pragma unroll 1
+  for (; pending > 0; --pending) emit((0xFFFF + c) & 0xFFFF);
+  emit(word);
+  if (lane == 0) {
+    __threadfence_block();
+    const uint8_t* o8 = out + (size_t)b * stride;
+    int64_t n = 2 * (int64_t)n16;
+    while (n > 0 && o8[n - 1] == 0) --n;
+    lens[b] = n;
+  }
 }
 
 // Concatenates the B strings: offsets[b] = sum of lens[0..b), offsets[B] = total; bytes beyond cap are dropped (error flag).
@@ -62,30 +116,35 @@ pack_strings_kernel(const uint8_t* __restrict__ in, int64_t stride, const int64_
 }
 
 constexpr int DEC_G = 32;                       // symbols per shared-memory window
-constexpr int DEC_MAXN = 64;                    // lane-parallel search: lane k tests entries k and k + 32
-constexpr int DEC_WARPS = 1;                    // cubes per block: a 32-thread block with a few KB of shared memory fits beside the
-                                                // persistent conv CTAs of another stream
+constexpr int DEC_MAXN = 64;                    // lane-parallel search: lane k tests entry k (and k + 32 in the WIDE form)
 
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 
-__global__ void __launch_bounds__(32 * DEC_WARPS)
+// One warp per cube, precision 16.  Per symbol the serial chain is: size -> one 32x32->64 multiply per lane -> compare with
+// value - base -> two warp reductions (REDUX max / min) -> new base / size.  Derivation (range_coder.h RangeDecoder):
+//   size*cdf[k] <= offset = ((d+1) << 16) - 1  with d = value - base   <=>   a_k := (size*cdf[k]) >> 16 <= d,
+//   so the decoded symbol s is the LAST lane whose a_k <= d, its interval starts at a_s = max{a_k : a_k <= d} (a_k is
+//   monotone) and ends at a_{s+1} - 1 = min{a_k - 1 : a_k > d}; lanes >= N hold cdf = 2^16, i.e. a_k - 1 = size - 1.
+// Nothing inside the 32-symbol loop touches memory: the lane's CDF entries are read into registers first, the next 16-bit
+// words of the string are prefetched one per lane and handed out by shuffles.
+template <bool WIDE>
+__global__ void __launch_bounds__(32)
 range_decode_rows_kernel(const uint8_t* __restrict__ packed, const int64_t* __restrict__ offsets, int B, int64_t E,
                          const uint16_t* __restrict__ rows, const int64_t* __restrict__ row_offset,
-                         const int32_t* __restrict__ minmax, int precision, float* __restrict__ y_hat, int* __restrict__ err,
-                         int win_elems) {
-  extern __shared__ __align__(16) uint16_t s_rows[];              // [DEC_WARPS][2][win_elems], win_elems >= DEC_G * max N of the launch
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * DEC_WARPS + warp;
-  if (b >= B) return;
+                         const int32_t* __restrict__ minmax, float* __restrict__ y_hat, int* __restrict__ err, int win_elems) {
+  extern __shared__ __align__(16) uint16_t s_rows[];              // [2][win_elems], win_elems >= DEC_G * max N of the launch
+  const int lane = threadIdx.x;
+  const int b = blockIdx.x;
+  const unsigned FULL = 0xffffffffu;
   const int min_v = minmax[2 * b], N = minmax[2 * b + 1] - min_v + 1;
-  if (N < 1 || N > DEC_MAXN || DEC_G * N > win_elems) { if (lane == 0) atomicExch(err, PCGC_ERR_BAD_RANGE); return; }
+  if (N < 1 || N > (WIDE ? DEC_MAXN : 32) || DEC_G * N > win_elems) { if (lane == 0) atomicExch(err, PCGC_ERR_BAD_RANGE); return; }
   const uint8_t* str = packed + offsets[b];
   const int64_t nbytes = offsets[b + 1] - offsets[b];
   const uint32_t* rsrc = reinterpret_cast<const uint32_t*>(rows + row_offset[b]);    // E*N is even: 4-byte aligned windows
   const int words = DEC_G * N / 2;                                                   // uint32 words per window
-  uint16_t* const wbuf[2] = {s_rows + (size_t)(2 * warp) * win_elems, s_rows + (size_t)(2 * warp + 1) * win_elems};
+  uint16_t* const wbuf[2] = {s_rows, s_rows + win_elems};
   const uint32_t sbuf[2] = {(uint32_t)__cvta_generic_to_shared(wbuf[0]), (uint32_t)__cvta_generic_to_shared(wbuf[1])};
   const int64_t groups = E / DEC_G;                                                  // E % 32 == 0 (checked by the host)
   auto fetch = [&](int64_t g, int buf) {
@@ -93,56 +152,80 @@ range_decode_rows_kernel(const uint8_t* __restrict__ packed, const int64_t* __re
     for (int w = lane; w < words; w += 32) cp_async4(sbuf[buf] + 4u * w, src + w);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  // decoder state, replicated in every lane (RangeDecoder of range_coder.h, unrolled for the warp)
-  int64_t pos = 0;
-  auto byte_at = [&](int64_t p) -> uint32_t { return p < nbytes ? (uint32_t)__ldg(str + p) : 0u; };
-  uint32_t value = (byte_at(0) << 24) | (byte_at(1) << 16) | (byte_at(2) << 8) | byte_at(3);
-  pos = 4;
-  uint32_t nxt = (byte_at(pos) << 8) | byte_at(pos + 1);                             // prefetched next word
-  uint32_t base = 0, size_minus1 = 0xFFFFFFFFu;
-  const uint32_t top = 1u << precision;
-  const bool wide = N > 32;                                                          // warp-uniform
+  // big-endian 16-bit word `i` of the string (zero beyond its end), i counted from the start of the string
+  auto word_at = [&](int64_t i) -> uint32_t {
+    const int64_t p = 2 * i;
+    const uint32_t hi = p < nbytes ? (uint32_t)__ldg(str + p) : 0u, lo = p + 1 < nbytes ? (uint32_t)__ldg(str + p + 1) : 0u;
+    return (hi << 8) | lo;
+  };
+  // decoder state, identical in every lane
+  uint32_t value = (word_at(0) << 16) | word_at(1);
+  int64_t wpos = 2;                                   // index of the next unread word
+  uint32_t w0 = word_at(wpos + lane), w1 = word_at(wpos + 32 + lane);      // words wpos + [0, 64) spread over the lanes
+  uint32_t base = 0, sm1 = 0xFFFFFFFFu;
   fetch(0, 0);
   for (int64_t g = 0; g < groups; ++g) {
     const int buf = (int)(g & 1);
     if (g + 1 < groups) { fetch(g + 1, buf ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
     else asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
-    const uint16_t* win = wbuf[buf];
-    int mine = 0;
-#pragma unroll 4
+    const uint32_t wb = sbuf[buf];
+    uint32_t c[DEC_G], c2[WIDE ? DEC_G : 1];
+#pragma unroll
     for (int j = 0; j < DEC_G; ++j) {
-      const uint16_t* row = win + j * N;
-      const uint32_t c_lo = lane < N ? (uint32_t)row[lane] : top;                    // cdf[lane]
-      const uint32_t c_hi = lane + 1 < N ? (uint32_t)row[lane + 1] : top;            // cdf[lane + 1] (cdf[N] = 2^precision)
-      const uint64_t offset = (((uint64_t)(uint32_t)(value - base) + 1) << precision) - 1;
-      const uint64_t p_lo = (uint64_t)size_minus1 * c_lo + c_lo;                     // size * cdf[lane]
-      const uint64_t p_hi = (uint64_t)size_minus1 * c_hi + c_hi;
-      const unsigned m = __ballot_sync(0xffffffffu, lane < N && (lane == 0 || p_lo <= offset));
-      int s = 31 - __clz((int)m);                                                    // last entry with size*cdf <= offset
-      uint32_t a_l = (uint32_t)(p_lo >> precision), n_l = (uint32_t)(p_hi >> precision) - 1u - a_l;
-      if (wide) {                                                                    // entries 32 .. N-1
-        const uint32_t d_lo = lane + 32 < N ? (uint32_t)row[lane + 32] : top, d_hi = lane + 33 < N ? (uint32_t)row[lane + 33] : top;
-        const uint64_t q_lo = (uint64_t)size_minus1 * d_lo + d_lo, q_hi = (uint64_t)size_minus1 * d_hi + d_hi;
-        const unsigned m2 = __ballot_sync(0xffffffffu, lane + 32 < N && q_lo <= offset);
-        if (m2) {
-          s = 63 - __clz((int)m2);
-          a_l = (uint32_t)(q_lo >> precision); n_l = (uint32_t)(q_hi >> precision) - 1u - a_l;
-        }
+      uint32_t v = 0x10000u;
+      if (lane < N) { uint16_t t; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(t) : "r"(wb + 2u * (uint32_t)(j * N + lane))); v = t; }
+      c[j] = v;
+      if (WIDE) {
+        uint32_t v2 = 0x10000u;
+        if (lane + 32 < N) { uint16_t t; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(t) : "r"(wb + 2u * (uint32_t)(j * N + lane + 32))); v2 = t; }
+        c2[j] = v2;
       }
-      const uint32_t a = __shfl_sync(0xffffffffu, a_l, s & 31);
-      size_minus1 = __shfl_sync(0xffffffffu, n_l, s & 31);
+    }
+    uint32_t r = 0;                                   // renormalisations (= words consumed) in this group
+    uint32_t nxt = __shfl_sync(FULL, w0, 0);
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < DEC_G; ++j) {
+      const uint32_t d = value - base;
+      const uint64_t q = ((uint64_t)sm1 * c[j] + c[j]) >> 16;                        // (size * cdf[lane]) >> 16
+      const uint32_t a_l = (uint32_t)q;
+      const bool pred = a_l <= d && c[j] < 0x10000u;
+      uint32_t va = pred ? a_l : 0u, vu = pred ? 0xFFFFFFFFu : a_l - 1u;
+      unsigned cnt = __ballot_sync(FULL, pred);
+      int s = __popc(cnt) - 1;
+      if (WIDE) {
+        const uint32_t a2 = (uint32_t)(((uint64_t)sm1 * c2[j] + c2[j]) >> 16);
+        const bool pred2 = a2 <= d && c2[j] < 0x10000u;
+        va = pred2 ? a2 : va;
+        vu = pred2 ? vu : min(vu, a2 - 1u);
+        s += __popc(__ballot_sync(FULL, pred2));
+      }
+      const uint32_t a = __reduce_max_sync(FULL, va);
+      const uint32_t bm1 = min(__reduce_min_sync(FULL, vu), sm1);
       base += a;
-      if ((size_minus1 >> 16) == 0) {
+      sm1 = bm1 - a;
+      if (sm1 < 0x10000u) {
         base <<= 16;
-        size_minus1 = (size_minus1 << 16) | 0xFFFF;
+        sm1 = (sm1 << 16) | 0xFFFFu;
         value = (value << 16) | nxt;
-        pos += 2;
-        nxt = (byte_at(pos) << 8) | byte_at(pos + 1);
+        ++r;
+        nxt = __shfl_sync(FULL, w0, r & 31);
       }
       if (lane == j) mine = s;
     }
     y_hat[(size_t)b * E + g * DEC_G + lane] = (float)(mine + min_v);
+    // advance the word window by r (<= 32): new w0 = words [r, r + 32) of the old 64, new w1 is fetched (latency hidden by the
+    // next group)
+    {
+      const uint32_t t = r + (uint32_t)lane;
+      const uint32_t x0 = __shfl_sync(FULL, w0, t & 31), x1 = __shfl_sync(FULL, w1, t & 31);
+      w0 = t < 32 ? x0 : x1;
+      wpos += r;
+      // w1 must become words [wpos + 32, wpos + 64): those below old wpos + 64 are already in w1 (shifted), the rest are new
+      const uint32_t y1 = __shfl_sync(FULL, w1, t & 31);
+      w1 = t < 32 ? y1 : word_at(wpos + 32 + lane);
+    }
     __syncwarp();                                                                     // window `buf` is refilled two iterations later
   }
 }
@@ -153,7 +236,10 @@ cudaError_t launch_range_encode_intervals(const uint32_t* iv, int B, int64_t E, 
                                           int64_t* lens, uint8_t* packed, int64_t cap, int64_t* offsets, int* err,
                                           cudaStream_t s, int64_t* launches) {
   if (B <= 0) return cudaSuccess;
-  range_encode_intervals_kernel<<<(B + ENC_CPW - 1) / ENC_CPW, 32, 0, s>>>(iv, B, E, precision, scratch, stride, lens, err);
+  if (precision != 16 || E % 32 || stride < 2 * E + 8 || (stride & 1)) return cudaErrorInvalidValue;
+  PCGC_CARVEOUT_ONCE(range_encode_intervals_kernel);
+  PCGC_CARVEOUT_ONCE(pack_strings_kernel);
+  range_encode_intervals_kernel<<<B, 32, 0, s>>>(iv, B, E, scratch, stride, lens);
   pack_strings_kernel<<<B, 256, 0, s>>>(scratch, stride, lens, B, packed, cap, offsets, err);
   if (launches) *launches += 2;
   return cudaGetLastError();
@@ -163,11 +249,15 @@ cudaError_t launch_range_decode_rows(const uint8_t* packed, const int64_t* offse
                                      const int64_t* row_offset, const int32_t* minmax, int max_n, int precision, float* y_hat, int* err,
                                      cudaStream_t s, int64_t* launches) {
   if (B <= 0) return cudaSuccess;
-  if (E % DEC_G || max_n < 1 || max_n > DEC_MAXN) return cudaErrorInvalidValue;
+  if (E % DEC_G || max_n < 1 || max_n > DEC_MAXN || precision != 16) return cudaErrorInvalidValue;
   const int win_elems = DEC_G * ((max_n + 7) / 8 * 8);              // 16-byte multiple per window
-  const size_t smem = (size_t)DEC_WARPS * 2 * win_elems * sizeof(uint16_t);
-  range_decode_rows_kernel<<<(B + DEC_WARPS - 1) / DEC_WARPS, 32 * DEC_WARPS, smem, s>>>(packed, offsets, B, E, rows, row_offset, minmax,
-                                                                                         precision, y_hat, err, win_elems);
+  const size_t smem = (size_t)2 * win_elems * sizeof(uint16_t);
+  PCGC_CARVEOUT_ONCE(range_decode_rows_kernel<true>);
+  PCGC_CARVEOUT_ONCE(range_decode_rows_kernel<false>);
+  if (max_n > 32)
+    range_decode_rows_kernel<true><<<B, 32, smem, s>>>(packed, offsets, B, E, rows, row_offset, minmax, y_hat, err, win_elems);
+  else
+    range_decode_rows_kernel<false><<<B, 32, smem, s>>>(packed, offsets, B, E, rows, row_offset, minmax, y_hat, err, win_elems);
   if (launches) ++*launches;
   return cudaGetLastError();
 }

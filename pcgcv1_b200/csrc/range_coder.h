@@ -71,6 +71,64 @@ struct RangeEncoder {
   }
 };
 
+// RangeEncoder specialised for precision 16 with the 33-bit base kept as 32 bits + a carry flag and no 64-bit shifts: the form
+// the GPU encoder runs (one thread per string; every 64-bit operation of the generic form costs several SASS instructions on
+// the serial chain).  Same decisions, same bytes as RangeEncoder (tests/test_host_coder.py compares them on random intervals).
+struct RangeEncoder16 {
+  uint32_t base = 0, carry = 0;          // base + (carry << 32) = RangeEncoder::base
+  uint32_t size_minus1 = 0xFFFFFFFFu;
+  uint32_t cache = 0, have_cache = 0;
+  uint32_t pending = 0;
+  uint8_t* out;
+  int64_t n = 0, cap;
+  bool overflow = false;
+
+  PCGC_RC RangeEncoder16(uint8_t* o, int64_t c) : out(o), cap(c) {}
+
+  PCGC_RC void emit16(uint32_t w) {
+    if (n + 2 > cap) { overflow = true; return; }
+    out[n] = (uint8_t)(w >> 8);
+    out[n + 1] = (uint8_t)w;
+    n += 2;
+  }
+  PCGC_RC void shift() {
+    if (base < 0xFFFF0000u || carry) {
+      if (have_cache) emit16((cache + carry) & 0xFFFF);
+      for (; pending > 0; --pending) emit16((0xFFFF + carry) & 0xFFFF);
+      cache = base >> 16;
+      have_cache = 1;
+    } else {
+      ++pending;
+    }
+    base <<= 16;
+    carry = 0;
+  }
+  // interval word of pcgc_laplace_intervals: lower | (upper - lower - 1) << 16
+  PCGC_RC void encode_word(uint32_t w) {
+    const uint32_t lower = w & 0xFFFFu, upper = lower + (w >> 16) + 1u;
+    const uint32_t a = (uint32_t)(((uint64_t)size_minus1 * lower + lower) >> 16);
+    const uint32_t b = (uint32_t)(((uint64_t)size_minus1 * upper + upper) >> 16) - 1u;     // (size*upper >> 16) <= 2^32: wraps correctly
+    const uint32_t nb = base + a;
+    carry |= (uint32_t)(nb < a);
+    base = nb;
+    size_minus1 = b - a;
+    if (size_minus1 < 0x10000u) {
+      shift();
+      size_minus1 = (size_minus1 << 16) | 0xFFFFu;
+    }
+  }
+  PCGC_RC int64_t finish() {
+    const uint64_t v = (((uint64_t)carry << 32) + base + 0xFFFF) >> 16;
+    const uint32_t c = (uint32_t)(v >> 16), word = (uint32_t)(v & 0xFFFF);
+    if (have_cache) emit16((cache + c) & 0xFFFF);
+    for (; pending > 0; --pending) emit16((0xFFFF + c) & 0xFFFF);
+    emit16(word);
+    if (overflow) return -1;
+    while (n > 0 && out[n - 1] == 0) --n;
+    return n;
+  }
+};
+
 struct RangeDecoder {
   const uint8_t* p;
   int64_t nbytes, pos = 0;

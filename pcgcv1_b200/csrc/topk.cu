@@ -145,6 +145,7 @@ topk_kernel(const float* __restrict__ logits, int64_t V, const int32_t* __restri
 cudaError_t launch_topk(const float* logits, int B, int64_t V, const int32_t* ks, uint8_t* mask, float* thres,
                         int32_t* count, int* err_flag, cudaStream_t s, int64_t* launches) {
   if (V % 4 != 0) return cudaErrorInvalidValue;
+  PCGC_CARVEOUT_ONCE(topk_kernel);
   topk_kernel<<<B, TK_THREADS, 0, s>>>(logits, V, ks, mask, thres, count, err_flag);
   if (launches) ++*launches;
   return cudaGetLastError();

@@ -997,6 +997,7 @@ int pick_zt(int n, int np, int cin, int epi, int wt, int n_mma, int kchunks) {
 
 template <int NP, int E, int TAPS, int WT>
 cudaError_t launch_one(const CUtensorMap& tm, const UmmaArgs& a, int grid, size_t smem, cudaStream_t s) {
+  PCGC_CARVEOUT_ONCE((conv_umma_kernel<NP, E, TAPS, WT>));
   cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<NP, E, TAPS, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   conv_umma_kernel<NP, E, TAPS, WT><<<grid, UMMA_THREADS, smem, s>>>(tm, a);
@@ -1031,6 +1032,7 @@ cudaError_t launch_banded(const CUtensorMap& tm, const UmmaArgs& a, int np, int 
 
 template <int NP, int E, bool PAIRED, int WT>
 cudaError_t launch_stream_one(const CUtensorMap& tm, const UmmaArgs& a, int grid, size_t smem, cudaStream_t s) {
+  PCGC_CARVEOUT_ONCE((conv_umma_stream_kernel<NP, E, PAIRED, WT>));
   cudaError_t e = cudaFuncSetAttribute(conv_umma_stream_kernel<NP, E, PAIRED, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   conv_umma_stream_kernel<NP, E, PAIRED, WT><<<grid, STREAM_THREADS, smem, s>>>(tm, a);
@@ -1242,6 +1244,7 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
       const int grid_z = std::min(segs, sm_count);
       if (launches) ++*launches;
       auto go = [&](auto kern, int threads) -> cudaError_t {
+        prefer_shared_carveout(kern);
         cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_z);
         if (e2 != cudaSuccess) return e2;
         kern<<<grid_z, threads, smem_z, s>>>(tmz, a);
@@ -1371,6 +1374,7 @@ cudaError_t launch_f32_to_pm(const float* in, int in_cs, int in_co, const PmTens
   const size_t vox = (size_t)out.n * out.n * out.n;
   const size_t total = vox * (out.c / 8) * out.B;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  PCGC_CARVEOUT_ONCE(f32_to_pm_kernel);
   f32_to_pm_kernel<<<blocks, 256, 0, s>>>(in, in_cs, in_co, out.p, out.c / 8, vox, total);
   if (launches) ++*launches;
   return cudaGetLastError();
@@ -1380,6 +1384,7 @@ cudaError_t launch_pm_to_f32(const PmTensor& in, float* out, int out_cs, int out
   const size_t vox = (size_t)in.n * in.n * in.n;
   const size_t total = vox * (in.c / 8) * in.B;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  PCGC_CARVEOUT_ONCE(pm_to_f32_kernel);
   pm_to_f32_kernel<<<blocks, 256, 0, s>>>(in.p, in.c / 8, out, out_cs, out_co, vox, total);
   if (launches) ++*launches;
   return cudaGetLastError();

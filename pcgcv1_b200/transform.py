@@ -106,6 +106,19 @@ def _chunks(B, small_first=False, small_last=False):
         tail.append((hi - e, hi)); hi -= e
     mid = [(a, min(hi, a + _CHUNK)) for a in range(lo, hi, _CHUNK)]
     return head + mid + tail
+def _gpu_decode_chunks(B):
+    """Chunks of the GPU-coder decode pipeline.  The range decoder's latency is one cube's string (a few ms) whatever the number
+    of cubes in the launch, so: one small first chunk (its decode is exposed), then large ones whose decode hides behind the
+    synthesis of the chunk before (a chunk's CDF rows take ~2.5 MB per cube of device memory)."""
+    first = int(os.environ.get("PCGC_DEC_FIRST", "48"))
+    rest = int(os.environ.get("PCGC_DEC_CHUNK", "512"))
+    if B <= max(first, 64):
+        return [(0, B)]
+    out = [(0, first)]
+    out += [(a, min(B, a + rest)) for a in range(first, B, rest)]
+    return out
+
+
 _POOL = None
 _POOL_Z = None
 
@@ -139,8 +152,25 @@ def encode_on_device(codec, entropy_bottleneck, cem, cubes, keep_side_info=False
     iv_all = torch.empty((B, E), dtype=torch.int32, device=dev)
     mm_all = torch.empty((B, 2), dtype=torch.int32, device=dev)
     z_hats, keep = [], []
-    for a, b in _chunks(B):
-        x = codec.to_device(cubes[a:b])
+    chunks = _chunks(B)
+    # host-resident input: every chunk's H2D copy is issued up front on the copy stream, so only the first one is exposed
+    uploads = None
+    if not (isinstance(cubes, torch.Tensor) and cubes.is_cuda):
+        cs = runtime.copy_stream(dev)
+        uploads = []
+        with torch.cuda.stream(cs):
+            for a, b in chunks:
+                xc = codec.to_device(cubes[a:b])
+                ev = torch.cuda.Event()
+                ev.record(cs)
+                uploads.append((xc, ev))
+    for k, (a, b) in enumerate(chunks):
+        if uploads is not None:
+            x, ev = uploads[k]
+            main.wait_event(ev)
+            x.record_stream(main)
+        else:
+            x = cubes[a:b]
         ys = codec.analysis(x)
         zs = codec.hyper_encode(ys)
         z_hat, _, _, _ = codec.factorized(entropy_bottleneck._slot, zs, want_p=want_likelihoods, want_bits=want_likelihoods)
@@ -334,11 +364,11 @@ def decompress_hyper(y_strings, y_min_vs, y_max_vs, y_shape, z_strings, z_min_v,
     start = time.time()
     if B == 0:
         return runtime.DeviceResult(torch.zeros((0, 64, 64, 64, 1), dtype=torch.float32, device=codec.dev))
-    chunks = _chunks(B, small_first=True)
     if runtime.coder_mode() == "gpu":
-        xs = _decompress_hyper_gpu_coder(codec, cem, strings, mins, maxs, y_shape, z_get, chunks)
+        xs = _decompress_hyper_gpu_coder(codec, cem, strings, mins, maxs, y_shape, z_get, _gpu_decode_chunks(B))
         _log("Hyper decoder + entropy decode (GPU coder) + synthesis", start)
         return runtime.DeviceResult(xs)
+    chunks = _chunks(B, small_first=True)
     xs_parts, pending = [], None
 
     def finish(p):

@@ -140,3 +140,41 @@ def test_coded_size_close_to_entropy():
     ideal_bits = -np.log2(pmf[0][sym]).sum()
     assert len(s) * 8 <= ideal_bits + 64
     assert len(s) * 8 >= ideal_bits - 64
+
+
+def test_encoder16_equals_generic_encoder():
+    """range_coder.h has two encoder state machines: the generic 64-bit one (host batch coder) and RangeEncoder16 (32-bit base +
+    carry flag, what the GPU encoder runs; reachable on the host through pcgc_range_encode_intervals at precision 16).  Same
+    bytes on random intervals, including long carry chains (tiny intervals at the top of the range) and certain symbols."""
+    import ctypes as C
+    from pcgcv1_b200 import _lib, runtime
+    L = _lib.lib()
+    rng = np.random.default_rng(5)
+    cases = []
+    for n, kind in ((1, "any"), (2, "any"), (5000, "any"), (20000, "top"), (20000, "sure"), (3000, "tiny"), (0, "any")):
+        if kind == "any":
+            lower = rng.integers(0, 65535, n)
+            width = np.minimum(rng.integers(1, 65536, n), 65536 - lower)
+        elif kind == "top":                   # intervals hugging the top of the range: carries and 0xFFFF runs
+            width = rng.integers(1, 4, n)
+            lower = 65536 - width - rng.integers(0, 2, n) * rng.integers(0, 3, n)
+            lower = np.clip(lower, 0, 65536 - width)
+        elif kind == "sure":                  # p ~ 1 symbols: the interval barely shrinks
+            lower = np.zeros(n, np.int64)
+            width = np.full(n, 65535)
+            lower[::7] = 1
+        else:                                 # width 1 everywhere: 16 bits per symbol
+            lower = rng.integers(0, 65536, n)
+            width = np.ones(n, np.int64)
+        cases.append((lower.astype(np.uint32) | ((width - 1).astype(np.uint32) << 16)).astype(np.uint32))
+    for iv in cases:
+        n = iv.size
+        cap = 2 * n + 64
+        out = np.zeros(cap, np.uint8)
+        ln = C.c_int64()
+        src = iv if n else np.zeros(1, np.uint32)
+        assert L.pcgc_range_encode_intervals(src.ctypes.data, n, 16, out.ctypes.data, cap, C.byref(ln)) == 0
+        fast = out[:ln.value].tobytes()
+        if n:
+            generic = runtime.range_encode_intervals_batch(iv[None], 1)[0]
+            assert fast == generic

@@ -1,0 +1,25 @@
+"""Dev tool: wall-clock split of one end-to-end step (compress_hyper / decompress_hyper / select_voxels) per coder mode."""
+import os, sys, time
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from pcgcv1_b200 import runtime, synthetic, transform
+from pcgcv1_b200.dataprocess import inout_points
+from pcgcv1_b200.models import model_voxception
+
+cubes, _, nums = synthetic.workload("vox10", seed=0)
+codec = runtime.get_codec("voxception", "")
+pinned = torch.from_numpy(cubes).pin_memory()
+for mode in (os.environ.get("MODES", "gpu,host").split(",")):
+    os.environ["PCGC_CODER"] = mode
+    for it in range(4):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        out = transform.compress_hyper(pinned, model_voxception, "")
+        host = [o.numpy() for o in out]
+        torch.cuda.synchronize(); t1 = time.perf_counter()
+        xs = transform.decompress_hyper(*host, model_voxception, "")
+        torch.cuda.synchronize(); t2 = time.perf_counter()
+        mask = inout_points.select_voxels(xs, nums, 1.0, codec=codec, dtype="uint8")
+        torch.cuda.synchronize(); t3 = time.perf_counter()
+    print("%s coder: compress %.1f ms, decompress %.1f ms, select %.1f ms, total %.1f ms -> %.0f cubes/s" %
+          (mode, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (t3 - t0) * 1e3, len(cubes) / (t3 - t0)))
