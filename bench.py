@@ -140,7 +140,7 @@ def device_step(codec, st):
     eb, cem = st["eb"], st["cem"]
     codec.deferred_checks(True)
     try:
-        _, _, z_hats, _, _, _ = transform.encode_on_device(codec, eb, cem, st["cubes"], want_likelihoods=True)
+        _, _, z_hats, _, _, _, _ = transform.encode_on_device(codec, eb, cem, st["cubes"], want_likelihoods=True)
         # decode side: headers (min/max) and the strings come from the stream, z_hat from the (host) hyper decoder
         z_all = torch_cat(z_hats)
         xs = transform._decompress_hyper_gpu_coder(codec, cem, None, st["mins"], st["maxs"], [1, 16, 16, 16, 16],
@@ -193,7 +193,7 @@ def run_gpu(args):
     from pcgcv1_b200.models.conditional_entropy_model import SymmetricConditional
     st["eb"] = transform._bottleneck(codec, 8)
     st["cem"] = SymmetricConditional().bind(codec)
-    _, mm_all, _, _, packed, offsets = transform.encode_on_device(codec, st["eb"], st["cem"], st["cubes"])
+    _, mm_all, _, _, packed, offsets, _ = transform.encode_on_device(codec, st["eb"], st["cem"], st["cubes"])
     torch.cuda.synchronize()
     codec.synchronize()
     mm = mm_all.cpu().numpy()

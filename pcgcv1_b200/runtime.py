@@ -37,12 +37,14 @@ _PINNED: Dict[tuple, torch.Tensor] = {}
 
 
 def pinned_buffer(tag: str, nbytes: int) -> torch.Tensor:
-    """Reusable page-locked staging buffer (uint8), grown on demand.  One per call-site tag: the returned
-    view is valid until the same tag is requested again."""
-    buf = _PINNED.get(tag)
+    """Reusable page-locked staging buffer (uint8), grown on demand.  One per (current device, calling thread's call-site
+    tag): the returned view is valid until the same tag is requested again on that device.  (Two codecs on two devices used to
+    share -- and overwrite -- one buffer per tag.)"""
+    key = (torch.cuda.current_device() if torch.cuda.is_available() else -1, tag)
+    buf = _PINNED.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes * 1.25), 1 << 16), dtype=torch.uint8).pin_memory()
-        _PINNED[tag] = buf
+        _PINNED[key] = buf
     return buf
 
 
@@ -392,13 +394,15 @@ class Codec:
         return rows, off
 
     # -- GPU-side range coder (csrc/gpu_coder.cu) ------------------------------------------------------
-    def coder_stream(self) -> "torch.cuda.Stream":
-        """Side stream of this codec for the (latency-bound, one warp / thread per cube) coder kernels: they run beside the
-        conv kernels of the next chunk instead of between them."""
-        s = getattr(self, "_coder_stream", None)
-        if s is None:
-            s = self._coder_stream = torch.cuda.Stream(device=self.dev)
-        return s
+    def coder_stream(self, which: int = 0) -> "torch.cuda.Stream":
+        """Side streams of this codec for the (latency-bound, one warp per cube) coder kernels: they run beside the conv kernels
+        of the main stream instead of between them.  0: encoder, 1: decoder (CDF rows + range decoder)."""
+        ss = getattr(self, "_coder_streams", None)
+        if ss is None:
+            ss = self._coder_streams = {}
+        if which not in ss:
+            ss[which] = torch.cuda.Stream(device=self.dev)
+        return ss[which]
 
     def deferred_checks(self, on: bool):
         """Pipelined sections: entry points stop synchronising just to read the device error flag; ``synchronize()`` at the

@@ -140,19 +140,36 @@ def _pool_z():
     return _POOL_Z
 
 
-def encode_on_device(codec, entropy_bottleneck, cem, cubes, keep_side_info=False, want_likelihoods=False):
+def _host_tail(B):
+    """(Opt-in, PCGC_HOST_TAIL=n; default 0.)  Cubes at the END of a compress call whose strings the host coder writes.  The GPU encoder's latency is one cube's string
+    (~4 ms, more beside the conv kernels) however few cubes it codes, so the cubes whose intervals only appear in the last few
+    milliseconds go to the host thread pool instead (0.35 ms per cube and thread); everything before them is coded on the GPU
+    while their transforms run.  Both coders write the same bytes (tests/test_gpu_coder.py)."""
+    t = int(os.environ.get("PCGC_HOST_TAIL", "0"))    # measured r02 (B200 + 16 host cores, 191 cubes): 48 -> compress 31.7 ms, 24 -> 32.5 ms,
+    return max(0, min(t, B - 1)) if B > 64 else 0      # 0 -> 28.0 ms: the worker threads' GIL traffic delays the kernel enqueue more than the tail saves
+
+
+def encode_on_device(codec, entropy_bottleneck, cem, cubes, keep_side_info=False, want_likelihoods=False, host_tail=0):
     """Every GPU kernel of the hyper encoder for ``cubes`` (host or device resident), enqueued without a host
-    synchronisation: transforms chunk by chunk on the current stream, then ONE range-encoder launch for all cubes on the coder
-    stream.  -> (intervals [B,E], minmax [B,2], [z_hat per chunk], [(loc, scale) per chunk], packed bytes, offsets [B+1]),
-    all device tensors.  The caller owns the synchronisation (codec.synchronize())."""
+    synchronisation: transforms chunk by chunk on the current stream, then ONE range-encoder launch for the first
+    B - host_tail cubes on the coder stream; the intervals of the last ``host_tail`` cubes go to pinned memory for the host
+    coder.  -> (intervals [B,E], minmax [B,2], [z_hat per chunk], [(loc, scale) per chunk], packed bytes, offsets [Bg+1],
+    [(a, b, pinned intervals, copy-done event) per tail chunk]); tensors on the device.  The caller owns the synchronisation."""
     B = cubes.shape[0]
     E = 16 * 16 * 16 * 16
     dev = codec.dev
     main, side = torch.cuda.current_stream(dev), codec.coder_stream()
     iv_all = torch.empty((B, E), dtype=torch.int32, device=dev)
     mm_all = torch.empty((B, 2), dtype=torch.int32, device=dev)
-    z_hats, keep = [], []
-    chunks = _chunks(B)
+    z_hats, keep, tails = [], [], []
+    Bg = B - host_tail                                                 # cubes [0, Bg) -> GPU coder, [Bg, B) -> host coder
+    chunks = _chunks(Bg)
+    if host_tail:
+        edge = max(8, min(16, host_tail // 2))                         # the very last chunk is small: its host coding is exposed
+        mid = host_tail - edge
+        if mid > 0:
+            chunks.append((Bg, Bg + mid))
+        chunks.append((Bg + mid, B))
     # host-resident input: every chunk's H2D copy is issued up front on the copy stream, so only the first one is exposed
     uploads = None
     if not (isinstance(cubes, torch.Tensor) and cubes.is_cuda):
@@ -164,7 +181,19 @@ def encode_on_device(codec, entropy_bottleneck, cem, cubes, keep_side_info=False
                 ev = torch.cuda.Event()
                 ev.record(cs)
                 uploads.append((xc, ev))
+    packed = offsets = None
+
+    def launch_gpu_coder():
+        ready = torch.cuda.Event()
+        ready.record(main)
+        iv_all.record_stream(side)
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            return cem.encode_dev(iv_all[:Bg])
+
     for k, (a, b) in enumerate(chunks):
+        if a == Bg and packed is None and Bg > 0:
+            packed, offsets = launch_gpu_coder()                       # beside the transforms of the tail chunks
         if uploads is not None:
             x, ev = uploads[k]
             main.wait_event(ev)
@@ -178,51 +207,54 @@ def encode_on_device(codec, entropy_bottleneck, cem, cubes, keep_side_info=False
         locs, scales = codec.hyper_decode(z_hat, 1e-9)                  # lower_bound = 1e-9, transform.py:145-146
         _, mm = cem.intervals_dev(ys, locs, scales, iv_out=iv_all[a:b], want_likelihoods=want_likelihoods)
         mm_all[a:b].copy_(mm)
+        if a >= Bg:
+            stage, done = runtime.to_host_async(iv_all[a:b], "intervals%d" % (len(tails) % 2))
+            tails.append((a, b, stage, done))
         if keep_side_info:
             keep.append((locs, scales))
-    ready = torch.cuda.Event()
-    ready.record(main)
-    iv_all.record_stream(side)
+    if packed is None and Bg > 0:
+        packed, offsets = launch_gpu_coder()
     mm_all.record_stream(side)
-    with torch.cuda.stream(side):
-        side.wait_event(ready)
-        packed, offsets = cem.encode_dev(iv_all)
-    return iv_all, mm_all, z_hats, keep, packed, offsets
+    return iv_all, mm_all, z_hats, keep, packed, offsets, tails
 
 
 def _compress_hyper_gpu_coder(codec, entropy_bottleneck, cem, cubes, decompress):
     """compress_hyper with the per-cube strings written ON THE GPU (csrc/gpu_coder.cu).  The chunks only enqueue kernels (no
-    host synchronisation in the loop); the intervals of every cube land in one device buffer and ONE encoder launch codes all
-    strings on the coder stream while this thread range-codes the single hyper string z on the host."""
+    host synchronisation in the loop); the intervals land in one device buffer, ONE encoder launch codes the strings of all
+    cubes but the last few (``_host_tail``) on the coder stream, and this thread range-codes the single hyper string z on the
+    host meanwhile."""
     B = cubes.shape[0]
-    dev = codec.dev
     side = codec.coder_stream()
+    tail = _host_tail(B)
+    Bg = B - tail
     codec.deferred_checks(True)
     try:
-        iv_all, mm_all, z_hats, keep, packed, offsets = encode_on_device(codec, entropy_bottleneck, cem, cubes, decompress)
-        hdr = runtime.pinned_buffer("enc_hdr", 8 * (B + 1) + 8 * B)
-        off_h = hdr[:8 * (B + 1)].view(torch.int64)
-        mm_h = hdr[8 * (B + 1):8 * (B + 1) + 8 * B].view(torch.int32).view(B, 2)
+        iv_all, mm_all, z_hats, keep, packed, offsets, tails = encode_on_device(codec, entropy_bottleneck, cem, cubes, decompress,
+                                                                               host_tail=tail)
+        tail_jobs = [_pool().submit(cem.encode_finish, stage, done) for (_, _, stage, done) in tails]
+        hdr = runtime.pinned_buffer("enc_hdr", 8 * (Bg + 1))
+        off_h = hdr[:8 * (Bg + 1)].view(torch.int64)
         with torch.cuda.stream(side):
             off_h.copy_(offsets, non_blocking=True)
-            mm_h.copy_(mm_all, non_blocking=True)
             hdr_done = torch.cuda.Event()
             hdr_done.record(side)
         # the ONE hyper string (global range, entropy_model.py:249-259) is coded here on the host beside the GPU encoder
         z_all = torch.cat(z_hats) if len(z_hats) > 1 else z_hats[0]
         sym, cdf, z_min, z_max = entropy_bottleneck.compress_begin(z_all)
+        mm = runtime.to_host(mm_all).copy()                                 # the main stream is idle by now (compress_begin synchronised it)
         z_string = entropy_bottleneck.compress_finish(sym, cdf)
         hdr_done.synchronize()
         off = off_h.numpy().copy()
-        mm = mm_h.numpy().copy()
-        total = int(off[B])
+        total = int(off[Bg])
         stage = runtime.pinned_buffer("enc_bytes", max(total, 1))[:total]
         with torch.cuda.stream(side):
             stage.copy_(packed[:total], non_blocking=True)
         side.synchronize()
         runtime.COUNTERS["d2h_bytes"] += total + hdr.numel()
         blob = stage.numpy()
-        strings = [blob[off[i]:off[i + 1]].tobytes() for i in range(B)]
+        strings = [blob[off[i]:off[i + 1]].tobytes() for i in range(Bg)]
+        for j in tail_jobs:
+            strings += j.result()
     finally:
         codec.deferred_checks(False)
     codec.synchronize()                                                   # raises if any kernel of the section flagged an error
@@ -310,7 +342,7 @@ def _decompress_hyper_gpu_coder(codec, cem, strings, mins, maxs, y_shape, z_get,
     """decompress_hyper with the per-cube strings read ON THE GPU: the strings go up once (a few KB per cube), CDF rows are
     built and consumed on the device.  Chunk k+1 is decoded on the coder stream while chunk k is synthesised."""
     dev = codec.dev
-    main, side = torch.cuda.current_stream(dev), codec.coder_stream()
+    main, side = torch.cuda.current_stream(dev), codec.coder_stream(1)
     packed, offsets = uploaded if uploaded is not None else codec.upload_strings(strings)
     xs_parts, pending = [], None
     codec.deferred_checks(True)

@@ -13,7 +13,7 @@ B = len(cubes)
 x = codec.to_device(cubes)
 eb = transform._bottleneck(codec, 8)
 cem = SymmetricConditional().bind(codec)
-iv, mm_all, z_hats, keep, packed, offsets = transform.encode_on_device(codec, eb, cem, x, keep_side_info=True)
+iv, mm_all, z_hats, keep, packed, offsets, _ = transform.encode_on_device(codec, eb, cem, x, keep_side_info=True)
 torch.cuda.synchronize()
 codec.synchronize()
 mm = mm_all.cpu().numpy()
