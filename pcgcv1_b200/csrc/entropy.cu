@@ -7,6 +7,7 @@
 // (block partials -> one finalising block), min/max use integer atomics: results are reproducible.
 #include <float.h>
 #include <limits.h>
+#include <stdlib.h>
 
 #include "cdf_norm.h"
 #include "common.cuh"
@@ -212,8 +213,17 @@ cudaError_t launch_laplace(const float* y, const float* loc, const float* scale,
 // r01 note: an 8-lanes-per-row variant (all state in registers, shuffle reductions) was measured 2x SLOWER on the real
 // symbol ranges (N = 5..12): most lanes idle and every greedy step pays 9 shuffles.  The cost that mattered was the
 // water-filling pass of the few heavy-tail rows that almost every warp contains; it is now a closed form (cdf_last_u).
+// r02 experiment, kept as a note: moving the three per-row arrays (pmf, counts, scores) from per-thread local memory (38 M local
+// loads per 64 cubes at a 10 % L1 hit rate, ncu) into shared memory interleaved over the block ([entry][thread], 48 KiB per 128
+// threads) made the kernel SLOWER (3.78 -> 4.90 ms per 191 cubes): 16 instead of 32 resident warps hide the exp / FP64 latencies
+// of the normaliser worse than the L2 hits of the local arrays cost.  quantize_pmf_row keeps its stride parameter for that form.
+constexpr int CDF_THREADS = 128;
+
+#ifndef PCGC_CDF_MINBLOCKS
+#define PCGC_CDF_MINBLOCKS 12
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(CDF_THREADS, PCGC_CDF_MINBLOCKS)
 laplace_cdf_kernel(const float* __restrict__ y_hat, const float* __restrict__ loc, const float* __restrict__ scale,
                    const float* __restrict__ pmf_in, int64_t E, const int32_t* __restrict__ minmax,
                    const int64_t* __restrict__ row_offset, float bound, int precision, uint32_t* __restrict__ intervals,
@@ -253,8 +263,19 @@ laplace_cdf_kernel(const float* __restrict__ y_hat, const float* __restrict__ lo
   }
 }
 
+static const size_t CDF_SMEM = [] { const char* e = getenv("PCGC_CDF_PAD_KB"); return (size_t)(e ? atoi(e) : 0) * 1024; }();   // occupancy experiments
+
+template <int MODE>
+static cudaError_t cdf_prepare() {
+  static const cudaError_t once = [] {
+    prefer_shared_carveout(laplace_cdf_kernel<MODE>);
+    return cudaFuncSetAttribute(laplace_cdf_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 * 1024));
+  }();
+  return once;
+}
+
 static inline dim3 cdf_grid(int64_t E, int B) {
-  int64_t gx = (E + 127) / 128;
+  int64_t gx = (E + CDF_THREADS - 1) / CDF_THREADS;
   if (gx > 2048) gx = 2048;
   return dim3((unsigned)gx, (unsigned)B);
 }
@@ -262,8 +283,9 @@ static inline dim3 cdf_grid(int64_t E, int B) {
 cudaError_t launch_laplace_intervals(const float* y_hat, const float* loc, const float* scale, int B, int64_t E,
                                      const int32_t* minmax, float bound, int precision, uint32_t* intervals,
                                      int* err_flag, cudaStream_t s, int64_t* launches) {
-  PCGC_CARVEOUT_ONCE(laplace_cdf_kernel<1>);
-  laplace_cdf_kernel<1><<<cdf_grid(E, B), 128, 0, s>>>(y_hat, loc, scale, nullptr, E, minmax, nullptr, bound, precision,
+  cudaError_t pe = cdf_prepare<1>();
+  if (pe != cudaSuccess) return pe;
+  laplace_cdf_kernel<1><<<cdf_grid(E, B), CDF_THREADS, CDF_SMEM, s>>>(y_hat, loc, scale, nullptr, E, minmax, nullptr, bound, precision,
                                                       intervals, nullptr, nullptr, err_flag);
   if (launches) ++*launches;
   return cudaGetLastError();
@@ -272,8 +294,9 @@ cudaError_t launch_laplace_intervals(const float* y_hat, const float* loc, const
 cudaError_t launch_laplace_cdf(const float* loc, const float* scale, int B, int64_t E, const int32_t* minmax_dev,
                                const int64_t* row_offset_dev, float bound, int precision, uint16_t* cdf,
                                int* err_flag, cudaStream_t s, int64_t* launches) {
-  PCGC_CARVEOUT_ONCE(laplace_cdf_kernel<0>);
-  laplace_cdf_kernel<0><<<cdf_grid(E, B), 128, 0, s>>>(nullptr, loc, scale, nullptr, E, minmax_dev, row_offset_dev, bound,
+  cudaError_t pe = cdf_prepare<0>();
+  if (pe != cudaSuccess) return pe;
+  laplace_cdf_kernel<0><<<cdf_grid(E, B), CDF_THREADS, CDF_SMEM, s>>>(nullptr, loc, scale, nullptr, E, minmax_dev, row_offset_dev, bound,
                                                       precision, nullptr, cdf, nullptr, err_flag);
   if (launches) ++*launches;
   return cudaGetLastError();
@@ -282,7 +305,9 @@ cudaError_t launch_laplace_cdf(const float* loc, const float* scale, int B, int6
 // pmf [rows, N] (device) -> int32 cdf [rows, N+1] with the device copy of the normaliser (test hook).  minmax_dev = {0, N-1}.
 cudaError_t launch_debug_quantize_pmf(const float* pmf, int64_t rows, const int32_t* minmax_dev, int precision,
                                       int32_t* cdf32, int* err_flag, cudaStream_t s, int64_t* launches) {
-  laplace_cdf_kernel<2><<<cdf_grid(rows, 1), 128, 0, s>>>(nullptr, nullptr, nullptr, pmf, rows, minmax_dev, nullptr, 0.f,
+  cudaError_t pe = cdf_prepare<2>();
+  if (pe != cudaSuccess) return pe;
+  laplace_cdf_kernel<2><<<cdf_grid(rows, 1), CDF_THREADS, CDF_SMEM, s>>>(nullptr, nullptr, nullptr, pmf, rows, minmax_dev, nullptr, 0.f,
                                                          precision, nullptr, nullptr, cdf32, err_flag);
   if (launches) ++*launches;
   return cudaGetLastError();
