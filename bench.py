@@ -257,47 +257,57 @@ def run_gpu(args):
     value = world * B * args.steps / (dev_ms / 1e3)
     e2e = world * B * e2e_steps / (e2e_wall_ms / 1e3)
     points = float(nums.sum())
-    # dominant kernel group
+    # dominant kernel group.  The GPU range-coder kernels (one warp per cube, latency-bound, on the coder streams BESIDE the conv
+    # kernels) have their own entry below: their event times overlap the main stream's and say nothing about a roofline.
     prof.sort(key=lambda r: -r["ms"])
     total_ms = sum(r["ms"] for r in prof)
-    top = prof[0]
+    main_prof = [r for r in prof if not r["tag"].startswith("range_")]
+    top = main_prof[0]
     per_launch_ms = top["ms"] / top["count"]
+    per_launch = int(os.environ.get("PCGC_SUB_BATCH", "64"))          # cubes per kernel launch in this run
+    tr = None
+    for name in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                tr = json.load(f).get(top["tag"])
+            if tr:
+                tr.setdefault("source", "profiles/" + name)
+                break
+        except (OSError, ValueError):
+            pass
     if top["flops"] > 0:
+        # the conv transforms are bounded by the TENSOR roofline on algorithmic FLOPs (split-bf16 passes, padded
+        # columns and halo recompute do not count).  The HBM picture stays beside it: DRAM bytes from the ncu capture over the same
+        # launch time, against the bytes a fused Voxception block would need (read x once, write out once).
         ach = top["flops"] / top["count"] / (per_launch_ms * 1e-3) / 1e12
         roof = {"kernel": top["tag"], "bound": "tensor", "achieved": round(ach, 3), "peak": peaks["bf16_tflops_sustained"],
-                "unit": "TFLOP/s", "frac": round(ach / peaks["bf16_tflops_sustained"], 5), "traffic": None}
-    else:
-        ach = top["bytes"] / top["count"] / (per_launch_ms * 1e-3) / 1e9
-        roof = {"kernel": top["tag"], "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": round(ach / peaks["hbm_gbs"], 5), "traffic": None}
-    roof.update({"peak_source": peaks["source"], "ms_per_launch": round(per_launch_ms, 4), "share_of_step": round(top["ms"] / total_ms, 4)})
-    # DRAM bytes per launch of that kernel from the committed ncu --set full capture (same launch shape: 32 cubes per launch)
-    tr = None
-    per_launch = int(os.environ.get("PCGC_SUB_BATCH", "64"))          # cubes per kernel launch in this run
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
-            tr = json.load(f).get(top["tag"])
+                "unit": "TFLOP/s", "frac": round(ach / peaks["bf16_tflops_sustained"], 5), "traffic": None,
+                "frac_of_burst_peak": round(ach / peaks["bf16_tflops"], 5), "peak_nominal": 2250.0}
         if tr:
-            roof["traffic"] = int(tr["dram_bytes_per_launch"] * per_launch / tr.get("cubes_per_launch", per_launch))
-            roof["traffic_source"] = tr.get("source", "profiles/r01_ncu_traffic.json")
+            scale = per_launch / tr.get("cubes_per_launch", per_launch)
+            traffic = tr["dram_bytes_per_launch"] * scale
+            roof["traffic"] = int(traffic)
+            roof["traffic_source"] = tr["source"]
+            hbm = {"achieved_gbs": round(traffic / (per_launch_ms * 1e-3) / 1e9, 1), "peak_gbs": peaks["hbm_gbs"]}
+            hbm["frac"] = round(hbm["achieved_gbs"] / peaks["hbm_gbs"], 4)
+            if tr.get("algorithmic_bytes_per_launch"):
+                hbm["kernel_algorithmic_bytes"] = int(tr["algorithmic_bytes_per_launch"] * scale)
+            if tr.get("fused_block_floor_bytes_per_cube"):
+                hbm["fused_block_floor_bytes"] = int(tr["fused_block_floor_bytes_per_cube"] * per_launch)
+                hbm["block_traffic_over_fused_floor"] = tr.get("block_traffic_over_fused_floor")
+            roof["hbm"] = hbm
             for k in ("sm__pipe_tc_cycles_active_pct", "utchmma_bf16_ops_pct_of_peak", "l1tex_tc_wavefronts_shared_pct_of_peak"):
                 if k in tr:
                     roof["ncu_" + k] = tr[k]
-    except (OSError, ValueError):
-        pass
-    # a conv kernel is bounded by whichever roofline it sits closer to: report that one (the other fraction stays beside it)
-    try:
-        if tr and roof["unit"] == "TFLOP/s" and tr.get("algorithmic_bytes_per_launch"):
-            alg = tr["algorithmic_bytes_per_launch"] * per_launch / tr.get("cubes_per_launch", per_launch)
-            gbs = alg / (per_launch_ms * 1e-3) / 1e9
-            hbm_frac = gbs / peaks["hbm_gbs"]
-            if hbm_frac > roof["frac"]:
-                roof.update({"tensor_achieved_tflops": roof["achieved"], "tensor_frac": roof["frac"], "bound": "hbm",
-                             "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(hbm_frac, 5),
-                             "algorithmic_bytes_per_launch": int(alg)})
-    except (NameError, KeyError):
-        pass
-    roof["peak_nominal"] = 2250.0 if roof["unit"] == "TFLOP/s" else 8000.0
+    else:
+        ach = top["bytes"] / top["count"] / (per_launch_ms * 1e-3) / 1e9
+        roof = {"kernel": top["tag"], "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": round(ach / peaks["hbm_gbs"], 5), "traffic": int(tr["dram_bytes_per_launch"]) if tr else None, "peak_nominal": 8000.0}
+    roof.update({"peak_source": peaks["source"], "ms_per_launch": round(per_launch_ms, 4), "share_of_step": round(top["ms"] / total_ms, 4)})
+    coder = [{"tag": r["tag"], "launches_per_step": r["count"] // max(1, args.steps), "ms_per_launch": round(r["ms"] / r["count"], 3),
+              "ns_per_symbol_of_one_cube": round(r["ms"] / r["count"] * 1e6 / 65536, 1),
+              "note": "one warp per cube, sequential in the string: latency-bound, runs beside the conv kernels"}
+             for r in prof if r["tag"].startswith("range_")]
     conv_ms = sum(r["ms"] for r in prof if r["tag"].startswith("conv"))
     conv_tflops = sum(r["flops"] for r in prof if r["tag"].startswith("conv")) / (conv_ms * 1e-3) / 1e12
     kernels = [{"tag": r["tag"], "share": round(r["ms"] / total_ms, 4),
@@ -306,7 +316,7 @@ def run_gpu(args):
     # memory-bound kernels (entropy models, top-k, voxel I/O): achieved algorithmic GB/s against the measured HBM peak, whatever their rank
     hbm_kernels = [{"tag": r["tag"], "share": round(r["ms"] / total_ms, 4), "achieved_gbs": round(r["bytes"] / 1e9 / (r["ms"] * 1e-3), 1),
                     "frac_of_hbm_peak": round(r["bytes"] / 1e9 / (r["ms"] * 1e-3) / peaks["hbm_gbs"], 4)}
-                   for r in prof if not r["flops"] and r["bytes"] and r["ms"] > 0]
+                   for r in prof if not r["flops"] and r["bytes"] and r["ms"] > 0 and not r["tag"].startswith("range_")]
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -322,6 +332,9 @@ def run_gpu(args):
         "config": {"workload": "%s synthetic cloud, %d cubes of 64^3 (%d points) per GPU, hyper mode, model_voxception, rho=1.0, "
                                "seeded synthetic weights" % (args.workload, B, int(points)),
                    "cubes_per_gpu": B, "points_per_gpu": int(points), "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)",
+                   "range_coder": os.environ.get("PCGC_CODER", "gpu"),
+                   "e2e_flow": "compress_hyper -> .numpy() of every stream field -> decompress_hyper (device handle) -> select_voxels(codec=, "
+                               "dtype=uint8): top-k on the GPU, uint8 masks to the host (the reference does .numpy() then NumPy top-k, test.py:115)",
                    "conv_engine": os.environ.get("PCGC_ENGINE", "auto")},
         "points_per_s": round(value * points / B, 1),
         "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -330,11 +343,227 @@ def run_gpu(args):
         "conv": {"achieved_tflops": round(conv_tflops, 2), "share_of_step": round(conv_ms / total_ms, 4),
                  "algorithmic_gflop_per_cube": GFLOP_PER_CUBE,
                  "frac_of_bf16_sustained": round(conv_tflops / peaks["bf16_tflops_sustained"], 5)},
-        "kernels": kernels, "hbm_kernels": hbm_kernels, "cpu_baseline": cpu,
+        "kernels": kernels, "hbm_kernels": hbm_kernels, "gpu_range_coder": coder, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------ other BASELINE configs
+def _dist_setup(args):
+    """(world, rank, local, host_group): NCCL for the timing barriers on N > 1, a gloo group for the host-object exchange."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        host_group = dist.new_group(backend="gloo")
+    else:
+        import socket
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=0, world_size=1)
+        host_group = None
+    return world, rank, local, host_group
+
+
+def run_sharded(args):
+    """BASELINE config 3: the sparse vox12 cloud (thousands of 64^3 cubes), hyper mode, STRONG scaling: the cloud's cubes are
+    split into contiguous slices over the ranks (pcgcv1_b200.sharding), no data-path collective; the exchange is a host-side
+    gather of strings / headers / quantised hyper-latents to rank 0, ONE global range coding of z there (the reference's format
+    has a single z string for the whole cloud, entropy_model.py:249-259) and the gather of the decoded points."""
+    import torch
+    import torch.distributed as dist
+    from pcgcv1_b200 import runtime, sharding, synthetic
+    world, rank, local, hg = _dist_setup(args)
+    cubes, pos, nums = synthetic.workload("vox12", seed=0, max_cubes=args.cubes)
+    B = len(cubes)
+    a, b = sharding.shard_slices(B, world)[rank]
+    lc = sharding.GpuLocalCodec("voxception", "", local)
+    mine_host = torch.from_numpy(cubes[a:b]).pin_memory()
+    mine_dev = mine_host.to(lc.codec.dev)
+    result = {}
+
+    def step(x):
+        stream = sharding.compress_sharded(x, lc, group=hg)
+        out = sharding.decompress_sharded(stream, nums if rank == 0 else None, 1.0, lc, group=hg, output="points")
+        if rank == 0:
+            result["stream"], result["points"] = stream, out
+
+    def timed(x, steps, warmup):
+        for _ in range(warmup):
+            step(x)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step(x)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=lc.codec.dev if world > 1 else "cpu")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = lc.codec.launch_count()
+    dev_ms = timed(mine_dev, args.steps, max(1, min(args.warmup, 2)))
+    launches = lc.codec.launch_count() - l0
+    clocks = sampler.finish()
+    runtime.COUNTERS["h2d_bytes"] = runtime.COUNTERS["d2h_bytes"] = 0
+    e2e_ms = timed(mine_host, args.steps, 0)
+    h2d, d2h = runtime.COUNTERS["h2d_bytes"] // args.steps, runtime.COUNTERS["d2h_bytes"] // args.steps
+    if rank == 0:
+        pts, counts = result["points"]
+        stream = result["stream"]
+        import hashlib
+        y_bytes = stream["y_blob"].tobytes() if "y_blob" in stream else b"".join(stream["y_strings"])
+        digest = hashlib.sha256(y_bytes + stream["z_string"]).hexdigest()[:16]
+        line = {
+            "metric": "hyper-mode encode+decode throughput of 64^3 cubes, one cloud sharded over the GPUs", "value": round(B * args.steps / (dev_ms / 1e3), 2),
+            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 2),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "vox12 synthetic sparse cloud, %d cubes of 64^3 (%d points) in total, contiguous slices per GPU, hyper mode, "
+                                   "model_voxception, rho=1.0, seeded synthetic weights" % (B, int(nums.sum())),
+                       "baseline_config": 3, "cubes_total": B, "points_total": int(nums.sum()), "range_coder": os.environ.get("PCGC_CODER", "gpu"),
+                       "exchange": "host-side gather of strings/headers/z_hat to rank 0 (gloo), one global z string coded there, points gathered back; "
+                                   "no collective on the data path"},
+            "points_per_s": round(float(nums.sum()) * args.steps / (dev_ms / 1e3), 1),
+            "e2e": {"value": round(B * args.steps / (e2e_ms / 1e3), 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "note": "h2d/d2h of rank 0 only; value = cube slices resident in HBM, e2e = slices in pinned host memory"},
+            "gpu_launches": int(launches) * world, "clocks": clocks,
+            "stream_sha256_16": digest, "stream_bytes": int(len(y_bytes) + len(stream["z_string"])),
+            "decoded_points": int(len(pts)), "decoded_ge_input_points": bool((counts >= nums).all()),
+            "roofline": None, "cpu_baseline": None,
+        }
+        print(json.dumps(line))
+    dist.destroy_process_group()
+
+
+def run_factorized(args):
+    """BASELINE config 2: the vox10 cloud in factorized mode (EntropyBottleneck only) with model_simple on one GPU."""
+    import torch
+    from pcgcv1_b200 import runtime, synthetic, transform
+    from pcgcv1_b200.dataprocess import inout_points
+    from pcgcv1_b200.models import model_simple
+    torch.cuda.set_device(0)
+    cubes, pos, nums = synthetic.workload("vox10", seed=0, max_cubes=args.cubes)
+    B = len(cubes)
+    codec = runtime.get_codec("simple", "", 0)
+    pinned = torch.from_numpy(cubes).pin_memory()
+    xd = pinned.to(codec.dev)
+    ks = torch.from_numpy(nums.astype(np.int32)).to(codec.dev)
+    slot = codec.bottleneck_slot(32)
+
+    def device_step():
+        y = codec.analysis(xd)
+        y_hat, _, _, _ = codec.factorized(slot, y, want_p=True, want_bits=True)
+        logits = codec.synthesis(y_hat)
+        return codec.topk(logits, ks)
+
+    def e2e_step():
+        s, mn, mx, shp = transform.compress_factorized(pinned, model_simple, "")
+        xs = transform.decompress_factorized(s.numpy(), mn.numpy(), mx.numpy(), shp.numpy(), model_simple, "")
+        return s, inout_points.select_voxels(xs, nums, 1.0, codec=codec, dtype="uint8")
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    for _ in range(args.warmup):
+        device_step()
+    codec.profile(True); codec.profile_report()
+    l0 = codec.launch_count()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        device_step()
+    b.record(); torch.cuda.synchronize()
+    dev_ms = a.elapsed_time(b)
+    launches = codec.launch_count() - l0
+    prof = codec.profile_report(); codec.profile(False)
+    clocks = sampler.finish()
+    e2e_step()
+    runtime.COUNTERS["h2d_bytes"] = runtime.COUNTERS["d2h_bytes"] = 0
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(args.steps):
+        s, mask = e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    peaks = load_peaks()
+    prof.sort(key=lambda r: -r["ms"])
+    total_ms = sum(r["ms"] for r in prof)
+    top = prof[0]
+    ach = top["flops"] / (top["ms"] * 1e-3) / 1e12 if top["flops"] else 0.0
+    GF = 5.4169                      # SURVEY.md 8(d): factorized simple enc+dec GFLOP per cube
+    line = {
+        "metric": "factorized-mode encode+decode throughput of 64^3 cubes (model_simple)", "value": round(B * args.steps / (dev_ms / 1e3), 2), "unit": UNIT,
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "vox10 synthetic cloud, %d cubes of 64^3 (%d points), factorized mode, model_simple, rho=1.0, seeded synthetic weights"
+                               % (B, int(nums.sum())), "baseline_config": 2, "cubes_per_gpu": B},
+        "e2e": {"value": round(B * args.steps / (e2e_ms / 1e3), 2), "unit": UNIT, "h2d_bytes_per_step": runtime.COUNTERS["h2d_bytes"] // args.steps,
+                "d2h_bytes_per_step": runtime.COUNTERS["d2h_bytes"] // args.steps, "string_bytes": len(s.numpy())},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"kernel": top["tag"], "bound": "tensor", "achieved": round(ach, 3), "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": round(ach / peaks["bf16_tflops_sustained"], 5), "traffic": None, "share_of_step": round(top["ms"] / total_ms, 4),
+                     "note": "model_simple's k9 / k5 stride-2 layers run on the exact-FP32 CUDA-core engine (conv_ffma.cu), not on tcgen05"},
+        "conv": {"achieved_tflops": round(GF * B * args.steps / (dev_ms / 1e3) / 1e3, 2), "algorithmic_gflop_per_cube": GF},
+        "kernels": [{"tag": r["tag"], "share": round(r["ms"] / total_ms, 4)} for r in prof[:8]], "cpu_baseline": None,
+    }
+    print(json.dumps(line))
+
+
+def run_sweep(args):
+    """BASELINE config 4: analysis + synthesis only, batch 8..512 cubes of 64^3, steady state, CUDA events."""
+    import torch
+    from pcgcv1_b200 import runtime, synthetic
+    torch.cuda.set_device(0)
+    codec = runtime.get_codec("voxception", "", 0)
+    base, _ = synthetic.surface_cubes(8, seed=3)
+    peaks = load_peaks()
+    GF = 20.7996                     # SURVEY.md 8(d): analysis + synthesis GFLOP per cube
+    sweep = {}
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = codec.launch_count()
+    for B in (8, 16, 32, 64, 128, 256, 512):
+        x = codec.to_device(np.tile(base, (B // 8, 1, 1, 1, 1)))
+        y = torch.round(codec.analysis(x))
+        for _ in range(5):
+            codec.analysis(x); codec.synthesis(y)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        it = max(args.steps, 20) if B <= 128 else max(args.steps // 2, 8)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(it):
+            codec.analysis(x); codec.synthesis(y)
+        b.record(); torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / it
+        sweep[str(B)] = {"ms": round(ms, 3), "cubes_per_s": round(B / ms * 1e3, 1), "tflops": round(B * GF / ms, 2),
+                         "frac_of_bf16_sustained": round(B * GF / ms / peaks["bf16_tflops_sustained"], 5)}
+        del x, y
+    clocks = sampler.finish()
+    best = sweep["64"]
+    line = {
+        "metric": "analysis+synthesis transform throughput of 64^3 cubes (batch sweep)", "value": best["cubes_per_s"], "unit": UNIT, "n_gpus": 1,
+        "steps": args.steps, "warmup": 5, "ms_per_step": best["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "random smooth-surface cubes of 64^3, analysis + synthesis of model_voxception only, batches 8..512 (value: batch 64)",
+                   "baseline_config": 4, "l2": "activations per batch >> 126 MB L2 for B >= 8"},
+        "sweep": sweep, "gpu_launches": int(codec.launch_count() - l0), "clocks": clocks,
+        "roofline": {"kernel": "analysis+synthesis (all conv kernels)", "bound": "tensor", "achieved": best["tflops"], "peak": peaks["bf16_tflops_sustained"],
+                     "unit": "TFLOP/s", "frac": best["frac_of_bf16_sustained"], "traffic": None},
+        "e2e": None, "cpu_baseline": None,
+    }
+    print(json.dumps(line))
 
 
 def run_reference(args):
@@ -378,13 +607,16 @@ def main():
     ap.add_argument("--cubes", type=int, default=None, help="limit the number of cubes (debug)")
     ap.add_argument("--cpu-cubes", type=int, default=6, help="cubes in the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4],
+                    help="BASELINE.json config: 1 vox10 hyper (default, the headline), 2 vox10 factorized + model_simple, "
+                         "3 vox12 cloud sharded over --gpus (strong scaling), 4 analysis+synthesis batch sweep")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     else:
         import __graft_entry__
         __graft_entry__.build()
-        run_gpu(args)
+        {1: run_gpu, 2: run_factorized, 3: run_sharded, 4: run_sweep}[args.config](args)
 
 
 if __name__ == "__main__":

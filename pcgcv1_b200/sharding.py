@@ -46,6 +46,14 @@ class LocalCodec:
         """-> uint8 occupancy masks [b,64,64,64,1] of the top int(rho*nums) voxels"""
         raise NotImplementedError
 
+    def decode_local_points(self, y_strings: Sequence[bytes], y_min, y_max, z_hat: np.ndarray, nums: np.ndarray, rho: float):
+        """-> (points int16 [n,3] in np.where order per cube, counts int32 [b]); default: from decode_local's masks."""
+        masks = np.asarray(self.decode_local(y_strings, y_min, y_max, z_hat, nums, rho))
+        pts = [np.argwhere((m[..., 0] if m.shape[-1] == 1 else m) > 0) for m in masks]
+        counts = np.array([len(p) for p in pts], np.int32)
+        width = masks.ndim - 1 - (1 if masks.shape[-1] == 1 else 0)
+        return (np.concatenate(pts).astype(np.int16) if pts else np.zeros((0, width), np.int16)), counts
+
 
 class GpuLocalCodec(LocalCodec):
     """The CUDA implementation: one ``runtime.Codec`` on this rank's GPU."""
@@ -60,10 +68,16 @@ class GpuLocalCodec(LocalCodec):
         self.sc = SymmetricConditional().bind(self.codec)
 
     def encode_local(self, cubes):
-        import torch
+        """The rank's slice through the SAME pipeline as transform.compress_hyper (chunked transforms, GPU range coder on the
+        coder stream), minus the hyper string: z is one global string (entropy_model.py:249-259) and is coded on rank 0."""
+        from . import transform
         c = self.codec
         if len(cubes) == 0:
             return {"y_strings": [], "y_min": np.zeros(0, np.int32), "y_max": np.zeros(0, np.int32), "z_hat": np.zeros((0, 8, 8, 8, 8), np.int16)}
+        if self.runtime.coder_mode() == "gpu":
+            strings, mm, z_all, _, _, _, _ = transform._compress_hyper_gpu_coder(c, self.eb, self.sc, cubes, False, code_z=False)
+            return {"y_strings": strings, "y_min": mm[:, 0].astype(np.int32), "y_max": mm[:, 1].astype(np.int32),
+                    "z_hat": self.runtime.to_host(z_all).astype(np.int16)}
         ys = c.analysis(c.to_device(cubes))
         z_hat, _, _, _ = c.factorized(self.eb._slot, c.hyper_encode(ys), want_p=False, want_bits=False)
         locs, scales = c.hyper_decode(z_hat, 1e-9)
@@ -78,17 +92,56 @@ class GpuLocalCodec(LocalCodec):
     def decode_z(self, z_string, z_min, z_max, z_shape):
         return self.eb.decompress(z_string, z_min, z_max, np.asarray(z_shape), z_shape[-1]).numpy().astype(np.int16)
 
-    def decode_local(self, y_strings, y_min, y_max, z_hat, nums, rho):
+    # ---- device-resident strings (the sharded fast path: the per-cube strings of a slice never become Python objects on the
+    # ranks; they move as ONE packed uint8 tensor, GPU -> GPU) -----------------------------------------------------------------
+    packed_exchange = True
+
+    def encode_local_packed(self, cubes):
+        """-> dict as encode_local with 'y_packed' (uint8 device tensor) + 'y_lens' (int64 [b]) instead of 'y_strings'."""
         import torch
+        from . import transform
         c = self.codec
-        if len(y_strings) == 0:
-            return np.zeros((0, 64, 64, 64, 1), np.uint8)
-        locs, scales = c.hyper_decode(c.to_device(z_hat.astype(np.float32)), 1e-9)
-        ys = self.sc.decompress_cubes(list(y_strings), locs, scales, y_min, y_max)
-        xs = c.synthesis(ys.reshape(len(y_strings), 16, 16, 16, 16))
+        if len(cubes) == 0:
+            return {"y_packed": torch.zeros(0, dtype=torch.uint8, device=c.dev), "y_lens": np.zeros(0, np.int64), "y_min": np.zeros(0, np.int32),
+                    "y_max": np.zeros(0, np.int32), "z_hat": np.zeros((0, 8, 8, 8, 8), np.int16)}
+        (packed, off), mm, z_all, _, _, _, _ = transform._compress_hyper_gpu_coder(c, self.eb, self.sc, cubes, False, code_z=False,
+                                                                                  strings_on_device=True)
+        return {"y_packed": packed, "y_lens": np.diff(off), "y_min": mm[:, 0].astype(np.int32), "y_max": mm[:, 1].astype(np.int32),
+                "z_hat": self.runtime.to_host(z_all).astype(np.int16)}
+
+    def _decode_masks_dev(self, y_strings, y_min, y_max, z_hat, nums, rho, uploaded=None):
+        """-> uint8 mask tensor [b,64,64,64,1] on the device (transform.decompress_hyper's pipeline + top-k).  ``uploaded`` =
+        (packed uint8 device tensor, offsets int64 device tensor [b+1]) when the strings are already in HBM."""
+        import torch
+        from . import transform
+        c = self.codec
+        b = len(y_min)
+        zd = c.to_device(np.ascontiguousarray(z_hat, dtype=np.float32))
+        if self.runtime.coder_mode() == "gpu":
+            xs = transform._decompress_hyper_gpu_coder(c, self.sc, None if uploaded is not None else list(y_strings), np.asarray(y_min),
+                                                       np.asarray(y_max), [1, 16, 16, 16, 16], lambda a, e: zd[a:e],
+                                                       transform._gpu_decode_chunks(b), uploaded=uploaded)
+        else:
+            locs, scales = c.hyper_decode(zd, 1e-9)
+            ys = self.sc.decompress_cubes(list(y_strings), locs, scales, y_min, y_max)
+            xs = c.synthesis(ys.reshape(b, 16, 16, 16, 16))
         ks = np.array([int(rho * np.array(n)) for n in nums], np.int32)
         mask, _, _ = c.topk(xs, c.to_device(ks))
-        return self.runtime.to_host(mask, "mask").copy()
+        return mask
+
+    def decode_local(self, y_strings, y_min, y_max, z_hat, nums, rho):
+        if len(y_strings) == 0:
+            return np.zeros((0, 64, 64, 64, 1), np.uint8)
+        return self.runtime.to_host(self._decode_masks_dev(y_strings, y_min, y_max, z_hat, nums, rho), "mask").copy()
+
+    def decode_local_points(self, y_strings, y_min, y_max, z_hat, nums, rho, uploaded=None):
+        """-> (points int16 [n,3], counts int32 [b]): the decoder's final product (voxels2points, inout_points.py:134-143) taken on
+        the device, 6 bytes per point instead of 256 KiB of mask per cube across PCIe and the host gather."""
+        if len(y_min) == 0:
+            return np.zeros((0, 3), np.int16), np.zeros(0, np.int32)
+        mask = self._decode_masks_dev(y_strings, y_min, y_max, z_hat, nums, rho, uploaded=uploaded)
+        cap = int(np.asarray(nums, np.int64).sum() * max(1.0, rho) * 1.25) + 1024
+        return self.codec.extract_points(mask, cap)
 
 
 def _dist():
@@ -96,11 +149,48 @@ def _dist():
     return dist
 
 
+def _packed_ok(local, group) -> bool:
+    """The packed GPU -> GPU exchange needs a CUDA local codec and, for more than one rank, an NCCL default group."""
+    dist = _dist()
+    if not getattr(local, "packed_exchange", False) or local.runtime.coder_mode() != "gpu":
+        return False
+    return dist.get_world_size(group) == 1 or dist.get_backend() == "nccl"
+
+
 def compress_sharded(cubes_local: np.ndarray, local: LocalCodec, group=None) -> Optional[dict]:
     """Every rank passes ITS slice (``shard_slices`` order).  Rank 0 returns the stream of the whole cloud
-    {'y_strings', 'y_min', 'y_max', 'y_shape', 'z_string', 'z_min', 'z_max', 'z_shape'}; other ranks None."""
+    {'y_strings', 'y_min', 'y_max', 'y_shape', 'z_string', 'z_min', 'z_max', 'z_shape'}; other ranks None.
+
+    With a GPU codec the per-cube strings of a slice stay packed in HBM and reach rank 0 as ONE uint8 tensor per rank (NCCL
+    send / recv on the default group; ``group`` carries the small host objects): the stream then also holds 'y_blob' (all
+    strings back to back, NumPy uint8) + 'y_lens', and 'y_strings' is a lazily sliced view of them."""
     dist = _dist()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if _packed_ok(local, group):
+        import torch
+        part = local.encode_local_packed(cubes_local)
+        packed = part.pop("y_packed")
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object(part, parts, dst=0, group=group)
+        if rank != 0:
+            if packed.numel():
+                dist.send(packed, dst=0)
+            return None
+        totals = [int(p["y_lens"].sum()) for p in parts]
+        dev_parts = [packed]
+        for r in range(1, world):
+            buf = torch.empty(totals[r], dtype=torch.uint8, device=packed.device)
+            if totals[r]:
+                dist.recv(buf, src=r)
+            dev_parts.append(buf)
+        allp = torch.cat(dev_parts) if world > 1 else packed
+        blob = local.runtime.to_host(allp, "stream_blob").copy() if allp.numel() else np.zeros(0, np.uint8)
+        lens = np.concatenate([p["y_lens"] for p in parts]).astype(np.int64)
+        z_hat = np.concatenate([p["z_hat"] for p in parts])
+        z_string, z_min, z_max = local.encode_z(z_hat)
+        return {"y_strings": BlobStrings(blob, lens), "y_blob": blob, "y_lens": lens, "y_min": np.concatenate([p["y_min"] for p in parts]),
+                "y_max": np.concatenate([p["y_max"] for p in parts]), "y_shape": np.array([1, 16, 16, 16, 16], np.int64),
+                "z_string": z_string, "z_min": z_min, "z_max": z_max, "z_shape": np.array(z_hat.shape, np.int32)}
     part = local.encode_local(cubes_local)
     parts = [None] * world if rank == 0 else None
     dist.gather_object(part, parts, dst=0, group=group)
@@ -114,11 +204,86 @@ def compress_sharded(cubes_local: np.ndarray, local: LocalCodec, group=None) -> 
             "z_string": z_string, "z_min": z_min, "z_max": z_max, "z_shape": np.array(z_hat.shape, np.int32)}
 
 
-def decompress_sharded(stream: Optional[dict], nums: Optional[np.ndarray], rho: float, local: LocalCodec, group=None) -> Optional[np.ndarray]:
+class BlobStrings:
+    """Read-only list of byte strings backed by one uint8 blob + lengths (7769 strings of 40 KB are sliced on demand)."""
+
+    def __init__(self, blob: np.ndarray, lens: np.ndarray):
+        self.blob, self.lens = blob, np.asarray(lens, np.int64)
+        self.off = np.zeros(len(self.lens) + 1, np.int64)
+        np.cumsum(self.lens, out=self.off[1:])
+
+    def __len__(self):
+        return len(self.lens)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        return self.blob[self.off[i]:self.off[i + 1]].tobytes()
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+
+def decompress_sharded(stream: Optional[dict], nums: Optional[np.ndarray], rho: float, local: LocalCodec, group=None, output: str = "masks"):
     """Rank 0 passes the stream (+ the per-cube point counts); every rank decodes its slice; rank 0 returns the
-    uint8 occupancy masks of all cubes in order."""
+    uint8 occupancy masks of all cubes in order (``output="masks"``) or ``(points int16 [n,3], counts int32 [B])``
+    (``output="points"``: what the decoder writes to the .ply; a few MB through the gather instead of 256 KiB per cube)."""
     dist = _dist()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if _packed_ok(local, group):
+        import torch
+        c = local.codec
+        pieces, up, off_all, slices = None, None, None, None
+        if rank == 0:
+            B = len(stream["y_min"])
+            z_hat = local.decode_z(stream["z_string"], stream["z_min"], stream["z_max"], stream["z_shape"])
+            if "y_blob" in stream:
+                blob, lens = stream["y_blob"], np.asarray(stream["y_lens"], np.int64)
+            else:
+                ys = list(stream["y_strings"])
+                lens = np.fromiter((len(x) for x in ys), np.int64, len(ys))
+                blob = np.frombuffer(b"".join(ys), np.uint8)
+            off_all = np.zeros(B + 1, np.int64)
+            np.cumsum(lens, out=off_all[1:])
+            slices = shard_slices(B, world)
+            pieces = [{"y_lens": lens[a:b], "y_min": stream["y_min"][a:b], "y_max": stream["y_max"][a:b], "z_hat": z_hat[a:b],
+                       "nums": np.asarray(nums)[a:b]} for a, b in slices]
+            up = c.to_device(blob) if len(blob) else torch.zeros(0, dtype=torch.uint8, device=c.dev)      # ONE H2D copy of the whole stream
+        mine = [None]
+        dist.scatter_object_list(mine, pieces, src=0, group=group)
+        m = mine[0]
+        total = int(m["y_lens"].sum())
+        if rank == 0:
+            torch.cuda.current_stream(c.dev).synchronize()
+            for r in range(1, world):
+                a, b = slices[r]
+                if off_all[b] > off_all[a]:
+                    dist.send(up[off_all[a]:off_all[b]].contiguous(), dst=r)
+            packed = up[:off_all[slices[0][1]]]
+        else:
+            packed = torch.empty(total, dtype=torch.uint8, device=c.dev)
+            if total:
+                dist.recv(packed, src=0)
+        off = np.zeros(len(m["y_lens"]) + 1, np.int64)
+        np.cumsum(m["y_lens"], out=off[1:])
+        uploaded = (packed if packed.numel() else torch.zeros(1, dtype=torch.uint8, device=c.dev), c.to_device(off))
+        if output == "points":
+            res = local.decode_local_points(None, m["y_min"], m["y_max"], m["z_hat"], m["nums"], rho, uploaded=uploaded)
+        else:
+            res = (local.runtime.to_host(local._decode_masks_dev(None, m["y_min"], m["y_max"], m["z_hat"], m["nums"], rho, uploaded=uploaded), "mask").copy()
+                   if len(m["y_min"]) else np.zeros((0, 64, 64, 64, 1), np.uint8))
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object(res, parts, dst=0, group=group)
+        if rank != 0:
+            return None
+        if output == "points":
+            return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+        return np.concatenate(parts)
     pieces = None
     if rank == 0:
         B = len(stream["y_strings"])
@@ -130,9 +295,14 @@ def decompress_sharded(stream: Optional[dict], nums: Optional[np.ndarray], rho: 
     mine = [None]
     dist.scatter_object_list(mine, pieces, src=0, group=group)
     m = mine[0]
-    mask = local.decode_local(m["y_strings"], m["y_min"], m["y_max"], m["z_hat"], m["nums"], rho)
-    masks = [None] * world if rank == 0 else None
-    dist.gather_object(mask, masks, dst=0, group=group)
+    if output == "points":
+        res = local.decode_local_points(m["y_strings"], m["y_min"], m["y_max"], m["z_hat"], m["nums"], rho)
+    else:
+        res = local.decode_local(m["y_strings"], m["y_min"], m["y_max"], m["z_hat"], m["nums"], rho)
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(res, parts, dst=0, group=group)
     if rank != 0:
         return None
-    return np.concatenate(masks)
+    if output == "points":
+        return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+    return np.concatenate(parts)

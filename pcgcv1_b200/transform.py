@@ -218,14 +218,14 @@ def encode_on_device(codec, entropy_bottleneck, cem, cubes, keep_side_info=False
     return iv_all, mm_all, z_hats, keep, packed, offsets, tails
 
 
-def _compress_hyper_gpu_coder(codec, entropy_bottleneck, cem, cubes, decompress):
+def _compress_hyper_gpu_coder(codec, entropy_bottleneck, cem, cubes, decompress, code_z=True, strings_on_device=False):
     """compress_hyper with the per-cube strings written ON THE GPU (csrc/gpu_coder.cu).  The chunks only enqueue kernels (no
     host synchronisation in the loop); the intervals land in one device buffer, ONE encoder launch codes the strings of all
     cubes but the last few (``_host_tail``) on the coder stream, and this thread range-codes the single hyper string z on the
     host meanwhile."""
     B = cubes.shape[0]
     side = codec.coder_stream()
-    tail = _host_tail(B)
+    tail = 0 if strings_on_device else _host_tail(B)
     Bg = B - tail
     codec.deferred_checks(True)
     try:
@@ -240,12 +240,21 @@ def _compress_hyper_gpu_coder(codec, entropy_bottleneck, cem, cubes, decompress)
             hdr_done.record(side)
         # the ONE hyper string (global range, entropy_model.py:249-259) is coded here on the host beside the GPU encoder
         z_all = torch.cat(z_hats) if len(z_hats) > 1 else z_hats[0]
-        sym, cdf, z_min, z_max = entropy_bottleneck.compress_begin(z_all)
+        z_string = z_min = z_max = None
+        if code_z:
+            sym, cdf, z_min, z_max = entropy_bottleneck.compress_begin(z_all)
         mm = runtime.to_host(mm_all).copy()                                 # the main stream is idle by now (compress_begin synchronised it)
-        z_string = entropy_bottleneck.compress_finish(sym, cdf)
+        if code_z:
+            z_string = entropy_bottleneck.compress_finish(sym, cdf)
         hdr_done.synchronize()
         off = off_h.numpy().copy()
         total = int(off[Bg])
+        if strings_on_device:
+            # sharded form: the strings stay packed in HBM (string i = packed[off[i]:off[i+1]]) and travel GPU -> GPU
+            side.synchronize()
+            codec.deferred_checks(False)
+            codec.synchronize()
+            return (packed[:total], off), mm, z_all, z_string, z_min, z_max, keep
         stage = runtime.pinned_buffer("enc_bytes", max(total, 1))[:total]
         with torch.cuda.stream(side):
             stage.copy_(packed[:total], non_blocking=True)

@@ -88,8 +88,9 @@ def _worker(rank, world, port, n_cubes, q):
         local = OracleLocalCodec()
         stream = sharding.compress_sharded(cubes[a:b], local)
         masks = sharding.decompress_sharded(stream, np.arange(n_cubes) if rank == 0 else None, 1.0, local)
+        points = sharding.decompress_sharded(stream, np.arange(n_cubes) if rank == 0 else None, 1.0, local, output="points")
         if rank == 0:
-            q.put((stream, masks))
+            q.put((stream, masks, points))
     finally:
         dist.destroy_process_group()
 
@@ -104,7 +105,7 @@ def test_world2_matches_single_process(n_cubes):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, n_cubes, q)) for r in range(2)]
     for p in procs:
         p.start()
-    stream, masks = q.get(timeout=120)
+    stream, masks, points = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -117,3 +118,7 @@ def test_world2_matches_single_process(n_cubes):
     assert stream["z_string"] == z_string and (stream["z_min"], stream["z_max"]) == (z_min, z_max)
     ref = local.decode_local(part["y_strings"], part["y_min"], part["y_max"], part["z_hat"], np.arange(n_cubes), 1.0)
     assert np.array_equal(masks, ref)
+    # output="points": the same voxels as coordinates, cube by cube in order
+    pts, counts = points
+    assert np.array_equal(counts, ref.reshape(n_cubes, -1).sum(1))
+    assert np.array_equal(pts, np.concatenate([np.argwhere(m > 0) for m in ref]).astype(np.int16))
