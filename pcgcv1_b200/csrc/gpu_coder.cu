@@ -64,6 +64,8 @@ range_encode_intervals_kernel(const uint32_t* __restrict__ iv, int B, int64_t E,
       const uint32_t t = bq - a;
       const bool renorm = t < 0x10000u;                                             // warp-uniform
       sm1 = renorm ? ((t << 16) | 0xFFFFu) : t;                                     // the size chain does not wait for the emission below
+      // (a straight-line predicated form of the block below -- one basic block per 32 symbols -- was measured slower: 4.48 vs
+      // 3.84 ms per string; the renormalisation happens for about one symbol in three and the branch skips ~15 instructions)
       if (renorm) {
         if (base < 0xFFFF0000u || carry) {
           if (have) emit((cache + carry) & 0xFFFF);
@@ -204,14 +206,13 @@ range_decode_rows_kernel(const uint8_t* __restrict__ packed, const int64_t* __re
       const uint32_t a = __reduce_max_sync(FULL, va);
       const uint32_t bm1 = min(__reduce_min_sync(FULL, vu), sm1);
       base += a;
-      sm1 = bm1 - a;
-      if (sm1 < 0x10000u) {
-        base <<= 16;
-        sm1 = (sm1 << 16) | 0xFFFFu;
-        value = (value << 16) | nxt;
-        ++r;
-        nxt = __shfl_sync(FULL, w0, r & 31);
-      }
+      const uint32_t t = bm1 - a;
+      const bool renorm = t < 0x10000u;                                             // warp-uniform; selects instead of a branch keep the
+      sm1 = renorm ? ((t << 16) | 0xFFFFu) : t;                                     // 32 symbols one basic block for the scheduler
+      base = renorm ? (base << 16) : base;
+      value = renorm ? ((value << 16) | nxt) : value;
+      r += renorm ? 1u : 0u;
+      nxt = __shfl_sync(FULL, w0, r & 31);
       if (lane == j) mine = s;
     }
     y_hat[(size_t)b * E + g * DEC_G + lane] = (float)(mine + min_v);
