@@ -237,6 +237,44 @@ int pcgc_range_decode_rows_batch_f32(const uint8_t* const* data, const int64_t* 
                                      const uint16_t* rows, const int64_t* row_offset, const int32_t* minmax,
                                      int precision, float* y_hat, int threads);
 
+/* ---- training step primitives (train_hyper.py:184-214, loss.py:8-33) -------------------------------
+ * Exact FP32 on CUDA cores, deterministic (fixed reduction orders, no atomics).  All pointers are DEVICE pointers, float32
+ * NDHWC activations, kernels in the Keras layouts ([k,k,k,Cin,Cout]; Conv3DTranspose [k,k,k,Cout,Cin]); nothing synchronises.
+ * pcgcv1_b200/training.py strings them into the reference's training graph (torch.autograd is only the tape). */
+/* y = act(conv(x) + bias): x [B,n,n,n,cin] -> out [B,m,m,m,cout], m = n/stride (conv) or n*stride (transposed); k odd, SAME. */
+int pcgc_train_conv_forward(pcgc_ctx* ctx, const float* x, int B, int n, int cin, int cout, int k, int stride, int transposed,
+                            const float* w_keras, const float* bias, int relu, float* out);
+/* dx [B,n,n,n,cin] from the output gradient g [B,m,m,m,cout] of the same layer (n = the layer's INPUT grid). */
+int pcgc_train_conv_dgrad(pcgc_ctx* ctx, const float* g, int B, int n, int cin, int cout, int k, int stride, int transposed,
+                          const float* w_keras, float* dx);
+/* dw (the layer's Keras layout) and db [cout] (NULL for use_bias=False layers) from the layer input x and g. */
+int pcgc_train_conv_wgrad(pcgc_ctx* ctx, const float* x, const float* g, int B, int n, int cin, int cout, int k, int stride,
+                          int transposed, float* dw, float* db);
+/* out = g where y > 0 else 0 (gradient through a fused ReLU; y = the layer output). */
+int pcgc_train_relu_backward(pcgc_ctx* ctx, const float* g, const float* y, int64_t n, float* out);
+/* _VoxceptionResNet merge (model_voxception.py:64-67): out = relu(x + concat[t12, t23]) over nvox voxels of c channels. */
+int pcgc_train_vrn_merge(pcgc_ctx* ctx, const float* x, const float* t12, const float* t23, int64_t nvox, int c, float* out);
+int pcgc_train_vrn_merge_backward(pcgc_ctx* ctx, const float* g, const float* out, int64_t nvox, int c, float* gx, float* g12, float* g23);
+/* scale = max(|s|, floor) (model_voxception.py:308, train_hyper.py:191) and its gradient. */
+int pcgc_train_abs_floor(pcgc_ctx* ctx, const float* s, int64_t n, float floor_v, float* out);
+int pcgc_train_abs_floor_backward(pcgc_ctx* ctx, const float* g, const float* s, int64_t n, float floor_v, float* out);
+/* Gradients of coef * sum(log max(likelihood, bound)) w.r.t. the (noisy) latents, loc and scale of the conditional model. */
+int pcgc_train_laplace_backward(pcgc_ctx* ctx, const float* y_t, const float* loc, const float* scale, int64_t n, float bound, float coef,
+                                float* gy, float* gloc, float* gscale);
+/* EntropyBottleneck(z, training=True) from the RAW variables (matrices / biases / factors concatenated in the pcgc_load_bottleneck
+ * order): z_t = z + U(-1/2, 1/2) (Philox, `seed`), logsum_dev double[1] = sum(log max(likelihood, bound)). */
+int pcgc_train_factorized_forward(pcgc_ctx* ctx, const float* matrices, const float* biases, const float* factors, int C, const float* z,
+                                  int64_t nvox, uint64_t seed, float bound, float* z_t, double* logsum_dev);
+/* The same for the EntropyBottleneck on z_t [nvox, C], with the gradients of its RAW variables (the pcgc_load_bottleneck order). */
+int pcgc_train_factorized_backward(pcgc_ctx* ctx, const float* matrices, const float* biases, const float* factors, int C, const float* z_t,
+                                   int64_t nvox, float bound, float coef, float* gz, float* gmatrices, float* gbiases, float* gfactors);
+/* get_bce_loss (loss.py:8-33): sums_dev double[4] = {sum_empty -log(1-occ), sum_full -log(occ), #empty, #full}. */
+int pcgc_train_bce(pcgc_ctx* ctx, const float* logits, const uint8_t* label, int64_t n, double* sums_dev);
+int pcgc_train_bce_backward(pcgc_ctx* ctx, const float* logits, const uint8_t* label, int64_t n, const double* sums_dev, float w_empty,
+                            float w_full, float* g);
+/* tf.train.AdamOptimizer update with the bias-corrected step lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t). */
+int pcgc_train_adam(pcgc_ctx* ctx, float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2, float eps);
+
 /* ---- point-cloud I/O either side of the codec ----------------------- */
 /* Multithreaded memcpy of a large host buffer (a pinned staging buffer -> the NumPy array handed to the caller; first-touch
  * page faults of the fresh destination are spread over the threads).  No reference counterpart: plumbing of this build. */

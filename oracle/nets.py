@@ -33,7 +33,9 @@ def _same_pads(n: int, k: int, s: int) -> Tuple[int, int]:
     return before, total - before
 
 
-def _t(a: np.ndarray, dtype) -> torch.Tensor:
+def _t(a, dtype) -> torch.Tensor:
+    if isinstance(a, torch.Tensor):                      # training oracle: weights are leaf tensors that require grad
+        return a.to(dtype)
     return torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
 
 

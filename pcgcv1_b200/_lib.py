@@ -68,6 +68,20 @@ SIGNATURES = {
     "pcgc_range_decode_rows_dev": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, C.c_double, _vp, _i, _i, _vp]),
     "pcgc_host_laplace_cdf": (_i, [_vp, _vp, _i, _i64, _vp, _f, _i, _vp, _vp, _i]),
     "pcgc_factorized_cdf_host": (_i, [_vp, _i, _i, _i, _f, _i, _vp]),
+    "pcgc_train_conv_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "pcgc_train_conv_dgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "pcgc_train_conv_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "pcgc_train_relu_backward": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "pcgc_train_vrn_merge": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
+    "pcgc_train_vrn_merge_backward": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp]),
+    "pcgc_train_abs_floor": (_i, [_vp, _vp, _i64, _f, _vp]),
+    "pcgc_train_abs_floor_backward": (_i, [_vp, _vp, _vp, _i64, _f, _vp]),
+    "pcgc_train_laplace_backward": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _vp, _vp, _vp]),
+    "pcgc_train_factorized_forward": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i64, C.c_uint64, _f, _vp, _vp]),
+    "pcgc_train_factorized_backward": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i64, _f, _f, _vp, _vp, _vp, _vp]),
+    "pcgc_train_bce": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "pcgc_train_bce_backward": (_i, [_vp, _vp, _vp, _i64, _vp, _f, _f, _vp]),
+    "pcgc_train_adam": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f]),
     "pcgc_host_copy": (_i, [_vp, _vp, _i64, _i]),
     "pcgc_ply_parse": (_i, [_vp, _i64, _vp, _i64, _vp, _i]),
     "pcgc_ply_format": (_i, [_vp, _i64, _vp, _i64, _vp, _i]),

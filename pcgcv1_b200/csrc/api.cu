@@ -191,6 +191,8 @@ struct pcgc_ctx {
   Net nets[PCGC_NET_COUNT];
   BottleneckDev bn[2];
   std::vector<float> bn_host[2];    // packed parameters (44 per channel) for the host twin of the pmf (pcgc_factorized_cdf_host)
+  float* train_ws[4] = {nullptr, nullptr, nullptr, nullptr};   // train.cu: packed weights / wgrad partials / reductions
+  size_t train_cap[4] = {0, 0, 0, 0};
   bool deferred_checks = false;     // pcgc_set_deferred_checks
   int quant_noise = 0;              // pcgc_set_quantize_mode: 0 = "symbols" (round), 1 = "noise" (training)
   uint64_t quant_seed = 0;
@@ -693,6 +695,27 @@ int run_net(pcgc_ctx* ctx, int kind, const float* in_ext, const void* cubes, int
 
 }  // namespace
 
+// ---- accessors for train.cu (the ctx layout stays private to this file) ----
+namespace pcgc {
+cudaStream_t ctx_stream(pcgc_ctx* c) { return c->stream; }
+int64_t* ctx_launches(pcgc_ctx* c) { return &c->launches; }
+int ctx_device(pcgc_ctx* c) { return c->device; }
+int* ctx_err_flag(pcgc_ctx* c) { return c->err_flag; }
+int ctx_fail(pcgc_ctx* c, int code, const char* msg) { return fail(c, code, "%s", msg); }
+float* ctx_workspace(pcgc_ctx* c, int slot, size_t floats) {
+  if (slot < 0 || slot > 3) return nullptr;
+  if (c->train_cap[slot] < floats) {
+    if (c->train_ws[slot]) { cudaStreamSynchronize(c->stream); cudaFree(c->train_ws[slot]); c->train_ws[slot] = nullptr; c->train_cap[slot] = 0; }
+    const size_t want = floats + floats / 4 + 1024;
+    if (cudaMalloc((void**)&c->train_ws[slot], want * sizeof(float)) != cudaSuccess) return nullptr;
+    c->train_cap[slot] = want;
+  }
+  return c->train_ws[slot];
+}
+void ctx_prof_begin(pcgc_ctx* c, const char* tag, double flops, double bytes) { prof_begin(c, tag, flops, bytes); }
+void ctx_prof_end(pcgc_ctx* c) { prof_end(c); }
+}  // namespace pcgc
+
 extern "C" {
 
 int pcgc_create(pcgc_ctx** out, int device) {
@@ -746,6 +769,7 @@ void pcgc_destroy(pcgc_ctx* ctx) {
   if (ctx->mm_dev) cudaFree(ctx->mm_dev);
   if (ctx->off_dev) cudaFree(ctx->off_dev);
   if (ctx->chunk_dev) cudaFree(ctx->chunk_dev);
+  for (auto p : ctx->train_ws) if (p) cudaFree(p);
   for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   delete ctx;

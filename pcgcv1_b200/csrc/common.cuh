@@ -84,6 +84,16 @@ cudaError_t launch_laplace_cdf(const float* loc, const float* scale, int B, int6
                                int* err_flag, cudaStream_t s, int64_t* launches);
 cudaError_t launch_debug_quantize_pmf(const float* pmf, int64_t rows, const int32_t* minmax_dev, int precision,
                                       int32_t* cdf32, int* err_flag, cudaStream_t s, int64_t* launches);
+// api.cu: what train.cu may touch of a ctx
+cudaStream_t ctx_stream(pcgc_ctx* c);
+int64_t* ctx_launches(pcgc_ctx* c);
+int ctx_device(pcgc_ctx* c);
+int* ctx_err_flag(pcgc_ctx* c);
+int ctx_fail(pcgc_ctx* c, int code, const char* msg);
+float* ctx_workspace(pcgc_ctx* c, int slot, size_t floats);
+void ctx_prof_begin(pcgc_ctx* c, const char* tag, double flops, double bytes);
+void ctx_prof_end(pcgc_ctx* c);
+
 // gpu_coder.cu
 cudaError_t launch_range_encode_intervals(const uint32_t* iv, int B, int64_t E, int precision, uint8_t* scratch, int64_t stride,
                                           int64_t* lens, uint8_t* packed, int64_t cap, int64_t* offsets, int* err,
