@@ -566,6 +566,91 @@ def run_sweep(args):
     print(json.dumps(line))
 
 
+def run_train(args):
+    """BASELINE config 5: train_hyper.py step (alpha = 0.75, beta = 3, gamma = delta = 1, lr = 1e-5, batch 8 cubes of 64^3, BCE
+    occupancy loss, noise quantisation), forward + backward + Adam.  N > 1: data parallel, one batch of 8 per GPU, gradients
+    averaged with one NCCL all-reduce (weak scaling)."""
+    import torch
+    import torch.distributed as dist
+    from pcgcv1_b200 import runtime, synthetic, training
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    codec = runtime.get_codec("voxception", "", local)
+    B = 8
+    cubes, _ = synthetic.surface_cubes(B, seed=100 + rank)
+    tr = training.HyperTrainer(codec, alpha=0.75, beta=3.0, gamma=1.0, delta=1.0, lr=1e-5)
+    pinned = torch.from_numpy(cubes).pin_memory()
+    xd = pinned.to(codec.dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    for i in range(max(args.warmup, 3)):
+        tr.train_step(xd, seed=i)
+    codec.profile(True); codec.profile_report()
+    l0 = codec.launch_count()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(args.steps):
+        out = tr.train_step(xd, seed=1000 + i)
+    b.record()
+    barrier()
+    dev_ms = a.elapsed_time(b)
+    launches = codec.launch_count() - l0
+    prof = codec.profile_report(); codec.profile(False)
+    clocks = sampler.finish()
+    terms = tr.loss_terms(out)
+    # end to end: the batch comes from pinned host memory every step and the loss terms go back to the host
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        out = tr.train_step(pinned, seed=2000 + i)
+        terms = tr.loss_terms(out)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=codec.dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        peaks = load_peaks()
+        GF = 3 * 21.217                                   # SURVEY.md 8(d): fwd 21.217 GFLOP per cube, bwd ~ 2x fwd
+        prof.sort(key=lambda r: -r["ms"])
+        total_ms = sum(r["ms"] for r in prof) or 1.0
+        steps_s = world * args.steps / (dev_ms / 1e3)
+        tfl = GF * B * steps_s / 1e3
+        line = {
+            "metric": "train_hyper.py step throughput (forward + backward + Adam)", "value": round(steps_s * B, 2), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(dev_ms / args.steps, 2), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "train_hyper.py step: batch 8 cubes of 64^3 per GPU, alpha=0.75 beta=3 gamma=delta=1, lr=1e-5, BCE occupancy loss, "
+                                   "noise quantisation (seeded Philox), random smooth-surface cubes, seeded synthetic weights",
+                       "baseline_config": 5, "batch_per_gpu": B, "engine": "exact FP32 CUDA cores (conv_ffma.cu + train.cu), deterministic"},
+            "steps_per_s": round(steps_s, 3),
+            "e2e": {"value": round(world * args.steps * B / (e2e_ms / 1e3), 2), "unit": UNIT, "h2d_bytes_per_step": int(pinned.numel()),
+                    "d2h_bytes_per_step": 48, "note": "batch from pinned host memory, loss terms read back every step"},
+            "gpu_launches": int(launches) * world, "clocks": clocks, "loss_terms_last_step": terms,
+            "roofline": {"kernel": prof[0]["tag"], "bound": "tensor", "achieved": round(tfl, 2), "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": round(tfl / peaks["bf16_tflops_sustained"], 5), "traffic": None,
+                         "note": "whole step on algorithmic FLOPs (3 x forward); the training path runs on FP32 CUDA cores, not on tcgen05"},
+            "kernels": [{"tag": r["tag"], "share": round(r["ms"] / total_ms, 4), "ms_per_step": round(r["ms"] / args.steps, 2)} for r in prof[:6]],
+            "cpu_baseline": None,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     """Reference arm: the reference's own CPU path.  TF 1.13 cannot be installed offline, so this is the
     oracle port driven exactly as transform.py drives TF (one cube per call), all host threads."""
@@ -607,16 +692,16 @@ def main():
     ap.add_argument("--cubes", type=int, default=None, help="limit the number of cubes (debug)")
     ap.add_argument("--cpu-cubes", type=int, default=6, help="cubes in the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4],
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4, 5],
                     help="BASELINE.json config: 1 vox10 hyper (default, the headline), 2 vox10 factorized + model_simple, "
-                         "3 vox12 cloud sharded over --gpus (strong scaling), 4 analysis+synthesis batch sweep")
+                         "3 vox12 cloud sharded over --gpus (strong scaling), 4 analysis+synthesis batch sweep, 5 training step (batch 8)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     else:
         import __graft_entry__
         __graft_entry__.build()
-        {1: run_gpu, 2: run_factorized, 3: run_sharded, 4: run_sweep}[args.config](args)
+        {1: run_gpu, 2: run_factorized, 3: run_sharded, 4: run_sweep, 5: run_train}[args.config](args)
 
 
 if __name__ == "__main__":
