@@ -152,6 +152,23 @@ def device_step(codec, st):
     return mask, cnt
 
 
+def device_step_transforms(codec, st):
+    """The r01 definition of ``value`` for comparison across rounds: every transform / entropy-model / top-k kernel of encode +
+    decode, WITHOUT the range coder (r01 ran it on the host, outside ``value``)."""
+    B = st["B"]
+    y = codec.analysis(st["cubes"])
+    z = codec.hyper_encode(y)
+    z_hat, _, _, _ = codec.factorized(0, z, want_p=True, want_bits=True)
+    loc, scale = codec.hyper_decode(z_hat, 1e-9)
+    y2, l2, s2 = y.reshape(B, -1), loc.reshape(B, -1), scale.reshape(B, -1)
+    y_hat, _, _, mm = codec.laplace(y2, l2, s2, want_p=True, want_bits=True)
+    codec.laplace_intervals(y_hat, l2, s2, mm)
+    loc_d, scale_d = codec.hyper_decode(z_hat, 1e-9)
+    codec.laplace_cdf(loc_d.reshape(B, -1), scale_d.reshape(B, -1), st["minmax_host"])
+    logits = codec.synthesis(y_hat.reshape(y.shape))
+    return codec.topk(logits, st["ks"])
+
+
 def torch_cat(parts):
     import torch
     return torch.cat(parts) if len(parts) > 1 else parts[0]
@@ -198,6 +215,7 @@ def run_gpu(args):
     codec.synchronize()
     mm = mm_all.cpu().numpy()
     st["mins"], st["maxs"] = mm[:, 0].copy(), mm[:, 1].copy()
+    st["minmax_host"] = mm
     st["packed"], st["offsets"] = packed, offsets
 
     def barrier():
@@ -237,6 +255,9 @@ def run_gpu(args):
     prof = codec.profile_report()
     codec.profile(False)
     clocks = sampler.finish()
+    # the same kernels without the range coder (the r01 definition of value, for comparison across rounds)
+    nocoder_steps = max(3, args.steps // 2)
+    nocoder_ms, _ = timed(lambda: device_step_transforms(codec, st), nocoder_steps, 1)
     # ---- end to end through the public API with host buffers ----
     runtime.COUNTERS["h2d_bytes"] = runtime.COUNTERS["d2h_bytes"] = 0
     e2e_steps = args.steps
@@ -337,6 +358,9 @@ def run_gpu(args):
                                "dtype=uint8): top-k on the GPU, uint8 masks to the host (the reference does .numpy() then NumPy top-k, test.py:115)",
                    "conv_engine": os.environ.get("PCGC_ENGINE", "auto")},
         "points_per_s": round(value * points / B, 1),
+        "value_without_range_coder": {"value": round(world * B * nocoder_steps / (nocoder_ms / 1e3), 2), "unit": UNIT, "steps": nocoder_steps,
+                                      "note": "r01's definition of value (range coder on the host, outside the timed kernels); `value` above "
+                                              "includes the GPU range-coder kernels on the coder streams"},
         "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "points_per_s": round(e2e * points / B, 1), "steps": e2e_steps, "host_threads": runtime.coder_threads()},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,

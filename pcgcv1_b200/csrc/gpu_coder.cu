@@ -12,6 +12,7 @@
 //           tests size*cdf[k] <= offset; a ballot gives the symbol without a division or a serial scan.  Rows stream
 //           through a double-buffered shared-memory window (cp.async), the next 16-bit word of the string is prefetched.
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "range_coder.h"
@@ -132,13 +133,15 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
 // Nothing inside the 32-symbol loop touches memory: the lane's CDF entries are read into registers first, the next 16-bit
 // words of the string are prefetched one per lane and handed out by shuffles.
 template <bool WIDE>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(256)
 range_decode_rows_kernel(const uint8_t* __restrict__ packed, const int64_t* __restrict__ offsets, int B, int64_t E,
                          const uint16_t* __restrict__ rows, const int64_t* __restrict__ row_offset,
                          const int32_t* __restrict__ minmax, float* __restrict__ y_hat, int* __restrict__ err, int win_elems) {
-  extern __shared__ __align__(16) uint16_t s_rows[];              // [2][win_elems], win_elems >= DEC_G * max N of the launch
+  extern __shared__ __align__(16) uint16_t s_rows_all[];          // [cubes per block][2][win_elems], win_elems >= DEC_G * max N of the launch
   const int lane = threadIdx.x;
-  const int b = blockIdx.x;
+  const int b = blockIdx.x * blockDim.y + threadIdx.y;            // blockDim = (32, cubes per block): one warp per cube
+  if (b >= B) return;
+  uint16_t* const s_rows = s_rows_all + (size_t)threadIdx.y * 2 * win_elems;
   const unsigned FULL = 0xffffffffu;
   const int min_v = minmax[2 * b], N = minmax[2 * b + 1] - min_v + 1;
   if (N < 1 || N > (WIDE ? DEC_MAXN : 32) || DEC_G * N > win_elems) { if (lane == 0) atomicExch(err, PCGC_ERR_BAD_RANGE); return; }
@@ -252,13 +255,16 @@ cudaError_t launch_range_decode_rows(const uint8_t* packed, const int64_t* offse
   if (B <= 0) return cudaSuccess;
   if (E % DEC_G || max_n < 1 || max_n > DEC_MAXN || precision != 16) return cudaErrorInvalidValue;
   const int win_elems = DEC_G * ((max_n + 7) / 8 * 8);              // 16-byte multiple per window
-  const size_t smem = (size_t)2 * win_elems * sizeof(uint16_t);
+  // cubes (= warps) per block.  1 spreads the decoder warps over all SMs; more packs them onto few SMs (experiments: PCGC_DEC_CPB)
+  static const int cpb = [] { const char* e = getenv("PCGC_DEC_CPB"); const int v = e ? atoi(e) : 1; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
+  const size_t smem = (size_t)cpb * 2 * win_elems * sizeof(uint16_t);
   PCGC_CARVEOUT_ONCE(range_decode_rows_kernel<true>);
   PCGC_CARVEOUT_ONCE(range_decode_rows_kernel<false>);
+  const dim3 block(32, cpb), grid((B + cpb - 1) / cpb);
   if (max_n > 32)
-    range_decode_rows_kernel<true><<<B, 32, smem, s>>>(packed, offsets, B, E, rows, row_offset, minmax, y_hat, err, win_elems);
+    range_decode_rows_kernel<true><<<grid, block, smem, s>>>(packed, offsets, B, E, rows, row_offset, minmax, y_hat, err, win_elems);
   else
-    range_decode_rows_kernel<false><<<B, 32, smem, s>>>(packed, offsets, B, E, rows, row_offset, minmax, y_hat, err, win_elems);
+    range_decode_rows_kernel<false><<<grid, block, smem, s>>>(packed, offsets, B, E, rows, row_offset, minmax, y_hat, err, win_elems);
   if (launches) ++*launches;
   return cudaGetLastError();
 }

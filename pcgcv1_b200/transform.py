@@ -110,7 +110,7 @@ def _gpu_decode_chunks(B):
     """Chunks of the GPU-coder decode pipeline.  The range decoder's latency is one cube's string (a few ms) whatever the number
     of cubes in the launch, so: one small first chunk (its decode is exposed), then large ones whose decode hides behind the
     synthesis of the chunk before (a chunk's CDF rows take ~2.5 MB per cube of device memory)."""
-    first = int(os.environ.get("PCGC_DEC_FIRST", "48"))
+    first = int(os.environ.get("PCGC_DEC_FIRST", "64"))
     rest = int(os.environ.get("PCGC_DEC_CHUNK", "512"))
     if B <= max(first, 64):
         return [(0, B)]
@@ -351,7 +351,7 @@ def _decompress_hyper_gpu_coder(codec, cem, strings, mins, maxs, y_shape, z_get,
     """decompress_hyper with the per-cube strings read ON THE GPU: the strings go up once (a few KB per cube), CDF rows are
     built and consumed on the device.  Chunk k+1 is decoded on the coder stream while chunk k is synthesised."""
     dev = codec.dev
-    main, side = torch.cuda.current_stream(dev), codec.coder_stream(1)
+    main = torch.cuda.current_stream(dev)
     packed, offsets = uploaded if uploaded is not None else codec.upload_strings(strings)
     xs_parts, pending = [], None
     codec.deferred_checks(True)
@@ -361,7 +361,10 @@ def _decompress_hyper_gpu_coder(codec, cem, strings, mins, maxs, y_shape, z_get,
             main.wait_event(done)
             xs_parts.append(codec.synthesis(y_hat.reshape([b - a] + y_shape[1:])))
 
-        for a, b in chunks:
+        for k, (a, b) in enumerate(chunks):
+            # every chunk decodes on its own stream (round robin over 3): the decoder of chunk k+1 must not queue behind the
+            # decoder of chunk k -- both are latency-bound single-warp-per-cube kernels that run side by side
+            side = codec.coder_stream(1 + k % 3)
             locs, scales = codec.hyper_decode(z_get(a, b), 1e-9)
             ready = torch.cuda.Event()
             ready.record(main)
