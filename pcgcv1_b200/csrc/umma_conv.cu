@@ -1271,6 +1271,11 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
     static const int ctas_env = getenv("PCGC_STREAM_CTAS") ? atoi(getenv("PCGC_STREAM_CTAS")) : 1;
     a.zs = std::min(n, std::max(1, zs_env));
     while (n % a.zs) --a.zs;
+    // small grids (16^3: deconv_in, the hyper nets): a 16-slice segment leaves 2 segments per cube -- fewer than the 148 persistent
+    // CTAs at 64 cubes per launch.  Shorter segments re-read two halo slices each but fill the machine (r02: deconv_in ran at
+    // 16 TFLOP/s where the same kernel reaches 100+ on the larger grids).
+    if (!getenv("PCGC_STREAM_ZS"))
+      while (a.zs > 4 && (n / TILE_X) * (n / (TILE_Y * w.wt)) * (n / a.zs) * c.in.B < 2 * sm_count && n % (a.zs / 2) == 0) a.zs /= 2;
     a.slice_plane = brick_ey(w.wt) * EXC * CELL;
     a.slot_bytes = a.ppc * a.slice_plane;
     const int per_sm = 1;
