@@ -136,6 +136,10 @@ int pcgc_factorized_cdf(pcgc_ctx* ctx, int slot, int min_v, int max_v, float lik
 int pcgc_laplace_quantize_likelihood(pcgc_ctx* ctx, const float* y_dev, const float* loc_dev,
                                      const float* scale_dev, int B, int64_t E, float likelihood_bound,
                                      float* y_hat_dev, float* p_dev, double* bits_dev, int32_t* minmax_dev);
+/* Makes per-cube symbol ranges codable and storable before the tables are built: min_v <- min(min_v, 0), max_v <- max(max_v, 0)
+ * (the container packs max*16 - min with min <= 0 <= max, dataprocess/inout_bitstream.py:95-96) and max_v <- 1 for the
+ * one-symbol range {0} (pmf_to_quantized_cdf needs two symbols, entropy_model.py:192-193).  minmax_dev int32[2*n_pairs]. */
+int pcgc_widen_symbol_ranges(pcgc_ctx* ctx, int32_t* minmax_dev, int n_pairs);
 /* Encoder side of SymmetricConditional._get_cdf + range_encode's table lookup (:95-124,142-161):
  * for every element builds its quantised CDF row over min_v[b]..max_v[b] and emits only the
  * interval of the element's own symbol: interval = lower | (upper-lower-1) << 16.

@@ -46,6 +46,7 @@ SIGNATURES = {
     "pcgc_factorized_quantize_likelihood": (_i, [_vp, _i, _vp, _i64, _i, _f, _vp, _vp, _vp, _vp]),
     "pcgc_factorized_cdf": (_i, [_vp, _i, _i, _i, _f, _i, _vp]),
     "pcgc_laplace_quantize_likelihood": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _f, _vp, _vp, _vp, _vp]),
+    "pcgc_widen_symbol_ranges": (_i, [_vp, _vp, _i]),
     "pcgc_laplace_intervals": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _vp, _f, _i, _vp]),
     "pcgc_laplace_cdf": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _f, _i, _vp, _vp]),
     "pcgc_debug_quantize_pmf": (_i, [_vp, _vp, _i64, _i, _i, _vp]),

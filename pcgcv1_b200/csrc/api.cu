@@ -1193,6 +1193,13 @@ int pcgc_extract_points(pcgc_ctx* ctx, const uint8_t* mask_dev, int B, int S, in
   return PCGC_OK;
 }
 
+int pcgc_widen_symbol_ranges(pcgc_ctx* ctx, int32_t* minmax_dev, int n_pairs) {
+  if (!ctx || !minmax_dev || n_pairs < 0) return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_widen_symbol_ranges: bad argument");
+  DeviceGuard g(ctx->device);
+  CK(launch_widen_minmax(minmax_dev, n_pairs, ctx->stream, &ctx->launches));
+  return PCGC_OK;
+}
+
 int pcgc_set_deferred_checks(pcgc_ctx* ctx, int on) {
   if (!ctx) return PCGC_ERR_BAD_ARG;
   ctx->deferred_checks = on != 0;

@@ -76,6 +76,7 @@ cudaError_t launch_factorized_pmf(const BottleneckDev& bn, int min_v, int max_v,
 cudaError_t launch_laplace(const float* y, const float* loc, const float* scale, int B, int64_t E, float bound,
                            float* y_hat, float* p, double* bits, int32_t* minmax, double* scratch,
                            cudaStream_t s, int64_t* launches, int noise = 0, uint64_t seed = 0);
+cudaError_t launch_widen_minmax(int32_t* minmax, int n_pairs, cudaStream_t s, int64_t* launches);
 cudaError_t launch_laplace_intervals(const float* y_hat, const float* loc, const float* scale, int B, int64_t E,
                                      const int32_t* minmax, float bound, int precision, uint32_t* intervals,
                                      int* err_flag, cudaStream_t s, int64_t* launches);

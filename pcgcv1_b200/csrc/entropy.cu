@@ -29,6 +29,24 @@ __global__ void init_minmax_kernel(int32_t* mm, int n_pairs) {
   if (i < n_pairs) { mm[2 * i] = INT_MAX; mm[2 * i + 1] = INT_MIN; }
 }
 
+// Per-cube symbol ranges made codable and storable: the range gets 0 inside it (the .strings_head byte packs max*16 - min with
+// min <= 0 <= max, inout_bitstream.py:95-96) and at least two symbols (pmf_to_quantized_cdf rejects a one-symbol alphabet,
+// entropy_model.py:192-193).  The decoder builds its tables from the header's (min, max) alone, so the stream stays readable.
+__global__ void widen_minmax_kernel(int32_t* mm, int n_pairs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pairs) return;
+  int lo = min(mm[2 * i], 0), hi = max(mm[2 * i + 1], 0);
+  if (lo == hi) hi = 1;
+  mm[2 * i] = lo; mm[2 * i + 1] = hi;
+}
+
+cudaError_t launch_widen_minmax(int32_t* minmax, int n_pairs, cudaStream_t s, int64_t* launches) {
+  if (n_pairs <= 0) return cudaSuccess;
+  widen_minmax_kernel<<<(n_pairs + 127) / 128, 128, 0, s>>>(minmax, n_pairs);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
 struct BlockStats { double bits; int mn, mx; };
 
 template <int THREADS>

@@ -14,6 +14,14 @@ import torch
 from .. import runtime
 
 
+# Per-cube symbol ranges are widened to contain 0 and at least two symbols before coding (pcgc_widen_symbol_ranges): a cube whose
+# latents are all zero, or all on one side of zero, would otherwise abort the whole cloud after all GPU work (one-symbol alphabet
+# / a range the container's header byte cannot hold; the reference has the same limitation).  The ranges the reference would
+# produce are unchanged whenever they already straddle zero with two symbols, i.e. for every cube seen in the test workloads.
+# PCGC_WIDEN_RANGES=0 restores the reference's exact (min, max).
+WIDEN_RANGES = bool(int(__import__("os").environ.get("PCGC_WIDEN_RANGES", "1")))
+
+
 class SymmetricConditional:
     def __init__(self, likelihood_bound=1e-9, range_coder_precision=16, codec=None):
         self._likelihood_bound = float(likelihood_bound)
@@ -82,6 +90,8 @@ class SymmetricConditional:
         B = ys.shape[0]
         y2, l2, s2 = ys.reshape(B, -1), locs.reshape(B, -1), scales.reshape(B, -1)
         y_hat, _, _, mm = c.laplace(y2, l2, s2, self._likelihood_bound, want_p=False, want_bits=False)
+        if WIDEN_RANGES:
+            c.widen_symbol_ranges(mm)
         iv = c.laplace_intervals(y_hat, l2, s2, mm, self._likelihood_bound)
         mm_h = runtime.to_host(mm)
         if runtime.coder_mode() == "gpu" and B > 0:
@@ -101,6 +111,8 @@ class SymmetricConditional:
         B = ys.shape[0]
         y2, l2, s2 = ys.reshape(B, -1), locs.reshape(B, -1), scales.reshape(B, -1)
         y_hat, _, _, mm = c.laplace(y2, l2, s2, self._likelihood_bound, want_p=False, want_bits=False)
+        if WIDEN_RANGES:
+            c.widen_symbol_ranges(mm)
         iv = c.laplace_intervals(y_hat, l2, s2, mm, self._likelihood_bound)
         stage, done = runtime.to_host_async(iv, "intervals%d" % slot)
         return stage, done, runtime.to_host(mm)
@@ -134,6 +146,8 @@ class SymmetricConditional:
         B = ys.shape[0]
         y2, l2, s2 = ys.reshape(B, -1), locs.reshape(B, -1), scales.reshape(B, -1)
         y_hat, _, _, mm = c.laplace(y2, l2, s2, self._likelihood_bound, want_p=want_likelihoods, want_bits=want_likelihoods)
+        if WIDEN_RANGES:
+            c.widen_symbol_ranges(mm)
         iv = c.laplace_intervals(y_hat, l2, s2, mm, self._likelihood_bound, out=iv_out)
         return iv, mm
 

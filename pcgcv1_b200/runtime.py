@@ -370,6 +370,13 @@ class Codec:
             p.data_ptr() if want_p else None, bits.data_ptr() if want_bits else None, mm.data_ptr()))
         return y_hat, p, bits, mm
 
+    def widen_symbol_ranges(self, mm: torch.Tensor):
+        """In place: every per-cube (min_v, max_v) gets 0 inside it and at least two symbols (codable by pmf_to_quantized_cdf,
+        storable in the .strings_head byte)."""
+        self._stream()
+        self._check(self.lib.pcgc_widen_symbol_ranges(self.ctx, mm.data_ptr(), mm.numel() // 2))
+        return mm
+
     def laplace_intervals(self, y_hat, loc, scale, mm: torch.Tensor, bound: float = 1e-9, out: torch.Tensor = None) -> torch.Tensor:
         B = y_hat.shape[0]
         E = y_hat.numel() // max(B, 1)

@@ -290,8 +290,31 @@ def test_single_symbol_alphabet_raises(codec):
     assert e.value.code == -2
     sc = conditional_entropy_model.SymmetricConditional().bind(codec)
     z = np.zeros((1, 4, 4, 4, 16), np.float32)
-    with pytest.raises(_lib.PcgcError):
-        sc.compress(z, z, z + 1.0)
+    old = conditional_entropy_model.WIDEN_RANGES
+    try:
+        conditional_entropy_model.WIDEN_RANGES = False                    # the reference's exact (min, max): TF raises here too
+        with pytest.raises(_lib.PcgcError):
+            sc.compress(z, z, z + 1.0)
+    finally:
+        conditional_entropy_model.WIDEN_RANGES = old
+
+
+def test_degenerate_cube_ranges_are_widened_and_round_trip(codec):
+    """An all-zero latent cube (plausible for sparse cubes at low rate) and a cube whose latents are all positive: the coded
+    range is widened to contain 0 and two symbols, so the cloud does not abort after all GPU work and the header byte of the
+    container (max*16 - min, min <= 0 <= max) can hold it; the decoder rebuilds the tables from the header alone."""
+    sc = conditional_entropy_model.SymmetricConditional().bind(codec)
+    rng = np.random.default_rng(0)
+    y = np.zeros((3, 4096), np.float32)
+    y[1] = rng.integers(2, 6, 4096)                                       # all positive: range [2, 5] -> [0, 5]
+    y[2] = rng.integers(-3, 4, 4096)
+    loc = np.zeros_like(y)
+    scale = np.ones_like(y)
+    yd, ld, sd = codec.to_device(y), codec.to_device(loc), codec.to_device(scale)
+    strings, mins, maxs = sc.compress_cubes(yd, ld, sd)
+    assert list(mins) == [0, 0, -3] and list(maxs) == [1, 5, 3]
+    back = sc.decompress_cubes(strings, ld, sd, mins, maxs)
+    assert torch.equal(back, yd)
 
 
 # ------------------------------------------------------------------------------- top-k
