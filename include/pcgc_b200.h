@@ -176,8 +176,9 @@ int pcgc_laplace_cdf_dev(pcgc_ctx* ctx, const float* loc_dev, const float* scale
                          const int32_t* minmax_dev, const int64_t* row_offset_dev, double rows_total, float likelihood_bound,
                          int precision, uint16_t* cdf_dev);
 /* range_encode of B cubes from pcgc_laplace_intervals' output (precision 16, E % 32 == 0): cube b is coded into
- * scratch_dev + b*stride (even stride >= 2*E+8: a symbol emits at most one 16-bit word), lens_dev[b] receives its length, then the strings are concatenated into packed_dev (capacity cap) with
- * offsets_dev int64[B+1] (offsets[B] = total bytes). */
+ * scratch_dev + b*stride (E <= 65536; stride a multiple of 16 and >= 6*E + 32: the string, at most one 16-bit word per symbol,
+ * followed by the encoder's 32-bit digit sums), lens_dev[b] receives its length, then the strings are concatenated into
+ * packed_dev (capacity cap; 2*E + 2 bytes per cube always suffice) with offsets_dev int64[B+1] (offsets[B] = total bytes). */
 int pcgc_range_encode_intervals_dev(pcgc_ctx* ctx, const uint32_t* intervals_dev, int B, int64_t E, int precision,
                                     uint8_t* scratch_dev, int64_t stride, int64_t* lens_dev, uint8_t* packed_dev, int64_t cap,
                                     int64_t* offsets_dev);

@@ -1244,9 +1244,9 @@ int pcgc_laplace_cdf_dev(pcgc_ctx* ctx, const float* loc_dev, const float* scale
 int pcgc_range_encode_intervals_dev(pcgc_ctx* ctx, const uint32_t* intervals_dev, int B, int64_t E, int precision,
                                     uint8_t* scratch_dev, int64_t stride, int64_t* lens_dev, uint8_t* packed_dev, int64_t cap,
                                     int64_t* offsets_dev) {
-  if (!ctx || !intervals_dev || !scratch_dev || !lens_dev || !packed_dev || !offsets_dev || B < 0 || E <= 0 || E % 32 || stride < 2 * E + 8 ||
-      (stride & 1) || precision != 16)
-    return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_range_encode_intervals_dev: bad argument (E %% 32 == 0, even stride >= 2*E + 8, precision 16)");
+  if (!ctx || !intervals_dev || !scratch_dev || !lens_dev || !packed_dev || !offsets_dev || B < 0 || E <= 0 || E % 32 || E > 65536 ||
+      stride < 6 * E + 32 || (stride & 15) || precision != 16)
+    return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_range_encode_intervals_dev: bad argument (E %% 32 == 0, E <= 65536, stride %% 16 == 0, stride >= 6*E + 32, precision 16)");
   DeviceGuard g(ctx->device);
   if (B == 0) { CK(cudaMemsetAsync(offsets_dev, 0, sizeof(int64_t), ctx->stream)); return PCGC_OK; }
   prof_begin(ctx, "range_encode_gpu", 0, 4.0 * B * E);

@@ -21,83 +21,130 @@ namespace pcgc {
 
 namespace {
 
-// One WARP per cube, precision 16, state replicated in every lane (RangeEncoder16 of range_coder.h, unrolled for the warp):
-// the lanes fetch 32 intervals with one coalesced load and hand them round by shuffles, the renormalisation branch is
-// warp-uniform (no divergence), lane 0 stores the emitted 16-bit words.  A thread-per-cube form with 4-8 cubes per warp was
-// measured at ~260 cycles per symbol (divergent renormalisation, 64-bit output bookkeeping on the serial chain).
-// Every symbol renormalises at most once and every renormalisation emits at most one word on average, so 2*E + 8 bytes always
-// suffice: the launcher checks the stride once instead of the kernel checking every store.
+// Encoder, one WARP per cube, precision 16.  A range encoder is sequential only in its SIZE: size_{i+1} depends on size_i and the
+// interval of symbol i, nothing else.  The base -- the number the string spells -- is a SUM,
+//     string = sum_i  a_i * 2^(-16 R_i),      a_i = (size_i * lower_i) >> 16,   R_i = renormalisations before symbol i,
+// whose cache / pending-0xFFFF bookkeeping in RangeEncoder16 is just lazy carry propagation.  So the kernel splits the work:
+//   1. chain   : 32 symbols at a time, state replicated in every lane, NOTHING but the size recurrence on the serial path
+//                (two IMAD.WIDE, two funnel shifts, one IADD3, one compare, one select); lane j keeps a_j, a bit mask keeps the
+//                renormalisation flags.  The intervals of the group come from shared memory as broadcast 8-byte loads.
+//   2. digits  : lane j adds hi16(a_j) to 16-bit digit R_j and lo16(a_j) to digit R_j + 1 of a 128-digit shared-memory window
+//                (R_j from a popcount of the flag mask); digits the chain has moved past are flushed to the cube's scratch as
+//                32-bit sums (Sum a_i < 2^32 between two renormalisations and E <= 65536 bound a digit below 2^32).
+//   3. carries : after the last symbol the digits are resolved right to left, 32 per step with shuffles (the loop runs until
+//                no lane carries: twice in expectation), byte-swapped into the string, trailing zero bytes dropped.
+// finish() of range_coder.h (round the base up to a multiple of 2^16, emit one more word) = +0xFFFF on digit R+1, words 0..R.
+// Same bytes as RangeEncoder16 / the host coder for every input (tests/test_gpu_coder.py); measured 3.8 -> see DESIGN.md.
+// The r02 first form ran the whole RangeEncoder16 per symbol on the serial path (~104 cycles per symbol).
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+
+constexpr int ENC_W = 128;                      // digit window: 31 unflushed + 32 new + 2 < 128
+
 __global__ void __launch_bounds__(32)
 range_encode_intervals_kernel(const uint32_t* __restrict__ iv, int B, int64_t E, uint8_t* __restrict__ out,
-                              int64_t stride, int64_t* __restrict__ lens) {
+                              int64_t stride, int64_t dig_off, int64_t* __restrict__ lens) {
+  __shared__ uint32_t s_win[ENC_W];
+  __shared__ uint4 s_lu[2][32];
+  __shared__ uint32_t s_w[4][32];
   const int lane = threadIdx.x;
   const int b = blockIdx.x;
   const unsigned FULL = 0xffffffffu;
   const uint32_t* src = iv + (size_t)b * E;
-  uint16_t* o16 = reinterpret_cast<uint16_t*>(out + (size_t)b * stride);          // stride and the buffer are 2-byte aligned
-  uint32_t base = 0, carry = 0, sm1 = 0xFFFFFFFFu, cache = 0, have = 0, pending = 0, n16 = 0;
-  auto emit = [&](uint32_t w) {                                                     // big-endian 16-bit word
-    if (lane == 0) o16[n16] = (uint16_t)(((w & 0xFF) << 8) | ((w >> 8) & 0xFF));
-    ++n16;
+  uint16_t* o16 = reinterpret_cast<uint16_t*>(out + (size_t)b * stride);          // stride and the buffer are 16-byte aligned
+  uint32_t* dig = reinterpret_cast<uint32_t*>(out + (size_t)b * stride + dig_off);
+  for (int i = lane; i < ENC_W; i += 32) s_win[i] = 0;
+  uint32_t sm1 = 0xFFFFFFFFu;                    // size - 1, identical in every lane
+  uint32_t R = 0, Rfl = 0;                       // renormalisations so far; digits [0, Rfl) are in the scratch
+  const int64_t groups = E / 32;                 // E % 32 == 0 (checked by the launcher)
+  // interval words reach the lanes through a 4-slot shared-memory ring filled by cp.async two groups ahead (a register
+  // prefetch put a false scoreboard wait on every iteration: 13 % of the kernel in the r02 ncu capture)
+  const uint32_t s_w_addr = (uint32_t)__cvta_generic_to_shared(&s_w[0][lane]);
+  auto prefetch = [&](int64_t g) {
+    if (g < groups) cp_async4(s_w_addr + (uint32_t)(g & 3) * 128u, src + g * 32 + lane);
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  const int64_t groups = E / 32;                                                    // E % 32 == 0 (checked by the launcher)
-  // Every lane reads the SAME 32 intervals (8 broadcast 16-byte loads) one group ahead into registers: nothing inside the
-  // 32-symbol loop touches memory or another lane (a shuffle per symbol sat on the serial chain: 186 cycles per symbol).
-  const uint4* src4 = reinterpret_cast<const uint4*>(src);
-  uint4 cur[8], nxt[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) cur[q] = __ldg(src4 + q);
+  prefetch(0);
+  prefetch(1);
   for (int64_t g = 0; g < groups; ++g) {
-    if (g + 1 < groups) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q) nxt[q] = __ldg(src4 + (g + 1) * 8 + q);
-    }
+    prefetch(g + 2);
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
+    const uint32_t w = s_w[g & 3][lane];
+    // Operands pre-shifted by the lanes so that the products' HIGH words are the interval ends (no shift on the chain):
+    //   a = (size*lower) >> 16 = hi32(sm1*L + L),  L = lower << 16;
+    //   (size*upper) >> 16 = hi32(sm1*Ul + Ul) + Uh*(sm1 + 1),  upper << 16 = Uh*2^32 + Ul  (Uh = 1 only for upper = 2^16, Ul = 0 then)
+    //   t = b - a = hi32(sm1*Ul + Ul) + (Uh*sm1 + Uh - 1) - a          -- all mod 2^32, as in range_coder.h
+    const uint32_t lower = w & 0xFFFFu, upper = lower + (w >> 16) + 1u;
+    s_lu[g & 1][lane] = make_uint4(lower << 16, upper << 16, upper >> 16, (upper >> 16) - 1u);
+    __syncwarp();
+    uint32_t a_keep = 0, rmask = 0;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const uint4 qv = cur[j >> 2];
-      const uint32_t w = (j & 3) == 0 ? qv.x : ((j & 3) == 1 ? qv.y : ((j & 3) == 2 ? qv.z : qv.w));
-      const uint32_t lower = w & 0xFFFFu, upper = lower + (w >> 16) + 1u;
-      const uint32_t a = (uint32_t)(((uint64_t)sm1 * lower + lower) >> 16);
-      const uint32_t bq = (uint32_t)(((uint64_t)sm1 * upper + upper) >> 16) - 1u;
-      const uint32_t nb = base + a;
-      carry |= (uint32_t)(nb < a);
-      base = nb;
-      const uint32_t t = bq - a;
-      const bool renorm = t < 0x10000u;                                             // warp-uniform
-      sm1 = renorm ? ((t << 16) | 0xFFFFu) : t;                                     // the size chain does not wait for the emission below
-      // (a straight-line predicated form of the block below -- one basic block per 32 symbols -- was measured slower: 4.48 vs
-      // 3.84 ms per string; the renormalisation happens for about one symbol in three and the branch skips ~15 instructions)
-      if (renorm) {
-        if (base < 0xFFFF0000u || carry) {
-          if (have) emit((cache + carry) & 0xFFFF);
-#pragma unroll 1
-          for (; pending > 0; --pending) emit((0xFFFF + carry) & 0xFFFF);
-          cache = base >> 16;
-          have = 1;
-        } else {
-          ++pending;
-        }
-        base <<= 16;
-        carry = 0;
-      }
+      const uint4 lu = s_lu[g & 1][j];                                            // broadcast
+      const uint32_t a = (uint32_t)(((uint64_t)sm1 * lu.x + lu.x) >> 32);
+      const uint32_t x = (uint32_t)(((uint64_t)sm1 * lu.y + lu.y) >> 32);
+      const uint32_t y = sm1 * lu.z + lu.w;
+      const uint32_t t = x + y - a;
+      const bool renorm = t < 0x10000u;
+      sm1 = renorm ? ((t << 16) | 0xFFFFu) : t;
+      a_keep = lane == j ? a : a_keep;
+      rmask |= renorm ? (1u << j) : 0u;
+    }
+    const uint32_t Rj = R + __popc(rmask & ((1u << lane) - 1u));
+    atomicAdd(&s_win[Rj & (ENC_W - 1)], a_keep >> 16);
+    atomicAdd(&s_win[(Rj + 1) & (ENC_W - 1)], a_keep & 0xFFFFu);
+    R += __popc(rmask);
+    __syncwarp();
+    while (R - Rfl >= 32) {
+      const uint32_t idx = Rfl + lane;
+      dig[idx] = s_win[idx & (ENC_W - 1)];
+      s_win[idx & (ENC_W - 1)] = 0;
+      Rfl += 32;
+    }
+    __syncwarp();
+  }
+  // finish(): round up to a multiple of 2^16 at digit R, i.e. +0xFFFF on digit R + 1, then words 0..R
+  if (lane == 0) s_win[(R + 1) & (ENC_W - 1)] += 0xFFFFu;
+  __syncwarp();
+  const uint32_t n_dig = R + 2;
+  for (uint32_t idx = Rfl + lane; idx < n_dig; idx += 32) dig[idx] = s_win[idx & (ENC_W - 1)];
+  __syncwarp();
+  // carries, right to left: lane l of block k holds digit 32k + l (more significant = lower lane)
+  const int nb = (int)((n_dig + 31) / 32);
+  uint32_t cb = 0;                               // carry out of the block to the right
+  uint32_t found = 0;                            // string length once the last non-zero byte is known
+  for (int k0 = nb - 1; k0 >= 0; k0 -= 8) {       // 8 blocks' loads in flight at a time (the digits sit in L2)
+    uint32_t vv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int p = 32 * (k0 - q) + lane;
+      vv[q] = (k0 - q >= 0 && (uint32_t)p < n_dig) ? dig[p] : 0u;
     }
 #pragma unroll
-    for (int q = 0; q < 8; ++q) cur[q] = nxt[q];
+    for (int q = 0; q < 8; ++q) {
+      const int k = k0 - q;
+      if (k < 0) break;
+      const uint32_t p = (uint32_t)(32 * k + lane);
+      uint32_t v = vv[q];
+      uint32_t c = v >> 16, cbn = __shfl_sync(FULL, c, 0);
+      uint32_t cin = __shfl_down_sync(FULL, c, 1);
+      v = (v & 0xFFFFu) + (lane == 31 ? cb : cin);
+      while (__any_sync(FULL, v >> 16)) {
+        c = v >> 16;
+        cbn += __shfl_sync(FULL, c, 0);
+        cin = __shfl_down_sync(FULL, c, 1);
+        v = (v & 0xFFFFu) + (lane == 31 ? 0u : cin);
+      }
+      cb = cbn;
+      if (p <= R) o16[p] = (uint16_t)(((v & 0xFF) << 8) | (v >> 8));              // big-endian 16-bit word
+      if (!found) {
+        const uint32_t cand = (p <= R && v) ? ((v & 0xFF) ? 2 * p + 2 : 2 * p + 1) : 0u;
+        found = __reduce_max_sync(FULL, cand);
+      }
+    }
   }
-  // finish(): the multiple of 2^16 inside the interval, then drop trailing zero bytes
-  const uint64_t v = (((uint64_t)carry << 32) + base + 0xFFFF) >> 16;
-  const uint32_t c = (uint32_t)(v >> 16), word = (uint32_t)(v & 0xFFFF);
-  if (have) emit((cache + c) & 0xFFFF);
-#pragma unroll 1
-  for (; pending > 0; --pending) emit((0xFFFF + c) & 0xFFFF);
-  emit(word);
-  if (lane == 0) {
-    __threadfence_block();
-    const uint8_t* o8 = out + (size_t)b * stride;
-    int64_t n = 2 * (int64_t)n16;
-    while (n > 0 && o8[n - 1] == 0) --n;
-    lens[b] = n;
-  }
+  if (lane == 0) lens[b] = (int64_t)found;
 }
 
 // Concatenates the B strings: offsets[b] = sum of lens[0..b), offsets[B] = total; bytes beyond cap are dropped (error flag).
@@ -121,9 +168,6 @@ pack_strings_kernel(const uint8_t* __restrict__ in, int64_t stride, const int64_
 constexpr int DEC_G = 32;                       // symbols per shared-memory window
 constexpr int DEC_MAXN = 64;                    // lane-parallel search: lane k tests entry k (and k + 32 in the WIDE form)
 
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
 
 // One warp per cube, precision 16.  Per symbol the serial chain is: size -> one 32x32->64 multiply per lane -> compare with
 // value - base -> two warp reductions (REDUX max / min) -> new base / size.  Derivation (range_coder.h RangeDecoder):
@@ -240,10 +284,12 @@ cudaError_t launch_range_encode_intervals(const uint32_t* iv, int B, int64_t E, 
                                           int64_t* lens, uint8_t* packed, int64_t cap, int64_t* offsets, int* err,
                                           cudaStream_t s, int64_t* launches) {
   if (B <= 0) return cudaSuccess;
-  if (precision != 16 || E % 32 || stride < 2 * E + 8 || (stride & 1)) return cudaErrorInvalidValue;
+  // per cube: the string (at most 2 * (E + 1) bytes) then E + 2 digit sums of 4 bytes
+  const int64_t dig_off = (2 * E + 2 + 15) / 16 * 16;
+  if (precision != 16 || E % 32 || E > 65536 || stride < dig_off + 4 * (E + 2) || (stride & 15)) return cudaErrorInvalidValue;
   PCGC_CARVEOUT_ONCE(range_encode_intervals_kernel);
   PCGC_CARVEOUT_ONCE(pack_strings_kernel);
-  range_encode_intervals_kernel<<<B, 32, 0, s>>>(iv, B, E, scratch, stride, lens);
+  range_encode_intervals_kernel<<<B, 32, 0, s>>>(iv, B, E, scratch, stride, dig_off, lens);
   pack_strings_kernel<<<B, 256, 0, s>>>(scratch, stride, lens, B, packed, cap, offsets, err);
   if (launches) *launches += 2;
   return cudaGetLastError();

@@ -442,9 +442,9 @@ class Codec:
         """iv int32 [B,E] (pcgc_laplace_intervals payload) on the device -> (packed uint8 [cap], offsets int64 [B+1]), both on the
         device; string b = packed[offsets[b]:offsets[b+1]].  Asynchronous on the current stream."""
         B, E = iv.shape
-        stride = 2 * E + 64
+        stride = 6 * E + 64                    # per cube: the string (<= 2E + 2 bytes) + the encoder's 32-bit digit sums
         scratch = torch.empty((max(B, 1), stride), dtype=torch.uint8, device=self.dev)
-        packed = torch.empty(max(B, 1) * stride, dtype=torch.uint8, device=self.dev)
+        packed = torch.empty(max(B, 1) * (2 * E + 8), dtype=torch.uint8, device=self.dev)
         lens = torch.empty(max(B, 1), dtype=torch.int64, device=self.dev)
         offsets = torch.empty(B + 1, dtype=torch.int64, device=self.dev)
         self._stream()
