@@ -278,6 +278,106 @@ range_decode_rows_kernel(const uint8_t* __restrict__ packed, const int64_t* __re
   }
 }
 
+
+// Decoder for alphabets of at most 31 symbols (every cube of the reference's models; wider ones take the kernel above).  Same
+// stream, same decisions as RangeDecoder of range_coder.h, with the serial path cut to what the recurrence needs.  State: size - 1
+// and D = value - base (base and value themselves never matter).  Lane l holds C_l = cdf[l] << 16 of the current row, so
+//     q_l = (size * cdf[l]) >> 16 = hi32(sm1 * C_l + C_l)                       (one IMAD.HI, no shift)
+// and with q_N := size (lane N: C = 0 plus a per-lane constant) the decoded symbol s is the last lane with q_l <= D, its interval
+// [a, b] = [q_s, q_{s+1} - 1].  Both ends come out of UNSIGNED MINIMA without a compare or select in front of the reductions:
+//     D - a = min_l (D - q_l)            lanes with q_l > D wrap to >= 2^32 - size + D >= D
+//     b - D = min_l (q_l - 1 - D)        lanes with q_l <= D wrap to >= 2^32 - 1 - D >= size - 1 - D (lane N)
+// (ties only at size = 2^32 and only between equal values), so  t = b - a = min + min,  D' = D - a = the first minimum.  Chain per
+// symbol: IMAD.HI -> IADD -> REDUX.MIN -> IADD -> ISETP -> SEL.  Off the chain: the symbol index (ballot, stored as a mask; the
+// popcount is taken lane-parallel after 32 symbols), the next 16-bit word (broadcast load from a shared-memory ring of the string's
+// words), the CDF rows (cp.async ring, two groups ahead).  No divergent branch inside the 32-symbol block.
+constexpr int DECN_SLOTS = 4;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(32)
+range_decode_rows_narrow_kernel(const uint8_t* __restrict__ packed, const int64_t* __restrict__ offsets, int B, int64_t E,
+                                const uint16_t* __restrict__ rows, const int64_t* __restrict__ row_offset,
+                                const int32_t* __restrict__ minmax, float* __restrict__ y_hat, int* __restrict__ err, int slot_elems) {
+  extern __shared__ __align__(16) uint16_t s_rows_n[];            // [DECN_SLOTS][slot_elems], slot_elems >= 32 * max N + 32, multiple of 8
+  __shared__ uint32_t s_words[128];                              // ring of the string's 16-bit words, indexed by word number & 127
+  __shared__ uint32_t s_mask[32];
+  const int lane = threadIdx.x;
+  const int b = blockIdx.x;
+  const unsigned FULL = 0xffffffffu;
+  const int min_v = minmax[2 * b], N = minmax[2 * b + 1] - min_v + 1;
+  if (N < 1 || N > 31 || 32 * N + 32 > slot_elems) { if (lane == 0) atomicExch(err, PCGC_ERR_BAD_RANGE); return; }
+  const uint8_t* str = packed + offsets[b];
+  const int64_t nbytes = offsets[b + 1] - offsets[b];
+  const uint4* rsrc = reinterpret_cast<const uint4*>(rows + row_offset[b]);          // 64 * N bytes per group, 16-byte aligned (launcher)
+  const int chunks = 4 * N;                                                          // 16-byte chunks per group
+  const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(s_rows_n);
+  const int64_t groups = E / 32;                                                     // E % 32 == 0 (checked by the host)
+  auto fetch = [&](int64_t g) {
+    if (g < groups) {
+      const uint4* src = rsrc + (size_t)g * chunks;
+      const uint32_t dst = slot0 + (uint32_t)(g & (DECN_SLOTS - 1)) * (uint32_t)slot_elems * 2u;
+      for (int c = lane; c < chunks; c += 32) cp_async16(dst + 16u * c, src + c);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // big-endian 16-bit word `i` of the string (zero beyond its end)
+  auto word_at = [&](int64_t i) -> uint32_t {
+    const int64_t p = 2 * i;
+    const uint32_t hi = p < nbytes ? (uint32_t)__ldg(str + p) : 0u, lo = p + 1 < nbytes ? (uint32_t)__ldg(str + p + 1) : 0u;
+    return (hi << 8) | lo;
+  };
+  fetch(0);
+  fetch(1);
+  // per-lane constants: valid lanes carry cdf << 16; lane N stands for cdf[N] = 2^16 (q_N - 1 = size - 1); lanes above never win
+  const bool valid = lane < N;
+  const uint32_t mul = valid ? 0x10000u : 0u, uh = lane == N ? 1u : 0u, um1 = uh - 1u;
+  uint32_t sm1 = 0xFFFFFFFFu;
+  uint32_t D = (word_at(0) << 16) | word_at(1);                  // value - base
+  uint32_t wpos = 2;                                             // next unread word
+  s_words[(2 + lane) & 127] = word_at(2 + lane);
+  s_words[(34 + lane) & 127] = word_at(34 + lane);
+  uint32_t filled = 66;                                          // words [.., filled) are in the ring
+  uint32_t pend = word_at(filled + lane);                        // words [filled, filled + 32), stored when the ring has room
+  __syncwarp();
+  for (int64_t g = 0; g < groups; ++g) {
+    if (filled - wpos <= 64) {                                   // uniform; keeps 32 <= filled - wpos <= 96 at every group start
+      s_words[(filled + lane) & 127] = pend;
+      filled += 32;
+      pend = word_at(filled + lane);                             // consumed a group later at the earliest
+    }
+    fetch(g + 2);
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
+    __syncwarp();
+    const uint16_t* slot = s_rows_n + (size_t)(g & (DECN_SLOTS - 1)) * slot_elems;
+    uint32_t C[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) C[j] = (uint32_t)slot[j * N + lane] * mul;
+    uint32_t nxt = s_words[wpos & 127];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const uint32_t q = (uint32_t)(((uint64_t)sm1 * C[j] + C[j]) >> 32);
+      const uint32_t e = D - q;
+      const uint32_t z = q + (sm1 * uh + um1) - D;
+      const uint32_t emin = __reduce_min_sync(FULL, e);
+      const uint32_t zmin = __reduce_min_sync(FULL, z);
+      const unsigned m = __ballot_sync(FULL, valid && q <= D);
+      if (lane == 0) s_mask[j] = m;
+      const uint32_t t = zmin + emin;
+      const bool renorm = t < 0x10000u;
+      sm1 = renorm ? ((t << 16) | 0xFFFFu) : t;
+      D = renorm ? ((emin << 16) | nxt) : emin;
+      wpos += renorm ? 1u : 0u;
+      nxt = s_words[wpos & 127];
+    }
+    __syncwarp();
+    y_hat[(size_t)b * E + g * 32 + lane] = (float)(__popc(s_mask[lane]) - 1 + min_v);
+    __syncwarp();                                                // s_mask, the row slot and the word ring are rewritten next
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_range_encode_intervals(const uint32_t* iv, int B, int64_t E, int precision, uint8_t* scratch, int64_t stride,
@@ -300,6 +400,15 @@ cudaError_t launch_range_decode_rows(const uint8_t* packed, const int64_t* offse
                                      cudaStream_t s, int64_t* launches) {
   if (B <= 0) return cudaSuccess;
   if (E % DEC_G || max_n < 1 || max_n > DEC_MAXN || precision != 16) return cudaErrorInvalidValue;
+  if (max_n <= 31 && (reinterpret_cast<uintptr_t>(rows) & 15) == 0 && !getenv("PCGC_DEC_WIDE")) {
+    // every row window is a multiple of 64 bytes (E % 32 == 0), so 16-byte cp.async needs only the base pointer aligned
+    const int slot_elems = (32 * max_n + 32 + 7) / 8 * 8;
+    PCGC_CARVEOUT_ONCE(range_decode_rows_narrow_kernel);
+    range_decode_rows_narrow_kernel<<<B, 32, (size_t)DECN_SLOTS * slot_elems * sizeof(uint16_t), s>>>(packed, offsets, B, E, rows, row_offset, minmax,
+                                                                                                    y_hat, err, slot_elems);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+  }
   const int win_elems = DEC_G * ((max_n + 7) / 8 * 8);              // 16-byte multiple per window
   // cubes (= warps) per block.  1 spreads the decoder warps over all SMs; more packs them onto few SMs (experiments: PCGC_DEC_CPB)
   static const int cpb = [] { const char* e = getenv("PCGC_DEC_CPB"); const int v = e ? atoi(e) : 1; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
