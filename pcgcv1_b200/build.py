@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libpcgc_b200.so")
-SOURCES = ["api.cu", "conv_ffma.cu", "umma_conv.cu", "entropy.cu", "gpu_coder.cu", "train.cu", "topk.cu", "voxelize.cu", "coder.cpp", "pointio.cpp"]
+SOURCES = ["api.cu", "conv_ffma.cu", "umma_conv.cu", "umma_win.cu", "entropy.cu", "gpu_coder.cu", "train.cu", "topk.cu", "voxelize.cu", "coder.cpp", "pointio.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function,-ffp-contract=off", "--expt-relaxed-constexpr"]

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "det_math.h"
 #include "umma_conv.cuh"
+#include "umma_win.cuh"
 
 using namespace pcgc;
 
@@ -56,6 +57,10 @@ struct UmmaProgram {
   int up_groups[2] = {0, 0};
   UmmaWeights down[2];          // analysis: down_1, down_2 as 8-tap GEMMs over the space-to-depth input
   float* conv_in_w = nullptr;   // analysis: conv_in weights [27][16] for the dedicated kernel
+  // model_simple (models/model_simple.py:21-42,58-86) on the window-GEMM kernel (umma_win.cu)
+  WinLayer s_conv1, s_conv2;    // analysis: 9^3 s2 1->32 (5^3 cells x 8 parities), 5^3 s2 32->32 (3^3 cells x 8 parities x 32)
+  WinLayer s_deconv2[4];        // synthesis: 5^3 s2 transposed 32->32, two output-parity classes per launch
+  WinLayer s_deconv3;           // synthesis: 9^3 s2 transposed 32->1, the 8 classes as 8 columns
 };
 
 struct Net {
@@ -624,6 +629,142 @@ int run_hyper_umma(pcgc_ctx* ctx, int kind, const float* in_ext, int B, float* o
   return PCGC_OK;
 }
 
+
+// model_simple with its four large layers on the tcgen05 window-GEMM kernel (umma_win.cu); the two 8^3 layers (conv_3,
+// deconv_1: 4.8 % of the MACs each way, grids smaller than one M tile) stay on the FP32 CUDA-core kernel.
+//   analysis : cube -> space-to-depth PM [32^3][8] -> conv_1 (5^3 cells) -> space-to-depth PM [16^3][256] -> conv_2 (3^3 cells)
+//              -> PM [16^3][32] -> conv_3 (FFMA) -> y float32 [8^3][32]
+//   synthesis: y -> deconv_1 (FFMA) -> PM [16^3][32] -> deconv_2 (4 launches x 2 parity classes) -> PM [32^3][32]
+//              -> deconv_3 (8 classes = 8 columns) -> logits float32 [64^3][1]
+int build_simple_program(pcgc_ctx* ctx, int kind) {
+  Net& n = ctx->nets[kind];
+  UmmaProgram& up = n.up;
+  if (up.ready) return PCGC_OK;
+  auto Lw = [&](const char* name) -> LayerW& { return n.w[n.find(name)]; };
+  cudaError_t e = cudaSuccess;
+  if (kind == PCGC_NET_SIMPLE_ANALYSIS) {
+    const LayerW &l1 = Lw("conv_1"), &l2 = Lw("conv_2");
+    // conv_1: x index = 2(o + c) + p, tap k = 2c + p + 3 (SAME pads (3,4)); Keras [9,9,9,1,32]
+    auto w1 = [&](int tz, int ty, int tx, int ci, int co) -> float {
+      const int kz = 2 * (tz - 2) + ((ci >> 2) & 1) + 3, ky = 2 * (ty - 2) + ((ci >> 1) & 1) + 3, kx = 2 * (tx - 2) + (ci & 1) + 3;
+      if (kz < 0 || kz > 8 || ky < 0 || ky > 8 || kx < 0 || kx > 8) return 0.f;
+      return l1.hk[(((size_t)kz * 9 + ky) * 9 + kx) * 32 + co];
+    };
+    e = pack_win_layer(8, 5, 5, 5, -2, -2, -2, 32, w1, l1.hb.data(), up.s_conv1);
+    // conv_2: tap k = 2c + p + 1 (SAME pads (1,2)); input channel = parity * 32 + c; Keras [5,5,5,32,32]
+    auto w2 = [&](int tz, int ty, int tx, int ci, int co) -> float {
+      const int par = ci / 32, c = ci % 32;
+      const int kz = 2 * (tz - 1) + ((par >> 2) & 1) + 1, ky = 2 * (ty - 1) + ((par >> 1) & 1) + 1, kx = 2 * (tx - 1) + (par & 1) + 1;
+      if (kz < 0 || kz > 4 || ky < 0 || ky > 4 || kx < 0 || kx > 4) return 0.f;
+      return l2.hk[((((size_t)kz * 5 + ky) * 5 + kx) * 32 + c) * 32 + co];
+    };
+    if (e == cudaSuccess) e = pack_win_layer(256, 3, 3, 3, -1, -1, -1, 32, w2, l2.hb.data(), up.s_conv2);
+  } else {
+    const LayerW &l2 = Lw("deconv_2"), &l3 = Lw("deconv_3");
+    // Conv3DTranspose: out[2t + r] gathers x[t + c] W[k], k = r + pad_before - 2c; Keras [k,k,k,Cout,Cin]
+    for (int g = 0; g < 4 && e == cudaSuccess; ++g) {
+      auto w = [&](int tz, int ty, int tx, int ci, int col) -> float {
+        const int rz = g >> 1, ry = g & 1, rx = col / 32, co = col % 32;
+        const int kz = rz + 1 - 2 * (tz - 1), ky = ry + 1 - 2 * (ty - 1), kx = rx + 1 - 2 * (tx - 1);
+        if (kz < 0 || kz > 4 || ky < 0 || ky > 4 || kx < 0 || kx > 4) return 0.f;
+        return l2.hk[((((size_t)kz * 5 + ky) * 5 + kx) * 32 + co) * 32 + ci];
+      };
+      std::vector<float> bb(64);
+      for (int i = 0; i < 64; ++i) bb[i] = l2.hb[i % 32];
+      e = pack_win_layer(32, 3, 3, 3, -1, -1, -1, 64, w, bb.data(), up.s_deconv2[g]);
+      up.s_deconv2[g].up_ncls = 2; up.s_deconv2[g].up_cout = 32;
+      up.s_deconv2[g].up_cls[0] = 2 * g; up.s_deconv2[g].up_cls[1] = 2 * g + 1;
+    }
+    auto w3 = [&](int tz, int ty, int tx, int ci, int col) -> float {
+      const int kz = ((col >> 2) & 1) + 3 - 2 * (tz - 2), ky = ((col >> 1) & 1) + 3 - 2 * (ty - 2), kx = (col & 1) + 3 - 2 * (tx - 2);
+      if (kz < 0 || kz > 8 || ky < 0 || ky > 8 || kx < 0 || kx > 8) return 0.f;
+      return l3.hk[(((size_t)kz * 9 + ky) * 9 + kx) * 32 + ci];
+    };
+    std::vector<float> b3(8, l3.hb.empty() ? 0.f : l3.hb[0]);
+    if (e == cudaSuccess) e = pack_win_layer(32, 5, 5, 5, -2, -2, -2, 8, w3, b3.data(), up.s_deconv3);
+    up.s_deconv3.up_ncls = 8; up.s_deconv3.up_cout = 1;
+    for (int i = 0; i < 8; ++i) up.s_deconv3.up_cls[i] = i;
+  }
+  if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "pack model_simple net %d: %s", kind, cudaGetErrorString(e));
+  up.ready = true;
+  return PCGC_OK;
+}
+
+int run_simple_umma(pcgc_ctx* ctx, int kind, const float* in_ext, const void* cubes, int cubes_dtype, int B, float* out0) {
+  Net& n = ctx->nets[kind];
+  for (size_t i = 0; i < n.w.size(); ++i)
+    if (!n.w[i].loaded) return fail(ctx, PCGC_ERR_NOT_READY, "net %d: layer '%s' has no weights", kind, n.specs[i].name.c_str());
+  int r = build_simple_program(ctx, kind);
+  if (r) return r;
+  if (B <= 0) return PCGC_OK;
+  const int SB = std::min(B, ctx->sub_batch);
+  for (int bi = BUF_X0; bi < BUF_OUT0; ++bi) {
+    size_t e = n.elems[bi];
+    if (bi == BUF_X0) e = std::max(e, (size_t)64 * 64 * 64);
+    if (e) { r = ensure(ctx, &ctx->bufs[bi], &ctx->buf_cap[bi], e * SB); if (r) return r; }
+  }
+  UmmaProgram& up = n.up;
+  auto pm = [&](int buf, int nn, int c, int nb) { PmTensor t; t.p = (__nv_bfloat16*)ctx->bufs[buf]; t.n = nn; t.c = c; t.B = nb; return t; };
+  auto ffma = [&](const char* name, const float* in_f32, const PmTensor* in_pm, int in_n, float* out_f32, const PmTensor* out_pm, int nb) -> int {
+    const int li = n.find(name);
+    const LayerSpec& s = n.specs[li];
+    LayerW& lw = n.w[li];
+    const int out_n = s.transposed ? in_n * s.stride : in_n / s.stride;
+    ConvCall c;
+    c.in = in_f32; c.in_n = in_n; c.in_cs = s.cin; c.in_co = 0;
+    c.out = out_f32; c.out_n = out_n; c.out_cs = s.cout; c.out_co = 0;
+    c.bias = lw.bias; c.res = nullptr; c.res_cs = c.res_co = 0;
+    c.flags = s.relu ? EPI_RELU : 0; c.floor_v = 0.f; c.B = nb;
+    c.in_pm = in_pm ? in_pm->p : nullptr; c.out_pm = out_pm ? out_pm->p : nullptr;
+    char tag[96];
+    snprintf(tag, sizeof tag, "conv_ffma k%d s%d%s c%d->%d n%d", s.k, s.stride, s.transposed ? "T" : "", s.cin, s.cout, in_n);
+    const double tvox = (double)(s.transposed ? in_n : out_n);
+    prof_begin(ctx, tag, 2.0 * nb * tvox * tvox * tvox * s.k * s.k * s.k * s.cin * s.cout, 0);
+    for (int k = 0; k < lw.n_classes; ++k) {
+      c.d = lw.cls[k];
+      c.tn = s.transposed ? in_n : out_n;
+      cudaError_t e = launch_conv_ffma(c, ctx->stream, &ctx->launches);
+      if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "conv '%s': %s", name, cudaGetErrorString(e));
+    }
+    prof_end(ctx);
+    return PCGC_OK;
+  };
+  auto win = [&](const char* what, const WinLayer& w, const PmTensor& in, WinCall c, bool open_tag = true, bool close_tag = true) -> int {
+    c.in = in; c.err = ctx->err_flag;
+    char tag[96];
+    snprintf(tag, sizeof tag, "conv_umma_win %s c%d->%d n%d", what, w.cin, w.n_cols, in.n);
+    if (open_tag) prof_begin(ctx, tag, 2.0 * in.B * (double)in.n * in.n * in.n * w.macs_per_row * (close_tag ? 1.0 : 4.0), 0);
+    cudaError_t e = launch_conv_umma_win(c, w, ctx->stream, &ctx->launches);
+    if (close_tag) prof_end(ctx);
+    if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "%s: %s", tag, cudaGetErrorString(e));
+    return PCGC_OK;
+  };
+  for (int b0 = 0; b0 < B; b0 += SB) {
+    const int nb = std::min(SB, B - b0);
+    if (kind == PCGC_NET_SIMPLE_ANALYSIS) {
+      const size_t esz = cubes_dtype == PCGC_DTYPE_U8 ? 1 : (cubes_dtype == PCGC_DTYPE_F32 ? 4 : 8);
+      const void* src = cubes ? (const void*)((const char*)cubes + (size_t)b0 * 262144 * esz) : (const void*)(in_ext + (size_t)b0 * 262144);
+      PmTensor x = pm(BUF_X0, 32, 8, nb), f1 = pm(BUF_A, 16, 256, nb), f2 = pm(BUF_B, 16, 32, nb);
+      CK(launch_cubes_to_s2d_pm(src, cubes ? cubes_dtype : PCGC_DTYPE_F32, x, ctx->stream, &ctx->launches));
+      WinCall c1; c1.epi = WEPI_PM; c1.flags = EPI_RELU; c1.out = f1; c1.out_s2d = 1;
+      if ((r = win("conv_1", up.s_conv1, x, c1))) return r;
+      WinCall c2; c2.epi = WEPI_PM; c2.flags = EPI_RELU; c2.out = f2;
+      if ((r = win("conv_2", up.s_conv2, f1, c2))) return r;
+      if ((r = ffma("conv_3", nullptr, &f2, 16, out0 + (size_t)b0 * 8 * 8 * 8 * 32, nullptr, nb))) return r;
+    } else {
+      PmTensor f1 = pm(BUF_A, 16, 32, nb), f2 = pm(BUF_B, 32, 32, nb);
+      if ((r = ffma("deconv_1", in_ext + (size_t)b0 * 8 * 8 * 8 * 32, nullptr, 8, nullptr, &f1, nb))) return r;
+      for (int g = 0; g < 4; ++g) {
+        WinCall c; c.epi = WEPI_UP_PM; c.flags = EPI_RELU; c.out = f2;
+        if ((r = win("deconv_2", up.s_deconv2[g], f1, c, g == 0, g == 3))) return r;
+      }
+      WinCall c3; c3.epi = WEPI_UP_F32; c3.flags = 0; c3.out_f32 = out0 + (size_t)b0 * 262144; c3.out_cs = 1; c3.out_co = 0;
+      if ((r = win("deconv_3", up.s_deconv3, f2, c3))) return r;
+    }
+  }
+  return PCGC_OK;
+}
+
 int run_net(pcgc_ctx* ctx, int kind, const float* in_ext, const void* cubes, int cubes_dtype, int B, float* out0,
             float* out1, float floor_v) {
   Net& n = ctx->nets[kind];
@@ -755,6 +896,8 @@ void pcgc_destroy(pcgc_ctx* ctx) {
     for (int u = 0; u < 2; ++u) for (int g = 0; g < 2; ++g) free_umma_weights(n.up.up[u][g]);
     free_umma_weights(n.up.down[0]); free_umma_weights(n.up.down[1]);
     if (n.up.conv_in_w) cudaFree(n.up.conv_in_w);
+    free_win_layer(n.up.s_conv1); free_win_layer(n.up.s_conv2); free_win_layer(n.up.s_deconv3);
+    for (int g2 = 0; g2 < 4; ++g2) free_win_layer(n.up.s_deconv2[g2]);
   }
   for (auto& n : ctx->nets)
     for (auto& lw : n.w) {
@@ -1010,6 +1153,7 @@ int pcgc_analysis(pcgc_ctx* ctx, int net, const void* cubes_dev, int dtype, int 
     return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_analysis: bad argument");
   DeviceGuard g(ctx->device);
   if (net == PCGC_NET_VOX_ANALYSIS && ctx->engine != PCGC_ENGINE_FFMA) return run_vox_umma(ctx, net, nullptr, cubes_dev, dtype, B, y_dev);
+  if (net == PCGC_NET_SIMPLE_ANALYSIS && ctx->engine != PCGC_ENGINE_FFMA) return run_simple_umma(ctx, net, nullptr, cubes_dev, dtype, B, y_dev);
   return run_net(ctx, net, nullptr, cubes_dev, dtype, B, y_dev, nullptr, 0.f);
 }
 
@@ -1018,6 +1162,7 @@ int pcgc_synthesis(pcgc_ctx* ctx, int net, const float* y_dev, int B, float* log
     return fail(ctx, PCGC_ERR_BAD_ARG, "pcgc_synthesis: bad argument");
   DeviceGuard g(ctx->device);
   if (net == PCGC_NET_VOX_SYNTHESIS && ctx->engine != PCGC_ENGINE_FFMA) return run_vox_umma(ctx, net, y_dev, nullptr, 0, B, logits_dev);
+  if (net == PCGC_NET_SIMPLE_SYNTHESIS && ctx->engine != PCGC_ENGINE_FFMA) return run_simple_umma(ctx, net, y_dev, nullptr, 0, B, logits_dev);
   return run_net(ctx, net, y_dev, nullptr, 0, B, logits_dev, nullptr, 0.f);
 }
 
