@@ -538,7 +538,8 @@ def run_factorized(args):
         "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"kernel": top["tag"], "bound": "tensor", "achieved": round(ach, 3), "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": round(ach / peaks["bf16_tflops_sustained"], 5), "traffic": None, "share_of_step": round(top["ms"] / total_ms, 4),
-                     "note": "model_simple's k9 / k5 stride-2 layers run on the exact-FP32 CUDA-core engine (conv_ffma.cu), not on tcgen05"},
+                     "note": "model_simple: conv_1 / conv_2 / deconv_2 / deconv_3 on the tcgen05 window-GEMM kernel (umma_win.cu); the two 8^3 "
+                             "layers (conv_3, deconv_1; 4.8 % of the MACs each way) on the exact-FP32 CUDA-core kernel"},
         "conv": {"achieved_tflops": round(GF * B * args.steps / (dev_ms / 1e3) / 1e3, 2), "algorithmic_gflop_per_cube": GF},
         "kernels": [{"tag": r["tag"], "share": round(r["ms"] / total_ms, 4)} for r in prof[:8]], "cpu_baseline": None,
     }

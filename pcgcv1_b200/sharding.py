@@ -86,11 +86,49 @@ class GpuLocalCodec(LocalCodec):
                 "z_hat": self.runtime.to_host(z_hat).astype(np.int16)}
 
     def encode_z(self, z_hat_all):
-        s, mn, mx = self.eb.compress(z_hat_all.astype(np.float32))
-        return s.numpy(), int(mn), int(mx)
+        """The quantised hyper latents of ALL cubes -> one string with one (min_v, max_v) (entropy_model.py:246-259).  The values
+        are integers already, so round() is the identity and floor(min) / ceil(max) are min / max: no GPU round trip of the
+        (cubes x 4096) tensor, just the per-channel CDF table and the host range coder."""
+        z = np.ascontiguousarray(z_hat_all)
+        flat = z.reshape(-1)
+        mn, mx = int(flat.min()), int(flat.max())
+        c, slot = self.eb._resolve(z.shape[-1])
+        cdf = c.factorized_cdf(slot, mn, mx, self.eb._likelihood_bound, self.eb._range_coder_precision)
+        sym = np.ascontiguousarray(flat.astype(np.int16) - np.int16(mn))
+        return self.runtime.range_encode(sym, cdf, self.eb._range_coder_precision), mn, mx
+
+    def encode_z_async(self, z_hat_all):
+        """encode_z with the host range coder (one sequential string, ~8 ns per symbol, GIL released) on a worker thread:
+        -> join() returning (string, min_v, max_v).  The CDF table is built here, on the caller's thread."""
+        z = np.ascontiguousarray(z_hat_all)
+        flat = z.reshape(-1)
+        mn, mx = int(flat.min()), int(flat.max())
+        c, slot = self.eb._resolve(z.shape[-1])
+        cdf = c.factorized_cdf(slot, mn, mx, self.eb._likelihood_bound, self.eb._range_coder_precision)
+        sym = np.ascontiguousarray(flat.astype(np.int16) - np.int16(mn))
+        from concurrent.futures import ThreadPoolExecutor
+        ex = ThreadPoolExecutor(max_workers=1)
+        job = ex.submit(self.runtime.range_encode, sym, cdf, self.eb._range_coder_precision)
+
+        def join():
+            out = job.result()
+            ex.shutdown(wait=False)
+            return out, mn, mx
+        return join
 
     def decode_z(self, z_string, z_min, z_max, z_shape):
-        return self.eb.decompress(z_string, z_min, z_max, np.asarray(z_shape), z_shape[-1]).numpy().astype(np.int16)
+        dec, mn, _ = self.decode_z_begin(z_string, z_min, z_max, z_shape)
+        return dec.finish().reshape([int(v) for v in z_shape]) + np.int16(mn)
+
+    def decode_z_begin(self, z_string, z_min, z_max, z_shape):
+        """-> (runtime.ProgressiveDecode, min_v, symbols per cube): the string decodes on a worker thread; ``dec.wait(k)`` returns
+        once the first k symbols (value - min_v, int16) exist.  The string is sequential, so the first cubes come first."""
+        shape = [int(v) for v in np.asarray(z_shape).reshape(-1)]
+        mn, mx = int(np.asarray(z_min)), int(np.asarray(z_max))
+        c, slot = self.eb._resolve(shape[-1])
+        cdf = c.factorized_cdf(slot, mn, mx, self.eb._likelihood_bound, self.eb._range_coder_precision)
+        per = int(np.prod(shape[1:]))
+        return self.runtime.ProgressiveDecode(bytes(z_string), shape[0] * per, cdf, self.eb._range_coder_precision), mn, per
 
     # ---- device-resident strings (the sharded fast path: the per-cube strings of a slice never become Python objects on the
     # ranks; they move as ONE packed uint8 tensor, GPU -> GPU) -----------------------------------------------------------------
@@ -116,13 +154,17 @@ class GpuLocalCodec(LocalCodec):
         from . import transform
         c = self.codec
         b = len(y_min)
-        zd = c.to_device(np.ascontiguousarray(z_hat, dtype=np.float32))
+        if callable(z_hat):
+            z_get = z_hat                                                    # (a, e) -> float32 device tensor [e-a,8,8,8,8]; may block
+        else:
+            zd = c.to_device(np.ascontiguousarray(z_hat, dtype=np.float32))
+            z_get = lambda a, e: zd[a:e]
         if self.runtime.coder_mode() == "gpu":
             xs = transform._decompress_hyper_gpu_coder(c, self.sc, None if uploaded is not None else list(y_strings), np.asarray(y_min),
-                                                       np.asarray(y_max), [1, 16, 16, 16, 16], lambda a, e: zd[a:e],
+                                                       np.asarray(y_max), [1, 16, 16, 16, 16], z_get,
                                                        transform._gpu_decode_chunks(b), uploaded=uploaded)
         else:
-            locs, scales = c.hyper_decode(zd, 1e-9)
+            locs, scales = c.hyper_decode(z_get(0, b), 1e-9)
             ys = self.sc.decompress_cubes(list(y_strings), locs, scales, y_min, y_max)
             xs = c.synthesis(ys.reshape(b, 16, 16, 16, 16))
         ks = np.array([int(rho * np.array(n)) for n in nums], np.int32)
@@ -176,6 +218,8 @@ def compress_sharded(cubes_local: np.ndarray, local: LocalCodec, group=None) -> 
             if packed.numel():
                 dist.send(packed, dst=0)
             return None
+        z_hat = np.concatenate([p["z_hat"] for p in parts])
+        z_join = local.encode_z_async(z_hat)                                  # the one hyper string, coded beside the string gather
         totals = [int(p["y_lens"].sum()) for p in parts]
         dev_parts = [packed]
         for r in range(1, world):
@@ -186,8 +230,7 @@ def compress_sharded(cubes_local: np.ndarray, local: LocalCodec, group=None) -> 
         allp = torch.cat(dev_parts) if world > 1 else packed
         blob = local.runtime.to_host(allp, "stream_blob").copy() if allp.numel() else np.zeros(0, np.uint8)
         lens = np.concatenate([p["y_lens"] for p in parts]).astype(np.int64)
-        z_hat = np.concatenate([p["z_hat"] for p in parts])
-        z_string, z_min, z_max = local.encode_z(z_hat)
+        z_string, z_min, z_max = z_join()
         return {"y_strings": BlobStrings(blob, lens), "y_blob": blob, "y_lens": lens, "y_min": np.concatenate([p["y_min"] for p in parts]),
                 "y_max": np.concatenate([p["y_max"] for p in parts]), "y_shape": np.array([1, 16, 16, 16, 16], np.int64),
                 "z_string": z_string, "z_min": z_min, "z_max": z_max, "z_shape": np.array(z_hat.shape, np.int32)}
@@ -238,10 +281,11 @@ def decompress_sharded(stream: Optional[dict], nums: Optional[np.ndarray], rho: 
     if _packed_ok(local, group):
         import torch
         c = local.codec
-        pieces, up, off_all, slices = None, None, None, None
+        pieces, up, off_all, slices, dec = None, None, None, None, None
         if rank == 0:
             B = len(stream["y_min"])
-            z_hat = local.decode_z(stream["z_string"], stream["z_min"], stream["z_max"], stream["z_shape"])
+            # the ONE hyper string starts decoding on a worker thread now; everything below overlaps it
+            dec, z_min, per = local.decode_z_begin(stream["z_string"], stream["z_min"], stream["z_max"], stream["z_shape"])
             if "y_blob" in stream:
                 blob, lens = stream["y_blob"], np.asarray(stream["y_lens"], np.int64)
             else:
@@ -251,8 +295,8 @@ def decompress_sharded(stream: Optional[dict], nums: Optional[np.ndarray], rho: 
             off_all = np.zeros(B + 1, np.int64)
             np.cumsum(lens, out=off_all[1:])
             slices = shard_slices(B, world)
-            pieces = [{"y_lens": lens[a:b], "y_min": stream["y_min"][a:b], "y_max": stream["y_max"][a:b], "z_hat": z_hat[a:b],
-                       "nums": np.asarray(nums)[a:b]} for a, b in slices]
+            pieces = [{"y_lens": lens[a:b], "y_min": stream["y_min"][a:b], "y_max": stream["y_max"][a:b], "z_min": z_min, "z_per": per,
+                       "z_tail": [int(v) for v in np.asarray(stream["z_shape"]).reshape(-1)[1:]], "nums": np.asarray(nums)[a:b]} for a, b in slices]
             up = c.to_device(blob) if len(blob) else torch.zeros(0, dtype=torch.uint8, device=c.dev)      # ONE H2D copy of the whole stream
         mine = [None]
         dist.scatter_object_list(mine, pieces, src=0, group=group)
@@ -272,11 +316,48 @@ def decompress_sharded(stream: Optional[dict], nums: Optional[np.ndarray], rho: 
         off = np.zeros(len(m["y_lens"]) + 1, np.int64)
         np.cumsum(m["y_lens"], out=off[1:])
         uploaded = (packed if packed.numel() else torch.zeros(1, dtype=torch.uint8, device=c.dev), c.to_device(off))
-        if output == "points":
-            res = local.decode_local_points(None, m["y_min"], m["y_max"], m["z_hat"], m["nums"], rho, uploaded=uploaded)
+        per, z_min, z_tail = m["z_per"], m["z_min"], m["z_tail"]
+        nb = len(m["y_min"])
+        sender = None
+        host_z = world == 1 or dist.get_backend(group) == "gloo"         # int16 symbols travel over the host group when there is one
+        if rank == 0:
+            a0 = slices[0][0]
+
+            def z_get(a, e):                                                 # blocks until cubes [a, e) of rank 0's slice are decoded
+                sym = dec.wait((a0 + e) * per)[(a0 + a) * per:(a0 + e) * per]
+                return c.to_device((sym.astype(np.float32) + np.float32(z_min)).reshape([e - a] + z_tail))
+
+            if world > 1:
+                # the other ranks' hyper latents leave as soon as the sequential decoder reaches the end of their slice (int16
+                # symbols, 8 KB per cube, host group), on a helper thread: this thread is busy feeding rank 0's own GPU
+                def ship():
+                    for r in range(1, world):
+                        a, b = slices[r]
+                        if b > a:
+                            t = torch.from_numpy(dec.wait(b * per)[a * per:b * per].copy())
+                            if host_z:
+                                dist.send(t, dst=r, group=group)
+                            else:
+                                dist.send(t.to(c.dev), dst=r)
+                import threading
+                sender = threading.Thread(target=ship, daemon=True)
+                sender.start()
         else:
-            res = (local.runtime.to_host(local._decode_masks_dev(None, m["y_min"], m["y_max"], m["z_hat"], m["nums"], rho, uploaded=uploaded), "mask").copy()
-                   if len(m["y_min"]) else np.zeros((0, 64, 64, 64, 1), np.uint8))
+            zs = torch.empty(nb * per, dtype=torch.int16, device=None if host_z else c.dev)
+            if nb:
+                if host_z:
+                    dist.recv(zs, src=0, group=group)
+                else:
+                    dist.recv(zs, src=0)
+            zd = c.to_device((zs.cpu().numpy().astype(np.float32) + np.float32(z_min)).reshape([nb] + z_tail)) if nb else None
+            z_get = lambda a, e: zd[a:e]
+        if output == "points":
+            res = local.decode_local_points(None, m["y_min"], m["y_max"], z_get, m["nums"], rho, uploaded=uploaded)
+        else:
+            res = (local.runtime.to_host(local._decode_masks_dev(None, m["y_min"], m["y_max"], z_get, m["nums"], rho, uploaded=uploaded), "mask").copy()
+                   if nb else np.zeros((0, 64, 64, 64, 1), np.uint8))
+        if sender is not None:
+            sender.join()
         parts = [None] * world if rank == 0 else None
         dist.gather_object(res, parts, dst=0, group=group)
         if rank != 0:

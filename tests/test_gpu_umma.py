@@ -69,3 +69,55 @@ def test_engines_agree_on_the_transforms(codec):
     # bit-reproducible and batch-invariant on the tcgen05 engine too
     assert torch.equal(y_u, codec.analysis(x))
     assert torch.equal(y_u[2:3], codec.analysis(x[2:3]))
+
+
+def test_simple_model_engines_agree(codec_simple):
+    """model_simple (model_simple.py:21-42,58-86): window-GEMM tcgen05 kernel (umma_win.cu; stride-2 layers as stride-1 windows
+    over space-to-depth channels / output-parity columns, split-bf16) vs the exact-FP32 CUDA-core engine, layer chain by layer
+    chain, on non-binary float cubes too (the occupancy grid is converted with a hi and a lo plane), different batch sizes."""
+    from pcgcv1_b200 import _lib, synthetic
+    codec = codec_simple
+    cubes, _ = synthetic.surface_cubes(5, seed=33)
+    rng = np.random.default_rng(5)
+    soft = (cubes.astype(np.float32) * rng.uniform(0.25, 1.0, size=cubes.shape).astype(np.float32))      # not representable in bf16
+    for x_host in (cubes, soft):
+        x = codec.to_device(x_host)
+        try:
+            codec.set_engine(_lib.ENGINE_FFMA)
+            y_f = codec.analysis(x)
+            g_f = codec.synthesis(torch.round(y_f))
+            codec.set_engine(_lib.ENGINE_AUTO)
+            y_u = codec.analysis(x)
+            g_u = codec.synthesis(torch.round(y_f))
+            codec.synchronize()
+        finally:
+            codec.set_engine(_lib.ENGINE_AUTO)
+        ey = (y_u - y_f).abs().max().item()
+        eg = (g_u - g_f).abs().max().item()
+        agree = (torch.round(y_u) == torch.round(y_f)).float().mean().item()
+        print("simple: analysis |d|max %.3g (|y|max %.3g), synthesis |d|max %.3g (|logit|max %.3g), rounding agreement %.6f"
+              % (ey, y_f.abs().max().item(), eg, g_f.abs().max().item(), agree))
+        assert ey < 1e-4 * max(1.0, y_f.abs().max().item())
+        assert eg < 1e-4 * max(1.0, g_f.abs().max().item())
+        assert agree >= 0.999
+        # bit-reproducible and batch-invariant
+        assert torch.equal(y_u, codec.analysis(x))
+        assert torch.equal(y_u[3:4], codec.analysis(x[3:4]))
+        assert torch.equal(g_u[1:3], codec.synthesis(torch.round(y_f)[1:3]))
+
+
+def test_simple_model_vs_fp64_reference(codec_simple):
+    """model_simple's analysis and synthesis chains against float64 torch convs with the TF SAME / Conv3DTranspose rules
+    (oracle.nets, pinned by tests/golden/golden_nets.npz): tolerance 2e-5 of the output scale, which a wrong tap, parity class or
+    crop offset in any layer misses by orders of magnitude (the FP32 CUDA-core engine sits at ~1e-6, split-bf16 at ~5e-6)."""
+    from oracle import nets
+    from pcgcv1_b200 import synthetic, weights as W
+    w = W.synthetic_weights("simple")
+    cubes, _ = synthetic.surface_cubes(2, seed=44)
+    y = codec_simple.analysis(codec_simple.to_device(cubes)).cpu().numpy().astype(np.float64)
+    ref = nets.run_net("simple", "analysis", cubes.astype(np.float64), W.net_weights(w, "analysis_transform"), dtype=torch.float64)
+    assert np.abs(y - ref).max() < 2e-5 * max(1.0, np.abs(ref).max())
+    yq = np.rint(ref)
+    g = codec_simple.synthesis(codec_simple.to_device(yq.astype(np.float32))).cpu().numpy().astype(np.float64)
+    ref_g = nets.run_net("simple", "synthesis", yq, W.net_weights(w, "synthesis_transform"), dtype=torch.float64)
+    assert np.abs(g - ref_g).max() < 2e-5 * max(1.0, np.abs(ref_g).max())

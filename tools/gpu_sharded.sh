@@ -11,7 +11,8 @@ for N in 1 2 4 8; do
   python - <<EOF
 import json
 try:
-    d = json.load(open("gpurun_out/${TAG}_sharded_n$N.json"))
+    s = open("gpurun_out/${TAG}_sharded_n$N.json").read()
+    d = json.loads(s[s.index("{"):])            # torchrun ranks may print an NCCL banner before the line
     print("config3 N=$N value", d["value"], "e2e", d["e2e"]["value"], "sha", d["stream_sha256_16"], "bytes", d["stream_bytes"])
 except Exception as e:
     print("config3 N=$N failed", e)
