@@ -58,8 +58,8 @@ struct UmmaProgram {
   UmmaWeights down[2];          // analysis: down_1, down_2 as 8-tap GEMMs over the space-to-depth input
   float* conv_in_w = nullptr;   // analysis: conv_in weights [27][16] for the dedicated kernel
   // model_simple (models/model_simple.py:21-42,58-86) on the window-GEMM kernel (umma_win.cu)
-  WinLayer s_conv1, s_conv2;    // analysis: 9^3 s2 1->32 (5^3 cells x 8 parities), 5^3 s2 32->32 (3^3 cells x 8 parities x 32)
-  WinLayer s_deconv2[4];        // synthesis: 5^3 s2 transposed 32->32, two output-parity classes per launch
+  WinLayer s_conv1, s_conv2, s_conv3;   // analysis: 9^3 s2 1->32 (5^3 cells x 8 parities), 5^3 s2 32->32 (3^3 cells x 8 parities x 32) twice
+  WinLayer s_deconv1[4], s_deconv2[4];  // synthesis: 5^3 s2 transposed 32->32 (8^3 -> 16^3, 16^3 -> 32^3), two output-parity classes per launch
   WinLayer s_deconv3;           // synthesis: 9^3 s2 transposed 32->1, the 8 classes as 8 columns
 };
 
@@ -630,11 +630,10 @@ int run_hyper_umma(pcgc_ctx* ctx, int kind, const float* in_ext, int B, float* o
 }
 
 
-// model_simple with its four large layers on the tcgen05 window-GEMM kernel (umma_win.cu); the two 8^3 layers (conv_3,
-// deconv_1: 4.8 % of the MACs each way, grids smaller than one M tile) stay on the FP32 CUDA-core kernel.
+// model_simple, every layer on the tcgen05 window-GEMM kernel (umma_win.cu; the 8^3 grids in its 8 x 8 x 2-voxel tile form).
 //   analysis : cube -> space-to-depth PM [32^3][8] -> conv_1 (5^3 cells) -> space-to-depth PM [16^3][256] -> conv_2 (3^3 cells)
-//              -> PM [16^3][32] -> conv_3 (FFMA) -> y float32 [8^3][32]
-//   synthesis: y -> deconv_1 (FFMA) -> PM [16^3][32] -> deconv_2 (4 launches x 2 parity classes) -> PM [32^3][32]
+//              -> space-to-depth PM [8^3][256] -> conv_3 (3^3 cells) -> y float32 [8^3][32]
+//   synthesis: y -> PM [8^3][32] -> deconv_1 (4 launches x 2 parity classes) -> PM [16^3][32] -> deconv_2 (the same) -> PM [32^3][32]
 //              -> deconv_3 (8 classes = 8 columns) -> logits float32 [64^3][1]
 int build_simple_program(pcgc_ctx* ctx, int kind) {
   Net& n = ctx->nets[kind];
@@ -659,21 +658,33 @@ int build_simple_program(pcgc_ctx* ctx, int kind) {
       return l2.hk[((((size_t)kz * 5 + ky) * 5 + kx) * 32 + c) * 32 + co];
     };
     if (e == cudaSuccess) e = pack_win_layer(256, 3, 3, 3, -1, -1, -1, 32, w2, l2.hb.data(), up.s_conv2);
+    const LayerW& l3 = Lw("conv_3");                         // the same form on the 8^3 output grid, no bias, no activation
+    auto w3 = [&](int tz, int ty, int tx, int ci, int co) -> float {
+      const int par = ci / 32, c = ci % 32;
+      const int kz = 2 * (tz - 1) + ((par >> 2) & 1) + 1, ky = 2 * (ty - 1) + ((par >> 1) & 1) + 1, kx = 2 * (tx - 1) + (par & 1) + 1;
+      if (kz < 0 || kz > 4 || ky < 0 || ky > 4 || kx < 0 || kx > 4) return 0.f;
+      return l3.hk[((((size_t)kz * 5 + ky) * 5 + kx) * 32 + c) * 32 + co];
+    };
+    if (e == cudaSuccess) e = pack_win_layer(256, 3, 3, 3, -1, -1, -1, 32, w3, nullptr, up.s_conv3, 2);
   } else {
-    const LayerW &l2 = Lw("deconv_2"), &l3 = Lw("deconv_3");
+    const LayerW &l1 = Lw("deconv_1"), &l2 = Lw("deconv_2"), &l3 = Lw("deconv_3");
     // Conv3DTranspose: out[2t + r] gathers x[t + c] W[k], k = r + pad_before - 2c; Keras [k,k,k,Cout,Cin]
-    for (int g = 0; g < 4 && e == cudaSuccess; ++g) {
-      auto w = [&](int tz, int ty, int tx, int ci, int col) -> float {
-        const int rz = g >> 1, ry = g & 1, rx = col / 32, co = col % 32;
-        const int kz = rz + 1 - 2 * (tz - 1), ky = ry + 1 - 2 * (ty - 1), kx = rx + 1 - 2 * (tx - 1);
-        if (kz < 0 || kz > 4 || ky < 0 || ky > 4 || kx < 0 || kx > 4) return 0.f;
-        return l2.hk[((((size_t)kz * 5 + ky) * 5 + kx) * 32 + co) * 32 + ci];
-      };
-      std::vector<float> bb(64);
-      for (int i = 0; i < 64; ++i) bb[i] = l2.hb[i % 32];
-      e = pack_win_layer(32, 3, 3, 3, -1, -1, -1, 64, w, bb.data(), up.s_deconv2[g]);
-      up.s_deconv2[g].up_ncls = 2; up.s_deconv2[g].up_cout = 32;
-      up.s_deconv2[g].up_cls[0] = 2 * g; up.s_deconv2[g].up_cls[1] = 2 * g + 1;
+    for (int layer = 0; layer < 2; ++layer) {
+      const LayerW& l = layer == 0 ? l1 : l2;
+      for (int g = 0; g < 4 && e == cudaSuccess; ++g) {
+        auto w = [&](int tz, int ty, int tx, int ci, int col) -> float {
+          const int rz = g >> 1, ry = g & 1, rx = col / 32, co = col % 32;
+          const int kz = rz + 1 - 2 * (tz - 1), ky = ry + 1 - 2 * (ty - 1), kx = rx + 1 - 2 * (tx - 1);
+          if (kz < 0 || kz > 4 || ky < 0 || ky > 4 || kx < 0 || kx > 4) return 0.f;
+          return l.hk[((((size_t)kz * 5 + ky) * 5 + kx) * 32 + co) * 32 + ci];
+        };
+        std::vector<float> bb(64);
+        for (int i = 0; i < 64; ++i) bb[i] = l.hb[i % 32];
+        WinLayer& wl = layer == 0 ? up.s_deconv1[g] : up.s_deconv2[g];
+        e = pack_win_layer(32, 3, 3, 3, -1, -1, -1, 64, w, bb.data(), wl, layer == 0 ? 2 : 1);
+        wl.up_ncls = 2; wl.up_cout = 32;
+        wl.up_cls[0] = 2 * g; wl.up_cls[1] = 2 * g + 1;
+      }
     }
     auto w3 = [&](int tz, int ty, int tx, int ci, int col) -> float {
       const int kz = ((col >> 2) & 1) + 3 - 2 * (tz - 2), ky = ((col >> 1) & 1) + 3 - 2 * (ty - 2), kx = (col & 1) + 3 - 2 * (tx - 2);
@@ -744,16 +755,21 @@ int run_simple_umma(pcgc_ctx* ctx, int kind, const float* in_ext, const void* cu
     if (kind == PCGC_NET_SIMPLE_ANALYSIS) {
       const size_t esz = cubes_dtype == PCGC_DTYPE_U8 ? 1 : (cubes_dtype == PCGC_DTYPE_F32 ? 4 : 8);
       const void* src = cubes ? (const void*)((const char*)cubes + (size_t)b0 * 262144 * esz) : (const void*)(in_ext + (size_t)b0 * 262144);
-      PmTensor x = pm(BUF_X0, 32, 8, nb), f1 = pm(BUF_A, 16, 256, nb), f2 = pm(BUF_B, 16, 32, nb);
+      PmTensor x = pm(BUF_X0, 32, 8, nb), f1 = pm(BUF_A, 16, 256, nb), f2 = pm(BUF_B, 8, 256, nb);
       CK(launch_cubes_to_s2d_pm(src, cubes ? cubes_dtype : PCGC_DTYPE_F32, x, ctx->stream, &ctx->launches));
       WinCall c1; c1.epi = WEPI_PM; c1.flags = EPI_RELU; c1.out = f1; c1.out_s2d = 1;
       if ((r = win("conv_1", up.s_conv1, x, c1))) return r;
-      WinCall c2; c2.epi = WEPI_PM; c2.flags = EPI_RELU; c2.out = f2;
+      WinCall c2; c2.epi = WEPI_PM; c2.flags = EPI_RELU; c2.out = f2; c2.out_s2d = 1;
       if ((r = win("conv_2", up.s_conv2, f1, c2))) return r;
-      if ((r = ffma("conv_3", nullptr, &f2, 16, out0 + (size_t)b0 * 8 * 8 * 8 * 32, nullptr, nb))) return r;
+      WinCall c3; c3.epi = WEPI_F32; c3.flags = 0; c3.out_f32 = out0 + (size_t)b0 * 8 * 8 * 8 * 32; c3.out_cs = 32; c3.out_co = 0;
+      if ((r = win("conv_3", up.s_conv3, f2, c3))) return r;
     } else {
-      PmTensor f1 = pm(BUF_A, 16, 32, nb), f2 = pm(BUF_B, 32, 32, nb);
-      if ((r = ffma("deconv_1", in_ext + (size_t)b0 * 8 * 8 * 8 * 32, nullptr, 8, nullptr, &f1, nb))) return r;
+      PmTensor yin = pm(BUF_B, 8, 32, nb), f1 = pm(BUF_A, 16, 32, nb), f2 = pm(BUF_B, 32, 32, nb);
+      CK(launch_f32_to_pm(in_ext + (size_t)b0 * 8 * 8 * 8 * 32, 32, 0, yin, ctx->stream, &ctx->launches));
+      for (int g = 0; g < 4; ++g) {
+        WinCall c; c.epi = WEPI_UP_PM; c.flags = EPI_RELU; c.out = f1;
+        if ((r = win("deconv_1", up.s_deconv1[g], yin, c, g == 0, g == 3))) return r;
+      }
       for (int g = 0; g < 4; ++g) {
         WinCall c; c.epi = WEPI_UP_PM; c.flags = EPI_RELU; c.out = f2;
         if ((r = win("deconv_2", up.s_deconv2[g], f1, c, g == 0, g == 3))) return r;
@@ -896,8 +912,8 @@ void pcgc_destroy(pcgc_ctx* ctx) {
     for (int u = 0; u < 2; ++u) for (int g = 0; g < 2; ++g) free_umma_weights(n.up.up[u][g]);
     free_umma_weights(n.up.down[0]); free_umma_weights(n.up.down[1]);
     if (n.up.conv_in_w) cudaFree(n.up.conv_in_w);
-    free_win_layer(n.up.s_conv1); free_win_layer(n.up.s_conv2); free_win_layer(n.up.s_deconv3);
-    for (int g2 = 0; g2 < 4; ++g2) free_win_layer(n.up.s_deconv2[g2]);
+    free_win_layer(n.up.s_conv1); free_win_layer(n.up.s_conv2); free_win_layer(n.up.s_conv3); free_win_layer(n.up.s_deconv3);
+    for (int g2 = 0; g2 < 4; ++g2) { free_win_layer(n.up.s_deconv1[g2]); free_win_layer(n.up.s_deconv2[g2]); }
   }
   for (auto& n : ctx->nets)
     for (auto& lw : n.w) {

@@ -16,6 +16,8 @@
 // Pipeline: one elected thread (warp 8) issues TMA + MMAs over a 2-stage ring (chunk g+1 loads while chunk g multiplies: the load
 // is issued after the MMAs of g are queued, when chunk g-1 -- the stage's previous user -- retires); two TMEM accumulator sets
 // alternate between tiles so the 8 epilogue warps drain tile i while tile i+1 multiplies.  Persistent, one CTA per SM.
+// 8^3 grids (smaller than a 16-line M tile) use zp = 2: the tensor map lists z before y, so the brick is [y][2 slices][x] and the 16
+// row groups (y, z) of an 8 x 8 x 2 tile are again equally spaced (SBO = one x run).
 // Deterministic: fixed chunk / tap order, no split-K, no atomics.
 #include <cuda.h>
 #include <stdlib.h>
@@ -40,6 +42,7 @@ struct WinArgs {
   int exc, ey;                 // brick cells along x, lines along y
   int ox, oy;                  // brick origin relative to the tile origin
   int paired;                  // cin == 8: K = 16 spans two taps (LBO per table entry)
+  int zp;                      // 1: M rows = 8 x * 16 y of one slice; 2: 8 x * 8 y * 2 z (8^3 grids: brick laid out [y][z][x])
   int n_chunks, n_entries;
   int plane_bytes, a_bytes, tile_bytes, stage_bytes;
   const __nv_bfloat16* wpacked;
@@ -64,7 +67,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_umma_win_kernel(const __g
   uint32_t* s_entries = reinterpret_cast<uint32_t*>(s_chunks + a.n_chunks);
   const uint32_t bar_full = smem_u32(s_bar), bar_free = smem_u32(s_bar + 2), bar_done = smem_u32(s_bar + 4), bar_accfree = smem_u32(s_bar + 6);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tx_n = a.n / 8, ty_n = a.n / 16, tz_n = a.n / a.zt;
+  const int tx_n = a.n / 8, ty_n = a.zp == 2 ? a.n / 8 : a.n / 16, tz_n = a.n / (a.zp == 2 ? 2 : a.zt);
   const int total_tiles = tx_n * ty_n * tz_n * a.batch;
   const int my_tiles = (int)blockIdx.x < total_tiles ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
@@ -90,8 +93,8 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_umma_win_kernel(const __g
   auto tile_origin = [&](int it, int& b, int& x0, int& y0, int& z0) {
     int r = (int)blockIdx.x + it * (int)gridDim.x;
     x0 = (r % tx_n) * 8; r /= tx_n;
-    y0 = (r % ty_n) * 16; r /= ty_n;
-    z0 = (r % tz_n) * a.zt; r /= tz_n;
+    y0 = (r % ty_n) * (a.zp == 2 ? 8 : 16); r /= ty_n;
+    z0 = (r % tz_n) * (a.zp == 2 ? 2 : a.zt); r /= tz_n;
     b = r;
   };
 
@@ -112,7 +115,8 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_umma_win_kernel(const __g
         const uint32_t dst = stage0 + (uint32_t)st * (uint32_t)a.stage_bytes;
         const uint32_t bytes_b = (uint32_t)ck.w * (uint32_t)a.tile_bytes;
         mbar_expect_tx(bar_full + 8 * st, (uint32_t)a.a_bytes + bytes_b);
-        tma_load_5d(dst, &tmap, bar_full + 8 * st, (x0 + a.ox) * 8, y0 + a.oy, z0 + ck.x, ck.y, b);
+        if (a.zp == 2) tma_load_5d(dst, &tmap, bar_full + 8 * st, (x0 + a.ox) * 8, z0 + ck.x, y0 + a.oy, ck.y, b);   // dims (x, z, y, plane, cube)
+        else tma_load_5d(dst, &tmap, bar_full + 8 * st, (x0 + a.ox) * 8, y0 + a.oy, z0 + ck.x, ck.y, b);
         bulk_load(dst + (uint32_t)a.a_bytes, reinterpret_cast<const uint8_t*>(a.wpacked) + (size_t)ck.z * a.tile_bytes, bytes_b, bar_full + 8 * st);
       };
       load(0, 0, 0);
@@ -162,11 +166,11 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_umma_win_kernel(const __g
       int b, x0, y0, z0;
       tile_origin(it, b, x0, y0, z0);
       const int set = it % a.nsets, suse = it / a.nsets;
-      const int vx = x0 + (row & 7), vy = y0 + (row >> 3);
+      const int vx = x0 + (row & 7), vy = y0 + (a.zp == 2 ? (row >> 4) : (row >> 3));
       if (!mbar_wait(bar_done + 8 * set, (uint32_t)suse & 1u, a.err, -133)) break;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int zi = (warp >> 2); zi < a.zt; zi += 2) {
-        const int vz = z0 + zi;
+        const int vz = z0 + (a.zp == 2 ? ((row >> 3) & 1) : zi);
         const uint32_t lane_base = tmem_base + (uint32_t)(set * a.set_cols + zi * 2 * NP) + ((uint32_t)((warp & 3) * 32) << 16);
         if (EPI == WEPI_UP_PM) {
           const int on = 2 * a.n;
@@ -288,13 +292,17 @@ EncodeTiledFn win_encode_fn() {
   return fn;
 }
 
-cudaError_t win_tmap(const PmTensor& t, int exc, int ey, int ez, int ppc, CUtensorMap* out) {
+cudaError_t win_tmap(const PmTensor& t, int exc, int ey, int ez, int ppc, int zp, CUtensorMap* out) {
   EncodeTiledFn fn = win_encode_fn();
   if (!fn) return cudaErrorNotSupported;
   const cuuint64_t n = (cuuint64_t)t.n, planes = (cuuint64_t)(2 * t.c / 8);
   cuuint64_t gdim[5] = {n * 8, n, n, planes, (cuuint64_t)t.B};
   cuuint64_t gstride[4] = {n * 16, n * n * 16, n * n * n * 16, planes * n * n * n * 16};
   cuuint32_t box[5] = {(cuuint32_t)(exc * 8), (cuuint32_t)ey, (cuuint32_t)ez, (cuuint32_t)ppc, 1};
+  if (zp == 2) {                       // dimension order (x, z, y, plane, cube): two z slices interleaved per y line
+    gstride[0] = n * n * 16; gstride[1] = n * 16;
+    box[1] = 2; box[2] = (cuuint32_t)ey;
+  }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)t.p, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -313,12 +321,13 @@ cudaError_t win_launch(const CUtensorMap& tm, const WinArgs& a, int grid, size_t
 }  // namespace
 
 cudaError_t pack_win_layer(int cin, int wz, int wy, int wx, int oz, int oy, int ox, int n_cols,
-                           const std::function<float(int, int, int, int, int)>& weight, const float* bias, WinLayer& out) {
+                           const std::function<float(int, int, int, int, int)>& weight, const float* bias, WinLayer& out, int zp) {
   free_win_layer(out);
+  if (zp != 1 && zp != 2) return cudaErrorInvalidValue;
   if (!(cin == 8 || (cin % 16 == 0 && cin <= 256)) || n_cols < 1 || n_cols > 64) return cudaErrorNotSupported;
   const int np = n_cols <= 16 ? 16 : (n_cols <= 32 ? 32 : 64);
   const bool paired = cin == 8;
-  const int kch = paired ? 1 : cin / 16, exc = 8 + wx - 1;
+  const int kch = paired ? 1 : cin / 16, exc = 8 + wx - 1, pitch = zp * exc;      // cells between consecutive y lines of the brick
   const size_t tile = (size_t)2 * np * 16;
   std::vector<__nv_bfloat16> packed;
   std::vector<int4> chunks;
@@ -354,9 +363,9 @@ cudaError_t pack_win_layer(int cin, int wz, int wy, int wx, int oz, int oy, int 
           }
         }
         if (!nz) continue;
-        const int off0 = ((t0 / wx) * exc + t0 % wx) * 16;
+        const int off0 = ((t0 / wx) * pitch + t0 % wx) * 16;
         uint32_t add = (uint32_t)(off0 >> 4);
-        if (paired && t1 >= 0) add |= (uint32_t)(((((t1 / wx) * exc + t1 % wx) * 16) - off0) >> 4) << 16;
+        if (paired && t1 >= 0) add |= (uint32_t)(((((t1 / wx) * pitch + t1 % wx) * 16) - off0) >> 4) << 16;
         entries.push_back(add);
         packed.insert(packed.end(), tl.begin(), tl.end());
       }
@@ -380,7 +389,7 @@ cudaError_t pack_win_layer(int cin, int wz, int wy, int wx, int oz, int oy, int 
   if ((e = cudaMemcpy(out.bias, bz.data(), np * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
   out.cin = cin; out.wz = wz; out.wy = wy; out.wx = wx; out.oz = oz; out.oy = oy; out.ox = ox;
   out.n_cols = n_cols; out.np = np; out.n_chunks = (int)chunks.size(); out.n_entries = (int)entries.size(); out.max_entries = max_entries;
-  out.ppc = paired ? 2 : 4; out.macs_per_row = macs; out.ok = true;
+  out.ppc = paired ? 2 : 4; out.macs_per_row = macs; out.zp = zp; out.ok = true;
   return cudaSuccess;
 }
 
@@ -394,20 +403,21 @@ void free_win_layer(WinLayer& w) {
 
 cudaError_t launch_conv_umma_win(const WinCall& c, const WinLayer& w, cudaStream_t s, int64_t* launches) {
   const int n = c.in.n;
-  if (!w.ok || c.in.c != w.cin || n % 16 != 0) return cudaErrorNotSupported;
+  if (!w.ok || c.in.c != w.cin || (w.zp == 1 ? n % 16 != 0 : n % 8 != 0)) return cudaErrorNotSupported;
   WinArgs a;
-  a.n = n; a.batch = c.in.B;
-  a.exc = 8 + w.wx - 1; a.ey = 16 + w.wy - 1; a.ox = w.ox; a.oy = w.oy;
+  a.n = n; a.batch = c.in.B; a.zp = w.zp;
+  a.exc = 8 + w.wx - 1; a.ey = (w.zp == 2 ? 8 : 16) + w.wy - 1; a.ox = w.ox; a.oy = w.oy;
   a.paired = w.cin == 8;
   a.n_chunks = w.n_chunks; a.n_entries = w.n_entries;
   a.tile_bytes = 2 * w.np * 32;
   const size_t fixed = 10 * 8 + (size_t)w.np * 4 + (size_t)w.n_chunks * 16 + (size_t)w.n_entries * 4 + 64;
-  int zt = 8;
-  auto stage_bytes = [&](int z) { return (w.ppc * z * a.ey * a.exc * 16 + w.max_entries * a.tile_bytes + 127) / 128 * 128; };
+  int zt = w.zp == 2 ? 1 : 8;                                 // zp = 2: one MMA row set = two slices; the brick holds exactly those
+  const int zmul = w.zp == 2 ? 2 : 1;
+  auto stage_bytes = [&](int z) { return (w.ppc * z * zmul * a.ey * a.exc * 16 + w.max_entries * a.tile_bytes + 127) / 128 * 128; };
   while (zt > 1 && (zt > n || zt * 2 * w.np > 256 || 2 * (size_t)stage_bytes(zt) + fixed > (size_t)200 * 1024)) zt /= 2;
   if (2 * (size_t)stage_bytes(zt) + fixed > (size_t)226 * 1024) return cudaErrorNotSupported;
   a.zt = zt;
-  a.plane_bytes = zt * a.ey * a.exc * 16;
+  a.plane_bytes = zt * zmul * a.ey * a.exc * 16;
   a.a_bytes = w.ppc * a.plane_bytes;
   a.stage_bytes = stage_bytes(zt);
   a.wpacked = (const __nv_bfloat16*)w.packed; a.chunks = (const int4*)w.chunks; a.entries = (const uint32_t*)w.entries; a.bias = w.bias;
@@ -427,10 +437,10 @@ cudaError_t launch_conv_umma_win(const WinCall& c, const WinLayer& w, cudaStream
   if (c.epi == WEPI_UP_F32 && (w.up_cout != 1 || w.up_ncls != w.n_cols || w.n_cols > 8 || !c.out_f32)) return cudaErrorInvalidValue;
   if (c.epi == WEPI_F32 && !c.out_f32) return cudaErrorInvalidValue;
   CUtensorMap tm;
-  cudaError_t e = win_tmap(c.in, a.exc, a.ey, zt, w.ppc, &tm);
+  cudaError_t e = win_tmap(c.in, a.exc, a.ey, zt, w.ppc, w.zp, &tm);
   if (e != cudaSuccess) return e;
   static const int sms = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
-  const int tiles = (n / 8) * (n / 16) * (n / zt) * c.in.B;
+  const int tiles = w.zp == 2 ? (n / 8) * (n / 8) * (n / 2) * c.in.B : (n / 8) * (n / 16) * (n / zt) * c.in.B;
   const int grid = std::min(tiles, sms);
   const size_t smem = 2 * (size_t)a.stage_bytes + fixed;
   if (launches) ++*launches;

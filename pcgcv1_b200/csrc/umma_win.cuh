@@ -23,6 +23,7 @@ struct WinLayer {
   int n_cols = 0, np = 0;      // real / padded (multiple of 16) output columns
   int n_chunks = 0, n_entries = 0, max_entries = 0;
   int ppc = 0;                 // planes per chunk: 2 (cin 8) or 4
+  int zp = 1;                  // 2: the 8 x 8 x 2-voxel tile form for 8^3 grids (umma_win.cu)
   void* packed = nullptr;      // device bf16: [entry][2*np x 16] canonical no-swizzle K-major tiles (hi rows, then lo rows)
   void* chunks = nullptr;      // device int4 {dz, plane0, first entry, entries}
   void* entries = nullptr;     // device uint32: A-descriptor increment (start offset >> 4 | LBO >> 4 << 16)
@@ -36,7 +37,7 @@ struct WinLayer {
 // weight(tz, ty, tx, ci, col): value of window cell (tz, ty, tx), input channel ci, output column col (0 where the reference
 // layer has no tap).  bias: host [n_cols] or null.
 cudaError_t pack_win_layer(int cin, int wz, int wy, int wx, int oz, int oy, int ox, int n_cols,
-                           const std::function<float(int, int, int, int, int)>& weight, const float* bias, WinLayer& out);
+                           const std::function<float(int, int, int, int, int)>& weight, const float* bias, WinLayer& out, int zp = 1);
 void free_win_layer(WinLayer& w);
 
 struct WinCall {
