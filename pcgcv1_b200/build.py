@@ -29,9 +29,14 @@ def _deps_mtime() -> float:
     return m
 
 
+# entropy.cu holds the device copy of the likelihood -> integer CDF path (det_math.h, cdf_norm.h) whose results must equal the host
+# copy's bit for bit: no mul+add contraction there (the host objects are built with -ffp-contract=off).
+PER_FILE = {"entropy.cu": ["-fmad=false"]}
+
+
 def _compile(src: str, verbose: bool) -> str:
     obj = os.path.join(OBJ, src + ".o")
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [NVCC] + FLAGS + PER_FILE.get(src, []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200)      # a ptxas blow-up must not hang the build
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))

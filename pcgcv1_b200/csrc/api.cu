@@ -61,6 +61,7 @@ struct UmmaProgram {
   WinLayer s_conv1, s_conv2, s_conv3;   // analysis: 9^3 s2 1->32 (5^3 cells x 8 parities), 5^3 s2 32->32 (3^3 cells x 8 parities x 32) twice
   WinLayer s_deconv1[4], s_deconv2[4];  // synthesis: 5^3 s2 transposed 32->32 (8^3 -> 16^3, 16^3 -> 32^3), two output-parity classes per launch
   WinLayer s_deconv3;           // synthesis: 9^3 s2 transposed 32->1, the 8 classes as 8 columns
+  WinLayer h_deconv1, h_deconv2[2];   // hyper decoder on its 8^3 grid: 3^3 conv 8->16 (paired taps), 3^3 s2 transposed 16->16 (2 x 4 classes)
 };
 
 struct Net {
@@ -315,6 +316,24 @@ int build_umma_program(pcgc_ctx* ctx, int kind) {
       }
       for (int co = 0; co < 16; ++co) { bb[co] = l41.hb[co]; bb[16 + co] = l42.hb[co]; }
       if (e == cudaSuccess) e = pack_umma_weights_dense(d.data(), bb.data(), 32, 32, up.last);
+      // the two 8^3 layers on the window kernel (8 x 8 x 2-voxel tiles): deconv1 = 3^3 conv 8 -> 16 (Keras [3,3,3,8,16]),
+      // deconv2 = 3^3 stride-2 transposed conv 16 -> 16 (Keras [3,3,3,Cout,Cin]; out[2t + r] gathers x[t + c] W[r - 2c], c in {-1, 0})
+      LayerW &l1 = Lw("deconv1"), &l2 = Lw("deconv2");
+      auto w1 = [&](int tz, int ty, int tx, int ci, int co) -> float { return l1.hk[((((size_t)tz * 3 + ty) * 3 + tx) * 8 + ci) * 16 + co]; };
+      if (e == cudaSuccess) e = pack_win_layer(8, 3, 3, 3, -1, -1, -1, 16, w1, l1.hb.data(), up.h_deconv1, 2);
+      for (int g = 0; g < 2 && e == cudaSuccess; ++g) {
+        auto w2 = [&](int tz, int ty, int tx, int ci, int col) -> float {
+          const int cl = col / 16, co = col % 16;
+          const int kz = g - 2 * (tz - 1), ky = ((cl >> 1) & 1) - 2 * (ty - 1), kx = (cl & 1) - 2 * (tx - 1);
+          if (kz < 0 || kz > 2 || ky < 0 || ky > 2 || kx < 0 || kx > 2) return 0.f;
+          return l2.hk[((((size_t)kz * 3 + ky) * 3 + kx) * 16 + co) * 16 + ci];
+        };
+        std::vector<float> b2(64);
+        for (int i = 0; i < 64; ++i) b2[i] = l2.hb[i % 16];
+        e = pack_win_layer(16, 2, 2, 2, -1, -1, -1, 64, w2, b2.data(), up.h_deconv2[g], 2);
+        up.h_deconv2[g].up_ncls = 4; up.h_deconv2[g].up_cout = 16;
+        for (int i = 0; i < 4; ++i) up.h_deconv2[g].up_cls[i] = 4 * g + i;
+      }
     }
     if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "pack hyper net %d: %s", kind, cudaGetErrorString(e));
     up.ready = true;
@@ -615,9 +634,25 @@ int run_hyper_umma(pcgc_ctx* ctx, int kind, const float* in_ext, int B, float* o
       if ((r = ffma("conv2", nullptr, &f1, 16, ctx->bufs[BUF_B], nullptr, nb))) return r;
       if ((r = ffma("conv3", ctx->bufs[BUF_B], nullptr, 8, out0 + (size_t)b0 * 4096, nullptr, nb))) return r;
     } else {
-      PmTensor f2 = pm(BUF_B, 16, 16, nb), f3 = pm(BUF_T1, 16, 32, nb);
-      if ((r = ffma("deconv1", in_ext + (size_t)b0 * 4096, nullptr, 8, ctx->bufs[BUF_A], nullptr, nb))) return r;
-      if ((r = ffma("deconv2", ctx->bufs[BUF_A], nullptr, 8, nullptr, &f2, nb))) return r;
+      PmTensor zin = pm(BUF_T1, 8, 8, nb), d1 = pm(BUF_A, 8, 16, nb), f2 = pm(BUF_B, 16, 16, nb), f3 = pm(BUF_T1, 16, 32, nb);
+      auto win = [&](const char* what, const WinLayer& w, const PmTensor& in, WinCall c, bool open_tag, bool close_tag, double mult) -> int {
+        c.in = in; c.err = ctx->err_flag;
+        char tag[96];
+        snprintf(tag, sizeof tag, "conv_umma_win %s c%d->%d n%d", what, w.cin, w.n_cols, in.n);
+        if (open_tag) prof_begin(ctx, tag, 2.0 * in.B * (double)in.n * in.n * in.n * w.macs_per_row * mult, 0);
+        cudaError_t e = launch_conv_umma_win(c, w, ctx->stream, &ctx->launches);
+        if (close_tag) prof_end(ctx);
+        if (e != cudaSuccess) return fail(ctx, PCGC_ERR_CUDA, "%s: %s", tag, cudaGetErrorString(e));
+        return PCGC_OK;
+      };
+      // pinned kernels from here on: loc / scale feed the integer CDF tables, so the decoder process must reproduce the encoder's bits
+      CK(launch_f32_to_pm(in_ext + (size_t)b0 * 4096, 8, 0, zin, ctx->stream, &ctx->launches));
+      WinCall c1; c1.epi = WEPI_PM; c1.flags = EPI_RELU; c1.out = d1;
+      if ((r = win("deconv1", up.h_deconv1, zin, c1, true, true, 1.0))) return r;
+      for (int g = 0; g < 2; ++g) {
+        WinCall c2; c2.epi = WEPI_UP_PM; c2.flags = EPI_RELU; c2.out = f2;
+        if ((r = win("deconv2", up.h_deconv2[g], d1, c2, g == 0, g == 1, 2.0))) return r;
+      }
       // pinned kernels: loc / scale feed the integer CDF tables, so the decoder process must reproduce the encoder's bits
       UmmaCall c; c.epi = UEPI_PM; c.flags = EPI_RELU; c.out = f3; c.pin_tile = true;
       if ((r = umma("deconv3", up.first, f2, c))) return r;
@@ -913,6 +948,7 @@ void pcgc_destroy(pcgc_ctx* ctx) {
     free_umma_weights(n.up.down[0]); free_umma_weights(n.up.down[1]);
     if (n.up.conv_in_w) cudaFree(n.up.conv_in_w);
     free_win_layer(n.up.s_conv1); free_win_layer(n.up.s_conv2); free_win_layer(n.up.s_conv3); free_win_layer(n.up.s_deconv3);
+    free_win_layer(n.up.h_deconv1); free_win_layer(n.up.h_deconv2[0]); free_win_layer(n.up.h_deconv2[1]);
     for (int g2 = 0; g2 < 4; ++g2) { free_win_layer(n.up.s_deconv1[g2]); free_win_layer(n.up.s_deconv2[g2]); }
   }
   for (auto& n : ctx->nets)

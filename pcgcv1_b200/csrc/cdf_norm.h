@@ -40,9 +40,21 @@ namespace pcgc {
 static PCGC_TABLE_QUAL const double pcgc_gain_tab[33] = {0x0.0p+0, 0x1.0000000000000p+0, 0x1.2b803473f7ad0p-1, 0x1.a8ff971810a60p-2, 0x1.49a784bcd1b88p-2, 0x1.0d58e42b1da18p-2, 0x1.c775ad8425790p-3, 0x1.8a8980abfbd30p-3, 0x1.5c01a39fbd680p-3, 0x1.374d65d9e6090p-3, 0x1.199b728cb9d10p-3, 0x1.011655c981720p-3, 0x1.d8fea38406fe0p-4, 0x1.b5ecb78443f40p-4, 0x1.97b2b7eafbf20p-4, 0x1.7d60496cfbb40p-4, 0x1.663f6fac91300p-4, 0x1.51c3d792e9a00p-4, 0x1.3f7f8fe0d2300p-4, 0x1.2f1b3bd2f9e40p-4, 0x1.20508f547ee00p-4, 0x1.12e655c4f4c00p-4, 0x1.06ad885e62d00p-4, 0x1.f6fe466940280p-5, 0x1.e275048da0b80p-5, 0x1.cf88427a6d400p-5, 0x1.be094776e7a80p-5, 0x1.add02791a0400p-5, 0x1.9eba920522280p-5, 0x1.90aaddd0d5c00p-5, 0x1.8387463c61d80p-5, 0x1.77394c9d95900p-5, 0x1.6bad3758efd80p-5};
 static PCGC_TABLE_QUAL const double pcgc_ln1p_tab[16] = {0x0.0p+0, 0x1.62e42fefa39efp-1, 0x1.9f323ecbf984cp-2, 0x1.269621134db92p-2, 0x1.c8ff7c79a9a22p-3, 0x1.7565011e49676p-3, 0x1.3bb35a041d2a9p-3, 0x1.1178e8227e47cp-3, 0x1.e27076e2af2e6p-4, 0x1.af8e8210a415dp-4, 0x1.8663f793c46c7p-4, 0x1.64660aa8ce626p-4, 0x1.47dadcbbdba83p-4, 0x1.2f8bd74c5eacfp-4, 0x1.1a9844eb18ef1p-4, 0x1.08598b59e3a06p-4};
 
+// log2(1 + 1/v) for v > 32 from correctly rounded IEEE operations only.  The first version called log2() twice: glibc's and
+// libdevice's log2 differ in the last ulp now and then, the difference log2(v+1) - log2(v) amplifies that to ~1e-10 relative, and
+// two entries whose gains are closer than that were ranked differently on host and device (r02: 2 of 5 M rows of the vox10 cloud
+// one unit apart).  ln(1 + x) = x (1 - x (1/2 - x (1/3 - ...))), x = 1/v < 1/32: 15 terms leave < 1e-23 relative.  entropy.cu is
+// compiled with -fmad=false and the host with -ffp-contract=off, so the same operations run on both sides.
+PCGC_HD double cdf_log2_ratio(int v) {
+  const double x = 1.0 / (double)v;
+  double p = 1.0 / 15.0;
+  for (int k = 14; k >= 1; --k) p = 1.0 / (double)k - x * p;
+  return (x * p) * 1.4426950408889634;
+}
+
 PCGC_HD double cdf_gain(double m, int v) {
   if (v <= 32) return m * pcgc_gain_tab[v];
-  return m * (log2((double)(v + 1)) - log2((double)v));
+  return m * cdf_log2_ratio(v);
 }
 
 // Float SCORE used to shortlist candidates: score = cdf_gain(m, v) * 2^precision / log2(e) - 1, a strictly increasing

@@ -446,6 +446,7 @@ cudaError_t launch_conv_umma_win(const WinCall& c, const WinLayer& w, cudaStream
   if (launches) ++*launches;
   switch (w.np * 10 + c.epi) {
     case 160 + WEPI_F32: return win_launch<16, WEPI_F32>(tm, a, grid, smem, s);
+    case 160 + WEPI_PM: return win_launch<16, WEPI_PM>(tm, a, grid, smem, s);
     case 160 + WEPI_UP_F32: return win_launch<16, WEPI_UP_F32>(tm, a, grid, smem, s);
     case 320 + WEPI_F32: return win_launch<32, WEPI_F32>(tm, a, grid, smem, s);
     case 320 + WEPI_PM: return win_launch<32, WEPI_PM>(tm, a, grid, smem, s);
