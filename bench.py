@@ -148,7 +148,7 @@ def device_step(codec, st):
                                                    uploaded=(st["packed"], st["offsets"]), sync=False)
     finally:
         codec.deferred_checks(False)
-    mask, _, cnt = codec.topk(xs, st["ks"])
+    mask, _, cnt = codec.topk(xs.raw, st["ks"])                 # same stream as the synthesis: stream order is enough
     return mask, cnt
 
 

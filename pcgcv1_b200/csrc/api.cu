@@ -998,6 +998,28 @@ int pcgc_profile_report(pcgc_ctx* ctx, char* buf, int64_t cap) {
   CK(cudaStreamSynchronize(ctx->stream));
   struct Agg { std::string tag; int count; double ms, flops, bytes; };
   std::vector<Agg> aggs;
+  if (getenv("PCGC_PROF_TIMELINE") && !ctx->prof.empty()) {
+    // dev form (tools/timeline.py): one entry per record with its start relative to the first record, so that the gaps
+    // between launches and the overlap of the streams can be read off
+    std::string out = "[";
+    for (size_t i = 0; i < ctx->prof.size(); ++i) {
+      auto& r = ctx->prof[i];
+      float t0 = 0.f, ms = 0.f;
+      cudaEventSynchronize(r.b);
+      cudaEventElapsedTime(&t0, ctx->prof[0].a, r.a);
+      cudaEventElapsedTime(&ms, r.a, r.b);
+      char line[256];
+      snprintf(line, sizeof line, "%s{\"tag\":\"%s\",\"count\":1,\"t0\":%.4f,\"ms\":%.4f,\"flops\":%.6e,\"bytes\":%.6e}", i ? "," : "",
+               r.tag.c_str(), t0, ms, r.flops, r.bytes);
+      out += line;
+    }
+    out += "]";
+    for (auto& r : ctx->prof) { ctx->ev_pool.push_back(r.a); ctx->ev_pool.push_back(r.b); }
+    ctx->prof.clear();
+    if ((int64_t)out.size() + 1 > cap) return fail(ctx, PCGC_ERR_OVERFLOW, "profile report needs %zu bytes", out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return PCGC_OK;
+  }
   for (auto& r : ctx->prof) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, r.a, r.b);

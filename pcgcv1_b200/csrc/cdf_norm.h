@@ -77,6 +77,12 @@ PCGC_HD float cdf_score(float m, int v, float scale) {
 #define PCGC_WATERFILL_MIN(n) (2 * (n) + 8)
 #endif
 #define PCGC_SCORE_TOL(mx) (4e-6f * fabsf(mx) + 1e-9f)
+#ifndef PCGC_CDF_ITER_HOOK
+#define PCGC_CDF_ITER_HOOK ((void)0)   // tools/cdf_check.cpp counts the loop iterations through this
+#endif
+#ifndef PCGC_CDF_RUNLEN
+#define PCGC_CDF_RUNLEN 1      // 0: the plain step-by-step loop (kept for the equivalence test of tools/cdf_check.cpp)
+#endif
 
 // Largest u >= 1 with cdf_gain(m, u) >= lambda (0 if none), i.e. u <= 1 / (2^(lambda/m) - 1).  Closed form with a short
 // exact check only when the bound is within rounding distance of an integer.
@@ -168,6 +174,7 @@ PCGC_HD_NOINLINE int quantize_pmf_row(const float* pmf, int n, int precision, in
   for (int i = 0; i < n; ++i)
     g[i * st] = dir > 0 ? cdf_score(pmf[i * st], v[i * st], scale) : (v[i * st] > 1 ? -cdf_score(pmf[i * st], v[i * st] - 1, scale) : -INFINITY);
   while (todo > 0) {
+    PCGC_CDF_ITER_HOOK;
     // one pass: the best score, its (first) index and the runner-up; only a runner-up within the tolerance needs the exact path
     float mx = -INFINITY, second = -INFINITY;
     int best = -1;
@@ -178,6 +185,7 @@ PCGC_HD_NOINLINE int quantize_pmf_row(const float* pmf, int n, int precision, in
     }
     if (!(mx > -INFINITY)) return -2;
     const float thr = mx - PCGC_SCORE_TOL(mx);
+    long long run = 1;
     if (second >= thr) {                    // near tie: decide on the exact gains, lowest index first
       double bs = -INFINITY;
       for (int i = 0; i < n; ++i)
@@ -186,9 +194,42 @@ PCGC_HD_NOINLINE int quantize_pmf_row(const float* pmf, int n, int precision, in
           if (e > bs) { bs = e; best = i; }
         }
     }
-    v[best * st] += dir;
+#if PCGC_CDF_RUNLEN
+    else if (todo > 1) {
+      // RUN of steps for a clear leader.  The step-by-step greedy re-scans after every step; while the leader's score stays
+      // above the runner-up's by more than the tolerance it picks the same entry again without the exact path, and the other
+      // scores do not change.  Scores fall strictly with every step (by ~1/v, far above their float evaluation error), so it is
+      // enough to check the LAST step of the run: the result equals the step-by-step one.  The run length comes from
+      // score(v) ~ (r - 1/2) / v  (r = m 2^p - v), aimed one short, and is only trusted after that check.
+      const int vb = v[best * st];
+      const float mS = pmf[best * st] * scale;
+      long long J = 1;
+      if (dir > 0) {
+        if (vb >= 16 && second > -1.0f) {
+          const float r = mS - (float)vb;
+          const float jm = (r - 0.5f - second * (float)vb) / (1.0f + second) - 1.0f;     // last step index whose score still leads, one short
+          if (jm >= 1.0f) J = jm >= (float)(todo - 1) ? todo : (long long)jm + 1;
+        }
+      } else {
+        const int w = vb - 1;                                                             // the score in play is -score(m, w)
+        if (w >= 17) {
+          const float t = -second, r = mS - (float)w;
+          float jm = t > -1.0f ? (t * (float)w - r + 0.5f) / (1.0f + t) - 1.0f : 0.0f;
+          if (second == -INFINITY) jm = (float)(w - 16);                                  // the only entry that can shrink
+          if (jm > (float)(w - 16)) jm = (float)(w - 16);                                 // stay on the v >= 16 branch of cdf_score
+          if (jm >= 1.0f) J = jm >= (float)(todo - 1) ? todo : (long long)jm + 1;
+        }
+      }
+      if (J > 1) {
+        const int ve = vb + dir * (int)(J - 1);                                           // the entry's count before the run's last step
+        const float se = dir > 0 ? cdf_score(pmf[best * st], ve, scale) : -cdf_score(pmf[best * st], ve - 1, scale);
+        if (se - 2.0f * PCGC_SCORE_TOL(se) > second) run = J;
+      }
+    }
+#endif
+    v[best * st] += dir * (int)run;
     g[best * st] = dir > 0 ? cdf_score(pmf[best * st], v[best * st], scale) : (v[best * st] > 1 ? -cdf_score(pmf[best * st], v[best * st] - 1, scale) : -INFINITY);
-    --todo;
+    todo -= run;
   }
   return 0;
 }

@@ -380,6 +380,32 @@ range_decode_rows_narrow_kernel(const uint8_t* __restrict__ packed, const int64_
 
 }  // namespace
 
+// One-warp CTAs are placed wherever a slot is free.  Measured (r02, tools/sweep_env.sh): launched with no shared-memory
+// request the 191 encoder CTAs of the vox10 cloud ran in one of two regimes, 1.7 ms or ~6-7 ms per launch, depending on what
+// the device was finishing when the launch became runnable: the hardware scheduler stacks up to 32 such CTAs on the SMs that
+// are free at that moment and they stay there for the whole launch, so a latency-bound warp shares its scheduler with 7
+// others.  Unused dynamic shared memory per CTA caps the CTAs per SM (about B / 148 + 1, at least 2) and so forces a launch
+// to spread over the device: 1.7 ms every time.  Large launches (thousands of cubes) keep up to 32 CTAs per SM: there the
+// throughput of the SM counts, not the latency of one string.  PCGC_ENC_PAD_KB / PCGC_DEC_PAD_KB override (0 = off).
+static size_t coder_pad_bytes(const char* env, const void* kernel, int B, bool on_by_default) {
+  static const int max_kb = 200;
+  const char* e = getenv(env);
+  int kb;
+  if (e) {
+    kb = atoi(e);
+  } else if (on_by_default) {
+    int per_sm = (B + 147) / 148 + 1;
+    if (per_sm < 2) per_sm = 2;
+    kb = per_sm >= 32 ? 0 : max_kb / per_sm - 2;
+  } else {
+    kb = 0;
+  }
+  if (kb <= 0) return 0;
+  if (kb > max_kb - 16) kb = max_kb - 16;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_kb * 1024);
+  return (size_t)kb * 1024;
+}
+
 cudaError_t launch_range_encode_intervals(const uint32_t* iv, int B, int64_t E, int precision, uint8_t* scratch, int64_t stride,
                                           int64_t* lens, uint8_t* packed, int64_t cap, int64_t* offsets, int* err,
                                           cudaStream_t s, int64_t* launches) {
@@ -389,7 +415,8 @@ cudaError_t launch_range_encode_intervals(const uint32_t* iv, int B, int64_t E, 
   if (precision != 16 || E % 32 || E > 65536 || stride < dig_off + 4 * (E + 2) || (stride & 15)) return cudaErrorInvalidValue;
   PCGC_CARVEOUT_ONCE(range_encode_intervals_kernel);
   PCGC_CARVEOUT_ONCE(pack_strings_kernel);
-  range_encode_intervals_kernel<<<B, 32, 0, s>>>(iv, B, E, scratch, stride, dig_off, lens);
+  const size_t enc_pad = coder_pad_bytes("PCGC_ENC_PAD_KB", (const void*)range_encode_intervals_kernel, B, true);
+  range_encode_intervals_kernel<<<B, 32, enc_pad, s>>>(iv, B, E, scratch, stride, dig_off, lens);
   pack_strings_kernel<<<B, 256, 0, s>>>(scratch, stride, lens, B, packed, cap, offsets, err);
   if (launches) *launches += 2;
   return cudaGetLastError();
@@ -404,7 +431,8 @@ cudaError_t launch_range_decode_rows(const uint8_t* packed, const int64_t* offse
     // every row window is a multiple of 64 bytes (E % 32 == 0), so 16-byte cp.async needs only the base pointer aligned
     const int slot_elems = (32 * max_n + 32 + 7) / 8 * 8;
     PCGC_CARVEOUT_ONCE(range_decode_rows_narrow_kernel);
-    range_decode_rows_narrow_kernel<<<B, 32, (size_t)DECN_SLOTS * slot_elems * sizeof(uint16_t), s>>>(packed, offsets, B, E, rows, row_offset, minmax,
+    const size_t dec_pad = coder_pad_bytes("PCGC_DEC_PAD_KB", (const void*)range_decode_rows_narrow_kernel, B, false);
+    range_decode_rows_narrow_kernel<<<B, 32, (size_t)DECN_SLOTS * slot_elems * sizeof(uint16_t) + dec_pad, s>>>(packed, offsets, B, E, rows, row_offset, minmax,
                                                                                                     y_hat, err, slot_elems);
     if (launches) ++*launches;
     return cudaGetLastError();

@@ -136,6 +136,8 @@ def select_voxels(vols, points_nums, offset_ratio=1.0, fixed_thres=None, codec=N
     included (``>=``), as NumPy like the reference.  ``dtype="uint8"`` skips the float32 widening that the
     reference's own consumer undoes again (voxels2points casts to uint8, inout_points.py:137)."""
     c = codec or runtime.get_codec("voxception", "")
+    if isinstance(vols, runtime.PendingDeviceResult) and not vols.finalized and fixed_thres is None and len(vols) > 0:
+        return _select_voxels_pipelined(vols._codec, vols, points_nums, offset_ratio, dtype)
     v = c.to_device(vols, torch.float32)
     B = v.shape[0]
     if fixed_thres is None:
@@ -148,6 +150,51 @@ def select_voxels(vols, points_nums, offset_ratio=1.0, fixed_thres=None, codec=N
         mask, _ = c.threshold(v, float(fixed_thres))
     m = runtime.to_host(mask, "mask")
     return m.astype(dtype) if np.dtype(dtype) != m.dtype else runtime.host_copy(m)
+
+
+def _select_voxels_pipelined(c, pend, points_nums, offset_ratio, dtype):
+    """select_voxels on a result that is still being produced (decompress_hyper's PendingDeviceResult): top-k and the mask's
+    device -> host copy of cubes [a, b) start when THAT part's synthesis has finished, beside the synthesis of the later parts;
+    the host copies a part out of the pinned staging buffer while the GPU works on the next one.  Same kernel per cube as the
+    plain path, so the masks are identical."""
+    full = pend.raw
+    B = full.shape[0]
+    V = full[0].numel()
+    pn = np.asarray(runtime.unwrap(points_nums)).reshape(-1)
+    ks = np.array([int(offset_ratio * np.array(pn[i])) for i in range(B)], np.int32)
+    if (ks > V).any():
+        raise IndexError("select_voxels: k exceeds the number of voxels (get_adaptive_thres would raise IndexError)")
+    dev = full.device
+    side, cs = c.coder_stream(7), runtime.copy_stream(dev)
+    stage = runtime.pinned_buffer("mask", B * V)[:B * V].view(B, V)
+    out = np.empty(tuple(full.shape), np.uint8)
+    out2 = out.reshape(B, V)
+    runtime.COUNTERS["d2h_bytes"] += B * V
+    jobs = []
+    c.deferred_checks(True)
+    try:
+        with torch.cuda.stream(side):
+            ksd = c.to_device(ks)
+        for a, b, ev in pend.parts:
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                m, _, _ = c.topk(full[a:b], ksd[a:b])
+                ready = torch.cuda.Event()
+                ready.record(side)
+            m.record_stream(cs)
+            with torch.cuda.stream(cs):
+                cs.wait_event(ready)
+                stage[a:b].copy_(m.view(b - a, V), non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(cs)
+            jobs.append((a, b, done))
+        for a, b, done in jobs:
+            done.synchronize()
+            runtime.host_copy_into(out2[a:b], stage[a:b].numpy())
+    finally:
+        c.deferred_checks(False)
+    pend.finalize()                                      # whole section done; raises if a kernel flagged an error
+    return out if np.dtype(dtype) == np.uint8 else out.astype(dtype)
 
 
 def select_voxels_device(codec, logits: torch.Tensor, ks: torch.Tensor):

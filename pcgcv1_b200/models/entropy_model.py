@@ -74,6 +74,19 @@ class EntropyBottleneck:
         sym = (runtime.to_host(x_hat).reshape(-1).astype(np.int32) - min_v).astype(np.int16)
         return sym, cdf, min_v, max_v
 
+    def compress_quantized_host(self, x_hat: np.ndarray, chunk_minmax: np.ndarray):
+        """Host-only tail of ``compress`` for latents that are already quantised and on the host (``x_hat`` float32 [..., C]) with
+        the (min, max) of their parts (int32 [parts, 2]): global range (entropy_model.py:249-250), the per-channel CDF from the host
+        twin of the CDF kernel (same det_math.h density and normaliser: bit-identical tables, tests/test_gpu_coder.py), ONE string.
+        -> (bytes, min_v, max_v).  No GPU call: the pipeline runs it while the device is still busy."""
+        channels = x_hat.shape[-1]
+        c, slot = self._resolve(channels)
+        mm = np.asarray(chunk_minmax).reshape(-1, 2)
+        min_v, max_v = int(mm[:, 0].min()), int(mm[:, 1].max())
+        cdf = c.factorized_cdf_host(slot, min_v, max_v, self._likelihood_bound, self._range_coder_precision)
+        sym = (x_hat.reshape(-1).astype(np.int32) - min_v).astype(np.int16)
+        return runtime.range_encode(sym, cdf, self._range_coder_precision), min_v, max_v
+
     def compress_finish(self, sym, cdf):
         return runtime.range_encode(sym, cdf, self._range_coder_precision)
 

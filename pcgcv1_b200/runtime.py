@@ -107,6 +107,16 @@ def host_copy(src: np.ndarray) -> np.ndarray:
     return out
 
 
+def host_copy_into(dst: np.ndarray, src: np.ndarray):
+    """dst[...] = src for two contiguous arrays of equal size, through the library's multithreaded memcpy when large."""
+    if dst.nbytes != src.nbytes or not dst.flags.c_contiguous or not src.flags.c_contiguous:
+        raise ValueError("host_copy_into needs contiguous arrays of equal size")
+    if src.nbytes < (8 << 20):
+        dst.reshape(-1).view(np.uint8)[...] = src.reshape(-1).view(np.uint8)
+        return
+    _lib.check(_lib.lib().pcgc_host_copy(dst.ctypes.data, src.ctypes.data, src.nbytes, coder_threads()))
+
+
 def model_name(model) -> str:
     """'voxception' | 'simple' from a model module (test.py:72 importlib seam), a name, or a class."""
     name = model if isinstance(model, str) else getattr(model, "MODEL_NAME", None) or getattr(model, "__name__", "")
@@ -141,6 +151,44 @@ class DeviceResult:
 
     def __getitem__(self, i):
         return DeviceResult(self.tensor[i])
+
+
+class PendingDeviceResult(DeviceResult):
+    """A DeviceResult whose kernels may still be running: ``decompress_hyper`` returns it right after the last launch is queued.
+    ``parts`` = [(a, b, event)]: cubes [a, b) of the tensor are final once ``event`` has fired, in this order -- a consumer that
+    understands parts (``select_voxels(codec=...)``) starts on the first cubes while the last ones are still being synthesised.
+    Every other access (``.tensor``, ``.numpy()``, ``unwrap``) first waits for the whole result and raises if a kernel of the
+    section flagged an error, i.e. it behaves like the plain DeviceResult."""
+
+    def __init__(self, tensor: torch.Tensor, parts, codec, done_event):
+        self._full = tensor
+        self.parts = list(parts)
+        self._codec = codec
+        self._done = done_event
+        self.finalized = False
+
+    @property
+    def raw(self) -> torch.Tensor:
+        """The tensor WITHOUT waiting: for consumers that queue their work on the producing stream (stream order is enough)."""
+        return self._full
+
+    def finalize(self):
+        if not self.finalized:
+            self.finalized = True
+            self._done.synchronize()
+            self._codec.synchronize()                  # raises if any kernel of the section flagged an error
+        return self._full
+
+    @property
+    def tensor(self):
+        return self.finalize()
+
+    @property
+    def shape(self):
+        return tuple(self._full.shape)
+
+    def __len__(self):
+        return self._full.shape[0]
 
 
 class HostResult:
@@ -303,12 +351,17 @@ class Codec:
                                            _TORCH_DTYPES[cubes.dtype], B, y.data_ptr()))
         return y
 
-    def synthesis(self, y: torch.Tensor) -> torch.Tensor:
+    def synthesis(self, y: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         n, c = self.latent_n, self.latent_c
         if tuple(y.shape[1:]) != (n, n, n, c) or y.dtype != torch.float32:
             raise ValueError("y must be float32 [B,%d,%d,%d,%d], got %s %s" % (n, n, n, c, tuple(y.shape), y.dtype))
         B = y.shape[0]
-        x = torch.empty((B, 64, 64, 64, 1), dtype=torch.float32, device=self.dev)
+        if out is not None:
+            if tuple(out.shape) != (B, 64, 64, 64, 1) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != self.dev:
+                raise ValueError("out must be a contiguous float32 [B,64,64,64,1] tensor on the codec's device")
+            x = out
+        else:
+            x = torch.empty((B, 64, 64, 64, 1), dtype=torch.float32, device=self.dev)
         self._stream()
         self._check(self.lib.pcgc_synthesis(self.ctx, _NET_IDS[(self.model, "synthesis_transform")], y.data_ptr(), B,
                                             x.data_ptr()))
@@ -469,22 +522,31 @@ class Codec:
                                                         float(total), mm_dev.data_ptr(), int(max_n), 16, y_hat.data_ptr()))
         return y_hat
 
-    def upload_strings(self, strings):
-        """list of byte strings -> (packed uint8 device tensor, offsets int64 [B+1] device tensor) in ONE H2D copy."""
+    def upload_strings(self, strings, slot: int = 0):
+        """list of byte strings -> (packed uint8 device tensor, offsets int64 [B+1] device tensor) in ONE H2D copy.  ``slot``
+        picks one of the rotating pinned staging buffers; a slot is only rewritten after its previous copy has completed."""
         B = len(strings)
+        prev = getattr(self, "_upload_events", None)
+        if prev is None:
+            prev = self._upload_events = {}
+        if slot in prev:
+            prev[slot].synchronize()
         lens = np.fromiter((len(s) for s in strings), np.int64, B)
         off = np.zeros(B + 1, np.int64)
         np.cumsum(lens, out=off[1:])
         total = int(off[B])
         pad = (-total) % 8                                                   # keep the offsets 8-byte aligned inside the buffer
         n = total + pad + 8 * (B + 1)
-        stage = pinned_buffer("dec_bytes", n)[:n]
+        stage = pinned_buffer("dec_bytes%d" % slot, n)[:n]
         h = stage.numpy()
         if total:
             h[:total] = np.frombuffer(b"".join(bytes(s) for s in strings), np.uint8)
         h[total + pad:] = off.view(np.uint8)
         COUNTERS["h2d_bytes"] += n
         up = stage.to(self.dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        prev[slot] = ev
         return up, up[total + pad:].view(torch.int64)
 
     def factorized_cdf_host(self, slot: int, min_v: int, max_v: int, bound: float = 1e-9, precision: int = 16) -> np.ndarray:

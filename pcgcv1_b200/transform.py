@@ -34,6 +34,14 @@ def _log(msg, start=None):
             print(msg)
 
 
+TRACE = None        # dev hook (tools/host_trace.py): a list that collects (perf_counter, label) marks of the pipelines below
+
+
+def _tr(label):
+    if TRACE is not None:
+        TRACE.append((time.perf_counter(), label))
+
+
 def _strings_array(strings):
     a = np.empty(len(strings), dtype=object)
     for i, s in enumerate(strings):
@@ -89,6 +97,7 @@ def decompress_factorized(strings, min_v, max_v, shape, model, ckpt_dir):
 _CHUNK = int(os.environ.get("PCGC_CHUNK", "64"))
 _CHUNK_EDGE = int(os.environ.get("PCGC_CHUNK_EDGE", "16"))
 _CHUNK_RAMP = bool(int(os.environ.get("PCGC_CHUNK_RAMP", "1")))
+_Z_EARLY = bool(int(os.environ.get("PCGC_Z_EARLY", "1")))     # hyper string coded from the staged copy of z while the GPU finishes
 
 
 def _chunks(B, small_first=False, small_last=False):
@@ -107,15 +116,21 @@ def _chunks(B, small_first=False, small_last=False):
     mid = [(a, min(hi, a + _CHUNK)) for a in range(lo, hi, _CHUNK)]
     return head + mid + tail
 def _gpu_decode_chunks(B):
-    """Chunks of the GPU-coder decode pipeline.  The range decoder's latency is one cube's string (a few ms) whatever the number
-    of cubes in the launch, so: one small first chunk (its decode is exposed), then large ones whose decode hides behind the
-    synthesis of the chunk before (a chunk's CDF rows take ~2.5 MB per cube of device memory)."""
-    first = int(os.environ.get("PCGC_DEC_FIRST", "64"))
+    """Chunks of the GPU-coder decode pipeline.  Nothing can be synthesised before the first chunk's hyper latents have come
+    out of the (sequential, host-side) hyper string, its CDF rows are built and its strings decoded -- a latency of one cube's
+    string (a few ms) whatever the number of cubes -- so the schedule starts small and grows: 8, 24, 64 cubes, then the rest
+    (decoded behind the synthesis of the chunk before; a chunk's CDF rows take ~2.5 MB per cube of device memory).  Measured on
+    the vox10 cloud (tools/sweep_dec.py, decompress + select): 34.2 ms with one 64-cube head, 31.3 ms with this ramp."""
+    ramp = [int(v) for v in os.environ.get("PCGC_DEC_RAMP", os.environ.get("PCGC_DEC_FIRST", "8,24,64")).split(",") if v]
     rest = int(os.environ.get("PCGC_DEC_CHUNK", "512"))
-    if B <= max(first, 64):
+    if B <= max(ramp[0], 64):
         return [(0, B)]
-    out = [(0, first)]
-    out += [(a, min(B, a + rest)) for a in range(first, B, rest)]
+    out, a = [], 0
+    for r in ramp:
+        if B - a <= r:
+            break
+        out.append((a, a + r)); a += r
+    out += [(s, min(B, s + rest)) for s in range(a, B, rest)]
     return out
 
 
@@ -149,12 +164,16 @@ def _host_tail(B):
     return max(0, min(t, B - 1)) if B > 64 else 0      # 0 -> 28.0 ms: the worker threads' GIL traffic delays the kernel enqueue more than the tail saves
 
 
-def encode_on_device(codec, entropy_bottleneck, cem, cubes, keep_side_info=False, want_likelihoods=False, host_tail=0):
+def encode_on_device(codec, entropy_bottleneck, cem, cubes, keep_side_info=False, want_likelihoods=False, host_tail=0, z_to_host=None):
     """Every GPU kernel of the hyper encoder for ``cubes`` (host or device resident), enqueued without a host
     synchronisation: transforms chunk by chunk on the current stream, then ONE range-encoder launch for the first
     B - host_tail cubes on the coder stream; the intervals of the last ``host_tail`` cubes go to pinned memory for the host
     coder.  -> (intervals [B,E], minmax [B,2], [z_hat per chunk], [(loc, scale) per chunk], packed bytes, offsets [Bg+1],
-    [(a, b, pinned intervals, copy-done event) per tail chunk]); tensors on the device.  The caller owns the synchronisation."""
+    [(a, b, pinned intervals, copy-done event) per tail chunk]); tensors on the device.  The caller owns the synchronisation.
+    ``z_to_host`` (a dict to fill): every chunk's quantised hyper latents and their (min, max) are also copied to pinned memory
+    on the copy stream as soon as they exist -- ["z"] float32 [B,8,8,8,8], ["mm"] int32 [chunks,2], ["done"] an event that fires
+    when the LAST chunk's copy has landed, i.e. before that chunk's hyper decoder, intervals and the range encoder have run:
+    the host codes the one hyper string beside them."""
     B = cubes.shape[0]
     E = 16 * 16 * 16 * 16
     dev = codec.dev
@@ -182,6 +201,12 @@ def encode_on_device(codec, entropy_bottleneck, cem, cubes, keep_side_info=False
                 ev.record(cs)
                 uploads.append((xc, ev))
     packed = offsets = None
+    if z_to_host is not None:
+        zcs = runtime.copy_stream(dev)
+        nz = B * 8 * 8 * 8 * 8
+        z_to_host["z"] = runtime.pinned_buffer("z_hat_enc", 4 * nz)[:4 * nz].view(torch.float32).view(B, 8, 8, 8, 8)
+        z_to_host["mm"] = runtime.pinned_buffer("z_mm_enc", 8 * len(chunks))[:8 * len(chunks)].view(torch.int32).view(len(chunks), 2)
+        runtime.COUNTERS["d2h_bytes"] += 4 * nz + 8 * len(chunks)
 
     def launch_gpu_coder():
         ready = torch.cuda.Event()
@@ -202,8 +227,19 @@ def encode_on_device(codec, entropy_bottleneck, cem, cubes, keep_side_info=False
             x = cubes[a:b]
         ys = codec.analysis(x)
         zs = codec.hyper_encode(ys)
-        z_hat, _, _, _ = codec.factorized(entropy_bottleneck._slot, zs, want_p=want_likelihoods, want_bits=want_likelihoods)
+        z_hat, _, _, z_mm = codec.factorized(entropy_bottleneck._slot, zs, want_p=want_likelihoods, want_bits=want_likelihoods)
         z_hats.append(z_hat)
+        if z_to_host is not None:
+            zr = torch.cuda.Event()
+            zr.record(main)
+            z_hat.record_stream(zcs); z_mm.record_stream(zcs)
+            with torch.cuda.stream(zcs):
+                zcs.wait_event(zr)
+                z_to_host["z"][a:b].copy_(z_hat, non_blocking=True)
+                z_to_host["mm"][k].copy_(z_mm, non_blocking=True)
+                if k == len(chunks) - 1:
+                    z_to_host["done"] = torch.cuda.Event()
+                    z_to_host["done"].record(zcs)
         locs, scales = codec.hyper_decode(z_hat, 1e-9)                  # lower_bound = 1e-9, transform.py:145-146
         _, mm = cem.intervals_dev(ys, locs, scales, iv_out=iv_all[a:b], want_likelihoods=want_likelihoods)
         mm_all[a:b].copy_(mm)
@@ -229,8 +265,9 @@ def _compress_hyper_gpu_coder(codec, entropy_bottleneck, cem, cubes, decompress,
     Bg = B - tail
     codec.deferred_checks(True)
     try:
+        z_host = {} if code_z and _Z_EARLY else None
         iv_all, mm_all, z_hats, keep, packed, offsets, tails = encode_on_device(codec, entropy_bottleneck, cem, cubes, decompress,
-                                                                               host_tail=tail)
+                                                                               host_tail=tail, z_to_host=z_host)
         tail_jobs = [_pool().submit(cem.encode_finish, stage, done) for (_, _, stage, done) in tails]
         hdr = runtime.pinned_buffer("enc_hdr", 8 * (Bg + 1))
         off_h = hdr[:8 * (Bg + 1)].view(torch.int64)
@@ -238,15 +275,24 @@ def _compress_hyper_gpu_coder(codec, entropy_bottleneck, cem, cubes, decompress,
             off_h.copy_(offsets, non_blocking=True)
             hdr_done = torch.cuda.Event()
             hdr_done.record(side)
-        # the ONE hyper string (global range, entropy_model.py:249-259) is coded here on the host beside the GPU encoder
+        # the ONE hyper string (global range, entropy_model.py:249-259) is coded here on the host, from the pinned copy of the
+        # quantised latents that landed before the last chunk's hyper decoder / intervals and the GPU range encoder started
         z_all = torch.cat(z_hats) if len(z_hats) > 1 else z_hats[0]
         z_string = z_min = z_max = None
-        if code_z:
+        _tr("enqueued")
+        if code_z and z_host is not None:
+            z_host["done"].synchronize()
+            _tr("z on host")
+            z_string, z_min, z_max = entropy_bottleneck.compress_quantized_host(z_host["z"].numpy(), z_host["mm"].numpy())
+            _tr("z coded")
+        elif code_z:
             sym, cdf, z_min, z_max = entropy_bottleneck.compress_begin(z_all)
-        mm = runtime.to_host(mm_all).copy()                                 # the main stream is idle by now (compress_begin synchronised it)
-        if code_z:
             z_string = entropy_bottleneck.compress_finish(sym, cdf)
+            _tr("z coded (late)")
+        mm = runtime.to_host(mm_all).copy()
+        _tr("minmax on host")
         hdr_done.synchronize()
+        _tr("encoder done")
         off = off_h.numpy().copy()
         total = int(off[Bg])
         if strings_on_device:
@@ -259,9 +305,11 @@ def _compress_hyper_gpu_coder(codec, entropy_bottleneck, cem, cubes, decompress,
         with torch.cuda.stream(side):
             stage.copy_(packed[:total], non_blocking=True)
         side.synchronize()
+        _tr("strings on host")
         runtime.COUNTERS["d2h_bytes"] += total + hdr.numel()
         blob = stage.numpy()
         strings = [blob[off[i]:off[i + 1]].tobytes() for i in range(Bg)]
+        _tr("strings sliced")
         for j in tail_jobs:
             strings += j.result()
     finally:
@@ -348,31 +396,44 @@ def compress_hyper(cubes, model, ckpt_dir, decompress=False):
 
 
 def _decompress_hyper_gpu_coder(codec, cem, strings, mins, maxs, y_shape, z_get, chunks, uploaded=None, sync=True):
-    """decompress_hyper with the per-cube strings read ON THE GPU: the strings go up once (a few KB per cube), CDF rows are
-    built and consumed on the device.  Chunk k+1 is decoded on the coder stream while chunk k is synthesised."""
+    """decompress_hyper with the per-cube strings read ON THE GPU: the strings go up chunk by chunk (a few KB per cube), CDF
+    rows are built and consumed on the device.  Chunk k+1 is decoded on the coder stream while chunk k is synthesised.
+    ``sync=False`` -> a PendingDeviceResult (the caller, or its first consumer, waits and checks for device-side errors)."""
     dev = codec.dev
     main = torch.cuda.current_stream(dev)
-    packed, offsets = uploaded if uploaded is not None else codec.upload_strings(strings)
-    xs_parts, pending = [], None
+    B = int(chunks[-1][1])
+    xs = torch.empty([B, 64, 64, 64, 1], dtype=torch.float32, device=dev)
+    parts, pending = [], None
+    sub = int(os.environ.get("PCGC_SYNTH_PART", "64"))             # cubes per synthesis call = granularity of `parts`
     codec.deferred_checks(True)
     try:
         def finish(p):
             (a, b), y_hat, done = p
             main.wait_event(done)
-            xs_parts.append(codec.synthesis(y_hat.reshape([b - a] + y_shape[1:])))
+            y5 = y_hat.reshape([b - a] + y_shape[1:])
+            for s0 in range(a, b, sub):
+                s1 = min(b, s0 + sub)
+                codec.synthesis(y5[s0 - a:s1 - a], out=xs[s0:s1])
+                ev = torch.cuda.Event()
+                ev.record(main)
+                parts.append((s0, s1, ev))
 
         for k, (a, b) in enumerate(chunks):
             # every chunk decodes on its own stream (round robin over 3): the decoder of chunk k+1 must not queue behind the
             # decoder of chunk k -- both are latency-bound single-warp-per-cube kernels that run side by side
             side = codec.coder_stream(1 + k % 3)
+            if uploaded is not None:
+                packed, offs = uploaded[0], uploaded[1][a:b + 1]
+            else:
+                packed, offs = codec.upload_strings(strings[a:b], slot=k % 4)     # this chunk's strings only: nothing waits for the rest
             locs, scales = codec.hyper_decode(z_get(a, b), 1e-9)
             ready = torch.cuda.Event()
             ready.record(main)
-            for t in (locs, scales, packed, offsets):
+            for t in (locs, scales, packed, offs):
                 t.record_stream(side)
             with torch.cuda.stream(side):
                 side.wait_event(ready)
-                y_hat = cem.decode_dev(packed, offsets[a:b + 1], locs, scales, mins[a:b], maxs[a:b])
+                y_hat = cem.decode_dev(packed, offs, locs, scales, mins[a:b], maxs[a:b])
                 done = torch.cuda.Event()
                 done.record(side)
             y_hat.record_stream(main)
@@ -384,7 +445,8 @@ def _decompress_hyper_gpu_coder(codec, cem, strings, mins, maxs, y_shape, z_get,
         codec.deferred_checks(False)
     if sync:
         codec.synchronize()                                                # raises if any kernel of the section flagged an error
-    return torch.cat(xs_parts) if len(xs_parts) > 1 else xs_parts[0]
+        return xs
+    return runtime.PendingDeviceResult(xs, parts, codec, parts[-1][2])
 
 
 def decompress_hyper(y_strings, y_min_vs, y_max_vs, y_shape, z_strings, z_min_v, z_max_v, z_shape, model, ckpt_dir):
@@ -409,9 +471,11 @@ def decompress_hyper(y_strings, y_min_vs, y_max_vs, y_shape, z_strings, z_min_v,
     if B == 0:
         return runtime.DeviceResult(torch.zeros((0, 64, 64, 64, 1), dtype=torch.float32, device=codec.dev))
     if runtime.coder_mode() == "gpu":
-        xs = _decompress_hyper_gpu_coder(codec, cem, strings, mins, maxs, y_shape, z_get, _gpu_decode_chunks(B))
+        # returned as soon as the last launch is queued: .numpy() / .tensor wait (and raise on a device-side error), and
+        # select_voxels(codec=...) consumes the cubes part by part while the rest is still being synthesised
+        xs = _decompress_hyper_gpu_coder(codec, cem, strings, mins, maxs, y_shape, z_get, _gpu_decode_chunks(B), sync=False)
         _log("Hyper decoder + entropy decode (GPU coder) + synthesis", start)
-        return runtime.DeviceResult(xs)
+        return xs
     chunks = _chunks(B, small_first=True)
     xs_parts, pending = [], None
 
