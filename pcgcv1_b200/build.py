@@ -31,7 +31,7 @@ def _deps_mtime() -> float:
 
 # entropy.cu holds the device copy of the likelihood -> integer CDF path (det_math.h, cdf_norm.h) whose results must equal the host
 # copy's bit for bit: no mul+add contraction there (the host objects are built with -ffp-contract=off).
-PER_FILE = {"entropy.cu": ["-fmad=false"]}
+PER_FILE = {"entropy.cu": ["-fmad=false"] + os.environ.get("PCGC_ENTROPY_FLAGS", "").split()}
 
 
 def _compile(src: str, verbose: bool) -> str:

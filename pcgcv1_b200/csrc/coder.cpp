@@ -343,7 +343,7 @@ int pcgc_host_laplace_cdf(const float* loc, const float* scale, int B, int64_t E
     int32_t v[PCGC_MAX_SYMBOLS];
     for (int64_t e = e0; e < e1; ++e) {
       const float l = loc[(int64_t)b * E + e], s = scale[(int64_t)b * E + e];
-      for (int k = 0; k < N; ++k) pmf[k] = fmaxf(pcgc::det_laplace_likelihood((float)(min_v + k), l, s), likelihood_bound);
+      pcgc::det_laplace_pmf_row(min_v, N, l, s, likelihood_bound, pmf);
       if (pcgc::quantize_pmf_row(pmf, N, precision, v, g) != 0) { rc.store(PCGC_ERR_BAD_RANGE); continue; }
       uint16_t* row = rows + row_offset[b] + e * N;
       uint32_t acc = 0;

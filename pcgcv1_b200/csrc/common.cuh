@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 #include <map>
@@ -23,6 +24,20 @@ inline void prefer_shared_carveout(K kernel) {
     static const bool once_ = (::pcgc::prefer_shared_carveout(kernel), true); \
     (void)once_;                                                              \
   } while (0)
+
+// SMs the persistent conv kernels size their grids for: the device's SM count, optionally capped (PCGC_SM_LIMIT, experiments:
+// leaving a few SMs to the one-warp-per-cube coder kernels that run beside the conv kernels on the coder streams).
+inline int conv_sm_count() {
+  static const int n = [] {
+    int d = 0, v = 148;
+    cudaGetDevice(&d);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d);
+    const char* e = getenv("PCGC_SM_LIMIT");
+    const int lim = e ? atoi(e) : 0;
+    return lim > 0 && lim < v ? lim : v;
+  }();
+  return n;
+}
 
 // One convolution as the kernels see it: a stride-S "gather" convolution over an input grid with
 // a (KZ,KY,KX) tap box.  Forward Conv3D layers map 1:1; a stride-2 Conv3DTranspose is split into

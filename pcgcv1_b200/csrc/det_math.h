@@ -104,6 +104,46 @@ PCGC_DET float det_laplace_likelihood(float x, float loc, float scale) {
   return fabsf(d_sub(det_laplace_cdf(upper, loc, scale), det_laplace_cdf(lower, loc, scale)));
 }
 
+// The likelihoods of the CONSECUTIVE integers min_v .. min_v + n - 1 (SymmetricConditional._get_cdf, :95-124), each floored at
+// `bound`: out[k] == max(det_laplace_likelihood(min_v + k, loc, scale), bound) bit for bit, with about half the exp() calls.
+// Symbol k's upper edge and symbol k+1's lower edge are the same float (k + 1/2 is exact), and the reflected argument
+// -s (t - loc) + loc only depends on the edge and on s = sign(2x - loc); s changes at most twice along the row, so the cdf at
+// the upper edge of one symbol is re-used as the cdf at the lower edge of the next whenever their signs agree.
+PCGC_DET void det_laplace_pmf_row(int min_v, int n, float loc, float scale, float bound, float* out, int st = 1) {
+  float s_prev = 2.0f, c_prev = 0.0f;                          // no sign equals 2: the first symbol evaluates both edges
+  for (int k = 0; k < n; ++k) {
+    const float x = (float)(min_v + k);
+    const float upper = d_add(x, 0.5f), lower = d_sub(x, 0.5f);
+    const float sgn = det_signf(d_sub(d_add(upper, lower), loc));
+    const float c_lo = (sgn == s_prev) ? c_prev : det_laplace_cdf(d_add(d_mul(-sgn, d_sub(lower, loc)), loc), loc, scale);
+    const float c_up = det_laplace_cdf(d_add(d_mul(-sgn, d_sub(upper, loc)), loc), loc, scale);
+    const float p = fabsf(d_sub(c_up, c_lo));
+    out[k * st] = p > bound ? p : bound;                         // fmaxf(p, bound), NaN -> bound like fmaxf
+    s_prev = sgn; c_prev = c_up;
+  }
+}
+
+// det_laplace_pmf_row into a register array: compile-time trip count, `k < n` predicate (see quantize_pmf_row_reg).
+template <int NMAX>
+PCGC_DET void det_laplace_pmf_row_reg(int min_v, int n, float loc, float scale, float bound, float (&out)[NMAX]) {
+  float s_prev = 2.0f, c_prev = 0.0f;
+#pragma unroll
+  for (int k = 0; k < NMAX; ++k) {
+    float r = 0.0f;
+    if (k < n) {
+      const float x = (float)(min_v + k);
+      const float upper = d_add(x, 0.5f), lower = d_sub(x, 0.5f);
+      const float sgn = det_signf(d_sub(d_add(upper, lower), loc));
+      const float c_lo = (sgn == s_prev) ? c_prev : det_laplace_cdf(d_add(d_mul(-sgn, d_sub(lower, loc)), loc), loc, scale);
+      const float c_up = det_laplace_cdf(d_add(d_mul(-sgn, d_sub(upper, loc)), loc), loc, scale);
+      const float p = fabsf(d_sub(c_up, c_lo));
+      r = p > bound ? p : bound;
+      s_prev = sgn; c_prev = c_up;
+    }
+    out[k] = r;
+  }
+}
+
 // ---- EntropyBottleneck (models/entropy_model.py:72-151) for filters (3,3,3) ------------------------------------------------
 // p: 44 floats per channel as packed by pcgc_load_bottleneck: softplus(matrix), bias, tanh(factor) per layer.
 PCGC_DET float det_bn_logits(float x, const float* p) {

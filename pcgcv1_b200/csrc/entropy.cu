@@ -215,6 +215,9 @@ cudaError_t launch_laplace(const float* y, const float* loc, const float* scale,
 // threads) made the kernel SLOWER (3.78 -> 4.90 ms per 191 cubes): 16 instead of 32 resident warps hide the exp / FP64 latencies
 // of the normaliser worse than the L2 hits of the local arrays cost.  quantize_pmf_row keeps its stride parameter for that form.
 constexpr int CDF_THREADS = 128;
+#ifndef PCGC_PMF_SHARED
+#define PCGC_PMF_SHARED 1
+#endif
 
 #ifndef PCGC_CDF_MINBLOCKS
 #define PCGC_CDF_MINBLOCKS 12
@@ -224,11 +227,12 @@ __global__ void __launch_bounds__(CDF_THREADS, PCGC_CDF_MINBLOCKS)
 laplace_cdf_kernel(const float* __restrict__ y_hat, const float* __restrict__ loc, const float* __restrict__ scale,
                    const float* __restrict__ pmf_in, int64_t E, const int32_t* __restrict__ minmax,
                    const int64_t* __restrict__ row_offset, float bound, int precision, uint32_t* __restrict__ intervals,
-                   uint16_t* __restrict__ cdf, int32_t* __restrict__ cdf32, int* __restrict__ err) {
+                   uint16_t* __restrict__ cdf, int32_t* __restrict__ cdf32, int* __restrict__ err, int skip_upto) {
   const int b = blockIdx.y;
   const int min_v = minmax[2 * b], max_v = minmax[2 * b + 1];
   const int N = max_v - min_v + 1;
   if (N < 2 || N > PCGC_MAX_SYMBOLS) { if (threadIdx.x == 0 && blockIdx.x == 0) atomicExch(err, PCGC_ERR_BAD_RANGE); return; }
+  if (N <= skip_upto) return;                    // this cube's rows are built by a register kernel (laplace_cdf_reg_kernel)
   float pmf[PCGC_MAX_SYMBOLS];
   int32_t v[PCGC_MAX_SYMBOLS];
   float g[PCGC_MAX_SYMBOLS];
@@ -238,7 +242,11 @@ laplace_cdf_kernel(const float* __restrict__ y_hat, const float* __restrict__ lo
       for (int k = 0; k < N; ++k) pmf[k] = __ldg(pmf_in + o * N + k);
     } else {
       const float l = __ldg(loc + o), s = __ldg(scale + o);
+#if PCGC_PMF_SHARED
+      det_laplace_pmf_row(min_v, N, l, s, bound, pmf);         // == max(laplace_likelihood(min_v + k), bound), shared edge evaluations
+#else
       for (int k = 0; k < N; ++k) pmf[k] = fmaxf(laplace_likelihood((float)(min_v + k), l, s), bound);
+#endif
     }
     if (quantize_pmf_row(pmf, N, precision, v, g) != 0) { atomicExch(err, PCGC_ERR_BAD_RANGE); continue; }
     if (MODE == 1) {
@@ -259,6 +267,50 @@ laplace_cdf_kernel(const float* __restrict__ y_hat, const float* __restrict__ lo
     }
   }
 }
+
+// Register-resident form for cubes with NLO < N <= NMAX symbols (quantize_pmf_row_reg, cdf_norm.h): pmf / counts / scores live in
+// registers, no per-thread local memory.  MODE 0: uint16 rows, 1: the interval of the element's own symbol.  A block whose cube
+// belongs to another class returns at once (the symbol range is per cube, i.e. per blockIdx.y).
+template <int MODE, int NMAX, int NLO>
+__global__ void __launch_bounds__(CDF_THREADS, NMAX <= 8 ? 8 : 5)
+laplace_cdf_reg_kernel(const float* __restrict__ y_hat, const float* __restrict__ loc, const float* __restrict__ scale, int64_t E,
+                       const int32_t* __restrict__ minmax, const int64_t* __restrict__ row_offset, float bound, int precision,
+                       uint32_t* __restrict__ intervals, uint16_t* __restrict__ cdf, int* __restrict__ err) {
+  const int b = blockIdx.y;
+  const int min_v = minmax[2 * b], max_v = minmax[2 * b + 1];
+  const int N = max_v - min_v + 1;
+  if (N <= NLO || N > NMAX) return;              // N < 2 / N > PCGC_MAX_SYMBOLS are reported by the pointer-form kernel
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+    const size_t o = (size_t)b * E + e;
+    float pmf[NMAX];
+    int32_t v[NMAX];
+    det_laplace_pmf_row_reg<NMAX>(min_v, N, __ldg(loc + o), __ldg(scale + o), bound, pmf);
+    if (quantize_pmf_row_reg<NMAX>(pmf, N, precision, v) != 0) { atomicExch(err, PCGC_ERR_BAD_RANGE); continue; }
+    if (MODE == 1) {
+      const int sym = (int)__ldg(y_hat + o) - min_v;
+      if (sym < 0 || sym >= N) { atomicExch(err, PCGC_ERR_BAD_RANGE); intervals[o] = 0; continue; }
+      uint32_t lower = 0, width = 0;
+#pragma unroll
+      for (int k = 0; k < NMAX; ++k) {
+        lower += k < sym ? (uint32_t)v[k] : 0u;
+        width = k == sym ? (uint32_t)v[k] : width;
+      }
+      intervals[o] = lower | ((width - 1) << 16);
+    } else {
+      uint16_t* row = cdf + row_offset[b] + (size_t)e * N;
+      uint32_t acc = 0;
+#pragma unroll
+      for (int k = 0; k < NMAX; ++k) {
+        if (k < N) row[k] = (uint16_t)acc;
+        acc += (uint32_t)v[k];
+      }
+    }
+  }
+}
+
+// 0 (default): everything through the pointer-form kernel; 1: cubes with N <= 16 symbols go to the register kernels (slower,
+// see cdf_norm.h: 5.57 vs 3.36 ms per 191 cubes)
+static const bool CDF_REG = [] { const char* e = getenv("PCGC_CDF_REG"); return e ? atoi(e) != 0 : false; }();
 
 static const size_t CDF_SMEM = [] { const char* e = getenv("PCGC_CDF_PAD_KB"); return (size_t)(e ? atoi(e) : 0) * 1024; }();   // occupancy experiments
 
@@ -282,8 +334,14 @@ cudaError_t launch_laplace_intervals(const float* y_hat, const float* loc, const
                                      int* err_flag, cudaStream_t s, int64_t* launches) {
   cudaError_t pe = cdf_prepare<1>();
   if (pe != cudaSuccess) return pe;
+  if (CDF_REG) {
+    PCGC_CARVEOUT_ONCE((laplace_cdf_reg_kernel<1, 8, 0>)); PCGC_CARVEOUT_ONCE((laplace_cdf_reg_kernel<1, 16, 8>));
+    laplace_cdf_reg_kernel<1, 8, 0><<<cdf_grid(E, B), CDF_THREADS, 0, s>>>(y_hat, loc, scale, E, minmax, nullptr, bound, precision, intervals, nullptr, err_flag);
+    laplace_cdf_reg_kernel<1, 16, 8><<<cdf_grid(E, B), CDF_THREADS, 0, s>>>(y_hat, loc, scale, E, minmax, nullptr, bound, precision, intervals, nullptr, err_flag);
+    if (launches) *launches += 2;
+  }
   laplace_cdf_kernel<1><<<cdf_grid(E, B), CDF_THREADS, CDF_SMEM, s>>>(y_hat, loc, scale, nullptr, E, minmax, nullptr, bound, precision,
-                                                      intervals, nullptr, nullptr, err_flag);
+                                                      intervals, nullptr, nullptr, err_flag, CDF_REG ? 16 : 0);
   if (launches) ++*launches;
   return cudaGetLastError();
 }
@@ -293,8 +351,14 @@ cudaError_t launch_laplace_cdf(const float* loc, const float* scale, int B, int6
                                int* err_flag, cudaStream_t s, int64_t* launches) {
   cudaError_t pe = cdf_prepare<0>();
   if (pe != cudaSuccess) return pe;
+  if (CDF_REG) {
+    PCGC_CARVEOUT_ONCE((laplace_cdf_reg_kernel<0, 8, 0>)); PCGC_CARVEOUT_ONCE((laplace_cdf_reg_kernel<0, 16, 8>));
+    laplace_cdf_reg_kernel<0, 8, 0><<<cdf_grid(E, B), CDF_THREADS, 0, s>>>(nullptr, loc, scale, E, minmax_dev, row_offset_dev, bound, precision, nullptr, cdf, err_flag);
+    laplace_cdf_reg_kernel<0, 16, 8><<<cdf_grid(E, B), CDF_THREADS, 0, s>>>(nullptr, loc, scale, E, minmax_dev, row_offset_dev, bound, precision, nullptr, cdf, err_flag);
+    if (launches) *launches += 2;
+  }
   laplace_cdf_kernel<0><<<cdf_grid(E, B), CDF_THREADS, CDF_SMEM, s>>>(nullptr, loc, scale, nullptr, E, minmax_dev, row_offset_dev, bound,
-                                                      precision, nullptr, cdf, nullptr, err_flag);
+                                                      precision, nullptr, cdf, nullptr, err_flag, CDF_REG ? 16 : 0);
   if (launches) ++*launches;
   return cudaGetLastError();
 }
@@ -305,7 +369,7 @@ cudaError_t launch_debug_quantize_pmf(const float* pmf, int64_t rows, const int3
   cudaError_t pe = cdf_prepare<2>();
   if (pe != cudaSuccess) return pe;
   laplace_cdf_kernel<2><<<cdf_grid(rows, 1), CDF_THREADS, CDF_SMEM, s>>>(nullptr, nullptr, nullptr, pmf, rows, minmax_dev, nullptr, 0.f,
-                                                         precision, nullptr, nullptr, cdf32, err_flag);
+                                                         precision, nullptr, nullptr, cdf32, err_flag, 0);
   if (launches) ++*launches;
   return cudaGetLastError();
 }

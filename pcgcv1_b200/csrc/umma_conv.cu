@@ -1136,7 +1136,7 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
   if (c.epi == UEPI_PM && (w.n_real % 8 != 0 || c.out.c != w.n_real || w.npj % 8 != 0)) return cudaErrorInvalidValue;
   if (c.epi == UEPI_UP && (w.up_ncls * w.up_cout != w.n_real || w.up_cout % 16 != 0 || c.out.c != w.up_cout || c.out.n != 2 * n)) return cudaErrorInvalidValue;
   const int vrn_floats = c.epi == UEPI_VRN ? w.c4 * w.c2 + w.c2 : 0;
-  static const int sm_count = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
+  const int sm_count = conv_sm_count();
   const int zband = umma_zband_mode();
   // 32-column z-banded forms (K_b16, K_b32): correct (tests run them with PCGC_KB_ZBAND=1) but no faster than the tile / streaming
   // kernels they would replace (r01: K_b16 0.647 vs 0.640 ms, K_b32 0.189 vs 0.166 ms per 64 cubes) -- those layers are bound by
@@ -1233,7 +1233,7 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
   const int cols = pow2(a.nsets * a.zt * 2 * w.np);
   a.tmem_cols = cols;
   per_sm = std::max(1, std::min(per_sm, 512 / cols));
-  static const int sms = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
+  const int sms = conv_sm_count();
   static const int persist = getenv("PCGC_UMMA_PERSIST") ? atoi(getenv("PCGC_UMMA_PERSIST")) : 1;  // 0: one tile per CTA
   const int grid = persist ? std::min(tiles, sms * per_sm) : tiles;
   if (launches) ++*launches;

@@ -439,7 +439,7 @@ cudaError_t launch_conv_umma_win(const WinCall& c, const WinLayer& w, cudaStream
   CUtensorMap tm;
   cudaError_t e = win_tmap(c.in, a.exc, a.ey, zt, w.ppc, w.zp, &tm);
   if (e != cudaSuccess) return e;
-  static const int sms = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
+  const int sms = conv_sm_count();
   const int tiles = w.zp == 2 ? (n / 8) * (n / 8) * (n / 2) * c.in.B : (n / 8) * (n / 16) * (n / zt) * c.in.B;
   const int grid = std::min(tiles, sms);
   const size_t smem = 2 * (size_t)a.stage_bytes + fixed;

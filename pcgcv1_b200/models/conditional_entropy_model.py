@@ -155,9 +155,9 @@ class SymmetricConditional:
         """iv int32 [B,E] on the device -> (packed uint8, offsets int64 [B+1]) device tensors (asynchronous)."""
         return self.codec.gpu_range_encode(iv)
 
-    def decode_dev(self, packed, offsets, locs, scales, min_vs, max_vs):
-        """Strings b = packed[offsets[b]:offsets[b+1]] (device) -> y_hat float32 [B,E] on the device; CDF rows are built and
-        consumed on the device (asynchronous on the current stream; headers come from the host)."""
+    def decode_rows_dev(self, locs, scales, min_vs, max_vs):
+        """First half of ``decode_dev``: the per-element CDF rows of the cubes, built on the device from (loc, scale) and the
+        header's symbol ranges (asynchronous on the current stream).  -> what ``decode_strings_dev`` needs."""
         c = self.codec
         B = locs.shape[0]
         l2, s2 = locs.reshape(B, -1), scales.reshape(B, -1)
@@ -171,7 +171,17 @@ class SymmetricConditional:
         hdr_d = c.to_device(hdr)
         off_d, mm_d = hdr_d[:B + 1], hdr_d[B + 1:].to(torch.int32)
         rows = c.laplace_cdf_dev(l2, s2, mm_d, off_d, int(off[-1]), self._likelihood_bound)
-        return c.gpu_range_decode(packed, offsets, rows, off_d, int(off[-1]), mm_d, int(n_sym.max()) if B else 2, B, E)
+        return rows, off_d, int(off[-1]), mm_d, (int(n_sym.max()) if B else 2), B, E
+
+    def decode_strings_dev(self, packed, offsets, rows_pack):
+        """Second half: strings b = packed[offsets[b]:offsets[b+1]] (device) read against the rows -> y_hat float32 [B,E]."""
+        rows, off_d, total, mm_d, max_n, B, E = rows_pack
+        return self.codec.gpu_range_decode(packed, offsets, rows, off_d, total, mm_d, max_n, B, E)
+
+    def decode_dev(self, packed, offsets, locs, scales, min_vs, max_vs):
+        """Strings b = packed[offsets[b]:offsets[b+1]] (device) -> y_hat float32 [B,E] on the device; CDF rows are built and
+        consumed on the device (asynchronous on the current stream; headers come from the host)."""
+        return self.decode_strings_dev(packed, offsets, self.decode_rows_dev(locs, scales, min_vs, max_vs))
 
     def decompress_cubes(self, strings, locs, scales, min_vs, max_vs, threads: int = 0):
         """-> torch float32 [B, E] on the device."""

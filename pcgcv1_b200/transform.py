@@ -97,6 +97,7 @@ def decompress_factorized(strings, min_v, max_v, shape, model, ckpt_dir):
 _CHUNK = int(os.environ.get("PCGC_CHUNK", "64"))
 _CHUNK_EDGE = int(os.environ.get("PCGC_CHUNK_EDGE", "16"))
 _CHUNK_RAMP = bool(int(os.environ.get("PCGC_CHUNK_RAMP", "1")))
+_ROWS_ON_MAIN = bool(int(os.environ.get("PCGC_ROWS_ON_MAIN", "0")))   # measured r02: 32.1 ms (rows on main) vs 31.6 ms (rows beside the conv kernels)
 _Z_EARLY = bool(int(os.environ.get("PCGC_Z_EARLY", "1")))     # hyper string coded from the staged copy of z while the GPU finishes
 
 
@@ -427,13 +428,18 @@ def _decompress_hyper_gpu_coder(codec, cem, strings, mins, maxs, y_shape, z_get,
             else:
                 packed, offs = codec.upload_strings(strings[a:b], slot=k % 4)     # this chunk's strings only: nothing waits for the rest
             locs, scales = codec.hyper_decode(z_get(a, b), 1e-9)
+            # PCGC_ROWS_ON_MAIN=1 (experiment): the CDF rows kernel on the main stream right behind the hyper decoder, only the
+            # range decoder on the side stream.  Not faster: the rows kernel then delays the synthesis of the chunk before.
+            rows_pack = cem.decode_rows_dev(locs, scales, mins[a:b], maxs[a:b]) if _ROWS_ON_MAIN else None
             ready = torch.cuda.Event()
             ready.record(main)
-            for t in (locs, scales, packed, offs):
+            for t in (locs, scales, packed, offs) + (tuple(x for x in rows_pack if isinstance(x, torch.Tensor)) if rows_pack else ()):
                 t.record_stream(side)
             with torch.cuda.stream(side):
                 side.wait_event(ready)
-                y_hat = cem.decode_dev(packed, offs, locs, scales, mins[a:b], maxs[a:b])
+                if rows_pack is None:
+                    rows_pack = cem.decode_rows_dev(locs, scales, mins[a:b], maxs[a:b])
+                y_hat = cem.decode_strings_dev(packed, offs, rows_pack)
                 done = torch.cuda.Event()
                 done.record(side)
             y_hat.record_stream(main)

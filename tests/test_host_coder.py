@@ -178,3 +178,18 @@ def test_encoder16_equals_generic_encoder():
         if n:
             generic = runtime.range_encode_intervals_batch(iv[None], 1)[0]
             assert fast == generic
+
+
+def test_register_normaliser_and_shared_edge_likelihoods_equal_the_plain_forms(tmp_path):
+    """tools/cdf_check.cpp (host build of cdf_norm.h / det_math.h, the headers the CUDA kernels compile): the register-array
+    normaliser quantize_pmf_row_reg<8|16|32> and the shared-edge likelihood row give the same bits as the pointer-form normaliser
+    and the per-symbol likelihood on ~1 M rows (all symbol counts, both directions, large deficits)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(str(tmp_path), "cdf_check")
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-I", os.path.join(root, "pcgcv1_b200", "csrc"), "-o", exe,
+                    os.path.join(root, "tools", "cdf_check.cpp")], check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "0 mismatches" in r.stdout.strip().splitlines()[-1]
