@@ -103,20 +103,18 @@ PCGC_HD_NOINLINE long long cdf_last_u(double m, double lambda) {
 }
 
 // pmf[n] -> v[n] (counts, sum == 2^precision).  g: scratch float[n].  Returns 0, or -2 if the row
-// cannot be shrunk (all ones and n > target).  st = element stride of the three arrays (the CDF kernels keep them in shared
-// memory interleaved over the threads of a block: per-thread arrays indexed at run time otherwise live in local memory, whose
-// loads missed L1 90 % of the time -- ncu r02).
+// cannot be shrunk (all ones and n > target).
 //
 // One loop serves both directions (dir = +1: grow the entry with the largest gain; dir = -1: shrink the entry with
 // the smallest penalty = largest negated gain at v-1) so that the 32 rows of a warp do not serialise two code paths.
-PCGC_HD_NOINLINE int quantize_pmf_row(const float* pmf, int n, int precision, int32_t* v, float* g, int st = 1) {
+PCGC_HD_NOINLINE int quantize_pmf_row(const float* pmf, int n, int precision, int32_t* v, float* g) {
   const int target = 1 << precision;
   const float scale = (float)target;
   long long sum = 0;
   for (int i = 0; i < n; ++i) {
-    int q = (int)rintf(pmf[i * st] * scale);
+    int q = (int)rintf(pmf[i] * scale);
     q = q < 1 ? 1 : q;
-    v[i * st] = q;
+    v[i] = q;
     sum += q;
   }
   long long todo = sum > target ? sum - target : target - sum;
@@ -131,7 +129,7 @@ PCGC_HD_NOINLINE int quantize_pmf_row(const float* pmf, int n, int precision, in
     const double L = 1.4426950408889634;
     double m_act = 0.0, t_act = (double)target;
     int n_act = n;
-    for (int i = 0; i < n; ++i) m_act += (double)pmf[i * st];
+    for (int i = 0; i < n; ++i) m_act += (double)pmf[i];
     double inv_lambda = 0.0;
     for (int it = 0; it < 4 && m_act > 0.0; ++it) {           // active set = entries that grow at the solution
       const double slack = 2.0 * sqrt((double)n_act / 12.0) + 1.0;
@@ -139,7 +137,7 @@ PCGC_HD_NOINLINE int quantize_pmf_row(const float* pmf, int n, int precision, in
       double t2 = (double)target, m2 = 0.0;
       int n2 = 0;
       for (int i = 0; i < n; ++i) {
-        if ((double)pmf[i * st] * L * inv_lambda >= (double)v[i * st]) { m2 += (double)pmf[i * st]; ++n2; } else { t2 -= (double)v[i * st]; }
+        if ((double)pmf[i] * L * inv_lambda >= (double)v[i]) { m2 += (double)pmf[i]; ++n2; } else { t2 -= (double)v[i]; }
       }
       if (n2 == n_act && m2 == m_act) break;
       t_act = t2; m_act = m2; n_act = n2;
@@ -151,13 +149,13 @@ PCGC_HD_NOINLINE int quantize_pmf_row(const float* pmf, int n, int precision, in
     for (int attempt = 0; attempt < 8 && !done; ++attempt) {
       long long granted = 0;
       for (int i = 0; i < n; ++i) {
-        long long lu = cdf_last_u((double)pmf[i * st], lambda);
+        long long lu = cdf_last_u((double)pmf[i], lambda);
         if (lu > 2 * (long long)target) lu = 2 * (long long)target;
-        g[i * st] = (float)lu;                                     // <= 2^17: exact in float
-        if (lu >= v[i * st]) granted += lu - v[i * st] + 1;
+        g[i] = (float)lu;                                     // <= 2^17: exact in float
+        if (lu >= v[i]) granted += lu - v[i] + 1;
       }
       if (granted <= todo) {
-        for (int i = 0; i < n; ++i) { const int32_t lu = (int32_t)g[i * st]; if (lu >= v[i * st]) v[i * st] = lu + 1; }
+        for (int i = 0; i < n; ++i) { const int32_t lu = (int32_t)g[i]; if (lu >= v[i]) v[i] = lu + 1; }
         todo -= granted;
         done = true;
       } else {
@@ -169,29 +167,32 @@ PCGC_HD_NOINLINE int quantize_pmf_row(const float* pmf, int n, int precision, in
 
   // scores: dir > 0: gain(v);  dir < 0: -gain(v-1) (= -penalty), entries at 1 can not shrink
   for (int i = 0; i < n; ++i)
-    g[i * st] = dir > 0 ? cdf_score(pmf[i * st], v[i * st], scale) : (v[i * st] > 1 ? -cdf_score(pmf[i * st], v[i * st] - 1, scale) : -INFINITY);
+    g[i] = dir > 0 ? cdf_score(pmf[i], v[i], scale) : (v[i] > 1 ? -cdf_score(pmf[i], v[i] - 1, scale) : -INFINITY);
   while (todo > 0) {
     PCGC_CDF_ITER_HOOK;
     // one pass: the best score, its (first) index and the runner-up; only a runner-up within the tolerance needs the exact path
     float mx = -INFINITY, second = -INFINITY;
     int best = -1;
-    for (int i = 0; i < n; ++i) {
-      const float gi = g[i * st];
-      if (gi > mx) { second = mx; mx = gi; best = i; }
-      else if (gi > second) second = gi;
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) {             // branch-free: (gi > mx) ? shift the leader down : second = max(second, gi)
+      const float gi = g[i];
+      const bool lead = gi > mx;
+      second = lead ? mx : (gi > second ? gi : second);
+      best = lead ? i : best;
+      mx = lead ? gi : mx;
     }
     if (!(mx > -INFINITY)) return -2;
     const float thr = mx - PCGC_SCORE_TOL(mx);
     if (second >= thr) {                    // near tie: decide on the exact gains, lowest index first
       double bs = -INFINITY;
       for (int i = 0; i < n; ++i)
-        if (g[i * st] >= thr) {
-          const double e = dir > 0 ? cdf_gain((double)pmf[i * st], v[i * st]) : -cdf_gain((double)pmf[i * st], v[i * st] - 1);
+        if (g[i] >= thr) {
+          const double e = dir > 0 ? cdf_gain((double)pmf[i], v[i]) : -cdf_gain((double)pmf[i], v[i] - 1);
           if (e > bs) { bs = e; best = i; }
         }
     }
-    v[best * st] += dir;
-    g[best * st] = dir > 0 ? cdf_score(pmf[best * st], v[best * st], scale) : (v[best * st] > 1 ? -cdf_score(pmf[best * st], v[best * st] - 1, scale) : -INFINITY);
+    v[best] += dir;
+    g[best] = dir > 0 ? cdf_score(pmf[best], v[best], scale) : (v[best] > 1 ? -cdf_score(pmf[best], v[best] - 1, scale) : -INFINITY);
     --todo;
   }
   return 0;

@@ -213,7 +213,7 @@ cudaError_t launch_laplace(const float* y, const float* loc, const float* scale,
 // r02 experiment, kept as a note: moving the three per-row arrays (pmf, counts, scores) from per-thread local memory (38 M local
 // loads per 64 cubes at a 10 % L1 hit rate, ncu) into shared memory interleaved over the block ([entry][thread], 48 KiB per 128
 // threads) made the kernel SLOWER (3.78 -> 4.90 ms per 191 cubes): 16 instead of 32 resident warps hide the exp / FP64 latencies
-// of the normaliser worse than the L2 hits of the local arrays cost.  quantize_pmf_row keeps its stride parameter for that form.
+// of the normaliser worse than the L2 hits of the local arrays cost.
 constexpr int CDF_THREADS = 128;
 #ifndef PCGC_PMF_SHARED
 #define PCGC_PMF_SHARED 1
