@@ -82,12 +82,32 @@ def decompress_factorized(strings, min_v, max_v, shape, model, ckpt_dir):
     codec = runtime.get_codec(model, ckpt_dir)
     shape = np.asarray(runtime.unwrap(shape)).reshape(-1)
     start = time.time()
-    ys = _bottleneck(codec, int(shape[-1])).decompress(strings, min_v, max_v, shape, shape[-1])
-    _log("Entropy Decode", start)
-    start = time.time()
-    xs = codec.synthesis(ys.tensor)
-    _log("Synthesis Transform", start)
-    return runtime.DeviceResult(xs)
+    B = int(shape[0])
+    if B <= _FACT_PART or _VERBOSE:
+        ys = _bottleneck(codec, int(shape[-1])).decompress(strings, min_v, max_v, shape, shape[-1])
+        _log("Entropy Decode", start)
+        start = time.time()
+        xs = codec.synthesis(ys.tensor)
+        _log("Synthesis Transform", start)
+        return runtime.DeviceResult(xs)
+    # The ONE string (global range, entropy_model.py:249-259) is sequential and decodes on a host thread (~12 ns per symbol);
+    # the cubes come out of it in order, so the synthesis of cubes [a, b) runs while the string's tail is still being read,
+    # and the caller gets a pending result whose parts select_voxels can consume as they finish.
+    get = _bottleneck(codec, int(shape[-1])).decompress_progressive(strings, min_v, max_v, shape, shape[-1])
+    main = torch.cuda.current_stream(codec.dev)
+    xs = torch.empty([B, 64, 64, 64, 1], dtype=torch.float32, device=codec.dev)
+    parts = []
+    codec.deferred_checks(True)
+    try:
+        for a in range(0, B, _FACT_PART):
+            b = min(B, a + _FACT_PART)
+            codec.synthesis(get(a, b), out=xs[a:b])
+            ev = torch.cuda.Event()
+            ev.record(main)
+            parts.append((a, b, ev))
+    finally:
+        codec.deferred_checks(False)
+    return runtime.PendingDeviceResult(xs, parts, codec, parts[-1][2])
 
 
 # ---------------------------------------------------------------- hyperprior (conditional) model
@@ -97,6 +117,7 @@ def decompress_factorized(strings, min_v, max_v, shape, model, ckpt_dir):
 _CHUNK = int(os.environ.get("PCGC_CHUNK", "64"))
 _CHUNK_EDGE = int(os.environ.get("PCGC_CHUNK_EDGE", "16"))
 _CHUNK_RAMP = bool(int(os.environ.get("PCGC_CHUNK_RAMP", "1")))
+_FACT_PART = int(os.environ.get("PCGC_FACT_PART", "48"))      # cubes per synthesis call of the progressive factorized decoder
 _ROWS_ON_MAIN = bool(int(os.environ.get("PCGC_ROWS_ON_MAIN", "0")))   # measured r02: 32.1 ms (rows on main) vs 31.6 ms (rows beside the conv kernels)
 _Z_EARLY = bool(int(os.environ.get("PCGC_Z_EARLY", "1")))     # hyper string coded from the staged copy of z while the GPU finishes
 

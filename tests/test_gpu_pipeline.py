@@ -74,3 +74,18 @@ def test_strings_do_not_depend_on_how_the_encoder_launch_is_spread(codec, cloud,
     ref = transform.decompress_hyper(*stream, model_voxception, "").tensor
     monkeypatch.delenv("PCGC_DEC_PAD_KB")
     assert torch.equal(ref, transform.decompress_hyper(*stream, model_voxception, "").tensor)
+
+
+def test_factorized_decode_is_progressive_and_equal_to_the_plain_form(codec_simple, cloud, monkeypatch):
+    from pcgcv1_b200.models import model_simple
+    cubes, nums = cloud
+    s, mn, mx, shp = transform.compress_factorized(cubes, model_simple, "")
+    args = (s.numpy(), mn.numpy(), mx.numpy(), shp.numpy(), model_simple, "")
+    xs = transform.decompress_factorized(*args)
+    assert isinstance(xs, runtime.PendingDeviceResult) and len(xs.parts) == 3            # 140 cubes in parts of 48
+    mask = inout_points.select_voxels(xs, nums, 1.0, codec=codec_simple, dtype="uint8")
+    monkeypatch.setattr(transform, "_FACT_PART", 1 << 20)                                 # one piece: the plain form
+    plain = transform.decompress_factorized(*args)
+    assert not isinstance(plain, runtime.PendingDeviceResult)
+    assert torch.equal(xs.tensor, plain.tensor)
+    assert np.array_equal(mask, inout_points.select_voxels(plain, nums, 1.0, codec=codec_simple, dtype="uint8"))
