@@ -305,6 +305,11 @@ def run_gpu(args):
                 "unit": "TFLOP/s", "frac": round(ach / peaks["bf16_tflops_sustained"], 5), "traffic": None,
                 "frac_of_burst_peak": round(ach / peaks["bf16_tflops"], 5), "peak_nominal": 2250.0}
         if tr:
+            # cubes per launch as this run issued them (the decode ramp launches 8 / 24 / 64-cube batches): from the launch's
+            # algorithmic FLOPs; the ncu capture's bytes scale with the cubes
+            if tr.get("algorithmic_flops_per_cube"):
+                per_launch = top["flops"] / top["count"] / tr["algorithmic_flops_per_cube"]
+                roof["cubes_per_launch_avg"] = round(per_launch, 2)
             scale = per_launch / tr.get("cubes_per_launch", per_launch)
             traffic = tr["dram_bytes_per_launch"] * scale
             roof["traffic"] = int(traffic)
@@ -354,8 +359,10 @@ def run_gpu(args):
                                "seeded synthetic weights" % (args.workload, B, int(points)),
                    "cubes_per_gpu": B, "points_per_gpu": int(points), "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)",
                    "range_coder": os.environ.get("PCGC_CODER", "gpu"),
-                   "e2e_flow": "compress_hyper -> .numpy() of every stream field -> decompress_hyper (device handle) -> select_voxels(codec=, "
-                               "dtype=uint8): top-k on the GPU, uint8 masks to the host (the reference does .numpy() then NumPy top-k, test.py:115)",
+                   "e2e_flow": "compress_hyper -> .numpy() of every stream field -> decompress_hyper (returns a pending device result once "
+                               "its last kernel is queued) -> select_voxels(codec=, dtype=uint8): top-k on the GPU and the uint8 masks to "
+                               "the host part by part behind the synthesis (the reference does .numpy() then NumPy top-k, test.py:115)",
+                   "decode_schedule": os.environ.get("PCGC_DEC_RAMP", "8,24,64") + " cubes, then the rest",
                    "conv_engine": os.environ.get("PCGC_ENGINE", "auto")},
         "points_per_s": round(value * points / B, 1),
         "value_without_range_coder": {"value": round(world * B * nocoder_steps / (nocoder_ms / 1e3), 2), "unit": UNIT, "steps": nocoder_steps,
