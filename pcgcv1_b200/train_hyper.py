@@ -248,10 +248,10 @@ def train(files: Sequence[str], ckpt_dir: str, alpha=2.0, beta=3.0, gamma=1.0, d
 def main(argv=None):
     p = argparse.ArgumentParser(formatter_class=argparse.ArgumentDefaultsHelpFormatter)
     p.add_argument("--data", required=True, help="glob of per-cube point files (.h5 / .npy / .npz with key 'data')")
-    p.add_argument("--alpha", type=float, default=2.0, help="weights for distoration.")
-    p.add_argument("--beta", type=float, default=3.0, help="Weight for empty position.")
-    p.add_argument("--gamma", type=float, default=1.0, help="Weight for hyper likelihoods.")
-    p.add_argument("--delta", type=float, default=1.0, help="Weight for latent likelihoods.")
+    p.add_argument("--alpha", type=float, default=2.0, help="weight of the distortion term (BCE) in the loss")
+    p.add_argument("--beta", type=float, default=3.0, help="weight of the empty-voxel part of the BCE against the occupied part")
+    p.add_argument("--gamma", type=float, default=1.0, help="weight of the hyper-latent rate (bpp of z)")
+    p.add_argument("--delta", type=float, default=1.0, help="weight of the latent rate (bpp of y)")
     p.add_argument("--lr", type=float, default=1e-5)
     p.add_argument("--num_iteration", type=int, default=int(3e5))
     p.add_argument("--batch_size", type=int, default=8)
