@@ -140,6 +140,8 @@ def select_voxels(vols, points_nums, offset_ratio=1.0, fixed_thres=None, codec=N
         return _select_voxels_pipelined(vols._codec, vols, points_nums, offset_ratio, dtype)
     v = c.to_device(vols, torch.float32)
     B = v.shape[0]
+    if B == 0:                                                           # the reference's loop over zero cubes: an empty mask
+        return np.zeros(tuple(v.shape), np.dtype(dtype))
     if fixed_thres is None:
         pn = np.asarray(runtime.unwrap(points_nums)).reshape(-1)
         ks = np.array([int(offset_ratio * np.array(pn[i])) for i in range(B)], np.int32)

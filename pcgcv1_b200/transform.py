@@ -350,6 +350,15 @@ def compress_hyper(cubes, model, ckpt_dir, decompress=False):
     cubes = runtime.unwrap(cubes)
     B = cubes.shape[0]
     start = time.time()
+    if B == 0:
+        # an empty cloud: nothing to code.  (The reference's tf.map_fn / reduce_min raise on an empty batch; an empty stream that
+        # decompress_hyper turns back into an empty [0,64,64,64,1] tensor is the useful behaviour for a partitioner that found no cube.)
+        out = (runtime.HostResult(_strings_array([])), runtime.HostResult(np.zeros(0, np.int32)), runtime.HostResult(np.zeros(0, np.int32)),
+               runtime.HostResult(np.array((1, 16, 16, 16, 16), dtype=np.int64)), runtime.HostResult(b""), runtime.HostResult(np.int32(0)),
+               runtime.HostResult(np.int32(0)), runtime.HostResult(np.array((0, 8, 8, 8, 8), dtype=np.int32)))
+        if decompress:
+            return out + (runtime.DeviceResult(torch.zeros((0, 64, 64, 64, 1), dtype=torch.float32, device=codec.dev)),)
+        return out
     if runtime.coder_mode() == "gpu" and B > 0:
         strings, mm, z_all, z_string, z_min, z_max, keep = _compress_hyper_gpu_coder(codec, entropy_bottleneck, cem, cubes, decompress)
         _log("Analysis + hyper transforms + entropy encode (GPU coder)", start)
@@ -485,6 +494,8 @@ def decompress_hyper(y_strings, y_min_vs, y_max_vs, y_shape, z_strings, z_min_v,
     z_shape = np.asarray(runtime.unwrap(z_shape)).reshape(-1)
     y_shape = [int(v) for v in np.asarray(runtime.unwrap(y_shape)).reshape(-1)]
     start = time.time()
+    if int(z_shape[0]) == 0:                                             # the empty cloud (see compress_hyper)
+        return runtime.DeviceResult(torch.zeros((0, 64, 64, 64, 1), dtype=torch.float32, device=codec.dev))
     # the hyper string decodes on a worker thread; each chunk below waits only for ITS cubes' symbols (they come first)
     z_get = entropy_bottleneck.decompress_progressive(z_strings, z_min_v, z_max_v, z_shape, z_shape[-1])
     _log("Entropy Decoder (Hyper) started", start)

@@ -89,3 +89,28 @@ def test_factorized_decode_is_progressive_and_equal_to_the_plain_form(codec_simp
     assert not isinstance(plain, runtime.PendingDeviceResult)
     assert torch.equal(xs.tensor, plain.tensor)
     assert np.array_equal(mask, inout_points.select_voxels(plain, nums, 1.0, codec=codec_simple, dtype="uint8"))
+
+
+@pytest.mark.parametrize("B", [0, 1, 9, 33, 65, 97])
+def test_round_trip_at_chunk_boundaries(codec, cloud, B):
+    """Cube counts on both sides of every chunk boundary of the two pipelines (decode ramp 8 / 24 / 64, encode chunks of 64),
+    the empty cloud included: the decoder's reconstruction equals the encoder-side one bit for bit and the masks hold >= k voxels."""
+    cubes, nums = cloud[0][:B], cloud[1][:B]
+    out = transform.compress_hyper(cubes, model_voxception, "", decompress=True)
+    host = [o.numpy() for o in out[:8]]
+    assert len(host[0]) == B and list(host[7]) == [B, 8, 8, 8, 8]
+    xs = transform.decompress_hyper(*host, model_voxception, "")
+    mask = inout_points.select_voxels(xs, nums, 1.0, codec=codec, dtype="uint8")
+    assert mask.shape == (B, 64, 64, 64, 1)
+    assert np.array_equal(xs.numpy(), out[8].numpy())
+    if B:
+        assert (mask.reshape(B, -1).sum(1) >= nums).all()
+
+
+def test_factorized_round_trip_just_over_one_part(codec_simple, cloud):
+    from pcgcv1_b200.models import model_simple
+    cubes = cloud[0][:49]
+    s, mn, mx, shp = transform.compress_factorized(cubes, model_simple, "")
+    xs = transform.decompress_factorized(s.numpy(), mn.numpy(), mx.numpy(), shp.numpy(), model_simple, "")
+    ref = codec_simple.synthesis(torch.round(codec_simple.analysis(codec_simple.to_device(cubes))))
+    assert torch.equal(xs.tensor, ref)
