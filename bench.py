@@ -614,7 +614,7 @@ def run_train(args):
     codec = runtime.get_codec("voxception", "", local)
     B = 8
     cubes, _ = synthetic.surface_cubes(B, seed=100 + rank)
-    tr = training.HyperTrainer(codec, alpha=0.75, beta=3.0, gamma=1.0, delta=1.0, lr=1e-5)
+    tr = training.HyperTrainer(codec, alpha=0.75, beta=3.0, gamma=1.0, delta=1.0, lr=1e-5, distortion=args.distortion)
     pinned = torch.from_numpy(cubes).pin_memory()
     xd = pinned.to(codec.dev)
 
@@ -665,8 +665,10 @@ def run_train(args):
             "metric": "train_hyper.py step throughput (forward + backward + Adam)", "value": round(steps_s * B, 2), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(dev_ms / args.steps, 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "train_hyper.py step: batch 8 cubes of 64^3 per GPU, alpha=0.75 beta=3 gamma=delta=1, lr=1e-5, BCE occupancy loss, "
-                                   "noise quantisation (seeded Philox), random smooth-surface cubes, seeded synthetic weights",
+            "config": {"workload": "train_hyper.py step: batch 8 cubes of 64^3 per GPU, alpha=0.75 beta=3 gamma=delta=1, lr=1e-5, %s, "
+                                   "noise quantisation (seeded Philox), random smooth-surface cubes, seeded synthetic weights"
+                                   % ("focal occupancy loss (loss.py:83-93, gamma 2, alpha 0.9, sum) on sigmoid(x_tilde)" if args.distortion == "focal"
+                                      else "BCE occupancy loss (loss.py:8-33, what train_hyper.py calls)"),
                        "baseline_config": 5, "batch_per_gpu": B, "engine": "exact FP32 CUDA cores (conv_ffma.cu + train.cu), deterministic"},
             "steps_per_s": round(steps_s, 3),
             "e2e": {"value": round(world * args.steps * B / (e2e_ms / 1e3), 2), "unit": UNIT, "h2d_bytes_per_step": int(pinned.numel()),
@@ -727,6 +729,8 @@ def main():
     ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4, 5],
                     help="BASELINE.json config: 1 vox10 hyper (default, the headline), 2 vox10 factorized + model_simple, "
                          "3 vox12 cloud sharded over --gpus (strong scaling), 4 analysis+synthesis batch sweep, 5 training step (batch 8)")
+    ap.add_argument("--distortion", default="bce", choices=["bce", "focal"],
+                    help="config 5: occupancy loss of the training step (bce = what train_hyper.py calls; focal = loss.py:83-93)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -277,6 +277,13 @@ int pcgc_train_factorized_backward(pcgc_ctx* ctx, const float* matrices, const f
 int pcgc_train_bce(pcgc_ctx* ctx, const float* logits, const uint8_t* label, int64_t n, double* sums_dev);
 int pcgc_train_bce_backward(pcgc_ctx* ctx, const float* logits, const uint8_t* label, int64_t n, const double* sums_dev, float w_empty,
                             float w_full, float* g);
+/* get_focal_loss (loss.py:83-93; BASELINE config 5's "focal occupancy loss") on y_pred = sigmoid(logits), label in {0, 1}:
+ * sums_dev double[2] = {-sum(alpha (1 - pt_1)^gamma log pt_1), -sum((1 - alpha) pt_0^gamma log(1 - pt_0))} with the reference's
+ * clip to [1e-3, .999] (the constant "other" branch of each tf.where included); the loss is their sum.  The backward entry
+ * writes g = weight * d loss / d logits (zero where the clip is active).  gamma >= 1. */
+int pcgc_train_focal(pcgc_ctx* ctx, const float* logits, const uint8_t* label, int64_t n, float gamma, float alpha, double* sums_dev);
+int pcgc_train_focal_backward(pcgc_ctx* ctx, const float* logits, const uint8_t* label, int64_t n, float gamma, float alpha, float weight,
+                              float* g);
 /* tf.train.AdamOptimizer update with the bias-corrected step lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t). */
 int pcgc_train_adam(pcgc_ctx* ctx, float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2, float eps);
 

@@ -1,4 +1,6 @@
 """Oracle of one training step (test infrastructure only): the reference's graph ``train_hyper.py:184-214`` + ``loss.py:8-33``
+(+ ``get_focal_loss`` ``loss.py:83-93``, ``get_classify_metrics`` ``:60-77``; the three loss functions are pinned by
+tests/golden/golden_loss.npz = the reference's own loss.py executed by tests/golden/make_golden_loss.py)
 restated with torch-CPU autograd in float64 (or float32), the gradients coming from ``loss.backward()`` instead of
 ``tf.GradientTape``.  Noise = the Philox stream of oracle/entropy.py (the CUDA path draws the same numbers; the reference itself
 is unseeded).  Adam restates ``tf.train.AdamOptimizer`` (TF 1.13 ``training/adam.py``: lr_t = lr*sqrt(1-b2^t)/(1-b1^t),
@@ -58,8 +60,25 @@ def bce_loss(pred, label):
     return (-torch.log(1.0 - o[neg])).mean(), (-torch.log(o[pos])).mean()
 
 
+def focal_loss(prob, label, gamma=2.0, alpha=0.9):
+    """get_focal_loss (loss.py:83-93) on probabilities: pt_1 = clip(where(label == 1, p, 1), 1e-3, .999), pt_0 = clip(where(label
+    == 0, p, 0), 1e-3, .999); -sum(alpha (1 - pt_1)^gamma log pt_1) - sum((1 - alpha) pt_0^gamma log(1 - pt_0)).  torch.clamp has
+    K.clip's gradient (zero outside the bounds); the constant branches of the two where() calls stay in the value."""
+    pt_1 = torch.clamp(torch.where(label == 1, prob, torch.ones_like(prob)), 1e-3, 0.999)
+    pt_0 = torch.clamp(torch.where(label == 0, prob, torch.zeros_like(prob)), 1e-3, 0.999)
+    return -(alpha * (1.0 - pt_1) ** gamma * torch.log(pt_1)).sum(), -((1.0 - alpha) * pt_0 ** gamma * torch.log(1.0 - pt_0)).sum()
+
+
+def classify_metrics(pred, label, th=0.0):
+    """get_classify_metrics (loss.py:60-77): precision, recall, IoU of (pred > th) against (label > th)."""
+    p, l = (pred > th).double(), (label > th).double()
+    tp, fp, fn = (p * l).sum(), (p * (1 - l)).sum(), ((1 - p) * l).sum()
+    return float(tp / (tp + fp)), float(tp / (tp + fn)), float(tp / (tp + fp + fn))
+
+
 def forward_backward(weights: Dict[str, np.ndarray], cubes: np.ndarray, seed: int = 0, alpha=0.75, beta=3.0, gamma=1.0, delta=1.0,
-                     lower_bound=1e-9, likelihood_bound=1e-9, dtype=torch.float64, noise_dtype=np.float32, entropy_dtype=torch.float32):
+                     lower_bound=1e-9, likelihood_bound=1e-9, dtype=torch.float64, noise_dtype=np.float32, entropy_dtype=torch.float32,
+                     distortion="bce", focal_gamma=2.0, focal_alpha=0.9):
     """-> (terms dict of floats, grads dict name -> np.ndarray keyed like the weight file).
 
     ``dtype`` is the arithmetic of the transforms; ``entropy_dtype`` that of the two likelihood formulas.  The reference runs
@@ -87,12 +106,17 @@ def forward_backward(weights: Dict[str, np.ndarray], cubes: np.ndarray, seed: in
     num_points = float((x.sum(-1) > 0).sum())
     bpp_ae = torch.log(p_y).sum() / (-LN2 * num_points)
     bpp_hyper = torch.log(p_z).sum() / (-LN2 * num_points)
-    zeros, ones = bce_loss(x_t, x)
-    dist = beta * zeros + 1.0 * ones
+    if distortion == "focal":           # loss.py:83-93 on sigmoid(x_tilde); the reference defines it, BASELINE config 5 names it
+        f_full, f_empty = focal_loss(torch.sigmoid(x_t), x, focal_gamma, focal_alpha)
+        dist = f_full + f_empty
+        parts = (("focal_full", f_full), ("focal_empty", f_empty))
+    else:
+        zeros, ones = bce_loss(x_t, x)
+        dist = beta * zeros + 1.0 * ones
+        parts = (("zeros", zeros), ("ones", ones))
     loss = alpha * dist + delta * bpp_ae + gamma * bpp_hyper
     loss.backward()
-    terms = {k: float(v.detach()) for k, v in (("zeros", zeros), ("ones", ones), ("distortion", dist), ("bpp_ae", bpp_ae), ("bpp_hyper", bpp_hyper),
-                                                ("loss", loss))}
+    terms = {k: float(v.detach()) for k, v in parts + (("distortion", dist), ("bpp_ae", bpp_ae), ("bpp_hyper", bpp_hyper), ("loss", loss))}
     grads = {k: (v.grad.numpy().copy() if v.grad is not None else np.zeros(v.shape)) for k, v in P.items()}
     return terms, grads, {"y": y.detach().numpy(), "x_tilde": x_t.detach().numpy()}
 

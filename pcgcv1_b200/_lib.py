@@ -82,6 +82,8 @@ SIGNATURES = {
     "pcgc_train_factorized_backward": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i64, _f, _f, _vp, _vp, _vp, _vp]),
     "pcgc_train_bce": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "pcgc_train_bce_backward": (_i, [_vp, _vp, _vp, _i64, _vp, _f, _f, _vp]),
+    "pcgc_train_focal": (_i, [_vp, _vp, _vp, _i64, _f, _f, _vp]),
+    "pcgc_train_focal_backward": (_i, [_vp, _vp, _vp, _i64, _f, _f, _f, _vp]),
     "pcgc_train_adam": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f]),
     "pcgc_host_copy": (_i, [_vp, _vp, _i64, _i]),
     "pcgc_ply_parse": (_i, [_vp, _i64, _vp, _i64, _vp, _i]),

@@ -463,6 +463,49 @@ __global__ void bce_backward_kernel(const float* __restrict__ logits, const uint
   }
 }
 
+// ---------------------------------------------------------------------------------------------- focal occupancy loss (loss.py:83-93)
+// get_focal_loss(y_pred, y_true, gamma, alpha) on y_pred = sigmoid(logits) (the reference's function takes probabilities; its
+// synthesis transform ends without an activation, so the sigmoid of get_bce_loss is applied first):
+//   pt_1 = clip(label == 1 ? p : 1, 1e-3, .999), pt_0 = clip(label == 0 ? p : 0, 1e-3, .999)
+//   loss = -sum(alpha (1 - pt_1)^gamma log pt_1) - sum((1 - alpha) pt_0^gamma log(1 - pt_0))            (a SUM, not a mean)
+// The "other" branch of each tf.where is a constant after the clip (pt_1 = .999 on empty voxels, pt_0 = 1e-3 on occupied ones) and
+// is part of the reference's value, so it is part of this one.  sums[0] = first sum, sums[1] = second sum.
+__device__ __forceinline__ void focal_terms(float p, bool occupied, float gamma, float alpha, float& t1, float& t0) {
+  const float pt1 = fminf(fmaxf(occupied ? p : 1.0f, 1e-3f), 0.999f), pt0 = fminf(fmaxf(occupied ? 0.0f : p, 1e-3f), 0.999f);
+  t1 = -alpha * powf(1.0f - pt1, gamma) * logf(pt1);
+  t0 = -(1.0f - alpha) * powf(pt0, gamma) * logf(1.0f - pt0);
+}
+__global__ void __launch_bounds__(256) focal_partial_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ label, size_t n, float gamma,
+                                                            float alpha, double* __restrict__ partial) {
+  __shared__ double s_r[2][256];
+  double a0 = 0, a1 = 0;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    float t1, t0;
+    focal_terms(sigm_(logits[i]), label[i] != 0, gamma, alpha, t1, t0);
+    a0 += (double)t1; a1 += (double)t0;
+  }
+  s_r[0][threadIdx.x] = a0; s_r[1][threadIdx.x] = a1;
+  __syncthreads();
+  if (threadIdx.x < 2) { double s = 0; for (int t = 0; t < 256; ++t) s += s_r[threadIdx.x][t]; partial[(size_t)blockIdx.x * 2 + threadIdx.x] = s; }
+}
+__global__ void focal_final_kernel(const double* __restrict__ partial, int blocks, double* __restrict__ sums) {
+  if (threadIdx.x < 2) { double s = 0; for (int b = 0; b < blocks; ++b) s += partial[(size_t)b * 2 + threadIdx.x]; sums[threadIdx.x] = s; }
+}
+// g = weight * d loss / d logits; K.clip has a zero gradient outside [1e-3, .999]
+__global__ void focal_backward_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ label, size_t n, float gamma, float alpha,
+                                      float weight, float* __restrict__ g) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float p = sigm_(logits[i]);
+    float d = 0.f;                                                   // d loss / d p
+    if (p >= 1e-3f && p <= 0.999f) {
+      const float q = 1.0f - p;
+      if (label[i]) d = alpha * (gamma * powf(q, gamma - 1.0f) * logf(p) - powf(q, gamma) / p);
+      else d = (1.0f - alpha) * (powf(p, gamma) / q - gamma * powf(p, gamma - 1.0f) * logf(q));
+    }
+    g[i] = weight * d * p * (1.0f - p);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- Adam (tf.train.AdamOptimizer)
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n, float lr_t,
                             float b1, float b2, float eps) {
@@ -633,6 +676,26 @@ int pcgc_train_bce_backward(pcgc_ctx* ctx, const float* logits, const uint8_t* l
                             float w_full, float* g) {
   if (!ctx || !logits || !label || !sums_dev || !g || n < 1) return PCGC_ERR_BAD_ARG;
   bce_backward_kernel<<<ew_blocks(n), 256, 0, ctx_stream(ctx)>>>(logits, label, (size_t)n, sums_dev, w_empty, w_full, g);
+  ++*ctx_launches(ctx);
+  return PCGC_OK;
+}
+
+/* get_focal_loss (loss.py:83-93) on sigmoid(logits): sums_dev double[2] = {-sum(alpha (1-pt_1)^gamma log pt_1), -sum((1-alpha) pt_0^gamma log(1-pt_0))}. */
+int pcgc_train_focal(pcgc_ctx* ctx, const float* logits, const uint8_t* label, int64_t n, float gamma, float alpha, double* sums_dev) {
+  if (!ctx || !logits || !label || !sums_dev || n < 1 || !(gamma >= 1.0f) || !(alpha >= 0.0f && alpha <= 1.0f)) return PCGC_ERR_BAD_ARG;
+  const int blocks = ew_blocks(n);
+  double* partial = reinterpret_cast<double*>(ctx_workspace(ctx, 3, (size_t)blocks * 4 + 64));
+  if (!partial) return ctx_fail(ctx, PCGC_ERR_OOM, "train: focal workspace");
+  focal_partial_kernel<<<blocks, 256, 0, ctx_stream(ctx)>>>(logits, label, (size_t)n, gamma, alpha, partial);
+  focal_final_kernel<<<1, 32, 0, ctx_stream(ctx)>>>(partial, blocks, sums_dev);
+  *ctx_launches(ctx) += 2;
+  return PCGC_OK;
+}
+
+int pcgc_train_focal_backward(pcgc_ctx* ctx, const float* logits, const uint8_t* label, int64_t n, float gamma, float alpha, float weight,
+                              float* g) {
+  if (!ctx || !logits || !label || !g || n < 1 || !(gamma >= 1.0f) || !(alpha >= 0.0f && alpha <= 1.0f)) return PCGC_ERR_BAD_ARG;
+  focal_backward_kernel<<<ew_blocks(n), 256, 0, ctx_stream(ctx)>>>(logits, label, (size_t)n, gamma, alpha, weight, g);
   ++*ctx_launches(ctx);
   return PCGC_OK;
 }

@@ -174,7 +174,7 @@ def evaluate(weights, files: Sequence[str], batch_size: int = 8, device: Optiona
 # ------------------------------------------------------------------------------------------- loop
 def train(files: Sequence[str], ckpt_dir: str, alpha=2.0, beta=3.0, gamma=1.0, delta=1.0, lr=1e-5, num_iteration=int(3e5), batch_size=8,
           init_ckpt_dir: str = "", reset_optimizer: int = 0, lower_bound: float = 1e-9, display_step: int = DISPLAY_STEP,
-          save_step: int = SAVE_STEP, eval_cubes: int = 256, log=print):
+          save_step: int = SAVE_STEP, eval_cubes: int = 256, log=print, distortion: str = "bce"):
     """``train()`` of train_hyper.py:165-266.  Returns the trainer (rank-local)."""
     import torch
     import torch.distributed as dist
@@ -191,7 +191,8 @@ def train(files: Sequence[str], ckpt_dir: str, alpha=2.0, beta=3.0, gamma=1.0, d
     src = ckpt_dir if resume else init_ckpt_dir
     w0 = W.load(src, "voxception") if src else None
     codec = runtime.get_codec("voxception", "", device)
-    tr = training.HyperTrainer(codec, weights=w0, alpha=alpha, beta=beta, gamma=gamma, delta=delta, lr=lr, lower_bound=lower_bound)
+    tr = training.HyperTrainer(codec, weights=w0, alpha=alpha, beta=beta, gamma=gamma, delta=delta, lr=lr, lower_bound=lower_bound,
+                               distortion=distortion)
     step0 = restore(tr, load_train_state(src) if src else None, with_opt)
     if not resume:
         step0 = 0
@@ -260,6 +261,8 @@ def main(argv=None):
     p.add_argument("--reset_optimizer", type=int, default=0)
     p.add_argument("--lower_bound", type=float, default=1e-9)
     p.add_argument("--checkpoint_dir", type=str, default="./checkpoints")
+    p.add_argument("--distortion", type=str, default="bce", choices=["bce", "focal"],
+                   help="occupancy loss: bce = get_bce_loss as the reference script calls it; focal = get_focal_loss (loss.py:83-93)")
     a = p.parse_args(argv)
     import torch
     import torch.distributed as dist
@@ -268,7 +271,8 @@ def main(argv=None):
         dist.init_process_group("nccl")
     files = sorted(glob.glob(a.data))
     ckpt = os.path.join(a.checkpoint_dir, a.prefix + "hyper|a{0:.2f}b{1:.2f}".format(a.alpha, a.beta))          # train_hyper.py:269-271
-    train(files, ckpt, a.alpha, a.beta, a.gamma, a.delta, a.lr, a.num_iteration, a.batch_size, a.init_ckpt_dir, a.reset_optimizer, a.lower_bound)
+    train(files, ckpt, a.alpha, a.beta, a.gamma, a.delta, a.lr, a.num_iteration, a.batch_size, a.init_ckpt_dir, a.reset_optimizer, a.lower_bound,
+          distortion=a.distortion)
 
 
 if __name__ == "__main__":

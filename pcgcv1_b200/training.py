@@ -219,7 +219,13 @@ class HyperTrainer:
     """Holds the trainable variables (Keras names / layouts) as device buffers and runs training steps."""
 
     def __init__(self, codec: Optional[runtime.Codec] = None, weights: Optional[Dict[str, np.ndarray]] = None, alpha=0.75, beta=3.0, gamma=1.0,
-                 delta=1.0, lr=1e-5, lower_bound=1e-9, likelihood_bound=1e-9):
+                 delta=1.0, lr=1e-5, lower_bound=1e-9, likelihood_bound=1e-9, distortion="bce", focal_gamma=2.0, focal_alpha=0.9):
+        """``distortion``: "bce" = ``get_bce_loss`` as ``train_hyper.py:199-203`` calls it (beta * empty + full); "focal" =
+        ``get_focal_loss`` (``loss.py:83-93``, gamma 2, alpha 0.9, a SUM over the batch) on sigmoid(x_tilde) -- the reference
+        defines it but neither train script calls it; BASELINE config 5 names it, so it is selectable and D = the focal sum."""
+        if distortion not in ("bce", "focal"):
+            raise ValueError("distortion must be 'bce' or 'focal', got %r" % (distortion,))
+        self.distortion, self.focal_gamma, self.focal_alpha = distortion, float(focal_gamma), float(focal_alpha)
         self.codec = codec or runtime.get_codec("voxception", "")
         self.ops = _Ops(self.codec)
         w = weights if weights is not None else W.synthetic_weights("voxception")
@@ -291,23 +297,35 @@ class HyperTrainer:
         scale = _AbsFloor.apply(s_raw, self.lower_bound, ops)
         y_t = _LaplaceRate.apply(y, loc, scale, coef_y, seed, self.likelihood_bound, ops, stats)
         x_t = self._run("synthesis_transform", y_t)
-        # distortion: BCE sums on the device, its gradient seeds the backward pass
-        sums = torch.empty(4, dtype=torch.float64, device=c.dev)
+        # distortion: loss sums on the device, its gradient seeds the backward pass
         g = torch.empty_like(x_t)
         c._stream()
-        c._check(c.lib.pcgc_train_bce(c.ctx, x_t.data_ptr(), label.data_ptr(), x_t.numel(), sums.data_ptr()))
-        c._check(c.lib.pcgc_train_bce_backward(c.ctx, x_t.data_ptr(), label.data_ptr(), x_t.numel(), sums.data_ptr(), self.alpha * self.beta, self.alpha,
-                                               g.data_ptr()))
+        if self.distortion == "focal":
+            sums = torch.empty(2, dtype=torch.float64, device=c.dev)
+            c._check(c.lib.pcgc_train_focal(c.ctx, x_t.data_ptr(), label.data_ptr(), x_t.numel(), self.focal_gamma, self.focal_alpha, sums.data_ptr()))
+            c._check(c.lib.pcgc_train_focal_backward(c.ctx, x_t.data_ptr(), label.data_ptr(), x_t.numel(), self.focal_gamma, self.focal_alpha, self.alpha,
+                                                     g.data_ptr()))
+        else:
+            sums = torch.empty(4, dtype=torch.float64, device=c.dev)
+            c._check(c.lib.pcgc_train_bce(c.ctx, x_t.data_ptr(), label.data_ptr(), x_t.numel(), sums.data_ptr()))
+            c._check(c.lib.pcgc_train_bce_backward(c.ctx, x_t.data_ptr(), label.data_ptr(), x_t.numel(), sums.data_ptr(), self.alpha * self.beta,
+                                                   self.alpha, g.data_ptr()))
         x_t.backward(g)
-        return {"bce_sums": sums, "bits_y": stats["bits_y"], "logsum_z": stats["logsum_z"], "num_points": num_points, "x_tilde": x_t.detach()}
+        return {"bce_sums" if self.distortion == "bce" else "focal_sums": sums, "bits_y": stats["bits_y"], "logsum_z": stats["logsum_z"],
+                "num_points": num_points, "x_tilde": x_t.detach()}
 
     def loss_terms(self, out) -> Dict[str, float]:
         """Host values of the step's loss terms (one synchronisation)."""
-        s = out["bce_sums"].cpu().numpy()
         n = out["num_points"]
-        zeros, ones = s[0] / max(s[2], 1.0), s[1] / max(s[3], 1.0)
         bpp_y = float(out["bits_y"].sum().item()) / n
         bpp_z = float(out["logsum_z"].item()) / (-math.log(2.0) * n)
+        if "focal_sums" in out:
+            s = out["focal_sums"].cpu().numpy()
+            dist = float(s[0] + s[1])
+            return {"focal_full": float(s[0]), "focal_empty": float(s[1]), "distortion": dist, "bpp_ae": bpp_y, "bpp_hyper": bpp_z,
+                    "loss": float(self.alpha * dist + self.delta * bpp_y + self.gamma * bpp_z)}
+        s = out["bce_sums"].cpu().numpy()
+        zeros, ones = s[0] / max(s[2], 1.0), s[1] / max(s[3], 1.0)
         dist = self.beta * zeros + ones
         return {"zeros": float(zeros), "ones": float(ones), "distortion": float(dist), "bpp_ae": bpp_y, "bpp_hyper": bpp_z,
                 "loss": float(self.alpha * dist + self.delta * bpp_y + self.gamma * bpp_z)}

@@ -124,3 +124,56 @@ def test_export_weights_round_trip(step):
     for k in step["w"]:
         if k.split("/")[0] in ("analysis_transform", "synthesis_transform", "hyper_encoder", "hyper_decoder", "estimator"):
             assert k in w2 and w2[k].shape == np.asarray(step["w"][k]).shape, k
+
+
+def test_focal_loss_kernels_vs_reference_golden_and_autograd(codec):
+    """pcgc_train_focal against golden_loss.npz (= /root/reference/loss.py:83-93 executed by tests/golden/make_golden_loss.py, fed
+    with float32 sigmoid(pred)), its backward against torch autograd of the oracle's restatement in float64."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_loss.npz"))
+    for tag in ("a", "b"):
+        pred, label = g[tag + "_pred"], g[tag + "_label"]
+        x = torch.tensor(pred, device=codec.dev).contiguous()
+        lab = torch.tensor(label.astype(np.uint8), device=codec.dev).contiguous()
+        for key, gamma, alpha in (("_focal", 2.0, 0.9), ("_focal_g3_a75", 3.0, 0.75)):
+            sums = torch.empty(2, dtype=torch.float64, device=codec.dev)
+            grad = torch.empty_like(x)
+            codec._stream()
+            codec._check(codec.lib.pcgc_train_focal(codec.ctx, x.data_ptr(), lab.data_ptr(), x.numel(), gamma, alpha, sums.data_ptr()))
+            codec._check(codec.lib.pcgc_train_focal_backward(codec.ctx, x.data_ptr(), lab.data_ptr(), x.numel(), gamma, alpha, 0.75, grad.data_ptr()))
+            codec.synchronize()
+            got = float(sums.sum().item())
+            assert abs(got - g[tag + key][0]) <= 5e-6 * g[tag + key][0], (tag, key, got, g[tag + key][0])
+            xo = torch.tensor(pred, dtype=torch.float64, requires_grad=True)
+            f1, f0 = otrain.focal_loss(torch.sigmoid(xo), torch.tensor(label, dtype=torch.float64), gamma, alpha)
+            (0.75 * (f1 + f0)).backward()
+            ref = xo.grad.numpy()
+            # voxels whose probability sits within float32 rounding of a clip bound may fall on either side of it
+            p64 = 1.0 / (1.0 + np.exp(-pred.astype(np.float64)))
+            clear = (np.abs(p64 - 1e-3) > 1e-6) & (np.abs(p64 - 0.999) > 1e-6)
+            assert np.abs(grad.cpu().numpy() - ref)[clear].max() <= 2e-5 * np.abs(ref).max(), (tag, key)
+            assert np.count_nonzero(ref == 0) > 0 or tag == "a"        # case b holds clipped voxels: zero gradient there
+
+
+def test_training_step_with_focal_distortion_vs_oracle(codec):
+    w = W.synthetic_weights("voxception")
+    cubes, _ = synthetic.surface_cubes(1, seed=4)
+    tr = training.HyperTrainer(codec, w, distortion="focal")
+    out = tr.forward_backward(cubes, seed=3)
+    terms = tr.loss_terms(out)
+    grads = {k: v.grad.detach().cpu().numpy().copy() for k, v in tr.params.items() if v.grad is not None}
+    ref_terms, ref_grads, _ = otrain.forward_backward(w, cubes, seed=3, distortion="focal")
+    for k in ("focal_full", "focal_empty", "distortion", "bpp_ae", "bpp_hyper", "loss"):
+        a, b = terms[k], ref_terms[k]
+        print("%-12s gpu %.8g oracle %.8g rel %.2e" % (k, a, b, abs(a - b) / abs(b)))
+        assert abs(a - b) <= 5e-5 * abs(b)
+    worst = ("", 0.0)
+    for key, ref in ref_grads.items():
+        if key.startswith("estimator/"):
+            continue
+        e = _rel(grads[key], ref)
+        worst = max(worst, (key, e), key=lambda t: t[1])
+        assert e < 2e-3, (key, e)
+    print("focal: worst relative gradient error %.2e (%s)" % (worst[1], worst[0]))
+    with pytest.raises(ValueError):
+        training.HyperTrainer(codec, w, distortion="dice")
