@@ -185,6 +185,20 @@ def e2e_step(st):
     return host, mask
 
 
+def config1(args, cubes_per_gpu, points_per_gpu):
+    """The `config` object of BASELINE config 1, printed identically by the CUDA arm and by --impl reference."""
+    return {"workload": "%s synthetic cloud, %d cubes of 64^3 (%d points) per GPU, hyper mode, model_voxception, rho=1.0, "
+                        "seeded synthetic weights" % (args.workload, cubes_per_gpu, int(points_per_gpu)),
+            "cubes_per_gpu": int(cubes_per_gpu), "points_per_gpu": int(points_per_gpu),
+            "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)",
+            "range_coder": os.environ.get("PCGC_CODER", "gpu"),
+            "e2e_flow": "compress_hyper -> .numpy() of every stream field -> decompress_hyper (returns a pending device result once "
+                        "its last kernel is queued) -> select_voxels(codec=, dtype=uint8): top-k on the GPU and the uint8 masks to "
+                        "the host part by part behind the synthesis (the reference does .numpy() then NumPy top-k, test.py:115)",
+            "decode_schedule": os.environ.get("PCGC_DEC_RAMP", "8,24,64") + " cubes, then the rest",
+            "conv_engine": os.environ.get("PCGC_ENGINE", "auto")}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -355,15 +369,7 @@ def run_gpu(args):
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(dev_ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s synthetic cloud, %d cubes of 64^3 (%d points) per GPU, hyper mode, model_voxception, rho=1.0, "
-                               "seeded synthetic weights" % (args.workload, B, int(points)),
-                   "cubes_per_gpu": B, "points_per_gpu": int(points), "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)",
-                   "range_coder": os.environ.get("PCGC_CODER", "gpu"),
-                   "e2e_flow": "compress_hyper -> .numpy() of every stream field -> decompress_hyper (returns a pending device result once "
-                               "its last kernel is queued) -> select_voxels(codec=, dtype=uint8): top-k on the GPU and the uint8 masks to "
-                               "the host part by part behind the synthesis (the reference does .numpy() then NumPy top-k, test.py:115)",
-                   "decode_schedule": os.environ.get("PCGC_DEC_RAMP", "8,24,64") + " cubes, then the rest",
-                   "conv_engine": os.environ.get("PCGC_ENGINE", "auto")},
+        "config": config1(args, B, points),
         "points_per_s": round(value * points / B, 1),
         "value_without_range_coder": {"value": round(world * B * nocoder_steps / (nocoder_ms / 1e3), 2), "unit": UNIT, "steps": nocoder_steps,
                                       "note": "r01's definition of value (range coder on the host, outside the timed kernels); `value` above "
@@ -707,11 +713,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        # the same workload description as the CUDA arm prints (the step here is a bounded sample of it: see cpu_baseline.sample)
-        "config": {"workload": "%s synthetic cloud, %d cubes of 64^3 (%d points) per GPU, hyper mode, model_voxception, rho=1.0, "
-                               "seeded synthetic weights" % (args.workload, len(cubes), int(nums.sum())),
-                   "cubes_per_gpu": len(cubes), "points_per_gpu": int(nums.sum()),
-                   "note": "TF 1.13 reference not installable offline: CPU oracle port of the same path, one cube per call"},
+        # exactly the CUDA arm's config object (the step here is a bounded sample of that workload: see cpu_baseline.sample)
+        "config": config1(args, len(cubes), int(nums.sum())),
+        "note": "TF 1.13 reference not installable offline: CPU oracle port of the same path, one cube per call",
         "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 

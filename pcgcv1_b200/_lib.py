@@ -12,7 +12,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpcgc_b200.so")
+LIB_PATH = os.environ.get("PCGC_LIB") or os.path.join(_HERE, "libpcgc_b200.so")   # PCGC_LIB: dev hook (A/B builds of one kernel, tools/)
 
 # enums of include/pcgc_b200.h
 NET_VOX_ANALYSIS, NET_VOX_SYNTHESIS, NET_HYPER_ENCODER, NET_HYPER_DECODER, NET_SIMPLE_ANALYSIS, NET_SIMPLE_SYNTHESIS = range(6)
