@@ -314,10 +314,18 @@ static const bool CDF_REG = [] { const char* e = getenv("PCGC_CDF_REG"); return 
 
 static const size_t CDF_SMEM = [] { const char* e = getenv("PCGC_CDF_PAD_KB"); return (size_t)(e ? atoi(e) : 0) * 1024; }();   // occupancy experiments
 
+// PCGC_CDF_L1 (experiment): 1 = the intervals kernel (encoder side) asks for the all-L1 carveout, 2 = the rows kernel too.  The per-thread
+// arrays of the normaliser live in local memory (3 x N x 128 B per warp, 48 warps per SM: 220 KB at N = 12), which the all-shared carveout
+// of the rest of the library leaves ~28 KB of L1 for (ncu: 10 % L1 hit rate).
+static const int CDF_L1 = [] { const char* e = getenv("PCGC_CDF_L1"); return e ? atoi(e) : 0; }();
+
 template <int MODE>
 static cudaError_t cdf_prepare() {
   static const cudaError_t once = [] {
-    prefer_shared_carveout(laplace_cdf_kernel<MODE>);
+    if ((MODE == 1 && CDF_L1 >= 1) || (MODE == 0 && CDF_L1 >= 2))
+      cudaFuncSetAttribute(laplace_cdf_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    else
+      prefer_shared_carveout(laplace_cdf_kernel<MODE>);
     return cudaFuncSetAttribute(laplace_cdf_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 * 1024));
   }();
   return once;
