@@ -24,6 +24,30 @@ def test_shard_slices():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_decode_slices_cover_in_order_and_equalise_the_finish_times():
+    for n in (0, 1, 5, 7, 191, 7769):
+        for w in (1, 2, 4, 8):
+            for ratio in (0.5, 2.2, 3.0, 10.0):
+                s = sharding.decode_slices(n, w, ratio)
+                assert len(s) == w and s[0][0] == 0 and s[-1][1] == n and all(a[1] == b[0] for a, b in zip(s, s[1:]))
+                assert all(b >= a for a, b in s)
+                sizes = [b - a for a, b in s]
+                assert sizes == sorted(sizes, reverse=True) or n < 4 * w        # earlier ranks wait less for the string: more cubes
+    assert sharding.decode_slices(100, 1, 3.0) == [(0, 100)]
+    assert sharding.decode_slices(100, 4, 0.0) == sharding.shard_slices(100, 4)          # <= 0: the balanced slices
+    assert sharding.decode_slices(100, 4, -1.0) == sharding.shard_slices(100, 4)
+    # the model behind it: rank 0 works through its slice at the GPU rate, rank r > 0 starts when the string decoder (ratio x the GPU
+    # rate) has passed the end of its slice -> every rank finishes at the same time (to within the rounding to whole cubes)
+    n, w, ratio = 7769, 8, 3.0
+    s = sharding.decode_slices(n, w, ratio)
+    finish = [(b - a) if r == 0 else b / ratio + (b - a) for r, (a, b) in enumerate(s)]
+    assert max(finish) - min(finish) <= 2.0
+    balanced = sharding.shard_slices(n, w)
+    assert max(finish) < 0.85 * max((b - a) if r == 0 else b / ratio + (b - a) for r, (a, b) in enumerate(balanced))
+    big = sharding.decode_slices(n, w, 1e9)                                       # an instant string decoder: balanced to within a cube
+    assert max(abs((b - a) - n / w) for a, b in big) <= 1.0
+
+
 class OracleLocalCodec(sharding.LocalCodec):
     """CPU stand-in: tiny 'latents' derived from the cubes, real oracle entropy coding."""
 
