@@ -114,13 +114,25 @@ int64_t orc_range_encode(const int16_t* sym, int64_t count, const int32_t* cdf, 
       e.size_minus1 = (e.size_minus1 << 16) | 0xFFFF;
     }
   }
-  uint64_t v = (e.base + 0xFFFF) >> 16;
-  uint32_t carry = (uint32_t)(v >> 16), word = (uint32_t)(v & 0xFFFF);
-  if (e.have_cache) emit16(&e, (e.cache + carry) & 0xFFFF);
-  for (int64_t i = 0; i < e.pending; ++i) emit16(&e, (0xFFFF + carry) & 0xFFFF);
-  emit16(&e, word);
+  /* RangeEncoder::Finalize of the upstream coder (see oracle/coder.py _Encoder.finish): an interval that still holds a multiple
+   * of 2^32 above base is closed with that multiple (delayed word + 1, zeros after it left out); otherwise base is rounded up to a
+   * multiple of 2^16, earlier words go out in full, the last word loses a zero low byte and is omitted when base's low 32 bits are 0. */
+  uint32_t carry = (uint32_t)(e.base >> 32), low32 = (uint32_t)e.base;
+  if (e.n + 2 * (e.pending + 2) > e.cap) return -3;
+  if (!carry && (uint32_t)(low32 + e.size_minus1) < low32) {
+    uint32_t w = (e.cache + 1) & 0xFFFF;
+    out[e.n++] = (uint8_t)(w >> 8);
+    if (w & 0xFF) out[e.n++] = (uint8_t)w;
+  } else {
+    if (e.have_cache) emit16(&e, (e.cache + carry) & 0xFFFF);
+    for (int64_t i = 0; i < e.pending; ++i) emit16(&e, (0xFFFF + carry) & 0xFFFF);
+    if (low32 != 0) {
+      uint32_t mid = ((low32 - 1) >> 16) + 1;
+      out[e.n++] = (uint8_t)(mid >> 8);
+      if (mid & 0xFF) out[e.n++] = (uint8_t)mid;
+    }
+  }
   if (e.overflow) return -3;
-  while (e.n > 0 && out[e.n - 1] == 0) e.n--;
   return e.n;
 }
 

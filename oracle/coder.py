@@ -15,9 +15,14 @@ algorithm and the tests anchor on round trips, CDF validity and coded size:
   (the upstream tie order is an artefact of ``std::sort`` and is not specified).
 * range coder: 32-bit ``base`` / ``size-1`` state, interval update
   ``a = (size*lower) >> precision``, ``b = ((size*upper) >> precision) - 1``, 16-bit
-  renormalisation when ``size-1 < 2^16``, carries propagated through a delayed word + a
-  counter of pending 0xFFFF words, big-endian 16-bit words, finalisation picks the multiple
-  of 2^16 inside the interval and drops trailing zero bytes (the decoder pads zeros).
+  renormalisation when ``size-1 < 2^16``, big-endian 16-bit words.  ``UpstreamRangeEncoder`` restates the
+  upstream ``RangeEncoder::Encode`` / ``Finalize`` state machine LITERALLY (32-bit base that may wrap, the
+  ``delay_`` word + byte counter for an interval that straddles 2^32, Finalize = "2^32" in the delayed
+  state, else base rounded up to a multiple of 2^16 with a zero low byte left out and nothing for base 0).
+  ``_Encoder`` is the carry-propagating form the product's C++ / CUDA coders use (33-bit base, delayed
+  word + counter of pending 0xFFFF words) with the same Finalize rule; the two agree byte for byte on
+  every input (tests/test_host_coder.py), so the product is pinned on the upstream ALGORITHM -- a TF
+  binary to pin the restatement itself is what is missing.
 
 The pure-Python versions below are the definition; ``oracle/c/oracle_coder.c`` is the same
 algorithm in C (built by ``oracle/build.py``) and is cross-checked against them in the tests.
@@ -135,18 +140,95 @@ class _Encoder:
             self.size_minus1 = ((self.size_minus1 << 16) | 0xFFFF) & 0xFFFFFFFF
 
     def finish(self) -> bytes:
-        v = (self.base + 0xFFFF) >> 16          # round base up to a multiple of 2^16 (17-bit)
-        carry, word = v >> 16, v & 0xFFFF
+        """RangeEncoder::Finalize of the upstream coder, in this state machine's terms.  The interval is [base, base + size_minus1]
+        (base exact, up to 33 bits).  If it still holds a multiple of 2^32 above base (upstream: ``delay_ != 0``), that multiple is
+        the value written: the delayed word + 1, everything after it zero and left out.  Otherwise base is rounded up to a multiple
+        of 2^16 (upstream ``mid``): the words before the last one go out in full, of the last one the low byte only if it is not
+        zero, and nothing at all if the low 32 bits of base are zero."""
+        carry, low32 = self.base >> 32, self.base & 0xFFFFFFFF
+        if carry == 0 and low32 + self.size_minus1 > 0xFFFFFFFF:
+            w = (self.cache + 1) & 0xFFFF           # a straddling interval only exists after a renormalisation: cache is set
+            self.out.append(w >> 8)
+            if w & 0xFF:
+                self.out.append(w & 0xFF)
+            return bytes(self.out)
         if self.cache is not None:
             self._emit16((self.cache + carry) & 0xFFFF)
         for _ in range(self.pending):
             self._emit16((0xFFFF + carry) & 0xFFFF)
-        self._emit16(word)
-        out = self.out
-        n = len(out)
-        while n > 0 and out[n - 1] == 0:
-            n -= 1
-        return bytes(out[:n])
+        if low32 != 0:
+            mid = ((low32 - 1) >> 16) + 1
+            self.out.append(mid >> 8)
+            if mid & 0xFF:
+                self.out.append(mid & 0xFF)
+        return bytes(self.out)
+
+
+class UpstreamRangeEncoder:
+    """``RangeEncoder`` of tensorflow/contrib/coder/kernels/range_coder.cc (tensorflow-gpu==1.13.1), restated statement by
+    statement: ``Encode(lower, upper)`` and ``Finalize()``.  uint32 ``base_`` / ``size_minus1_`` wrap like the C++ types; ``delay_``
+    holds, in its low 16 bits, the delayed word + 1 and, above them, the number of delayed BYTES after it."""
+
+    M = 0xFFFFFFFF
+
+    def __init__(self, precision: int):
+        self.precision = precision
+        self.base = 0
+        self.size_minus1 = self.M
+        self.delay = 0
+        self.out = bytearray()
+
+    def encode(self, lower: int, upper: int):
+        M = self.M
+        size = self.size_minus1 + 1
+        a = ((size * lower) >> self.precision) & M
+        b = (((size * upper) >> self.precision) - 1) & M
+        self.base = (self.base + a) & M
+        self.size_minus1 = (b - a) & M
+        base_overflow = self.base < a
+        if ((self.base + self.size_minus1) & M) < self.base:
+            # the interval [base, base + size) wraps around 2^32: the carry is not known yet
+            assert self.delay & 0xFFFF
+            if (self.size_minus1 >> 16) == 0:
+                assert (self.base >> 16) == 0xFFFF
+                self.base = (self.base << 16) & M
+                self.size_minus1 = ((self.size_minus1 << 16) | 0xFFFF) & M
+                self.delay += 0x20000                        # two more delayed bytes
+            return
+        if self.delay != 0:
+            if base_overflow:                                # carry: delayed word + 1, then zero bytes
+                self.out.append((self.delay >> 8) & 0xFF)
+                self.out.append(self.delay & 0xFF)
+                self.out.extend(b"\x00" * (self.delay >> 16))
+            else:                                            # no carry: the delayed word, then 0xFF bytes
+                self.delay -= 1
+                self.out.append((self.delay >> 8) & 0xFF)
+                self.out.append(self.delay & 0xFF)
+                self.out.extend(b"\xff" * (self.delay >> 16))
+            self.delay = 0
+        if (self.size_minus1 >> 16) == 0:
+            top = self.base >> 16
+            self.base = (self.base << 16) & M
+            self.size_minus1 = ((self.size_minus1 << 16) | 0xFFFF) & M
+            if self.base <= ((self.base + self.size_minus1) & M):
+                self.out.append((top >> 8) & 0xFF)
+                self.out.append(top & 0xFF)
+            else:
+                assert top < 0xFFFF
+                self.delay = top + 1
+
+    def finish(self) -> bytes:
+        if self.delay != 0:                                  # the last state was the wrapped one: take the value 2^32
+            self.out.append((self.delay >> 8) & 0xFF)
+            if self.delay & 0xFF:
+                self.out.append(self.delay & 0xFF)
+        elif self.base != 0:                                 # base rounded up to the next multiple of 2^16 (base 0: nothing)
+            mid = ((self.base - 1) >> 16) + 1
+            assert mid & 0xFFFF == mid
+            self.out.append((mid >> 8) & 0xFF)
+            if mid & 0xFF:
+                self.out.append(mid & 0xFF)
+        return bytes(self.out)
 
 
 class _Decoder:

@@ -5,9 +5,9 @@
 // tensorflow/contrib/coder/kernels/range_coder.cc) is not vendored; this is a fresh
 // carry-propagating 32-bit range coder with 16-bit renormalisation built to the published
 // contract: interval update a=(size*lower)>>p, b=((size*upper)>>p)-1; big-endian 16-bit words;
-// finalisation picks the multiple of 2^16 inside the interval and drops trailing zero bytes.
-// Symbol-compatible with tensorflow.contrib.coder, NOT verified byte-identical to it: TF's RangeEncoder keeps a delayed-carry
-// counter and finalises differently at the tail, and the reference holds no golden stream to pin either.
+// finalisation by the upstream Finalize rule (range_coder.h finish()).
+// Byte-identical to the literal restatement of the upstream delay-based RangeEncoder in oracle/coder.py (UpstreamRangeEncoder;
+// tests/test_host_coder.py); NOT verified against a TF binary: the reference holds no golden stream to pin either.
 // Per-cube strings are independent, so the batch entry points fan out over a thread pool.  The state machines live in
 // range_coder.h and are shared with the GPU coder (gpu_coder.cu).
 #include <stdint.h>

@@ -32,8 +32,8 @@ namespace {
 //                (R_j from a popcount of the flag mask); digits the chain has moved past are flushed to the cube's scratch as
 //                32-bit sums (Sum a_i < 2^32 between two renormalisations and E <= 65536 bound a digit below 2^32).
 //   3. carries : after the last symbol the digits are resolved right to left, 32 per step with shuffles (the loop runs until
-//                no lane carries: twice in expectation), byte-swapped into the string, trailing zero bytes dropped.
-// finish() of range_coder.h (round the base up to a multiple of 2^16, emit one more word) = +0xFFFF on digit R+1, words 0..R.
+//                no lane carries: twice in expectation), byte-swapped into the string; the length follows the upstream Finalize rule.
+// finish() of range_coder.h = the upstream Finalize rule on the last two digits (see the end of the kernel).
 // Same bytes as RangeEncoder16 / the host coder for every input (tests/test_gpu_coder.py); measured 3.8 -> see DESIGN.md.
 // The r02 first form ran the whole RangeEncoder16 per symbol on the serial path (~104 cycles per symbol).
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
@@ -104,8 +104,23 @@ range_encode_intervals_kernel(const uint32_t* __restrict__ iv, int B, int64_t E,
     }
     __syncwarp();
   }
-  // finish(): round up to a multiple of 2^16 at digit R, i.e. +0xFFFF on digit R + 1, then words 0..R
-  if (lane == 0) s_win[(R + 1) & (ENC_W - 1)] += 0xFFFFu;
+  // finish() of range_coder.h (the upstream Finalize rule).  Digits R and R + 1 are the coder's current 32-bit window and have nothing to
+  // their right, so their exact value mod 2^32 is local: low32.  If [low32, low32 + size - 1] wraps, the interval still holds a multiple
+  // of 2^32 and THAT is the value written (+ (2^32 - low32): both digits become zero, one carry leaves to the left); otherwise the base
+  // is rounded up to a multiple of 2^16 at digit R (+0xFFFF on digit R + 1).  Words 0..R are produced either way.
+  const uint32_t w1 = s_win[(R + 1) & (ENC_W - 1)], w0 = s_win[R & (ENC_W - 1)] + (w1 >> 16);
+  const uint32_t low32 = (w0 << 16) | (w1 & 0xFFFFu);
+  const bool straddle = (uint32_t)(low32 + sm1) < low32;
+  __syncwarp();
+  if (lane == 0) {
+    if (straddle) {
+      const uint32_t x = 0u - low32;
+      s_win[R & (ENC_W - 1)] += x >> 16;
+      s_win[(R + 1) & (ENC_W - 1)] += x & 0xFFFFu;
+    } else {
+      s_win[(R + 1) & (ENC_W - 1)] += 0xFFFFu;
+    }
+  }
   __syncwarp();
   const uint32_t n_dig = R + 2;
   for (uint32_t idx = Rfl + lane; idx < n_dig; idx += 32) dig[idx] = s_win[idx & (ENC_W - 1)];
@@ -144,6 +159,9 @@ range_encode_intervals_kernel(const uint32_t* __restrict__ iv, int B, int64_t E,
       }
     }
   }
+  // length: the words before the last one are written in full (upstream emits them while coding), the last word loses a zero low byte
+  // and is left out when it is zero; after a straddle everything from the delayed word's last non-zero byte on is zero and left out
+  if (!straddle && found < 2u * R) found = 2u * R;
   if (lane == 0) lens[b] = (int64_t)found;
 }
 

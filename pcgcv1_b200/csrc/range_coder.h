@@ -3,9 +3,10 @@
 // (models/entropy_model.py:258-259,298-299; models/conditional_entropy_model.py:161,195).  The upstream C++
 // (tensorflow-gpu==1.13.1, tensorflow/contrib/coder/kernels/range_coder.cc) is not vendored; this is a fresh
 // carry-propagating 32-bit range coder with 16-bit renormalisation built to the published contract: interval update
-// a=(size*lower)>>p, b=((size*upper)>>p)-1; big-endian 16-bit words; finalisation picks the multiple of 2^16 inside the
-// interval and drops trailing zero bytes.  Symbol-compatible with the reference's coder; byte identity with TF is unpinned
-// (no TF wheel, no golden stream in the reference).
+// a=(size*lower)>>p, b=((size*upper)>>p)-1; big-endian 16-bit words; finalisation by the upstream Finalize rule (see finish()).
+// oracle/coder.py holds a literal restatement of the upstream delay-based encoder; this carry-propagating form produces the same
+// bytes (tests/test_host_coder.py, tests/test_gpu_coder.py).  Byte identity with a TF BINARY stays unpinned (no TF wheel, no
+// golden stream in the reference).
 #pragma once
 #include <stdint.h>
 
@@ -59,15 +60,31 @@ struct RangeEncoder {
       size_minus1 = (size_minus1 << 16) | 0xFFFF;
     }
   }
+  // RangeEncoder::Finalize of the upstream coder in this state machine's terms (oracle/coder.py restates the upstream one literally;
+  // tests compare the two byte for byte).  The interval is [base, base + size_minus1], base exact (33 bits).  If it still holds a
+  // multiple of 2^32 above base (upstream: delay_ != 0) that multiple is written: the delayed word + 1, the zeros after it left
+  // out.  Otherwise base is rounded up to a multiple of 2^16: earlier words in full, of the last word the low byte only if it is
+  // not zero, and nothing when the low 32 bits of base are zero.
+  PCGC_RC void emit8(uint32_t b) {
+    if (n + 1 > cap) { overflow = true; return; }
+    out[n++] = (uint8_t)b;
+  }
   PCGC_RC int64_t finish() {
-    const uint64_t v = (base + 0xFFFF) >> 16;
-    const uint32_t carry = (uint32_t)(v >> 16), word = (uint32_t)(v & 0xFFFF);
-    if (have_cache) emit16((cache + carry) & 0xFFFF);
-    for (; pending > 0; --pending) emit16((0xFFFF + carry) & 0xFFFF);
-    emit16(word);
-    if (overflow) return -1;
-    while (n > 0 && out[n - 1] == 0) --n;
-    return n;
+    const uint32_t carry = (uint32_t)(base >> 32), low32 = (uint32_t)base;
+    if (!carry && (uint32_t)(low32 + size_minus1) < low32) {
+      const uint32_t w = (cache + 1) & 0xFFFF;
+      emit8(w >> 8);
+      if (w & 0xFF) emit8(w & 0xFF);
+    } else {
+      if (have_cache) emit16((cache + carry) & 0xFFFF);
+      for (; pending > 0; --pending) emit16((0xFFFF + carry) & 0xFFFF);
+      if (low32 != 0) {
+        const uint32_t mid = ((low32 - 1) >> 16) + 1;
+        emit8(mid >> 8);
+        if (mid & 0xFF) emit8(mid & 0xFF);
+      }
+    }
+    return overflow ? -1 : n;
   }
 };
 
@@ -117,15 +134,25 @@ struct RangeEncoder16 {
       size_minus1 = (size_minus1 << 16) | 0xFFFFu;
     }
   }
-  PCGC_RC int64_t finish() {
-    const uint64_t v = (((uint64_t)carry << 32) + base + 0xFFFF) >> 16;
-    const uint32_t c = (uint32_t)(v >> 16), word = (uint32_t)(v & 0xFFFF);
-    if (have_cache) emit16((cache + c) & 0xFFFF);
-    for (; pending > 0; --pending) emit16((0xFFFF + c) & 0xFFFF);
-    emit16(word);
-    if (overflow) return -1;
-    while (n > 0 && out[n - 1] == 0) --n;
-    return n;
+  PCGC_RC void emit8(uint32_t b) {
+    if (n + 1 > cap) { overflow = true; return; }
+    out[n++] = (uint8_t)b;
+  }
+  PCGC_RC int64_t finish() {                      // the same rule as RangeEncoder::finish
+    if (!carry && (uint32_t)(base + size_minus1) < base) {
+      const uint32_t w = (cache + 1) & 0xFFFF;
+      emit8(w >> 8);
+      if (w & 0xFF) emit8(w & 0xFF);
+    } else {
+      if (have_cache) emit16((cache + carry) & 0xFFFF);
+      for (; pending > 0; --pending) emit16((0xFFFF + carry) & 0xFFFF);
+      if (base != 0) {
+        const uint32_t mid = ((base - 1) >> 16) + 1;
+        emit8(mid >> 8);
+        if (mid & 0xFF) emit8(mid & 0xFF);
+      }
+    }
+    return overflow ? -1 : n;
   }
 };
 

@@ -195,3 +195,34 @@ def test_noise_quantisation_matches_oracle_philox(codec, latents):
     ref_z, ref_pz = eb_or(z.cpu().numpy(), training=True, seed=seed)
     assert np.array_equal(z_t.numpy(), ref_z)
     np.testing.assert_allclose(pz.numpy(), ref_pz, rtol=1e-3, atol=3e-7)
+
+
+def test_gpu_encoder_equals_the_literal_upstream_state_machine(codec):
+    """Raw interval words through the GPU encoder against oracle.coder.UpstreamRangeEncoder (tensorflow/contrib/coder's
+    RangeEncoder::Encode / Finalize restated statement by statement): random intervals, intervals with lower = 0 (bases that end at
+    zero: nothing is written for the last word, earlier zero words stay) and intervals hugging the top of the range (strings that END
+    in the delayed, wrapped state: the value 2^32 is written)."""
+    rng = np.random.default_rng(21)
+    B, E = 384, 64
+    lower = rng.integers(0, 65535, (B, E))
+    width = np.minimum(rng.integers(1, 65536, (B, E)), 65536 - lower)
+    k = B // 3
+    zero = rng.random((k, E)) < 0.7                                            # cubes [k, 2k): mostly [0, w)
+    lower[k:2 * k][zero] = 0
+    top = rng.random((B - 2 * k, E)) < 0.7                                      # cubes [2k, B): mostly [2^16 - w, 2^16)
+    lower[2 * k:][top] = (65536 - width[2 * k:])[top]
+    iv = (lower.astype(np.uint32) | ((width - 1).astype(np.uint32) << 16)).astype(np.uint32)
+    packed, offsets = codec.gpu_range_encode(codec.to_device(iv.view(np.int32)))
+    codec.synchronize()
+    o, blob = offsets.cpu().numpy(), packed.cpu().numpy()
+    delayed = zero_base = 0
+    for b in range(B):
+        up = ocoder.UpstreamRangeEncoder(16)
+        for lo, w in zip(lower[b].tolist(), width[b].tolist()):
+            up.encode(lo, lo + w)
+        delayed += up.delay != 0
+        zero_base += up.delay == 0 and up.base == 0
+        assert blob[o[b]:o[b + 1]].tobytes() == up.finish(), b
+    print("%d strings: %d ended in the delayed state, %d with base 0" % (B, delayed, zero_base))
+    assert delayed >= 10 and zero_base >= 3
+    assert [blob[o[b]:o[b + 1]].tobytes() for b in range(B)] == _host_strings(iv)

@@ -193,3 +193,48 @@ def test_register_normaliser_and_shared_edge_likelihoods_equal_the_plain_forms(t
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:]
     assert "0 mismatches" in r.stdout.strip().splitlines()[-1]
+
+
+def test_every_encoder_equals_the_literal_upstream_state_machine():
+    """oracle.coder.UpstreamRangeEncoder restates tensorflow/contrib/coder's RangeEncoder::Encode / Finalize statement by statement
+    (32-bit wrapping base, delay_ word + byte count, Finalize's three cases).  The carry-propagating coders -- the oracle's Python
+    definition, the oracle's C, the library's generic host encoder and its RangeEncoder16 (what the GPU encoder runs) -- must
+    write the same bytes, including strings that END in the delayed (wrapped) state and strings whose base ends at zero."""
+    L = _lib.lib()
+    rng = np.random.default_rng(11)
+    ended_delayed = ended_zero = total = 0
+    for trial in range(1500):
+        N = int(rng.integers(2, 33))
+        cuts = np.sort(rng.choice(np.arange(1, 65536), N - 1, replace=False))
+        cdf = np.concatenate([[0], cuts, [65536]]).astype(np.int32)
+        n = int(rng.integers(0, 120))
+        kind = trial % 3
+        if kind == 0:
+            sym = rng.integers(0, N, n)
+        elif kind == 1:                                   # mostly the first symbol (lower = 0): bases that end at zero
+            sym = np.where(rng.random(n) < 0.7, 0, rng.integers(0, N, n))
+        else:                                             # mostly the last symbol (upper = 2^16): intervals at the top, long delays
+            sym = np.where(rng.random(n) < 0.7, N - 1, rng.integers(0, N, n))
+        sym = sym.astype(np.int16)
+        up = coder.UpstreamRangeEncoder(16)
+        for s in sym.tolist():
+            up.encode(int(cdf[s]), int(cdf[s + 1]))
+        ended_delayed += up.delay != 0
+        ended_zero += up.delay == 0 and up.base == 0 and n > 0
+        want = up.finish()
+        idx = np.zeros(n, np.int32)
+        assert coder.range_encode(sym, cdf[None], idx, force_python=True) == want, trial
+        assert coder.range_encode(sym, cdf[None], idx) == want, trial
+        assert runtime.range_encode(sym, cdf[None]) == want, trial
+        if n:
+            iv = (cdf[sym].astype(np.uint32) | ((cdf[sym + 1] - cdf[sym] - 1).astype(np.uint32) << 16)).astype(np.uint32)
+            out = np.zeros(2 * n + 64, np.uint8)
+            ln = C.c_int64()
+            assert L.pcgc_range_encode_intervals(iv.ctypes.data, n, 16, out.ctypes.data, out.size, C.byref(ln)) == 0
+            assert out[:ln.value].tobytes() == want, trial
+            assert runtime.range_encode_intervals_batch(iv[None], 1)[0] == want, trial
+        assert np.array_equal(coder.range_decode(want, n, cdf[None], idx), sym)
+        assert np.array_equal(runtime.range_decode(want, n, cdf[None]), sym)
+        total += 1
+    print("%d strings: %d ended in the delayed state, %d with base 0" % (total, ended_delayed, ended_zero))
+    assert ended_delayed > 30 and ended_zero > 10
