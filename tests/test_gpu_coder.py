@@ -128,7 +128,9 @@ def test_gpu_coder_wide_and_narrow_alphabets(codec, span):
 
 
 def test_gpu_coder_empty_and_ragged_strings(codec):
-    """A cube whose symbols are all certain codes to an (almost) empty string; the packed buffer then holds ragged pieces."""
+    """Cubes whose symbols are all (almost) certain code to short strings of zero words -- the upstream coder writes every word it
+    renormalises out, only the LAST word is trimmed (Finalize), so such a string is not empty; the packed buffer then holds ragged
+    pieces."""
     B, E = 4, 2048
     y = np.zeros((B, E), np.float32)
     y[:, 0] = 1.0                                                           # two symbols (N >= 2 is a format requirement)
@@ -144,7 +146,12 @@ def test_gpu_coder_empty_and_ragged_strings(codec):
     codec.synchronize()
     o, blob = offsets.cpu().numpy(), packed.cpu().numpy()
     lens = np.diff(o)
-    assert lens[2] > 100 and lens[0] <= 4 and lens[1] <= 4
+    assert lens[2] > 1500 and lens[0] < lens[2] // 4 and lens[1] == lens[0]
+    iv_h = iv.cpu().numpy().view(np.uint32)
+    up = ocoder.UpstreamRangeEncoder(16)
+    for w in iv_h[0].tolist():
+        up.encode(w & 0xFFFF, (w & 0xFFFF) + (w >> 16) + 1)
+    assert blob[o[0]:o[1]].tobytes() == up.finish()
     assert [blob[o[b]:o[b + 1]].tobytes() for b in range(B)] == _host_strings(iv.cpu().numpy())
     mm_h = mm.cpu().numpy()
     y_hat = cem.decode_dev(packed, offsets, ld, sd, mm_h[:, 0], mm_h[:, 1])
