@@ -1,8 +1,9 @@
 """On-disk container of the codec, interface-compatible with the reference's ``dataprocess/inout_bitstream.py``
 (``write_binary_files_factorized`` :10-44, ``read_binary_files_factorized`` :46-70, ``write_binary_files_hyper`` :75-141,
 ``read_binary_files_hyper`` :144-198; layout in SURVEY.md Appendix B).  The CONTAINER (headers, length fields, side files) written by either side reads on the other; the range-coded payloads are
-symbol-compatible with ``tensorflow.contrib.coder`` by construction but their byte identity with TF is unpinned (no TF wheel and
-no golden stream in the reference), so payload interchange with a TF 1.13 run is untested.
+byte-identical to a literal restatement of ``tensorflow.contrib.coder``'s RangeEncoder (oracle/coder.py, tests/test_host_coder.py); that
+restatement against a TF binary is unpinned (no TF wheel and no golden stream in the reference), so payload interchange with a TF 1.13 run
+is untested.
 
 Files next to ``<rootdir>/<filename>``:
 
