@@ -44,6 +44,54 @@ void parallel_for(int n, int threads, F f) {
   for (auto& th : pool) th.join();
 }
 
+// One long string (the hyper latents of a whole cloud, the factorized latents of model_simple: millions of symbols on ONE thread, the
+// serial tail of the sharded codec) without the unpredictable renormalisation branch.  The number a range encoder writes is a SUM of
+// the interval offsets, so every renormalised word can be stored at once and a later carry simply walks back through the bytes already
+// written (rare, well predicted); what is left per symbol is the size recurrence with selects and one unconditional 16-bit store whose
+// position advances by 0 or 2.  Same bytes as Encoder (range_coder.h) incl. the upstream Finalize rule: tests/test_host_coder.py.
+inline void carry_back(uint8_t* out, int64_t n) {
+  int64_t i = n - 1;
+  while (i >= 0 && out[i] == 0xFF) out[i--] = 0;
+  if (i >= 0) ++out[i];
+}
+
+int encode_string_branch_free(const int16_t* sym, int64_t n, const int32_t* cdf, int cdf_rows, int N, int precision, uint8_t* out,
+                              int64_t* len) {
+  uint32_t low = 0, sm1 = 0xFFFFFFFFu;
+  int64_t pos = 0;                                   // bytes written; out has room for 2 n + 8
+  int r = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int s = sym[i];
+    if (s < 0 || s >= N) return PCGC_ERR_BAD_RANGE;
+    const int32_t* row = cdf + (int64_t)r * (N + 1);
+    const uint32_t lower = (uint32_t)row[s], upper = (uint32_t)row[s + 1];
+    if (!(lower < upper)) return PCGC_ERR_BAD_ARG;
+    const uint64_t size = (uint64_t)sm1 + 1;
+    const uint32_t a = (uint32_t)((size * lower) >> precision);
+    const uint32_t t = (uint32_t)(((size * upper) >> precision) - 1) - a;
+    low += a;
+    if (low < a) carry_back(out, pos);
+    const bool renorm = t < 0x10000u;
+    out[pos] = (uint8_t)(low >> 24);
+    out[pos + 1] = (uint8_t)(low >> 16);
+    pos += renorm ? 2 : 0;
+    low = renorm ? low << 16 : low;
+    sm1 = renorm ? ((t << 16) | 0xFFFFu) : t;
+    if (++r == cdf_rows) r = 0;
+  }
+  if ((uint32_t)(low + sm1) < low) {                 // upstream Finalize, delayed state: the value 2^32
+    if (pos == 0) return PCGC_ERR_NOT_READY;         // cannot happen (a wrapped interval needs a renormalisation); use the generic coder
+    carry_back(out, pos);
+    while (pos > 0 && out[pos - 1] == 0) --pos;      // the delayed word + 1 is not zero: this stops inside it
+  } else if (low != 0) {
+    const uint32_t mid = ((low - 1) >> 16) + 1;
+    out[pos++] = (uint8_t)(mid >> 8);
+    if (mid & 0xFF) out[pos++] = (uint8_t)mid;
+  }
+  *len = pos;
+  return PCGC_OK;
+}
+
 // K independent per-cube streams decoded in ONE loop: the serial dependency chain of a range decoder (division -> search ->
 // interval update -> renormalise, ~60 cycles per symbol) leaves an out-of-order core mostly idle; interleaving K cubes lets it
 // overlap their chains.  Same arithmetic per stream, so the symbols are identical to the one-at-a-time decoder's.
@@ -150,6 +198,10 @@ int pcgc_pmf_to_quantized_cdf(const float* pmf, int64_t rows, int N, int precisi
 int pcgc_range_encode(const int16_t* sym, int64_t n, const int32_t* cdf, int cdf_rows, int N, int precision,
                       uint8_t* out, int64_t cap, int64_t* len) {
   if (!sym || !cdf || !out || !len || cdf_rows < 1 || N < 1) return PCGC_ERR_BAD_ARG;
+  if (precision >= 1 && precision <= 16 && cap >= 2 * n + 8) {
+    const int rc = encode_string_branch_free(sym, n, cdf, cdf_rows, N, precision, out, len);
+    if (rc != PCGC_ERR_NOT_READY) return rc;
+  }
   Encoder e(out, cap, precision);
   int r = 0;
   for (int64_t i = 0; i < n; ++i) {
