@@ -294,6 +294,7 @@ cudaError_t launch_conv_ffma(const ConvCall& c, cudaStream_t s, int64_t* launche
 // a thread owns two voxels (y and y+4) so every broadcast weight load feeds 8 FMAs; lanes run along x (conflict-free).
 // The 27x16 weights + bias travel as a by-value kernel parameter: they sit in the constant bank and every FFMA takes its
 // weight as a constant operand (no shared-memory weight loads; the first version was LDS.128-bound at 9 TFLOP/s).
+// r02 last session: all-zero taps are skipped per warp (see the loop).
 struct ConvInParams { float w[27 * 16]; float b[16]; };
 
 template <typename T>
@@ -327,6 +328,9 @@ __global__ void __launch_bounds__(256) conv_in_pm_kernel(const T* __restrict__ i
     for (int t = 0; t < 27; ++t) {
       const int kz = t / 9, ky = (t / 3) % 3, kx = t % 3;
       const float v0 = s_in[z + kz][yy + ky][x + kx], v1 = s_in[z + kz][yy + 4 + ky][x + kx];
+      // occupancy cubes are ~98 % zeros: a tap none of the warp's 64 voxels sees occupied adds exactly nothing (0 * w + a = a), skip its
+      // 32 FMAs (warp-uniform branch; the result is bit-identical)
+      if (!__any_sync(0xffffffffu, v0 != 0.f || v1 != 0.f)) continue;
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         a0[c] = fmaf(v0, prm.w[t * 16 + c], a0[c]);
