@@ -77,6 +77,10 @@ struct UmmaArgs {
   int out_s2d;               // UEPI_VRN: write the output space-to-depth (grid n/2, 8*C channels) for a following stride-2 conv
   int up_ncls, up_cls0, up_cout;   // UEPI_UP: classes in this launch, first class, channels per class
   int dbg;                   // PCGC_UMMA_DBG bit mask (timing experiments only): 1 skip MMAs, 2 skip the A TMA, 4 skip epilogue
+  // far-field tiles (tile kernel, UEPI_VRN on the 64^3 grid): ff_mask[(b*n + z)*ty_n + by] bit bx = 1 when some occupied voxel lies inside the
+  // receptive field of that (z, y tile, x tile); a tile whose zt slices are all clear is COPIED from ff_src, the same layer's output for
+  // the all-zero cube (one cube, same layout as out_pm) -- bit-identical to computing it.  nullptr: every tile is computed.
+  const uint8_t* ff_mask; const __nv_bfloat16* ff_src;
   // z-streaming kernel (conv_umma_stream_kernel)
   int ring, zs, nacc;        // input-slice ring slots, output slices per segment, accumulator slots
   int slot_bytes;            // bytes of one ring slot = planes * slice_plane
@@ -265,6 +269,44 @@ __device__ __forceinline__ void epilogue_voxel(const UmmaArgs& a, float* v, cons
   }
 }
 
+// Far-field tiles: is tile (b, by, bx, z0 .. z0 + zt) free of occupied voxels inside its receptive field?  Both roles of the kernel
+// evaluate this on the same read-only mask, so they agree on which tiles exist for the barrier protocol.
+// (__noinline__, scalar arguments: inlined into the single-thread producer branch this loop crashes nvcc 12.9's optimiser.)
+__device__ __noinline__ bool ff_tile_clear(const uint8_t* mask, int n, int zt, int b, int by, int bx, int z0, int ty_n) {
+  const uint8_t* m = mask + ((size_t)b * n + z0) * ty_n + by;
+  uint32_t need = 0;
+  for (int zi = 0; zi < zt; ++zi) need |= m[zi * ty_n];
+  return !((need >> bx) & 1u);
+}
+// WT output voxels (the lines vy .. vy + WT - 1) of a far-field tile: the cells of the empty cube's output at the same positions
+// (addressing as epilogue_voxel's).  All loads are issued before the first store: the copy is latency-bound (L2 hits), not bandwidth-bound.
+template <int NPJ, int WT>
+__device__ __forceinline__ void ff_copy_voxels(const UmmaArgs& a, int b, int vz, int vy, int vx, size_t plane_elems) {
+  constexpr int RC = VrnRc<NPJ>::value;
+  uint4 t[WT][2 * RC];
+  size_t ops = plane_elems, offs[WT], cube = (size_t)a.out_planes * plane_elems;
+#pragma unroll
+  for (int j = 0; j < WT; ++j) {
+    offs[j] = (((size_t)vz * a.n + (vy + j)) * a.n + vx) * 8;
+    if (a.out_s2d) {
+      const int h = a.n >> 1;
+      ops = plane_elems >> 3;
+      const int par = ((vz & 1) << 2) | (((vy + j) & 1) << 1) | (vx & 1);
+      offs[j] = ((size_t)par * a.out_planes) * ops + ((((size_t)(vz >> 1) * h + ((vy + j) >> 1)) * h + (vx >> 1)) * 8);
+      cube = (size_t)a.out_planes * 8 * ops;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < WT; ++j)
+#pragma unroll
+    for (int p = 0; p < 2 * RC; ++p) t[j][p] = __ldg(reinterpret_cast<const uint4*>(a.ff_src + offs[j] + (size_t)p * ops));
+  __nv_bfloat16* dst = a.out_pm + (size_t)b * cube;
+#pragma unroll
+  for (int j = 0; j < WT; ++j)
+#pragma unroll
+    for (int p = 0; p < 2 * RC; ++p) *reinterpret_cast<uint4*>(dst + offs[j] + (size_t)p * ops) = t[j][p];
+}
+
 // PERSISTENT kernel: a CTA allocates TMEM, initialises its mbarriers, stages bias / 1x1x1 weights and (single-chunk
 // layers) the B tiles ONCE, then walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The r01 timing experiments showed
 // that per-CTA set-up + the 27 KB weight reload was ~40 % of the non-persistent kernel (0.23 of 0.58 ms for K_a16).
@@ -326,15 +368,17 @@ __global__ void __launch_bounds__(UMMA_THREADS, (NP <= 16 ? 3 : (NP <= 32 ? 2 : 
       bool alive = true;
       uint32_t n_full = 0, n_mma = 0;                  // completed phases of bar_full / bar_mma
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles && alive; tile += gridDim.x, ++it) {
+      for (int tile = blockIdx.x; tile < total_tiles && alive; tile += gridDim.x) {
         int r = tile;
         const int bx = r % tx_n; r /= tx_n;
         const int by = r % ty_n; r /= ty_n;
         const int bz = r % tz_n; r /= tz_n;
         const int b = r;
         const int x0 = bx * TILE_X, y0 = by * TILE_Y * WT, z0 = bz * a.zt;
-        const int set = it % a.nsets, use = it / a.nsets;          // use-th time this accumulator set is filled
-        for (int ch = 0; ch < a.kchunks && alive; ++ch) {
+        bool computed = true;                                      // far-field tiles are copied by the epilogue warps instead
+        if constexpr (EPI == UEPI_VRN) computed = !(a.ff_mask && ff_tile_clear(a.ff_mask, a.n, a.zt, b, by, bx, z0, ty_n));
+        const int set = it % a.nsets, use = it / a.nsets;          // use-th time this accumulator set is filled (it counts COMPUTED tiles)
+        for (int ch = 0; ch < a.kchunks && alive && computed; ++ch) {
           const bool load_b = !b_resident || it == 0;
           if (it > 0 || ch > 0) { alive = mbar_wait(bar_mma, (n_mma - 1) & 1, a.err, -102); if (!alive) break; }   // brick (and B) free
           mbar_expect_tx(bar_full, (uint32_t)(((a.dbg & 2) ? 0 : a.a_bytes) + (load_b ? a.b_bytes : 0)));
@@ -355,6 +399,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, (NP <= 16 ? 3 : (NP <= 32 ? 2 : 
           umma_commit(bar_mma);                       // brick reusable once these MMAs retire
           ++n_mma;
         }
+        it += computed ? 1 : 0;
       }
     }
     __syncwarp();
@@ -363,15 +408,22 @@ __global__ void __launch_bounds__(UMMA_THREADS, (NP <= 16 ? 3 : (NP <= 32 ? 2 : 
     const int row = (warp & 3) * 32 + lane;          // M row = TMEM lane = (y group, x) of the tile
     const size_t plane_elems = (size_t)a.n * a.n * a.n * 8;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int r = tile;
       const int bx = r % tx_n; r /= tx_n;
       const int by = r % ty_n; r /= ty_n;
       const int bz = r % tz_n; r /= tz_n;
       const int b = r;
       const int x0 = bx * TILE_X, y0 = by * TILE_Y * WT, z0 = bz * a.zt;
-      const int set = it % a.nsets, use = it / a.nsets;
       const int vx = x0 + (row & 7), vyb = y0 + WT * (row >> 3);
+      if constexpr (EPI == UEPI_VRN) {
+        if (a.ff_mask && ff_tile_clear(a.ff_mask, a.n, a.zt, b, by, bx, z0, ty_n)) {
+          // far-field tile: no MMA, no barrier -- every voxel is the empty cube's at the same position
+          for (int zi = (warp >> 2); zi < a.zt; zi += 2) ff_copy_voxels<NPJ, WT>(a, b, z0 + zi, vyb, vx, plane_elems);
+          continue;
+        }
+      }
+      const int set = it % a.nsets, use = it / a.nsets;
       const uint32_t lane_base = tmem_base + set * set_cols + ((uint32_t)((warp & 3) * 32) << 16);
       for (int zi = (warp >> 2); zi < ((a.dbg & 4) ? 0 : a.zt); zi += 2) {
         const int vz = z0 + zi;
@@ -435,6 +487,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, (NP <= 16 ? 3 : (NP <= 32 ? 2 : 
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_free + 8 * set) : "memory");
+      ++it;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1129,6 +1182,7 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
   a.w23 = w.w23; a.b23 = w.b23; a.c4 = w.c4; a.c2 = w.c2;
   a.up_ncls = w.up_ncls; a.up_cls0 = w.up_cls0; a.up_cout = w.up_cout;
   a.origin = w.origin; a.out_s2d = c.out_s2d;
+  a.ff_mask = nullptr; a.ff_src = nullptr;               // set below, on the tile-kernel path only
   for (int i = 0; i < 16; ++i) a.tap_mask[i] = w.tap_mask[i];
   a.err = c.err;
   { static const int dbg = getenv("PCGC_UMMA_DBG") ? atoi(getenv("PCGC_UMMA_DBG")) : 0; a.dbg = dbg; }
@@ -1237,6 +1291,7 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
   static const int persist = getenv("PCGC_UMMA_PERSIST") ? atoi(getenv("PCGC_UMMA_PERSIST")) : 1;  // 0: one tile per CTA
   const int grid = persist ? std::min(tiles, sms * per_sm) : tiles;
   if (launches) ++*launches;
+  if (c.ff_mask && c.ff_src && c.epi == UEPI_VRN && w.wt == 2 && n == 64) { a.ff_mask = c.ff_mask; a.ff_src = c.ff_src; }
   if (w.wt > 1) return launch_banded(tm, a, w.np, c.epi, a.cin8 != 0, w.wt, grid, smem, s);
   if (c.epi == UEPI_UP) {
     if (w.ntaps != 8 || w.np != 128) return cudaErrorNotSupported;
@@ -1260,6 +1315,62 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
     case 64: return launch_np<64, TAPS_27>(tm, a, c.epi, grid, smem, s);
   }
   return cudaErrorNotSupported;
+}
+
+// ---------------------------------------------------------------------------------------------- far-field classification
+// Kernel 1: one thread per row (b, z, y): the 64 occupancy bytes -> a 64-bit mask, dilated along x by r = 3 / 5 / 7 (shifts drop what
+// leaves the cube, like the zero padding) and collapsed to one bit per 8-voxel x tile.
+__global__ void __launch_bounds__(256) ff_row_mask_kernel(const uint8_t* __restrict__ cubes, int rows, uint8_t* __restrict__ row_mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  const uint4* src = reinterpret_cast<const uint4*>(cubes + (size_t)i * 64);
+  uint64_t m = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 v = __ldg(src + q);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int bb = 0; bb < 4; ++bb)
+        if ((w[k] >> (8 * bb)) & 0xFFu) m |= 1ull << (q * 16 + k * 4 + bb);
+  }
+  uint64_t d = m;
+  int done = 0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int r = 3 + 2 * k;
+    for (; done < r; ++done) d |= (d << 1) | (d >> 1);             // one more voxel of dilation per step
+    uint32_t t = 0;
+#pragma unroll
+    for (int bx = 0; bx < 8; ++bx) t |= ((d >> (8 * bx)) & 0xFFull) ? (1u << bx) : 0u;
+    row_mask[(size_t)k * rows + i] = (uint8_t)t;
+  }
+}
+// Kernel 2: one thread per (k, b, z, by): OR of the row masks over z +- r and the tile's 32 lines +- r.
+__global__ void __launch_bounds__(128) ff_tile_mask_kernel(const uint8_t* __restrict__ row_mask, int nb, uint8_t* __restrict__ ff_mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = nb * 128;
+  if (i >= 3 * per) return;
+  const int k = i / per, j = i - k * per;
+  const int by = j & 1, z = (j >> 1) & 63, b = j >> 7;
+  const int r = 3 + 2 * k;
+  const uint8_t* rm = row_mask + (size_t)k * nb * 4096 + (size_t)b * 4096;
+  const int z0 = max(z - r, 0), z1 = min(z + r, 63), y0 = max(32 * by - r, 0), y1 = min(32 * by + 31 + r, 63);
+  uint32_t t = 0;
+  for (int zz = z0; zz <= z1; ++zz)
+    for (int yy = y0; yy <= y1; ++yy) t |= rm[zz * 64 + yy];
+  ff_mask[i] = (uint8_t)t;
+}
+
+cudaError_t launch_ff_classify(const uint8_t* cubes, int nb, uint8_t* row_mask, uint8_t* ff_mask, cudaStream_t s, int64_t* launches) {
+  if (nb <= 0) return cudaSuccess;
+  PCGC_CARVEOUT_ONCE(ff_row_mask_kernel); PCGC_CARVEOUT_ONCE(ff_tile_mask_kernel);
+  const int rows = nb * 4096;
+  ff_row_mask_kernel<<<(rows + 255) / 256, 256, 0, s>>>(cubes, rows, row_mask);
+  ff_tile_mask_kernel<<<(3 * nb * 128 + 127) / 128, 128, 0, s>>>(row_mask, nb, ff_mask);
+  if (launches) *launches += 2;
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------- format converters

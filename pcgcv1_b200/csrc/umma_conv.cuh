@@ -61,6 +61,9 @@ struct UmmaCall {
   PmTensor res;                // UEPI_VRN: the block input x
   int out_s2d = 0;             // UEPI_VRN: write `out` space-to-depth (out = the n/2-grid, 8*C-channel tensor)
   int* err = nullptr;          // device int, set on device-side timeouts
+  // far-field tiles (UEPI_VRN on the tile kernel, 64^3 grid, y-band 2): mask from launch_ff_classify for this layer's radius + the layer's
+  // output for the all-zero cube; see UmmaArgs::ff_mask.  Ignored (every tile computed) by the other kernel forms.
+  const uint8_t* ff_mask = nullptr; const __nv_bfloat16* ff_src = nullptr;
   bool pin_tile = false;       // always the tile kernel, whatever PCGC_UMMA_STREAM / PCGC_UMMA_ZBAND / PCGC_KB_ZBAND say: the hyper
                                // decoder's loc / scale must have the same bits in the encoding and the decoding process
 };
@@ -70,6 +73,10 @@ cudaError_t launch_conv_umma_pm(const UmmaCall& c, const UmmaWeights& w, cudaStr
 int umma_stream_mode();
 // PCGC_UMMA_ZBAND (default 1, needs streaming): z-banded kernel for the NP = 16 layers (K_a16, K_a32, K_b16, deconv_out)
 int umma_zband_mode();
+// Far-field classification of a batch of uint8 occupancy cubes [nb][64][64][64] for the three VRN-16 blocks of the analysis transform
+// (receptive-field radii 3, 5, 7 voxels): ff_mask[k][(b*64 + z)*2 + by] bit bx = 1 when an occupied voxel lies within radius r_k of the
+// 8 (x) x 32 (y) voxels of tile (by, bx) in slice z.  row_mask: scratch [3][nb*4096] bytes; ff_mask: [3][nb*128] bytes.
+cudaError_t launch_ff_classify(const uint8_t* cubes, int nb, uint8_t* row_mask, uint8_t* ff_mask, cudaStream_t s, int64_t* launches);
 // float32 NDHWC (channel stride/offset) <-> PM
 cudaError_t launch_f32_to_pm(const float* in, int in_cs, int in_co, const PmTensor& out, cudaStream_t s, int64_t* launches);
 cudaError_t launch_pm_to_f32(const PmTensor& in, float* out, int out_cs, int out_co, cudaStream_t s, int64_t* launches);
