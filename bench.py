@@ -196,7 +196,9 @@ def config1(args, cubes_per_gpu, points_per_gpu):
                         "its last kernel is queued) -> select_voxels(codec=, dtype=uint8): top-k on the GPU and the uint8 masks to "
                         "the host part by part behind the synthesis (the reference does .numpy() then NumPy top-k, test.py:115)",
             "decode_schedule": os.environ.get("PCGC_DEC_RAMP", "8,24,64") + " cubes, then the rest",
-            "conv_engine": os.environ.get("PCGC_ENGINE", "auto")}
+            "conv_engine": os.environ.get("PCGC_ENGINE", "auto"),
+            "far_field_tiles": "off" if os.environ.get("PCGC_FARFIELD", "1") == "0" else "on (analysis K_b16: tiles without an occupied voxel in "
+                               "their receptive field are copied from the empty cube's activations, bit-identical)"}
 
 
 def run_gpu(args):
@@ -325,7 +327,10 @@ def run_gpu(args):
                 per_launch = top["flops"] / top["count"] / tr["algorithmic_flops_per_cube"]
                 roof["cubes_per_launch_avg"] = round(per_launch, 2)
             scale = per_launch / tr.get("cubes_per_launch", per_launch)
-            traffic = tr["dram_bytes_per_launch"] * scale
+            per_capture = tr["dram_bytes_per_launch"]
+            if os.environ.get("PCGC_FARFIELD", "1") == "0":          # every tile computed: the capture without far-field copies
+                per_capture = tr.get("dram_bytes_per_launch_all_tiles_computed", per_capture)
+            traffic = per_capture * scale
             roof["traffic"] = int(traffic)
             roof["traffic_source"] = tr["source"]
             hbm = {"achieved_gbs": round(traffic / (per_launch_ms * 1e-3) / 1e9, 1), "peak_gbs": peaks["hbm_gbs"]}
